@@ -1,0 +1,146 @@
+/*
+ * include/rogtk_gpu.h -- C ABI of the B200-native per-UMI de Bruijn k-mer count / prune engine.
+ *
+ * This is the drop-in boundary for ONE path of tzeitim/rogtk: everything that
+ *     debruijn::filter::filter_kmers::<K,_,_,_,_>(seq_tuples, &Box::new(CountFilter::new(min_coverage)), true, true, 4)
+ * does inside analyze_dbg (reference src/fracture.rs:105-158, call at :110-116), for many groups (UMIs)
+ * per call, on one B200.  The Rust host (src/fracture.rs, src/expressions.rs, src/fracture_opt.rs) keeps
+ * its signatures; only the filter_kmers call is replaced by a call into this library (INTEGRATION.md shows
+ * the Rust FFI stub).  No torch / Python types appear here: plain pointers and sizes only.
+ *
+ * Semantics per group (restated in oracle/dbg_oracle.c):
+ *   - null rows are dropped                                        (src/expressions.rs:737-740)
+ *   - a read is used iff every byte is one of ACGTacgt             (src/fracture.rs:218-229)
+ *   - K = 4/8/16/32/64, the smallest >= k                          (src/fracture.rs:246-256)
+ *   - every window of K bases is one observation; exts.left = bit(previous base) (absent at read start),
+ *     exts.right = bit(next base) << 4 (absent at read end); no reverse-complement canonicalisation
+ *   - per distinct k-mer: count = min(65535, #observations), exts = OR over observations
+ *   - survivors: count >= min_coverage, emitted in ascending k-mer order (k-mer read as a base-4
+ *     big-endian number, A<C<G<T) -- exactly the three vectors filter_kmers passes to BoomHashMap2::new.
+ */
+#ifndef ROGTK_GPU_H
+#define ROGTK_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROGTK_GPU_ABI_VERSION 1
+
+/* error codes (0 = success; never throws, never aborts) */
+#define ROGTK_OK 0
+#define ROGTK_ERR_INVALID_ARG (-1)
+#define ROGTK_ERR_CUDA (-2)
+#define ROGTK_ERR_OOM (-3)
+#define ROGTK_ERR_UNSUPPORTED (-4)
+#define ROGTK_ERR_INTERNAL (-5)
+
+/* string column layouts (Arrow C Data Interface buffers of the Series handed to the plugin,
+ * reference src/expressions.rs:734 `inputs[0].str()`) */
+#define ROGTK_UTF8_I32 0  /* Arrow Utf8: int32 offsets + one data buffer */
+#define ROGTK_UTF8_I64 1  /* Arrow LargeUtf8: int64 offsets + one data buffer */
+#define ROGTK_UTF8_VIEW 2 /* Arrow Utf8View (Polars >= 0.43 String): 16-byte views + N data buffers */
+
+/* flags */
+#define ROGTK_EMIT_CSR (1u << 0)         /* successor adjacency among survivors (BaseGraph r_edges, fracture.rs:343-348) */
+#define ROGTK_EMIT_STATS (1u << 1)       /* node / terminal / isolated counts (fracture.rs:124-141) */
+#define ROGTK_EXACT_K (1u << 2)          /* NON-REFERENCE extension: use k itself (1..64) instead of K_eff rounding */
+#define ROGTK_INPUT_ON_DEVICE (1u << 3)  /* all rogtk_strcol / group_offsets pointers are device pointers */
+#define ROGTK_OUTPUT_ON_DEVICE (1u << 4) /* leave the result arrays in device memory */
+#define ROGTK_FORCE_SPILL (1u << 5)      /* testing: bypass the shared-memory tables, use the HBM tables only */
+
+typedef struct rogtk_gpu_ctx rogtk_gpu_ctx;
+
+/* One chunk of a string column.  A multi-chunk Series is passed as several calls or concatenated by the caller. */
+typedef struct rogtk_strcol {
+    int32_t layout;                 /* ROGTK_UTF8_* */
+    int32_t n_buffers;              /* number of data buffers (1 for I32/I64) */
+    int64_t n_rows;
+    const uint8_t *validity;        /* Arrow validity bitmap, LSB first, or NULL (= all valid) */
+    int64_t validity_bit_offset;    /* bit index of row 0 inside validity (Arrow array offset) */
+    const void *offsets_or_views;   /* int32[n_rows+1] | int64[n_rows+1] | view[n_rows] (16 B each) */
+    const uint8_t *const *data;     /* data[n_buffers] */
+    const int64_t *data_len;        /* byte length of each data buffer */
+} rogtk_strcol;
+
+/* Result of one batch.  All arrays are callee-allocated (pinned host memory, or device memory with
+ * ROGTK_OUTPUT_ON_DEVICE) and released with rogtk_gpu_free_batch. */
+typedef struct rogtk_graph_batch {
+    int64_t n_groups;
+    int64_t n_kmers;         /* total survivors */
+    int64_t n_edges;         /* total CSR entries (0 unless ROGTK_EMIT_CSR) */
+    int64_t n_observations;  /* sum over used reads of max(0, len-K+1) */
+    int32_t k_eff;           /* K used (after rounding); -1 when k > 64 (empty result, fracture.rs:212-215) */
+    int32_t on_device;       /* 1 if the arrays below live in device memory */
+    int64_t *kmer_offsets;   /* [n_groups+1] survivors of group g are [kmer_offsets[g], kmer_offsets[g+1]) */
+    uint64_t *kmers_lo;      /* [n_kmers] low 64 bits of the k-mer value, ascending inside each group */
+    uint64_t *kmers_hi;      /* [n_kmers] high 64 bits; NULL unless k_eff > 32 */
+    uint8_t *exts;           /* [n_kmers] debruijn::Exts byte: low nibble left, high nibble right, bit = base code */
+    uint16_t *counts;        /* [n_kmers] saturating u16 */
+    int64_t *csr_row_ptr;    /* [n_kmers+1] or NULL */
+    int32_t *csr_col;        /* [n_edges] successor index inside the group, or NULL */
+    uint32_t *stats;         /* [3*n_groups] node, terminal, isolated counts, or NULL */
+    float ms_total;          /* device time of the whole pipeline (CUDA events on the context stream) */
+    float ms_count;          /* device time of the counting phase (shared-memory path + HBM-table path) */
+    float ms_hot_kernel;     /* device time of the k_smem_count launch alone (the dominant kernel; roofline numerator) */
+    float _pad0;
+    int64_t n_spilled_groups;/* groups that went through the HBM-table path */
+    void *_owner;            /* internal */
+} rogtk_graph_batch;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------------- */
+int rogtk_gpu_abi_version(void);
+int rogtk_gpu_device_count(void);
+/* workspace_bytes: upper bound for transient HBM tables + pools (0 = 25% of free device memory) */
+rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, int *err);
+void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx);
+const char *rogtk_gpu_last_error(rogtk_gpu_ctx *ctx);
+
+/* ---- host helpers that mirror reference host logic (no GPU needed) ------------------------------------------ */
+/* src/fracture.rs:246-256; returns -1 for k > 64 */
+int rogtk_gpu_k_eff(int64_t k);
+/* src/fracture.rs:24-54 over the non-null rows of a (host) column with int64 offsets */
+int64_t rogtk_gpu_estimate_k(const int64_t *offsets, const uint8_t *validity, int64_t n_rows);
+/* UMI -> GPU shard: splitmix64(umi_id) mod n_shards */
+int32_t rogtk_gpu_shard_of(uint64_t umi_id, int32_t n_shards);
+
+/* ---- the hot path --------------------------------------------------------------------------------------------
+ * Replaces, for n_groups groups at once, the filter_kmers call at reference src/fracture.rs:110-116.
+ *   reads          one column chunk; rows of a group are contiguous
+ *   group_offsets  [n_groups+1] row boundaries (a List(String) column's offsets, or {0,n_rows} for the legacy
+ *                  one-group-per-call plugin form, src/expressions.rs:695)
+ *   k, min_coverage as in AssemblyKwargs (src/expressions.rs:669-687)
+ * Thread-safe: calls on one ctx are serialised internally; use one ctx per host thread for concurrency
+ * (Polars calls the plugin concurrently from its rayon workers). */
+int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets,
+                                int64_t n_groups, int64_t k, uint32_t min_coverage, uint32_t flags,
+                                rogtk_graph_batch *out);
+void rogtk_gpu_free_batch(rogtk_gpu_ctx *ctx, rogtk_graph_batch *batch);
+
+/* ---- bench / test utilities (not part of the reference surface) ------------------------------------------------ */
+/* Synthetic reads of SURVEY 8(d) generated directly in HBM: n_umis groups x reads_per_umi reads of read_len bases
+ * drawn from a per-UMI random template of template_len bases with iid substitution errors (err_per_64k / 65536).
+ * d_data must hold n_umis*reads_per_umi*read_len bytes, d_offsets n_umis*reads_per_umi+1 int64,
+ * d_group_offsets n_umis+1 int64 (all device pointers).  umi_base = global index of the first UMI. */
+int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t reads_per_umi,
+                          int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data,
+                          int64_t *d_offsets, int64_t *d_group_offsets);
+/* raw device/pinned memory for harnesses that must not depend on torch */
+void *rogtk_gpu_device_alloc(rogtk_gpu_ctx *ctx, size_t bytes);
+void rogtk_gpu_device_free(rogtk_gpu_ctx *ctx, void *p);
+void *rogtk_gpu_pinned_alloc(rogtk_gpu_ctx *ctx, size_t bytes);
+void rogtk_gpu_pinned_free(rogtk_gpu_ctx *ctx, void *p);
+int rogtk_gpu_memcpy_h2d(rogtk_gpu_ctx *ctx, void *dst, const void *src, size_t bytes);
+int rogtk_gpu_memcpy_d2h(rogtk_gpu_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx);
+/* write a >L2 scratch buffer (L2 flush between timed iterations) */
+int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,351 @@
+"""oracle/dbg_oracle.py -- Python face of the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module; nothing under rogtk_b200/ does.  PARITY STATUS: "parity unpinned" at the k-mer level (see
+oracle/dbg_oracle.h): the arithmetic lives in the un-vendored crates debruijn ^0.3.4 / boomphf ^0.5
+(reference Cargo.toml:51,55).
+
+Two independent implementations live here:
+
+* ``count_prune_batch``  -- ctypes call into oracle/libdbg_oracle.so (sort-based literal restatement of
+  debruijn::filter::filter_kmers + CountFilter as called at reference src/fracture.rs:110-116);
+* ``count_prune_group_py`` -- a dict-based pure-Python restatement written separately from the C one
+  (different data structure, string based) used to cross-check it on small inputs.
+
+plus small pure-Python restatements of the steps downstream of the hot path (``compress_unitigs`` ~
+debruijn::compression::compress_graph as called at src/fracture.rs:361-362; ``shortest_path_contig`` ~
+src/djfind.rs:257-304) which are used ONLY to pin the oracle against the contig-level expectations of the
+reference's own unit tests (src/fracture.rs:593-679).
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import heapq
+import math
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdbg_oracle.so")
+_lib = None
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [
+        ("n_groups", ctypes.c_int64),
+        ("n_kmers", ctypes.c_int64),
+        ("n_observations", ctypes.c_int64),
+        ("k_eff", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
+        ("kmer_offsets", ctypes.POINTER(ctypes.c_int64)),
+        ("kmers_lo", ctypes.POINTER(ctypes.c_uint64)),
+        ("kmers_hi", ctypes.POINTER(ctypes.c_uint64)),
+        ("exts", ctypes.POINTER(ctypes.c_uint8)),
+        ("counts", ctypes.POINTER(ctypes.c_uint16)),
+        ("stats", ctypes.POINTER(ctypes.c_uint32)),
+        ("csr_row_ptr", ctypes.POINTER(ctypes.c_int64)),
+        ("csr_col", ctypes.POINTER(ctypes.c_int32)),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/libdbg_oracle.so with the committed Makefile (gcc, OpenMP)."""
+    src = [os.path.join(_HERE, f) for f in ("dbg_oracle.c", "dbg_oracle_impl.inc", "dbg_oracle.h")]
+    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
+        subprocess.run(["make", "-C", _HERE, "clean", "all"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = ctypes.CDLL(_LIB_PATH)
+        lib.oracle_k_eff.argtypes = [ctypes.c_int64]
+        lib.oracle_k_eff.restype = ctypes.c_int
+        lib.oracle_estimate_k.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        lib.oracle_estimate_k.restype = ctypes.c_int64
+        lib.oracle_count_prune_batch.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+            ctypes.c_int64, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Batch)]
+        lib.oracle_count_prune_batch.restype = ctypes.c_int
+        lib.oracle_free_batch.argtypes = [ctypes.POINTER(_Batch)]
+        lib.oracle_max_threads.restype = ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+@dataclass
+class GraphBatch:
+    """Per-group pruned de Bruijn nodes: exactly the three vectors filter_kmers hands to BoomHashMap2::new
+    (ascending k-mers, Exts bytes, u16 counts) for every group, concatenated, plus group offsets."""
+    k_eff: int
+    n_observations: int
+    kmer_offsets: np.ndarray  # int64 [n_groups+1]
+    kmers_lo: np.ndarray      # uint64
+    kmers_hi: np.ndarray | None
+    exts: np.ndarray          # uint8
+    counts: np.ndarray        # uint16
+    stats: np.ndarray         # uint32 [n_groups,3]
+    csr_row_ptr: np.ndarray | None = None
+    csr_col: np.ndarray | None = None
+
+    @property
+    def n_groups(self) -> int:
+        return len(self.kmer_offsets) - 1
+
+    def group(self, g: int):
+        a, b = int(self.kmer_offsets[g]), int(self.kmer_offsets[g + 1])
+        hi = self.kmers_hi[a:b] if self.kmers_hi is not None else None
+        return self.kmers_lo[a:b], hi, self.exts[a:b], self.counts[a:b]
+
+
+def max_threads() -> int:
+    return int(_load().oracle_max_threads())
+
+
+def k_eff(k: int) -> int:
+    """reference src/fracture.rs:246-256"""
+    return int(_load().oracle_k_eff(int(k)))
+
+
+def estimate_k(offsets: np.ndarray, validity: np.ndarray | None = None) -> int:
+    """reference src/fracture.rs:24-54"""
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    vp = validity.ctypes.data if validity is not None else None
+    return int(_load().oracle_estimate_k(offsets.ctypes.data, vp, len(offsets) - 1))
+
+
+def count_prune_batch(data: np.ndarray, offsets: np.ndarray, group_offsets: np.ndarray, k: int,
+                      min_coverage: int, validity: np.ndarray | None = None, exact_k: bool = False,
+                      emit_csr: bool = False, n_threads: int = 0) -> GraphBatch:
+    lib = _load()
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    group_offsets = np.ascontiguousarray(group_offsets, dtype=np.int64)
+    if validity is not None:
+        validity = np.ascontiguousarray(validity, dtype=np.uint8)
+    b = _Batch()
+    n_rows, n_groups = len(offsets) - 1, len(group_offsets) - 1
+    rc = lib.oracle_count_prune_batch(
+        data.ctypes.data if data.size else None, offsets.ctypes.data,
+        validity.ctypes.data if validity is not None else None, n_rows,
+        group_offsets.ctypes.data, n_groups, int(k), int(min_coverage), int(exact_k), int(emit_csr),
+        int(n_threads), ctypes.byref(b))
+    if rc != 0:
+        raise ValueError(f"oracle_count_prune_batch failed rc={rc}")
+    n = int(b.n_kmers)
+
+    def arr(ptr, count, dt):
+        if not ptr or count == 0:
+            return np.zeros(0, dtype=dt)
+        return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dt, copy=True)
+
+    out = GraphBatch(
+        k_eff=int(b.k_eff), n_observations=int(b.n_observations),
+        kmer_offsets=arr(b.kmer_offsets, n_groups + 1, np.int64),
+        kmers_lo=arr(b.kmers_lo, n, np.uint64),
+        kmers_hi=arr(b.kmers_hi, n, np.uint64) if b.kmers_hi else None,
+        exts=arr(b.exts, n, np.uint8), counts=arr(b.counts, n, np.uint16),
+        stats=arr(b.stats, n_groups * 3, np.uint32).reshape(n_groups, 3),
+    )
+    if emit_csr:
+        out.csr_row_ptr = arr(b.csr_row_ptr, n + 1, np.int64)
+        ne = int(out.csr_row_ptr[-1]) if n + 1 > 0 else 0
+        out.csr_col = arr(b.csr_col, ne, np.int32)
+    lib.oracle_free_batch(ctypes.byref(b))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# helpers shared by tests / bench
+# ----------------------------------------------------------------------------------------------------
+def strings_to_arrow(reads):
+    """list[str|bytes|None] -> (data u8, offsets i64, validity bitmap u8 or None)"""
+    offs = np.zeros(len(reads) + 1, dtype=np.int64)
+    chunks = []
+    valid = np.ones(len(reads), dtype=bool)
+    for i, r in enumerate(reads):
+        if r is None:
+            valid[i] = False
+            r = b""
+        if isinstance(r, str):
+            r = r.encode("utf-8")
+        chunks.append(r)
+        offs[i + 1] = offs[i] + len(r)
+    data = np.frombuffer(b"".join(chunks), dtype=np.uint8).copy() if chunks else np.zeros(0, np.uint8)
+    validity = None if valid.all() else np.packbits(valid, bitorder="little")
+    return data, offs, validity
+
+
+def kmer_to_str(lo: int, hi: int, K: int) -> str:
+    v = (int(hi) << 64) | int(lo)
+    return "".join("ACGT"[(v >> (2 * (K - 1 - p))) & 3] for p in range(K))
+
+
+def digest(batch: GraphBatch, g: int = 0) -> str:
+    """SHA-256 of 'KMER<TAB>EE<TAB>COUNT\\n' lines (SURVEY Appendix B.1 digest format)."""
+    lo, hi, ex, ct = batch.group(g)
+    h = hashlib.sha256()
+    for i in range(len(lo)):
+        s = kmer_to_str(int(lo[i]), int(hi[i]) if hi is not None else 0, batch.k_eff)
+        h.update(f"{s}\t{int(ex[i]):02x}\t{int(ct[i])}\n".encode())
+    return h.hexdigest()
+
+
+# ----------------------------------------------------------------------------------------------------
+# independent implementation #2 (dict over strings; no shared code with the C oracle)
+# ----------------------------------------------------------------------------------------------------
+def k_eff_py(k: int) -> int:
+    for K in (4, 8, 16, 32, 64):
+        if k <= K:
+            return K
+    return -1
+
+
+def count_prune_group_py(reads, k: int, min_coverage: int, exact_k: bool = False):
+    """One group.  reads: list[str|None].  Returns list of (kmer_str, exts_byte, count) ascending.
+    Follows reference src/expressions.rs:737-740 (drop nulls), src/fracture.rs:218-229 (upper-case; drop reads
+    with a non-ACGT byte), :246-256 (K rounding) and the filter_kmers/CountFilter semantics."""
+    K = k if exact_k else k_eff_py(k)
+    if K < 0:
+        return []
+    table: dict[str, list[int]] = {}
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for r in reads:
+        if r is None:
+            continue
+        if isinstance(r, bytes):
+            try:
+                r = r.decode("utf-8")
+            except UnicodeDecodeError:
+                continue
+        s = r.upper()
+        if any(ch not in code for ch in s):
+            continue
+        for pos in range(0, len(s) - K + 1):
+            km = s[pos:pos + K]
+            e = 0
+            if pos > 0:
+                e |= 1 << code[s[pos - 1]]
+            if pos + K < len(s):
+                e |= 16 << code[s[pos + K]]
+            ent = table.setdefault(km, [0, 0])
+            ent[0] = min(65535, ent[0] + 1)
+            ent[1] |= e
+    return [(km, ent[1], ent[0]) for km, ent in sorted(table.items()) if ent[0] >= min_coverage]
+
+
+def batch_group_as_tuples(batch: GraphBatch, g: int):
+    lo, hi, ex, ct = batch.group(g)
+    return [(kmer_to_str(int(lo[i]), int(hi[i]) if hi is not None else 0, batch.k_eff), int(ex[i]), int(ct[i]))
+            for i in range(len(lo))]
+
+
+# ----------------------------------------------------------------------------------------------------
+# downstream restatements, used only to pin against the reference's contig-level test expectations
+# ----------------------------------------------------------------------------------------------------
+def compress_unitigs(nodes, K: int):
+    """nodes: list of (kmer_str, exts, count) (any order).  Maximal non-branching paths, K-1 overlap merge,
+    saturating-u16 count fold (reference src/fracture.rs:361-362).  Returns the SET of contig strings
+    (order in the reference depends on boomphf slot order, SURVEY D-3, so only the set is comparable)."""
+    present = {km: (e, c) for km, e, c in nodes}
+
+    def fixed(km):
+        e, _ = present[km]
+        f = 0
+        for b in range(4):
+            if e & (1 << b) and ("ACGT"[b] + km[:-1]) in present:
+                f |= 1 << b
+            if e & (16 << b) and (km[1:] + "ACGT"[b]) in present:
+                f |= 16 << b
+        return f
+
+    fx = {km: fixed(km) for km in present}
+
+    def sole(nib):
+        return bin(nib).count("1") == 1
+
+    def step(km, right: bool):
+        e = fx[km]
+        nib = (e >> 4) if right else (e & 15)
+        if not sole(nib):
+            return None
+        b = nib.bit_length() - 1
+        nxt = (km[1:] + "ACGT"[b]) if right else ("ACGT"[b] + km[:-1])
+        back = (fx[nxt] & 15) if right else (fx[nxt] >> 4)
+        if not sole(back) or nxt == km:
+            return None
+        return nxt
+
+    used, contigs = set(), []
+    for km in sorted(present):
+        if km in used:
+            continue
+        path = [km]
+        used.add(km)
+        cur = km
+        while True:
+            n = step(cur, True)
+            if n is None or n in used:
+                break
+            path.append(n)
+            used.add(n)
+            cur = n
+        cur = km
+        while True:
+            n = step(cur, False)
+            if n is None or n in used:
+                break
+            path.insert(0, n)
+            used.add(n)
+            cur = n
+        contigs.append(path[0] + "".join(p[-1] for p in path[1:]))
+    return set(contigs)
+
+
+def shortest_path_contig(nodes, K: int, start_anchor: str, end_anchor: str):
+    """reference src/djfind.rs:257-304 on the uncompressed node graph: nodes whose k-mer string starts with
+    start_anchor / ends with end_anchor (djfind.rs:124-154), edge weight -ln(mean coverage) (:113-114),
+    first start x first end with a path wins.  Small graphs only; tie behaviour is not reproduced (the pinned
+    fixture is a single chain)."""
+    order = [km for km, _, _ in nodes]
+    cov = {km: c for km, _, c in nodes}
+    ext = {km: e for km, e, _ in nodes}
+    starts = [km for km in order if km.startswith(start_anchor)]
+    ends = [km for km in order if km.endswith(end_anchor)]
+    if not starts or not ends:
+        return None
+
+    def succ(km):
+        for b in range(4):
+            if ext[km] & (16 << b):
+                n = km[1:] + "ACGT"[b]
+                if n in cov:
+                    yield n, -math.log((cov[km] + cov[n]) / 2.0)
+
+    for s in starts:
+        dist, prev, seen = {s: 0.0}, {}, set()
+        pq = [(0.0, s)]
+        while pq:
+            d, u = heapq.heappop(pq)
+            if u in seen:
+                continue
+            seen.add(u)
+            for v, w in succ(u):
+                if v not in seen and d + w < dist.get(v, math.inf):
+                    dist[v] = d + w
+                    prev[v] = u
+                    heapq.heappush(pq, (d + w, v))
+        for e in ends:
+            if e in dist:
+                path = [e]
+                while path[-1] != s:
+                    path.append(prev[path[-1]])
+                path.reverse()
+                return path[0] + "".join(p[K - 1:] for p in path[1:])
+    return None

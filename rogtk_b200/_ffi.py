@@ -1,0 +1,126 @@
+"""ctypes binding of include/rogtk_gpu.h (the C ABI a Rust/PyO3 host would bind with `extern "C"`).
+
+The product path has no CPU fallback: if librogtk_gpu.so is missing this module raises, and if no B200 is visible
+``rogtk_gpu_create`` fails with ROGTK_ERR_CUDA and :class:`rogtk_b200.Engine` raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librogtk_gpu.so")
+
+ROGTK_OK = 0
+ROGTK_ERR_INVALID_ARG = -1
+ROGTK_ERR_CUDA = -2
+ROGTK_ERR_OOM = -3
+ROGTK_ERR_UNSUPPORTED = -4
+ROGTK_ERR_INTERNAL = -5
+
+UTF8_I32, UTF8_I64, UTF8_VIEW = 0, 1, 2
+
+EMIT_CSR = 1 << 0
+EMIT_STATS = 1 << 1
+EXACT_K = 1 << 2
+INPUT_ON_DEVICE = 1 << 3
+OUTPUT_ON_DEVICE = 1 << 4
+FORCE_SPILL = 1 << 5
+
+# every symbol include/rogtk_gpu.h declares (tests/test_abi.py checks the .so exports all of them)
+SYMBOLS = [
+    "rogtk_gpu_abi_version", "rogtk_gpu_device_count", "rogtk_gpu_create", "rogtk_gpu_destroy", "rogtk_gpu_last_error",
+    "rogtk_gpu_k_eff", "rogtk_gpu_estimate_k", "rogtk_gpu_shard_of", "rogtk_gpu_count_prune_batch", "rogtk_gpu_free_batch",
+    "rogtk_gpu_synth_reads", "rogtk_gpu_device_alloc", "rogtk_gpu_device_free", "rogtk_gpu_pinned_alloc",
+    "rogtk_gpu_pinned_free", "rogtk_gpu_memcpy_h2d", "rogtk_gpu_memcpy_d2h", "rogtk_gpu_launch_count", "rogtk_gpu_flush_l2",
+]
+
+
+class StrCol(ctypes.Structure):
+    _fields_ = [
+        ("layout", ctypes.c_int32),
+        ("n_buffers", ctypes.c_int32),
+        ("n_rows", ctypes.c_int64),
+        ("validity", ctypes.c_void_p),
+        ("validity_bit_offset", ctypes.c_int64),
+        ("offsets_or_views", ctypes.c_void_p),
+        ("data", ctypes.POINTER(ctypes.c_void_p)),
+        ("data_len", ctypes.POINTER(ctypes.c_int64)),
+    ]
+
+
+class GraphBatchC(ctypes.Structure):
+    _fields_ = [
+        ("n_groups", ctypes.c_int64),
+        ("n_kmers", ctypes.c_int64),
+        ("n_edges", ctypes.c_int64),
+        ("n_observations", ctypes.c_int64),
+        ("k_eff", ctypes.c_int32),
+        ("on_device", ctypes.c_int32),
+        ("kmer_offsets", ctypes.c_void_p),
+        ("kmers_lo", ctypes.c_void_p),
+        ("kmers_hi", ctypes.c_void_p),
+        ("exts", ctypes.c_void_p),
+        ("counts", ctypes.c_void_p),
+        ("csr_row_ptr", ctypes.c_void_p),
+        ("csr_col", ctypes.c_void_p),
+        ("stats", ctypes.c_void_p),
+        ("ms_total", ctypes.c_float),
+        ("ms_count", ctypes.c_float),
+        ("ms_hot_kernel", ctypes.c_float),
+        ("_pad0", ctypes.c_float),
+        ("n_spilled_groups", ctypes.c_int64),
+        ("_owner", ctypes.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load librogtk_gpu.so (built in-tree by rogtk_b200/csrc/Makefile).  Raises if it is missing: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make -C rogtk_b200/csrc` (or __graft_entry__.build()); "
+            "rogtk_b200 has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, u32, u64, sz = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64,
+                                  ctypes.c_size_t)
+    lib.rogtk_gpu_abi_version.restype = ctypes.c_int
+    lib.rogtk_gpu_device_count.restype = ctypes.c_int
+    lib.rogtk_gpu_create.argtypes = [ctypes.c_int, sz, ctypes.POINTER(ctypes.c_int)]
+    lib.rogtk_gpu_create.restype = vp
+    lib.rogtk_gpu_destroy.argtypes = [vp]
+    lib.rogtk_gpu_last_error.argtypes = [vp]
+    lib.rogtk_gpu_last_error.restype = ctypes.c_char_p
+    lib.rogtk_gpu_k_eff.argtypes = [i64]
+    lib.rogtk_gpu_k_eff.restype = ctypes.c_int
+    lib.rogtk_gpu_estimate_k.argtypes = [vp, vp, i64]
+    lib.rogtk_gpu_estimate_k.restype = i64
+    lib.rogtk_gpu_shard_of.argtypes = [u64, i32]
+    lib.rogtk_gpu_shard_of.restype = i32
+    lib.rogtk_gpu_count_prune_batch.argtypes = [vp, ctypes.POINTER(StrCol), vp, i64, i64, u32, u32,
+                                                ctypes.POINTER(GraphBatchC)]
+    lib.rogtk_gpu_count_prune_batch.restype = ctypes.c_int
+    lib.rogtk_gpu_free_batch.argtypes = [vp, ctypes.POINTER(GraphBatchC)]
+    lib.rogtk_gpu_synth_reads.argtypes = [vp, u64, i64, i64, i32, i32, i32, u32, vp, vp, vp]
+    lib.rogtk_gpu_synth_reads.restype = ctypes.c_int
+    lib.rogtk_gpu_device_alloc.argtypes = [vp, sz]
+    lib.rogtk_gpu_device_alloc.restype = vp
+    lib.rogtk_gpu_device_free.argtypes = [vp, vp]
+    lib.rogtk_gpu_pinned_alloc.argtypes = [vp, sz]
+    lib.rogtk_gpu_pinned_alloc.restype = vp
+    lib.rogtk_gpu_pinned_free.argtypes = [vp, vp]
+    lib.rogtk_gpu_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    lib.rogtk_gpu_memcpy_h2d.restype = ctypes.c_int
+    lib.rogtk_gpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    lib.rogtk_gpu_memcpy_d2h.restype = ctypes.c_int
+    lib.rogtk_gpu_launch_count.argtypes = [vp]
+    lib.rogtk_gpu_launch_count.restype = i64
+    lib.rogtk_gpu_flush_l2.argtypes = [vp]
+    lib.rogtk_gpu_flush_l2.restype = ctypes.c_int
+    _lib = lib
+    return lib

@@ -1,0 +1,193 @@
+// kernels_post.cuh -- kernels either side of the counting step: Utf8View gather (ingest), final assembly of the
+// dense per-group output, node statistics (reference src/fracture.rs:124-141) and the successor CSR that stands in
+// for BaseGraph::finish()'s neighbour lookup (reference src/fracture.rs:343-348), plus the synthetic
+// read generator used by bench.py / tests.
+#pragma once
+#include "common.cuh"
+
+namespace rogtk {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Arrow Utf8View -> contiguous (LargeUtf8-like) column
+// view = { u32 len; if len<=12: 12 inline bytes; else u32 prefix, u32 buffer_index, u32 offset }
+// ---------------------------------------------------------------------------------------------------------------
+struct View16 {
+    uint32_t len, a, b, c;
+};
+
+__global__ void k_view_len(const View16 *views, int64_t n_rows, const uint8_t *validity, int64_t vbo, int64_t *lens)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    bool ok = true;
+    if (validity) {
+        int64_t b = r + vbo;
+        ok = (validity[b >> 3] >> (b & 7)) & 1;
+    }
+    lens[r] = ok ? (int64_t)views[r].len : 0;
+}
+
+// one warp per row
+__global__ void k_view_gather(const View16 *views, int64_t n_rows, const uint8_t *const *bufs, const int64_t *offsets,
+                              uint8_t *out)
+{
+    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    const unsigned lane = lane_id();
+    int64_t o = offsets[r];
+    int64_t len = offsets[r + 1] - o;   // 0 for null rows
+    if (len == 0) return;
+    const View16 v = views[r];
+    const uint8_t *src = (v.len <= 12) ? reinterpret_cast<const uint8_t *>(&views[r]) + 4 : bufs[v.b] + v.c;
+    for (int64_t j = lane; j < len; j += 32) out[o + j] = src[j];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// final assembly
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory path survivors sit in a pool in completion order; copy group g's run to its dense position.
+// one warp per group (runs are ~1k entries), grid-stride.
+__global__ void k_gather_pool(int64_t n_groups, const int64_t *pool_start /* -1: not in pool */, const int64_t *kmer_offsets,
+                              const uint64_t *p_lo, const uint64_t *p_hi, const uint8_t *p_exts, const uint16_t *p_counts,
+                              uint64_t *o_lo, uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts)
+{
+    const unsigned lane = lane_id();
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += nw) {
+        const int64_t ps = pool_start[g];
+        if (ps < 0) continue;
+        const int64_t o = kmer_offsets[g], n = kmer_offsets[g + 1] - o;
+        for (int64_t j = lane; j < n; j += 32) {
+            o_lo[o + j] = p_lo[ps + j];
+            if (o_hi) o_hi[o + j] = p_hi[ps + j];
+            o_exts[o + j] = p_exts[ps + j];
+            o_counts[o + j] = p_counts[ps + j];
+        }
+    }
+}
+
+// node / terminal / isolated counts per group (reference src/fracture.rs:124-141); one warp per group
+__global__ void k_stats(int64_t n_groups, const int64_t *kmer_offsets, const uint8_t *exts, uint32_t *stats)
+{
+    const unsigned lane = lane_id();
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += nw) {
+        const int64_t o = kmer_offsets[g], n = kmer_offsets[g + 1] - o;
+        uint32_t term = 0, iso = 0;
+        for (int64_t j = lane; j < n; j += 32) {
+            uint32_t e = exts[o + j];
+            bool l0 = (e & 0x0fu) == 0, r0 = (e & 0xf0u) == 0;
+            term += (l0 || r0);
+            iso += (l0 && r0);
+        }
+        for (int d = 16; d; d >>= 1) {
+            term += __shfl_xor_sync(0xffffffffu, term, d);
+            iso += __shfl_xor_sync(0xffffffffu, iso, d);
+        }
+        if (lane == 0) {
+            stats[3 * g] = (uint32_t)n;
+            stats[3 * g + 1] = term;
+            stats[3 * g + 2] = iso;
+        }
+    }
+}
+
+// successor lookup: for survivor i and right-ext base b, j with kmers[j] == extend_right(kmers[i], b) inside the group
+__device__ __forceinline__ int64_t find_in_group(const uint64_t *lo, const uint64_t *hi, int64_t n, uint64_t khi, uint64_t klo)
+{
+    int64_t a = 0, b = n;
+    while (a < b) {
+        int64_t m = (a + b) >> 1;
+        uint64_t mh = hi ? hi[m] : 0ull, ml = lo[m];
+        if (mh == khi && ml == klo) return m;
+        if (mh < khi || (mh == khi && ml < klo)) a = m + 1; else b = m;
+    }
+    return -1;
+}
+
+// pass 0 (cols == nullptr): degree per node; pass 1: fill.  thread per node; group found by binary search.
+__global__ void k_csr(int64_t n_kmers, int64_t n_groups, const int64_t *kmer_offsets, const uint64_t *lo, const uint64_t *hi,
+                      const uint8_t *exts, int K, int32_t *degree, const int64_t *row_ptr, int32_t *cols)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_kmers) return;
+    int64_t a = 0, b = n_groups;   // last g with kmer_offsets[g] <= i
+    while (b - a > 1) {
+        int64_t m = (a + b) >> 1;
+        if (kmer_offsets[m] <= i) a = m; else b = m;
+    }
+    const int64_t o = kmer_offsets[a], n = kmer_offsets[a + 1] - o;
+    const int kbits = 2 * K;
+    const uint64_t xl = lo[i], xh = hi ? hi[i] : 0ull;
+    const uint32_t e = exts[i] >> 4;
+    int deg = 0;
+    int64_t w = cols ? row_ptr[i] : 0;
+    for (uint32_t bb = 0; bb < 4; bb++) {
+        if (!((e >> bb) & 1u)) continue;
+        uint64_t yl = (xl << 2) | bb, yh = (xh << 2) | (xl >> 62);
+        if (kbits < 64) { yl &= (1ull << kbits) - 1ull; yh = 0; }
+        else if (kbits == 64) yh = 0;
+        else if (kbits < 128) yh &= (1ull << (kbits - 64)) - 1ull;
+        int64_t j = find_in_group(lo + o, hi ? hi + o : nullptr, n, yh, yl);
+        if (j >= 0) {
+            if (cols) cols[w++] = (int32_t)j;
+            deg++;
+        }
+    }
+    if (!cols) degree[i] = deg;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// synthetic reads: per UMI u (global index) s_u = splitmix_out(seed, u);
+//   template base i      = (splitmix_out(s_u, i>>5) >> 2*(i&31)) & 3
+//   read r start         = splitmix_out(s_u, 2^20 + 4096 r) mod (T-L+1)
+//   read r base j error  : v = 16-bit field (j&3) of splitmix_out(s_u, 2^20 + 4096 r + 1 + (j>>2));
+//                          if v < err_per_64k: base = (base + 1 + v%3) & 3
+// The same function in numpy: rogtk_b200/synth.py.
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint8_t synth_base(uint64_t seed, int64_t umi, int32_t r, int32_t j, int32_t L, int32_t T,
+                                                       uint32_t err)
+{
+    const uint64_t su = splitmix_out(seed, (uint64_t)umi);
+    const uint64_t rc = (1ull << 20) + 4096ull * (uint64_t)r;
+    const uint32_t start = (uint32_t)(splitmix_out(su, rc) % (uint64_t)(T - L + 1));
+    const uint32_t i = start + (uint32_t)j;
+    uint32_t b = (uint32_t)(splitmix_out(su, i >> 5) >> (2 * (i & 31))) & 3u;
+    const uint32_t v = (uint32_t)(splitmix_out(su, rc + 1 + (uint64_t)(j >> 2)) >> (16 * (j & 3))) & 0xffffu;
+    if (v < err) b = (b + 1 + v % 3u) & 3u;
+    return (uint8_t)("ACGT"[b]);
+}
+
+__global__ void k_synth(uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t R, int32_t L, int32_t T, uint32_t err,
+                        uint8_t *data, int64_t *offsets, int64_t *group_offsets)
+{
+    const int64_t total = n_umis * (int64_t)R * L;
+    const int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int64_t n_reads = n_umis * (int64_t)R;
+    // offsets / group offsets (threads double as writers for the small arrays)
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= n_reads) offsets[t] = t * (int64_t)L;
+    if (t <= n_umis) group_offsets[t] = t * (int64_t)R;
+    if (q0 >= total) return;
+    uint8_t out[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int64_t q = q0 + x;
+        if (q < total) {
+            int64_t read = q / L;
+            int32_t j = (int32_t)(q - read * L);
+            int64_t u = read / R;
+            int32_t r = (int32_t)(read - u * R);
+            out[x] = synth_base(seed, umi_base + u, r, j, L, T, err);
+        } else {
+            out[x] = 0;
+        }
+    }
+    if (q0 + 3 < total) {
+        *reinterpret_cast<uint32_t *>(data + q0) = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+    } else {
+        for (int x = 0; x < 4 && q0 + x < total; x++) data[q0 + x] = out[x];
+    }
+}
+
+}  // namespace rogtk

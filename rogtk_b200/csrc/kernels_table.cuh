@@ -1,0 +1,297 @@
+// kernels_table.cuh -- HBM-resident per-group open-addressing tables: the spill path.
+//
+// Groups whose distinct k-mers do not fit a shared-memory table (kernels_smem.cuh), or every group when
+// ROGTK_FORCE_SPILL is set, are counted here.  Same semantics as debruijn::filter::filter_kmers + CountFilter at
+// reference src/fracture.rs:110-116: every window of every valid read is one observation; per distinct k-mer
+// count saturates at u16 and exts are OR-ed; survivors (count >= min_coverage) are emitted as records, sorted by
+// (group, k-mer) afterwards.
+#pragma once
+#include "common.cuh"
+
+namespace rogtk {
+
+template <int W>
+struct KeySlot;
+template <>
+struct KeySlot<1> {
+    using T = unsigned long long;
+    __device__ __forceinline__ static T empty() { return ~0ull; }
+    __device__ __forceinline__ static T pack(const Key<1> &k) { return k.lo; }
+    __device__ __forceinline__ static Key<1> unpack(T s) { return Key<1>{(uint64_t)s}; }
+};
+template <>
+struct KeySlot<2> {
+    using T = unsigned __int128;
+    __device__ __forceinline__ static T empty() { return ~(unsigned __int128)0; }
+    __device__ __forceinline__ static T pack(const Key<2> &k) { return ((unsigned __int128)k.hi << 64) | k.lo; }
+    __device__ __forceinline__ static Key<2> unpack(T s) { return Key<2>{(uint64_t)s, (uint64_t)(s >> 64)}; }
+};
+
+// value word of the HBM tables: bits 0..23 observation count (clamped later to u16), bits 24..31 exts
+constexpr uint32_t TV_COUNT_MASK = 0x00FFFFFFu;
+constexpr uint32_t TV_COUNT_STOP = 0x00800000u;
+
+struct SpillRec {       // one survivor, sortable by (group rank, k-mer)
+    uint64_t hi, lo;
+    uint32_t grank;     // rank of the group inside the spill list (ascending group index)
+    uint32_t val;       // count (low 16) | exts << 16
+};
+struct SpillRecLess {
+    __device__ __forceinline__ bool operator()(const SpillRec &a, const SpillRec &b) const
+    {
+        if (a.grank != b.grank) return a.grank < b.grank;
+        if (a.hi != b.hi) return a.hi < b.hi;
+        return a.lo < b.lo;
+    }
+};
+
+struct SpillArgs {
+    ColView col;
+    const int64_t *group_offsets;  // all groups
+    const int32_t *ids;            // spill list (ascending group indices) or nullptr = identity
+    int64_t n_list;                // groups in this wave
+    int64_t list_base;             // rank of the first group of this wave inside the whole list
+    const int64_t *row_off;        // [n_list+1] exclusive scan of rows per listed group (wave-local)
+    const int64_t *slot_off;       // [n_list+1] exclusive scan of table capacities (wave-local)
+    uint32_t *special;             // [n_list] value word of the all-ones k-mer (the table's EMPTY sentinel)
+    void *keys;                    // KeySlot<W>::T [slot_off[n_list]]
+    uint32_t *vals;                // [slot_off[n_list]]
+    int K;
+    uint32_t min_cov;
+    unsigned long long *n_obs;     // global accumulator
+    // extraction
+    SpillRec *pool;
+    unsigned long long *pool_cursor;
+    int64_t pool_cap;
+    int64_t *nsurv;                // [n_groups] survivors per group (global index)
+    int *overflow;                 // set when the record pool is too small
+    int count_only;                // extraction dry run: only bump pool_cursor
+};
+
+// per listed group: rows and table capacity (power of two >= 1.5x the observation upper bound)
+__global__ void k_spill_plan(ColView col, const int64_t *group_offsets, const int32_t *ids, int64_t n_list,
+                             int64_t list_base, int K, int64_t *rows, int64_t *caps)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    int64_t g = ids ? ids[list_base + i] : list_base + i;
+    int64_t r0 = group_offsets[g], r1 = group_offsets[g + 1];
+    int64_t ub = 0;
+    int64_t prev = col_off(col, r0);
+    for (int64_t r = r0; r < r1; r++) {
+        int64_t nxt = col_off(col, r + 1);
+        int64_t len = nxt - prev;
+        prev = nxt;
+        if (len >= K) ub += len - K + 1;
+    }
+    int64_t want = ub + (ub >> 1) + 8;
+    int64_t cap = 16;
+    while (cap < want) cap <<= 1;
+    rows[i] = r1 - r0;
+    caps[i] = cap;
+}
+
+template <int W>
+__device__ __forceinline__ void table_insert_global(typename KeySlot<W>::T *keys, uint32_t *vals, uint64_t mask,
+                                                    const Key<W> &key, uint32_t exts, uint32_t *special)
+{
+    using S = KeySlot<W>;
+    const typename S::T kp = S::pack(key);
+    uint32_t *vp;
+    if (kp == S::empty()) {
+        vp = special;
+    } else {
+        uint64_t h = key.hash() & mask;
+        while (true) {
+            typename S::T cur = keys[h];
+            if (cur == kp) break;
+            if (cur == S::empty()) {
+                typename S::T prev = atomicCAS(&keys[h], S::empty(), kp);
+                if (prev == S::empty() || prev == kp) break;
+            }
+            h = (h + 1) & mask;
+        }
+        vp = vals + h;
+    }
+    uint32_t v = *reinterpret_cast<volatile uint32_t *>(vp);
+    if ((v & TV_COUNT_MASK) < TV_COUNT_STOP) atomicAdd(vp, 1u);
+    uint32_t need = (exts << 24) & ~v;
+    if (need) atomicOr(vp, need);
+}
+
+constexpr int SPILL_TILE = 2048;                 // bases staged per warp per step
+constexpr int SPILL_TILE_WORDS = SPILL_TILE / 16;
+constexpr int SPILL_WARPS = 8;
+
+// one warp per read
+template <int W>
+__global__ void __launch_bounds__(SPILL_WARPS * 32) k_spill_insert(SpillArgs a)
+{
+    __shared__ uint32_t tiles[SPILL_WARPS][SPILL_TILE_WORDS];
+    using S = KeySlot<W>;
+    const unsigned lane = lane_id();
+    uint32_t *tile = tiles[threadIdx.x >> 5];
+    const int K = a.K, kbits = 2 * K;
+    const int64_t total_rows = a.row_off[a.n_list];
+    const int64_t n_warps = (int64_t)gridDim.x * SPILL_WARPS;
+    for (int64_t wr = (int64_t)blockIdx.x * SPILL_WARPS + (threadIdx.x >> 5); wr < total_rows; wr += n_warps) {
+        // listed group of this row: last i with row_off[i] <= wr
+        int64_t lo = 0, hi = a.n_list;
+        while (hi - lo > 1) {
+            int64_t m = (lo + hi) >> 1;
+            if (a.row_off[m] <= wr) lo = m; else hi = m;
+        }
+        const int64_t i = lo;
+        const int64_t g = a.ids ? a.ids[a.list_base + i] : a.list_base + i;
+        const int64_t row = a.group_offsets[g] + (wr - a.row_off[i]);
+        if (!col_valid(a.col, row)) continue;
+        const int64_t off = col_off(a.col, row);
+        const int64_t len = col_off(a.col, row + 1) - off;
+        if (len < K) continue;   // contributes nothing whether valid or not
+        const uint8_t *s = a.col.data + off;
+        // validate the whole read first (src/fracture.rs:222: any bad byte drops the read)
+        bool ok = true;
+        for (int64_t j = lane; j < len; j += 32) ok &= base_ok(s[j]);
+        if (!__all_sync(0xffffffffu, ok)) continue;
+        const int64_t nk = len - K + 1;
+        if (lane == 0) atomicAdd(a.n_obs, (unsigned long long)nk);
+        typename S::T *keys = reinterpret_cast<typename S::T *>(a.keys) + a.slot_off[i];
+        uint32_t *vals = a.vals + a.slot_off[i];
+        const uint64_t mask = (uint64_t)(a.slot_off[i + 1] - a.slot_off[i]) - 1;
+        int64_t w0 = 0;  // first base staged in the tile
+        while (true) {
+            const int64_t wend = (w0 + SPILL_TILE < len) ? w0 + SPILL_TILE : len;
+            __syncwarp();
+            for (int j = lane; j < SPILL_TILE_WORDS; j += 32) {
+                int64_t b0 = w0 + 16 * j;
+                uint32_t word = 0;
+                if (b0 < wend) {
+#pragma unroll
+                    for (int t = 0; t < 16; t++) {
+                        uint32_t c = (b0 + t < wend) ? base_code(s[b0 + t]) : 0u;
+                        word |= c << (30 - 2 * t);
+                    }
+                }
+                tile[j] = word;
+            }
+            __syncwarp();
+            // positions whose window and right neighbour (when it exists) lie inside the tile
+            const int64_t p_begin = (w0 == 0) ? 0 : w0 + 1;
+            int64_t p_end = (wend == len) ? nk : (wend - K);   // exclusive
+            const int64_t npos = p_end - p_begin;
+            const int64_t per = (npos + 31) / 32;
+            int64_t p = p_begin + (int64_t)lane * per;
+            const int64_t pe = (p + per < p_end) ? p + per : p_end;
+            if (p < pe) {
+                Key<W> key = Key<W>::zero();
+                auto base_at = [&](int64_t q) -> uint32_t {  // absolute base index -> code
+                    int64_t t = q - w0;
+                    return (tile[t >> 4] >> (30 - 2 * (int)(t & 15))) & 3u;
+                };
+                for (int t = 0; t < K - 1; t++) key.push(base_at(p + t), kbits);
+                uint32_t left = (p > 0) ? (1u << base_at(p - 1)) : 0u;
+                for (; p < pe; p++) {
+                    key.push(base_at(p + K - 1), kbits);
+                    uint32_t right = (p + K < len) ? (16u << base_at(p + K)) : 0u;
+                    table_insert_global<W>(keys, vals, mask, key, left | right, a.special + i);
+                    left = 1u << key.top_base(kbits);
+                }
+            }
+            if (wend == len) break;
+            w0 = p_end - 1;
+        }
+    }
+}
+
+// one thread per slot: survivors -> record pool, per-group survivor counts
+template <int W>
+__global__ void k_spill_extract(SpillArgs a)
+{
+    using S = KeySlot<W>;
+    const int64_t total = a.slot_off[a.n_list];
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    SpillRec rec;
+    int64_t g = 0;
+    if (slot < total) {
+        int64_t lo = 0, hi = a.n_list;
+        while (hi - lo > 1) {
+            int64_t m = (lo + hi) >> 1;
+            if (a.slot_off[m] <= slot) lo = m; else hi = m;
+        }
+        const int64_t i = lo;
+        g = a.ids ? a.ids[a.list_base + i] : a.list_base + i;
+        const typename S::T kp = reinterpret_cast<const typename S::T *>(a.keys)[slot];
+        if (kp != S::empty()) {
+            uint32_t v = a.vals[slot];
+            uint32_t c = v & TV_COUNT_MASK;
+            if (c > 65535u) c = 65535u;
+            if (c >= a.min_cov && c > 0) {
+                Key<W> k = S::unpack(kp);
+                rec.hi = k.hi_word();
+                rec.lo = k.lo;
+                rec.grank = (uint32_t)(a.list_base + i);
+                rec.val = c | ((v >> 24) << 16);
+                keep = true;
+            }
+        }
+        // the all-ones k-mer lives outside the table; emitted by the thread of the group's first slot
+        if (slot == a.slot_off[i]) {
+            uint32_t v = a.special[i];
+            uint32_t c = v & TV_COUNT_MASK;
+            if (c > 65535u) c = 65535u;
+            if (c >= a.min_cov && c > 0) {
+                unsigned long long pos = atomicAdd(a.pool_cursor, 1ull);
+                if (a.count_only) {
+                } else if ((int64_t)pos < a.pool_cap) {
+                    SpillRec r2;
+                    const int kbits = 2 * a.K;
+                    r2.lo = kbits >= 64 ? ~0ull : ((1ull << kbits) - 1ull);
+                    r2.hi = kbits >= 128 ? ~0ull : (kbits > 64 ? ((1ull << (kbits - 64)) - 1ull) : 0ull);
+                    r2.grank = (uint32_t)(a.list_base + i);
+                    r2.val = c | ((v >> 24) << 16);
+                    a.pool[pos] = r2;
+                } else {
+                    *a.overflow = 1;
+                }
+                if (!a.count_only) atomicAdd(reinterpret_cast<unsigned long long *>(a.nsurv + g), 1ull);
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        const unsigned lane = lane_id();
+        unsigned long long base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(a.pool_cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (keep && !a.count_only) {
+            unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+            if ((int64_t)pos < a.pool_cap) a.pool[pos] = rec; else *a.overflow = 1;
+            atomicAdd(reinterpret_cast<unsigned long long *>(a.nsurv + g), 1ull);
+        }
+    }
+}
+
+// sorted records -> structure-of-arrays output for the listed groups
+__global__ void k_gather_i64(const int64_t *src, const int32_t *ids, int64_t list_base, int64_t n, int64_t *dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[ids ? ids[list_base + i] : list_base + i];
+}
+
+__global__ void k_spill_scatter(const SpillRec *recs, int64_t n_recs, const int32_t *ids, int64_t list_base, const int64_t *list_rec_off,
+                                const int64_t *kmer_offsets, uint64_t *out_lo, uint64_t *out_hi, uint8_t *out_exts,
+                                uint16_t *out_counts)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_recs) return;
+    SpillRec rec = recs[r];
+    int64_t g = ids ? ids[rec.grank] : (int64_t)rec.grank;
+    int64_t dst = kmer_offsets[g] + (r - list_rec_off[rec.grank - list_base]);
+    out_lo[dst] = rec.lo;
+    if (out_hi) out_hi[dst] = rec.hi;
+    out_exts[dst] = (uint8_t)(rec.val >> 16);
+    out_counts[dst] = (uint16_t)(rec.val & 0xffffu);
+}
+
+}  // namespace rogtk

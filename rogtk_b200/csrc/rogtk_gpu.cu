@@ -1,0 +1,705 @@
+// rogtk_gpu.cu -- C ABI (include/rogtk_gpu.h) and batch orchestration of the B200 k-mer count/prune engine.
+//
+// Replaces, for many groups per call, the filter_kmers call of reference src/fracture.rs:110-116.  There is no CPU
+// fallback in this file: every entry point that computes needs a CUDA device and fails with ROGTK_ERR_CUDA otherwise.
+#include "../../include/rogtk_gpu.h"
+
+#include <cub/device/device_merge_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "host_util.cuh"
+#include "kernels_post.cuh"
+#include "kernels_smem.cuh"
+#include "kernels_table.cuh"
+#include "scan.cuh"
+
+using namespace rogtk;
+
+// -----------------------------------------------------------------------------------------------------------------
+// context
+// -----------------------------------------------------------------------------------------------------------------
+struct rogtk_gpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    size_t workspace_bytes = 0;
+    std::mutex mu;
+    std::string last_error;
+    int64_t launches = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    // cache of pinned host blocks (size -> pointers) so steady-state calls do not pay cudaHostAlloc
+    std::multimap<size_t, void *> pinned_free;
+    std::map<void *, size_t> pinned_size;
+};
+
+namespace {
+
+void set_error(rogtk_gpu_ctx *ctx, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+}
+
+void *pinned_get(rogtk_gpu_ctx *ctx, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    auto it = ctx->pinned_free.lower_bound(bytes);
+    if (it != ctx->pinned_free.end() && it->first <= bytes + bytes / 4 + 4096) {
+        void *p = it->second;
+        ctx->pinned_free.erase(it);
+        return p;
+    }
+    void *p = nullptr;
+    CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    ctx->pinned_size[p] = bytes;
+    return p;
+}
+void pinned_put(rogtk_gpu_ctx *ctx, void *p)
+{
+    if (!p) return;
+    auto it = ctx->pinned_size.find(p);
+    if (it == ctx->pinned_size.end()) return;
+    ctx->pinned_free.emplace(it->second, p);
+}
+
+struct BatchOwner {
+    bool on_device = false;
+    std::vector<void *> ptrs;
+};
+
+inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
+
+int k_eff_host(int64_t k)
+{
+    if (k < 0) return -1;
+    if (k <= 4) return 4;
+    if (k <= 8) return 8;
+    if (k <= 16) return 16;
+    if (k <= 32) return 32;
+    if (k <= 64) return 64;
+    return -1;
+}
+
+// ---- spill path (HBM tables) ---------------------------------------------------------------------------------------
+struct SpillWave {
+    DevBuf recs;       // sorted SpillRec
+    DevBuf rec_off;    // [n_list+1] exclusive scan of survivors per listed group
+    int64_t list_base = 0, n_list = 0, n_recs = 0;
+};
+
+template <int W>
+void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_offsets, const int32_t *d_ids, int64_t n_list_total,
+               int K, uint32_t min_cov, unsigned long long *d_nobs, int64_t *d_nsurv, std::vector<SpillWave> &waves)
+{
+    cudaStream_t st = ctx->stream;
+    if (n_list_total == 0) return;
+    // capacities of every listed group -> host decides the waves
+    DevBuf rows(n_list_total * 8, st), caps(n_list_total * 8, st);
+    k_spill_plan<<<blocks_for(n_list_total, 256), 256, 0, st>>>(col, d_group_offsets, d_ids, n_list_total, 0, K,
+                                                                rows.as<int64_t>(), caps.as<int64_t>());
+    ctx->launches++;
+    std::vector<int64_t> h_caps((size_t)n_list_total);
+    CK(cudaMemcpyAsync(h_caps.data(), caps.p, n_list_total * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const size_t slot_bytes = sizeof(typename KeySlot<W>::T) + 4;
+    const int64_t budget_slots = std::max<int64_t>(1 << 16, (int64_t)(ctx->workspace_bytes / 2 / slot_bytes));
+    int64_t i0 = 0;
+    while (i0 < n_list_total) {
+        int64_t i1 = i0, slots = 0;
+        while (i1 < n_list_total && (i1 == i0 || slots + h_caps[i1] <= budget_slots)) slots += h_caps[i1++];
+        const int64_t nl = i1 - i0;
+        SpillWave wv;
+        wv.list_base = i0;
+        wv.n_list = nl;
+        DevBuf row_off((nl + 1) * 8, st), slot_off((nl + 1) * 8, st), scratch(scan_scratch_bytes(nl), st);
+        exclusive_scan<int64_t>(rows.as<int64_t>() + i0, nl, row_off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
+        exclusive_scan<int64_t>(caps.as<int64_t>() + i0, nl, slot_off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
+        int64_t h_tot[2];
+        CK(cudaMemcpyAsync(&h_tot[0], row_off.as<int64_t>() + nl, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_tot[1], slot_off.as<int64_t>() + nl, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int64_t total_rows = h_tot[0], total_slots = h_tot[1];
+        DevBuf keys((size_t)total_slots * sizeof(typename KeySlot<W>::T), st), vals((size_t)total_slots * 4, st),
+            special((size_t)nl * 4, st), cursor(16, st);
+        CK(cudaMemsetAsync(keys.p, 0xff, keys.bytes, st));
+        CK(cudaMemsetAsync(vals.p, 0, vals.bytes, st));
+        CK(cudaMemsetAsync(special.p, 0, special.bytes, st));
+        CK(cudaMemsetAsync(cursor.p, 0, 16, st));
+        SpillArgs a{};
+        a.col = col;
+        a.group_offsets = d_group_offsets;
+        a.ids = d_ids;
+        a.n_list = nl;
+        a.list_base = i0;
+        a.row_off = row_off.as<int64_t>();
+        a.slot_off = slot_off.as<int64_t>();
+        a.special = special.as<uint32_t>();
+        a.keys = keys.p;
+        a.vals = vals.as<uint32_t>();
+        a.K = K;
+        a.min_cov = min_cov;
+        a.n_obs = d_nobs;
+        a.nsurv = d_nsurv;
+        a.pool_cursor = cursor.as<unsigned long long>();
+        a.overflow = reinterpret_cast<int *>(cursor.as<unsigned long long>() + 1);
+        if (total_rows > 0) {
+            const int64_t want_blocks = (total_rows + SPILL_WARPS - 1) / SPILL_WARPS;
+            const unsigned grid = (unsigned)std::min<int64_t>(want_blocks, (int64_t)ctx->sm_count * 16);
+            k_spill_insert<W><<<grid, SPILL_WARPS * 32, 0, st>>>(a);
+            ctx->launches++;
+        }
+        // pass 1: count the wave's survivors so that the record pool is sized exactly
+        DevBuf cnt(8, st);
+        CK(cudaMemsetAsync(cnt.p, 0, 8, st));
+        {
+            SpillArgs c = a;
+            c.count_only = 1;
+            c.pool_cursor = cnt.as<unsigned long long>();
+            k_spill_extract<W><<<blocks_for(total_slots, 256), 256, 0, st>>>(c);
+            ctx->launches++;
+        }
+        unsigned long long h_cnt = 0;
+        CK(cudaMemcpyAsync(&h_cnt, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        wv.n_recs = (int64_t)h_cnt;
+        wv.recs.alloc((size_t)std::max<int64_t>(1, wv.n_recs) * sizeof(SpillRec), st);
+        a.pool = wv.recs.as<SpillRec>();
+        a.pool_cap = wv.n_recs;
+        CK(cudaMemsetAsync(cursor.p, 0, 16, st));
+        k_spill_extract<W><<<blocks_for(total_slots, 256), 256, 0, st>>>(a);
+        ctx->launches++;
+        if (wv.n_recs > 1) {
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, wv.recs.as<SpillRec>(), wv.n_recs, SpillRecLess(), st));
+            DevBuf tmp(tmp_bytes, st);
+            CK(cub::DeviceMergeSort::SortKeys(tmp.p, tmp_bytes, wv.recs.as<SpillRec>(), wv.n_recs, SpillRecLess(), st));
+            ctx->launches += 3;
+        }
+        // survivors per listed group -> record offsets of the wave
+        DevBuf ns((size_t)nl * 8, st);
+        k_gather_i64<<<blocks_for(nl, 256), 256, 0, st>>>(d_nsurv, d_ids, i0, nl, ns.as<int64_t>());
+        ctx->launches++;
+        wv.rec_off.alloc((size_t)(nl + 1) * 8, st);
+        exclusive_scan<int64_t>(ns.as<int64_t>(), nl, wv.rec_off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
+        waves.push_back(std::move(wv));
+        i0 = i1;
+    }
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------------------------------
+// lifecycle
+// -----------------------------------------------------------------------------------------------------------------
+extern "C" int rogtk_gpu_abi_version(void) { return ROGTK_GPU_ABI_VERSION; }
+
+extern "C" int rogtk_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, int *err)
+{
+    auto fail = [&](int code) -> rogtk_gpu_ctx * {
+        if (err) *err = code;
+        return nullptr;
+    };
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(ROGTK_ERR_CUDA);   // no CPU fallback: the product path needs a GPU
+    }
+    if (device < 0 || device >= n) return fail(ROGTK_ERR_INVALID_ARG);
+    rogtk_gpu_ctx *ctx = new rogtk_gpu_ctx();
+    try {
+        ctx->device = device;
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) {
+            delete ctx;
+            return fail(ROGTK_ERR_UNSUPPORTED);   // sm_100a only
+        }
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->smem_optin = prop.sharedMemPerBlockOptin;
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        ctx->workspace_bytes = workspace_bytes ? workspace_bytes : free_b / 4;
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        smem_path_configure();
+    } catch (const CudaFail &f) {
+        fprintf(stderr, "rogtk_gpu_create: %s: %s\n", f.what, cudaGetErrorString(f.e));
+        delete ctx;
+        return fail(ROGTK_ERR_CUDA);
+    }
+    if (err) *err = ROGTK_OK;
+    return ctx;
+}
+
+extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->pinned_size) cudaFreeHost(kv.first);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" const char *rogtk_gpu_last_error(rogtk_gpu_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" int rogtk_gpu_k_eff(int64_t k) { return k_eff_host(k); }
+
+extern "C" int64_t rogtk_gpu_estimate_k(const int64_t *offsets, const uint8_t *validity, int64_t n_rows)
+{
+    // reference src/fracture.rs:24-54
+    uint64_t total = 0, count = 0;
+    for (int64_t r = 0; r < n_rows; r++) {
+        if (validity && !((validity[r >> 3] >> (r & 7)) & 1)) continue;
+        int64_t len = offsets[r + 1] - offsets[r];
+        if (len > 0) {
+            total += (uint64_t)len;
+            count++;
+        }
+    }
+    if (count == 0) return 31;
+    const double mean = (double)total / (double)count;
+    uint64_t k = (uint64_t)std::round(mean / 3.0);
+    if (k % 2 == 0) k = k - 1;   // usize wrap for k == 0 as in a release build -> clamps to 63
+    if (k < 11) return 11;
+    if (k > 63) return 63;
+    return (int64_t)k;
+}
+
+extern "C" int32_t rogtk_gpu_shard_of(uint64_t umi_id, int32_t n_shards)
+{
+    if (n_shards <= 1) return 0;
+    return (int32_t)(splitmix_mix(umi_id + 0x9E3779B97F4A7C15ull) % (uint64_t)n_shards);
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// the hot path
+// -----------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Staged {   // device-resident contiguous column
+    ColView col{};
+    const int64_t *group_offsets = nullptr;
+    const uint8_t *data_end = nullptr;
+    std::vector<DevBuf> keep;
+};
+
+const void *to_device(rogtk_gpu_ctx *ctx, Staged &s, const void *host, size_t bytes, bool on_device)
+{
+    if (on_device || host == nullptr) return host;
+    s.keep.emplace_back(bytes, ctx->stream);
+    if (bytes) CK(cudaMemcpyAsync(s.keep.back().p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return s.keep.back().p;
+}
+
+void stage_input(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group_offsets, int64_t n_groups, bool on_device, Staged &s)
+{
+    cudaStream_t st = ctx->stream;
+    const int64_t n = c->n_rows;
+    const size_t vbytes = c->validity ? (size_t)((n + c->validity_bit_offset + 7) / 8) : 0;
+    s.col.n_rows = n;
+    s.col.validity = (const uint8_t *)to_device(ctx, s, c->validity, vbytes, on_device);
+    s.col.validity_bit_offset = c->validity_bit_offset;
+    s.group_offsets = (const int64_t *)to_device(ctx, s, group_offsets, (size_t)(n_groups + 1) * 8, on_device);
+    if (c->layout == ROGTK_UTF8_I32 || c->layout == ROGTK_UTF8_I64) {
+        if (c->n_buffers != 1 || !c->data || !c->data_len) throw ArgFail{ROGTK_ERR_INVALID_ARG, "offset layouts need exactly one data buffer"};
+        const bool o64 = c->layout == ROGTK_UTF8_I64;
+        s.col.off64 = o64;
+        s.col.offsets = to_device(ctx, s, c->offsets_or_views, (size_t)(n + 1) * (o64 ? 8 : 4), on_device);
+        s.col.data = (const uint8_t *)to_device(ctx, s, c->data[0], (size_t)c->data_len[0], on_device);
+        s.data_end = s.col.data + c->data_len[0];
+        return;
+    }
+    if (c->layout != ROGTK_UTF8_VIEW) throw ArgFail{ROGTK_ERR_INVALID_ARG, "unknown string layout"};
+    // Utf8View: gather on the device into a contiguous LargeUtf8-like column
+    const View16 *views = (const View16 *)to_device(ctx, s, c->offsets_or_views, (size_t)n * 16, on_device);
+    std::vector<const uint8_t *> h_bufs((size_t)std::max(1, c->n_buffers), nullptr);
+    for (int b = 0; b < c->n_buffers; b++) h_bufs[b] = (const uint8_t *)to_device(ctx, s, c->data[b], (size_t)c->data_len[b], on_device);
+    s.keep.emplace_back(h_bufs.size() * sizeof(void *), st);
+    const uint8_t *const *d_bufs = s.keep.back().as<const uint8_t *>();
+    CK(cudaMemcpyAsync(s.keep.back().p, h_bufs.data(), h_bufs.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
+    DevBuf lens((size_t)std::max<int64_t>(1, n) * 8, st), scratch(scan_scratch_bytes(n), st);
+    s.keep.emplace_back((size_t)(n + 1) * 8, st);
+    int64_t *offs = s.keep.back().as<int64_t>();
+    k_view_len<<<blocks_for(n, 256), 256, 0, st>>>(views, n, s.col.validity, s.col.validity_bit_offset, lens.as<int64_t>());
+    exclusive_scan<int64_t>(lens.as<int64_t>(), n, offs, scratch.as<int64_t>(), st, &ctx->launches);
+    int64_t total = 0;
+    CK(cudaMemcpyAsync(&total, offs + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // also keeps h_bufs alive long enough
+    s.keep.emplace_back((size_t)total, st);
+    uint8_t *data = s.keep.back().as<uint8_t>();
+    k_view_gather<<<blocks_for(n * 32, 256), 256, 0, st>>>(views, n, d_bufs, offs, data);
+    ctx->launches += 2;
+    s.col.off64 = 1;
+    s.col.offsets = offs;
+    s.col.data = data;
+    s.data_end = data + total;
+}
+
+void fill_empty_batch(rogtk_gpu_ctx *ctx, int64_t n_groups, bool out_dev, uint32_t flags, rogtk_graph_batch *out, BatchOwner *own)
+{
+    // k > 64: every group yields nothing (reference src/fracture.rs:212-215)
+    const size_t ob = (size_t)(n_groups + 1) * 8;
+    if (out_dev) {
+        void *p;
+        CK(cudaMallocAsync(&p, ob, ctx->stream));
+        CK(cudaMemsetAsync(p, 0, ob, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        out->kmer_offsets = (int64_t *)p;
+        own->ptrs.push_back(p);
+    } else {
+        void *p = pinned_get(ctx, ob);
+        memset(p, 0, ob);
+        out->kmer_offsets = (int64_t *)p;
+        own->ptrs.push_back(p);
+        if (flags & ROGTK_EMIT_STATS) {
+            void *q = pinned_get(ctx, (size_t)n_groups * 12 + 16);
+            memset(q, 0, (size_t)n_groups * 12 + 16);
+            out->stats = (uint32_t *)q;
+            own->ptrs.push_back(q);
+        }
+    }
+}
+
+int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets, int64_t n_groups, int64_t k,
+                     uint32_t min_coverage, uint32_t flags, rogtk_graph_batch *out)
+{
+    if (!reads || !out || n_groups < 0 || (n_groups > 0 && !group_offsets) || reads->n_rows < 0)
+        throw ArgFail{ROGTK_ERR_INVALID_ARG, "null or negative argument"};
+    if (n_groups >= (int64_t)1 << 31) throw ArgFail{ROGTK_ERR_UNSUPPORTED, "more than 2^31 groups per batch"};
+    memset(out, 0, sizeof(*out));
+    const bool in_dev = flags & ROGTK_INPUT_ON_DEVICE, out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
+    int K;
+    if (flags & ROGTK_EXACT_K) {
+        if (k < 1 || k > 64) throw ArgFail{ROGTK_ERR_INVALID_ARG, "EXACT_K needs 1 <= k <= 64"};
+        K = (int)k;
+    } else {
+        K = k_eff_host(k);
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    BatchOwner *own = new BatchOwner();
+    own->on_device = out_dev;
+    out->_owner = own;
+    out->n_groups = n_groups;
+    out->k_eff = K;
+    out->on_device = out_dev ? 1 : 0;
+    if (K < 0) {
+        fill_empty_batch(ctx, n_groups, out_dev, flags, out, own);
+        return ROGTK_OK;
+    }
+
+    Staged in;
+    stage_input(ctx, reads, group_offsets, n_groups, in_dev, in);
+
+    CK(cudaEventRecord(ctx->ev[0], st));
+    DevBuf nsurv((size_t)(n_groups + 1) * 8, st), misc(64, st);
+    CK(cudaMemsetAsync(nsurv.p, 0, nsurv.bytes, st));
+    CK(cudaMemsetAsync(misc.p, 0, 64, st));
+    unsigned long long *d_nobs = misc.as<unsigned long long>();
+
+    // ---- counting -------------------------------------------------------------------------------------------
+    CK(cudaEventRecord(ctx->ev[1], st));
+    SmemResult sm;            // survivors of the shared-memory path (pool, per-group start) + deferred groups
+    std::vector<SpillWave> waves;
+    const int32_t *d_spill_ids = nullptr;
+    int64_t n_spill = n_groups;
+    if (!(flags & ROGTK_FORCE_SPILL) && n_groups > 0) {
+        run_smem_path(ctx->stream, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_end, in.group_offsets, n_groups, K,
+                      min_coverage, d_nobs, nsurv.as<int64_t>(), sm, &ctx->launches, ctx->ev[4], ctx->ev[5]);
+        d_spill_ids = sm.deferred_ids;
+        n_spill = sm.n_deferred;
+    }
+    if (n_spill > 0) {
+        if (K <= 32)
+            run_spill<1>(ctx, in.col, in.group_offsets, d_spill_ids, n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), waves);
+        else
+            run_spill<2>(ctx, in.col, in.group_offsets, d_spill_ids, n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), waves);
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- dense, group-ordered output ----------------------------------------------------------------------------
+    DevBuf d_off((size_t)(n_groups + 1) * 8, st), scratch(scan_scratch_bytes(n_groups), st);
+    exclusive_scan<int64_t>(nsurv.as<int64_t>(), n_groups, d_off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
+    int64_t n_kmers = 0;
+    unsigned long long h_nobs = 0;
+    CK(cudaMemcpyAsync(&n_kmers, d_off.as<int64_t>() + n_groups, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_nobs, d_nobs, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const size_t nk = (size_t)std::max<int64_t>(n_kmers, 1);
+    DevBuf o_lo(nk * 8, st), o_hi(K > 32 ? nk * 8 : 0, st), o_exts(nk, st), o_counts(nk * 2, st);
+    uint64_t *p_hi = K > 32 ? o_hi.as<uint64_t>() : nullptr;
+    if (sm.n_pool_groups > 0) {
+        k_gather_pool<<<ctx->sm_count * 8, 256, 0, st>>>(n_groups, sm.pool_start, d_off.as<int64_t>(), sm.pool_lo, sm.pool_hi,
+                                                         sm.pool_exts, sm.pool_counts, o_lo.as<uint64_t>(), p_hi,
+                                                         o_exts.as<uint8_t>(), o_counts.as<uint16_t>());
+        ctx->launches++;
+    }
+    for (auto &wv : waves) {
+        if (wv.n_recs == 0) continue;
+        k_spill_scatter<<<blocks_for(wv.n_recs, 256), 256, 0, st>>>(wv.recs.as<SpillRec>(), wv.n_recs, d_spill_ids, wv.list_base,
+                                                                    wv.rec_off.as<int64_t>(), d_off.as<int64_t>(),
+                                                                    o_lo.as<uint64_t>(), p_hi, o_exts.as<uint8_t>(),
+                                                                    o_counts.as<uint16_t>());
+        ctx->launches++;
+    }
+    out->n_spilled_groups = n_spill;
+
+    // ---- optional node statistics and successor CSR ---------------------------------------------------------------------
+    DevBuf d_stats, d_rowptr, d_cols;
+    int64_t n_edges = 0;
+    if (flags & ROGTK_EMIT_STATS) {
+        d_stats.alloc((size_t)n_groups * 12 + 16, st);
+        if (n_groups > 0) {
+            k_stats<<<ctx->sm_count * 8, 256, 0, st>>>(n_groups, d_off.as<int64_t>(), o_exts.as<uint8_t>(), d_stats.as<uint32_t>());
+            ctx->launches++;
+        }
+    }
+    if (flags & ROGTK_EMIT_CSR) {
+        DevBuf deg(nk * 4, st), scr(scan_scratch_bytes(n_kmers), st);
+        d_rowptr.alloc((size_t)(n_kmers + 1) * 8, st);
+        if (n_kmers > 0) {
+            k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, d_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi,
+                                                            o_exts.as<uint8_t>(), K, deg.as<int32_t>(), nullptr, nullptr);
+            ctx->launches++;
+        }
+        exclusive_scan<int32_t>(deg.as<int32_t>(), n_kmers, d_rowptr.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+        CK(cudaMemcpyAsync(&n_edges, d_rowptr.as<int64_t>() + n_kmers, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        d_cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
+        if (n_kmers > 0) {
+            k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, d_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi,
+                                                            o_exts.as<uint8_t>(), K, nullptr, d_rowptr.as<int64_t>(),
+                                                            d_cols.as<int32_t>());
+            ctx->launches++;
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+
+    // ---- hand over ------------------------------------------------------------------------------------------------------
+    out->n_kmers = n_kmers;
+    out->n_edges = n_edges;
+    out->n_observations = (int64_t)h_nobs;
+    auto give = [&](DevBuf &b, size_t bytes) -> void * {
+        if (!b.p) return nullptr;
+        if (out_dev) {
+            void *p = b.detach();
+            own->ptrs.push_back(p);
+            return p;
+        }
+        void *h = pinned_get(ctx, bytes);
+        own->ptrs.push_back(h);
+        if (bytes) CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, st));
+        return h;
+    };
+    out->kmer_offsets = (int64_t *)give(d_off, (size_t)(n_groups + 1) * 8);
+    out->kmers_lo = (uint64_t *)give(o_lo, (size_t)n_kmers * 8);
+    out->kmers_hi = K > 32 ? (uint64_t *)give(o_hi, (size_t)n_kmers * 8) : nullptr;
+    out->exts = (uint8_t *)give(o_exts, (size_t)n_kmers);
+    out->counts = (uint16_t *)give(o_counts, (size_t)n_kmers * 2);
+    if (flags & ROGTK_EMIT_STATS) out->stats = (uint32_t *)give(d_stats, (size_t)n_groups * 12);
+    if (flags & ROGTK_EMIT_CSR) {
+        out->csr_row_ptr = (int64_t *)give(d_rowptr, (size_t)(n_kmers + 1) * 8);
+        out->csr_col = (int32_t *)give(d_cols, (size_t)n_edges * 4);
+    }
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+    out->ms_total = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+    out->ms_count = ms;
+    out->ms_hot_kernel = sm.ms_kernel;
+    CK(cudaGetLastError());
+    return ROGTK_OK;
+}
+
+}  // namespace
+
+extern "C" void rogtk_gpu_free_batch(rogtk_gpu_ctx *ctx, rogtk_graph_batch *b)
+{
+    if (!ctx || !b || !b->_owner) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BatchOwner *own = reinterpret_cast<BatchOwner *>(b->_owner);
+    cudaSetDevice(ctx->device);
+    for (void *p : own->ptrs) {
+        if (own->on_device) cudaFreeAsync(p, ctx->stream);
+        else pinned_put(ctx, p);
+    }
+    delete own;
+    memset(b, 0, sizeof(*b));
+}
+
+extern "C" int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets,
+                                           int64_t n_groups, int64_t k, uint32_t min_coverage, uint32_t flags,
+                                           rogtk_graph_batch *out)
+{
+    if (!ctx) return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = ROGTK_ERR_INTERNAL;
+    try {
+        rc = count_prune_impl(ctx, reads, group_offsets, n_groups, k, min_coverage, flags, out);
+    } catch (const ArgFail &a) {
+        set_error(ctx, "%s", a.msg.c_str());
+        rc = a.code;
+    } catch (const CudaFail &f) {
+        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
+        rc = (f.e == cudaErrorMemoryAllocation) ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
+        cudaGetLastError();
+    } catch (const std::bad_alloc &) {
+        set_error(ctx, "host out of memory");
+        rc = ROGTK_ERR_OOM;
+    } catch (...) {
+        set_error(ctx, "unexpected internal error");
+        rc = ROGTK_ERR_INTERNAL;
+    }
+    if (rc != ROGTK_OK && out && out->_owner) {
+        BatchOwner *own = reinterpret_cast<BatchOwner *>(out->_owner);
+        for (void *p : own->ptrs) {
+            if (own->on_device) cudaFreeAsync(p, ctx->stream);
+            else pinned_put(ctx, p);
+        }
+        delete own;
+        memset(out, 0, sizeof(*out));
+    }
+    return rc;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// bench / test utilities
+// -----------------------------------------------------------------------------------------------------------------
+extern "C" int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t reads_per_umi,
+                                     int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data,
+                                     int64_t *d_offsets, int64_t *d_group_offsets)
+{
+    if (!ctx || n_umis < 0 || reads_per_umi < 1 || read_len < 1 || template_len < read_len) return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    try {
+        CK(cudaSetDevice(ctx->device));
+        const int64_t total = n_umis * (int64_t)reads_per_umi * read_len;
+        const int64_t threads = std::max<int64_t>((total + 3) / 4, n_umis * (int64_t)reads_per_umi + 1);
+        k_synth<<<blocks_for(threads, 256), 256, 0, ctx->stream>>>(seed, umi_base, n_umis, reads_per_umi, read_len, template_len,
+                                                                   err_per_64k, d_data, d_offsets, d_group_offsets);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+    } catch (const CudaFail &f) {
+        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
+        return ROGTK_ERR_CUDA;
+    }
+    return ROGTK_OK;
+}
+
+extern "C" void *rogtk_gpu_device_alloc(rogtk_gpu_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+        set_error(ctx, "cudaMalloc(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void rogtk_gpu_device_free(rogtk_gpu_ctx *ctx, void *p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(p);
+}
+extern "C" void *rogtk_gpu_pinned_alloc(rogtk_gpu_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+        set_error(ctx, "cudaHostAlloc(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void rogtk_gpu_pinned_free(rogtk_gpu_ctx *ctx, void *p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(p);
+}
+extern "C" int rogtk_gpu_memcpy_h2d(rogtk_gpu_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return ROGTK_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        set_error(ctx, "h2d copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return ROGTK_ERR_CUDA;
+    }
+    return ROGTK_OK;
+}
+extern "C" int rogtk_gpu_memcpy_d2h(rogtk_gpu_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return ROGTK_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        set_error(ctx, "d2h copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return ROGTK_ERR_CUDA;
+    }
+    return ROGTK_OK;
+}
+extern "C" int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx)
+{
+    if (!ctx) return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
+        if (cudaMalloc(&ctx->flush_buf, ctx->flush_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return ROGTK_ERR_OOM;
+        }
+    }
+    static int tick = 0;
+    cudaMemsetAsync(ctx->flush_buf, ++tick & 0xff, ctx->flush_bytes, ctx->stream);
+    return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? ROGTK_OK : ROGTK_ERR_CUDA;
+}

@@ -1,0 +1,278 @@
+"""Host-side driver of the GPU k-mer engine (thin layer over the C ABI, include/rogtk_gpu.h).
+
+`Engine.count_prune` is the batched form of the reference's per-group
+``filter_kmers::<K,..>(seq_tuples, &Box::new(CountFilter::new(min_coverage)), true, true, 4)`` call
+(reference src/fracture.rs:110-116): one call carries every group (UMI) of a frame.  Inputs are Arrow string buffers
+(data + offsets [+ validity]) plus group row offsets, exactly what the Polars plugin receives
+(reference src/expressions.rs:734-740); outputs are the three vectors the reference hands to ``BoomHashMap2::new``
+(ascending k-mers, Exts bytes, saturating u16 counts) concatenated over groups.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+
+_ERR = {-1: "invalid argument", -2: "CUDA error", -3: "out of memory", -4: "unsupported", -5: "internal error"}
+
+
+class RogtkGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rogtk_gpu error {code} ({_ERR.get(code, '?')}): {msg}")
+        self.code = code
+
+
+@dataclass
+class GraphBatch:
+    """Pruned de Bruijn nodes of every group.  Survivors of group g are [kmer_offsets[g], kmer_offsets[g+1])."""
+    k_eff: int
+    n_observations: int
+    kmer_offsets: np.ndarray          # int64 [n_groups+1]
+    kmers_lo: np.ndarray              # uint64, ascending inside a group
+    kmers_hi: np.ndarray | None       # uint64 when k_eff > 32
+    exts: np.ndarray                  # uint8  (low nibble left, high nibble right, bit = base code)
+    counts: np.ndarray                # uint16 saturating
+    stats: np.ndarray | None = None   # uint32 [n_groups,3]: node, terminal, isolated (fracture.rs:124-141)
+    csr_row_ptr: np.ndarray | None = None
+    csr_col: np.ndarray | None = None
+    ms_total: float = 0.0
+    ms_count: float = 0.0
+    ms_hot_kernel: float = 0.0
+    n_spilled_groups: int = 0
+
+    @property
+    def n_groups(self) -> int:
+        return len(self.kmer_offsets) - 1
+
+    def group(self, g: int):
+        a, b = int(self.kmer_offsets[g]), int(self.kmer_offsets[g + 1])
+        hi = self.kmers_hi[a:b] if self.kmers_hi is not None else None
+        return self.kmers_lo[a:b], hi, self.exts[a:b], self.counts[a:b]
+
+
+@dataclass
+class DeviceBatch:
+    """Result left in HBM (ROGTK_OUTPUT_ON_DEVICE); only sizes and timings are visible on the host."""
+    k_eff: int
+    n_groups: int
+    n_kmers: int
+    n_edges: int
+    n_observations: int
+    ms_total: float
+    ms_count: float
+    ms_hot_kernel: float
+    n_spilled_groups: int
+    _c: _ffi.GraphBatchC
+    _engine: "Engine"
+
+    def free(self):
+        if self._c is not None:
+            self._engine._lib.rogtk_gpu_free_batch(self._engine._ctx, ctypes.byref(self._c))
+            self._c = None
+
+    def to_host(self) -> GraphBatch:
+        e, c = self._engine, self._c
+
+        def pull(ptr, n, dt):
+            out = np.empty(n, dtype=dt)
+            if n and ptr:
+                e._check(e._lib.rogtk_gpu_memcpy_d2h(e._ctx, out.ctypes.data, ptr, out.nbytes))
+            return out
+
+        return GraphBatch(
+            k_eff=self.k_eff, n_observations=self.n_observations,
+            kmer_offsets=pull(c.kmer_offsets, self.n_groups + 1, np.int64),
+            kmers_lo=pull(c.kmers_lo, self.n_kmers, np.uint64),
+            kmers_hi=pull(c.kmers_hi, self.n_kmers, np.uint64) if c.kmers_hi else None,
+            exts=pull(c.exts, self.n_kmers, np.uint8), counts=pull(c.counts, self.n_kmers, np.uint16),
+            stats=pull(c.stats, 3 * self.n_groups, np.uint32).reshape(-1, 3) if c.stats else None,
+            csr_row_ptr=pull(c.csr_row_ptr, self.n_kmers + 1, np.int64) if c.csr_row_ptr else None,
+            csr_col=pull(c.csr_col, self.n_edges, np.int32) if c.csr_col else None,
+            ms_total=self.ms_total, ms_count=self.ms_count, ms_hot_kernel=self.ms_hot_kernel,
+            n_spilled_groups=self.n_spilled_groups)
+
+
+def k_eff(k: int) -> int:
+    """reference src/fracture.rs:246-256: K = 4/8/16/32/64, the smallest >= k; -1 when k > 64."""
+    return int(_ffi.load().rogtk_gpu_k_eff(int(k)))
+
+
+def estimate_k(offsets: np.ndarray, validity: np.ndarray | None = None) -> int:
+    """reference src/fracture.rs:24-54 (auto_k)."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    vp = np.ascontiguousarray(validity, dtype=np.uint8).ctypes.data if validity is not None else None
+    return int(_ffi.load().rogtk_gpu_estimate_k(offsets.ctypes.data, vp, len(offsets) - 1))
+
+
+def shard_of(umi_id: int, n_shards: int) -> int:
+    """UMI -> GPU: splitmix64(umi_id) mod n_shards (no collective on the per-UMI path)."""
+    return int(_ffi.load().rogtk_gpu_shard_of(int(umi_id) & 0xFFFFFFFFFFFFFFFF, int(n_shards)))
+
+
+class Engine:
+    """One context == one GPU + one stream.  Not a fallback-capable object: construction fails without a B200."""
+
+    def __init__(self, device: int = 0, workspace_bytes: int = 0):
+        self._lib = _ffi.load()
+        err = ctypes.c_int(0)
+        self._ctx = self._lib.rogtk_gpu_create(int(device), int(workspace_bytes), ctypes.byref(err))
+        if not self._ctx:
+            raise RogtkGpuError(err.value, "rogtk_gpu_create failed (no usable sm_100 GPU?) - there is no CPU fallback")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.rogtk_gpu_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RogtkGpuError(rc, self._lib.rogtk_gpu_last_error(self._ctx).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.rogtk_gpu_launch_count(self._ctx))
+
+    def flush_l2(self):
+        self._check(self._lib.rogtk_gpu_flush_l2(self._ctx))
+
+    # ---- raw memory helpers (harness use) ------------------------------------------------------------------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = self._lib.rogtk_gpu_device_alloc(self._ctx, int(nbytes))
+        if not p:
+            raise RogtkGpuError(-3, self._lib.rogtk_gpu_last_error(self._ctx).decode())
+        return int(p)
+
+    def device_free(self, p: int):
+        self._lib.rogtk_gpu_device_free(self._ctx, ctypes.c_void_p(p))
+
+    def pinned_alloc(self, nbytes: int) -> int:
+        p = self._lib.rogtk_gpu_pinned_alloc(self._ctx, int(nbytes))
+        if not p:
+            raise RogtkGpuError(-3, self._lib.rogtk_gpu_last_error(self._ctx).decode())
+        return int(p)
+
+    def pinned_free(self, p: int):
+        self._lib.rogtk_gpu_pinned_free(self._ctx, ctypes.c_void_p(p))
+
+    def h2d(self, dst: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self._check(self._lib.rogtk_gpu_memcpy_h2d(self._ctx, ctypes.c_void_p(dst), src.ctypes.data, src.nbytes))
+
+    def d2h(self, src: int, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        out = np.empty(nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+        self._check(self._lib.rogtk_gpu_memcpy_d2h(self._ctx, out.ctypes.data, ctypes.c_void_p(src), out.nbytes))
+        return out
+
+    def synth_reads_device(self, seed: int, umi_base: int, n_umis: int, reads_per_umi: int, read_len: int,
+                           template_len: int, err_per_64k: int):
+        """Generate the SURVEY 8(d) synthetic reads directly in HBM.  Returns (d_data, d_offsets, d_group_offsets,
+        n_bytes) as raw device pointers (free with device_free)."""
+        n_reads = n_umis * reads_per_umi
+        n_bytes = n_reads * read_len
+        d_data = self.device_alloc(n_bytes + 16)
+        d_off = self.device_alloc((n_reads + 1) * 8)
+        d_goff = self.device_alloc((n_umis + 1) * 8)
+        self._check(self._lib.rogtk_gpu_synth_reads(self._ctx, seed & 0xFFFFFFFFFFFFFFFF, umi_base, n_umis, reads_per_umi,
+                                                    read_len, template_len, err_per_64k, ctypes.c_void_p(d_data),
+                                                    ctypes.c_void_p(d_off), ctypes.c_void_p(d_goff)))
+        return d_data, d_off, d_goff, n_bytes
+
+    # ---- the hot path ----------------------------------------------------------------------------------------------------
+    def _call(self, col: _ffi.StrCol, goff_ptr, n_groups: int, k: int, min_coverage: int, flags: int):
+        out = _ffi.GraphBatchC()
+        rc = self._lib.rogtk_gpu_count_prune_batch(self._ctx, ctypes.byref(col), goff_ptr, n_groups, int(k),
+                                                   int(min_coverage), int(flags), ctypes.byref(out))
+        self._check(rc)
+        return out
+
+    def _to_numpy(self, c: _ffi.GraphBatchC) -> GraphBatch:
+        def arr(ptr, n, dt):
+            if not ptr or n == 0:
+                return np.zeros(0, dtype=dt)
+            ct = np.ctypeslib.as_ctypes_type(np.dtype(dt))
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,)).copy()
+
+        ng, nk = int(c.n_groups), int(c.n_kmers)
+        res = GraphBatch(
+            k_eff=int(c.k_eff), n_observations=int(c.n_observations),
+            kmer_offsets=arr(c.kmer_offsets, ng + 1, np.int64), kmers_lo=arr(c.kmers_lo, nk, np.uint64),
+            kmers_hi=arr(c.kmers_hi, nk, np.uint64) if c.kmers_hi else None,
+            exts=arr(c.exts, nk, np.uint8), counts=arr(c.counts, nk, np.uint16),
+            stats=arr(c.stats, 3 * ng, np.uint32).reshape(ng, 3) if c.stats else None,
+            csr_row_ptr=arr(c.csr_row_ptr, nk + 1, np.int64) if c.csr_row_ptr else None,
+            csr_col=arr(c.csr_col, int(c.n_edges), np.int32) if c.csr_row_ptr else None,
+            ms_total=float(c.ms_total), ms_count=float(c.ms_count), ms_hot_kernel=float(c.ms_hot_kernel),
+            n_spilled_groups=int(c.n_spilled_groups))
+        self._lib.rogtk_gpu_free_batch(self._ctx, ctypes.byref(c))
+        return res
+
+    def count_prune(self, data: np.ndarray, offsets: np.ndarray, group_offsets: np.ndarray, k: int, min_coverage: int,
+                    validity: np.ndarray | None = None, validity_bit_offset: int = 0, flags: int = 0) -> GraphBatch:
+        """Host buffers in, host arrays out (H2D and D2H inside the call).  offsets may be int32 (Utf8) or int64
+        (LargeUtf8)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets)
+        if offsets.dtype == np.int32:
+            layout = _ffi.UTF8_I32
+        else:
+            offsets = offsets.astype(np.int64, copy=False)
+            layout = _ffi.UTF8_I64
+        group_offsets = np.ascontiguousarray(group_offsets, dtype=np.int64)
+        if validity is not None:
+            validity = np.ascontiguousarray(validity, dtype=np.uint8)
+        dptr = (ctypes.c_void_p * 1)(data.ctypes.data if data.size else None)
+        dlen = (ctypes.c_int64 * 1)(data.size)
+        col = _ffi.StrCol(layout=layout, n_buffers=1, n_rows=len(offsets) - 1,
+                          validity=validity.ctypes.data if validity is not None else None,
+                          validity_bit_offset=validity_bit_offset, offsets_or_views=offsets.ctypes.data,
+                          data=dptr, data_len=dlen)
+        c = self._call(col, group_offsets.ctypes.data, len(group_offsets) - 1, k, min_coverage,
+                       flags & ~(_ffi.INPUT_ON_DEVICE | _ffi.OUTPUT_ON_DEVICE))
+        return self._to_numpy(c)
+
+    def count_prune_views(self, views: np.ndarray, buffers: list[np.ndarray], group_offsets: np.ndarray, k: int,
+                          min_coverage: int, validity: np.ndarray | None = None, flags: int = 0) -> GraphBatch:
+        """Arrow Utf8View input (Polars >= 0.43 String columns): views = uint8[n_rows,16], buffers = data buffers."""
+        views = np.ascontiguousarray(views, dtype=np.uint8).reshape(-1, 16)
+        buffers = [np.ascontiguousarray(b, dtype=np.uint8) for b in buffers]
+        group_offsets = np.ascontiguousarray(group_offsets, dtype=np.int64)
+        nb = len(buffers)
+        dptr = (ctypes.c_void_p * max(nb, 1))(*[b.ctypes.data if b.size else None for b in buffers])
+        dlen = (ctypes.c_int64 * max(nb, 1))(*[b.size for b in buffers])
+        if validity is not None:
+            validity = np.ascontiguousarray(validity, dtype=np.uint8)
+        col = _ffi.StrCol(layout=_ffi.UTF8_VIEW, n_buffers=nb, n_rows=views.shape[0],
+                          validity=validity.ctypes.data if validity is not None else None, validity_bit_offset=0,
+                          offsets_or_views=views.ctypes.data, data=dptr, data_len=dlen)
+        c = self._call(col, group_offsets.ctypes.data, len(group_offsets) - 1, k, min_coverage,
+                       flags & ~(_ffi.INPUT_ON_DEVICE | _ffi.OUTPUT_ON_DEVICE))
+        return self._to_numpy(c)
+
+    def count_prune_device(self, d_data: int, n_bytes: int, d_offsets: int, n_rows: int, d_group_offsets: int,
+                           n_groups: int, k: int, min_coverage: int, flags: int = 0) -> DeviceBatch:
+        """Inputs already resident in HBM (int64 offsets), outputs left in HBM.  Used by bench.py's `value`."""
+        dptr = (ctypes.c_void_p * 1)(d_data)
+        dlen = (ctypes.c_int64 * 1)(n_bytes)
+        col = _ffi.StrCol(layout=_ffi.UTF8_I64, n_buffers=1, n_rows=n_rows, validity=None, validity_bit_offset=0,
+                          offsets_or_views=d_offsets, data=dptr, data_len=dlen)
+        c = self._call(col, ctypes.c_void_p(d_group_offsets), n_groups, k, min_coverage,
+                       flags | _ffi.INPUT_ON_DEVICE | _ffi.OUTPUT_ON_DEVICE)
+        return DeviceBatch(k_eff=int(c.k_eff), n_groups=int(c.n_groups), n_kmers=int(c.n_kmers), n_edges=int(c.n_edges),
+                           n_observations=int(c.n_observations), ms_total=float(c.ms_total), ms_count=float(c.ms_count),
+                           ms_hot_kernel=float(c.ms_hot_kernel), n_spilled_groups=int(c.n_spilled_groups), _c=c, _engine=self)

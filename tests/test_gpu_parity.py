@@ -1,0 +1,197 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes -> librogtk_gpu.so), against the oracle
+on identical inputs.  Bit-exact: k-mers, exts bytes, u16 counts, group offsets, node statistics and successor CSR."""
+import numpy as np
+import pytest
+
+from util import assert_batches_equal, check_invariants, groups_to_arrow, load_golden, random_groups
+
+pytestmark = pytest.mark.gpu
+
+EMIT_CSR, EMIT_STATS, EXACT_K, FORCE_SPILL = 1, 2, 4, 32
+
+
+def _both(engine, oracle, data, offs, goff, k, mc, validity=None, exact=False, spill=False, csr=True, ctx=""):
+    flags = EMIT_STATS | (EMIT_CSR if csr else 0) | (EXACT_K if exact else 0) | (FORCE_SPILL if spill else 0)
+    got = engine.count_prune(data, offs, goff, k, mc, validity=validity, flags=flags)
+    ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity, exact_k=exact, emit_csr=csr)
+    assert_batches_equal(got, ref, check_csr=csr, ctx=ctx)
+    return got, ref
+
+
+@pytest.mark.parametrize("spill", [False, True])
+def test_golden_fixtures(engine, oracle, spill):
+    for c in load_golden()["cases"]:
+        data, offs, validity = oracle.strings_to_arrow(c["reads"])
+        goff = np.array([0, len(c["reads"])])
+        got, _ = _both(engine, oracle, data, offs, goff, c["k"], c["min_coverage"], validity=validity, spill=spill,
+                       ctx=f"{c['name']} k={c['k']} mc={c['min_coverage']}")
+        rows = oracle.batch_group_as_tuples(got, 0)
+        assert [r[0] for r in rows] == c["kmers"] and [r[1] for r in rows] == c["exts"] and [r[2] for r in rows] == c["counts"]
+        assert oracle.digest(got, 0) == c["sha256"]
+        assert [int(x) for x in got.stats[0]] == c["stats"]
+        assert [int(x) for x in got.csr_col] == c["csr_col"]
+
+
+@pytest.mark.parametrize("spill", [False, True])
+@pytest.mark.parametrize("k,exact", [(3, False), (8, False), (13, False), (17, False), (31, False), (33, False), (47, False),
+                                     (64, False), (5, True), (21, True), (27, True), (40, True), (63, True), (1, True)])
+def test_random_groups(engine, oracle, k, exact, spill):
+    rng = np.random.default_rng(4242 + k + (7 if spill else 0))
+    for mc in (0, 1, 2, 3):
+        groups = random_groups(rng, 60, max_reads=14, max_len=150, tmpl_len=220)
+        data, offs, validity, goff = groups_to_arrow(groups)
+        _both(engine, oracle, data, offs, goff, k, mc, validity=validity, exact=exact, spill=spill, ctx=f"k={k} mc={mc}")
+
+
+def test_empty_and_degenerate_batches(engine, oracle):
+    e = np.zeros(0, np.uint8)
+    # no groups, no rows
+    got = engine.count_prune(e, np.array([0]), np.array([0]), 17, 2, flags=EMIT_STATS | EMIT_CSR)
+    assert got.n_groups == 0 and len(got.kmers_lo) == 0
+    # groups without rows, rows without bases, reads shorter than K, only invalid reads, only nulls
+    groups = [[], [""], ["ACG"], ["ACGTNACGTACGTACGTACGTACGTACGTACGTACGTACGT"], [None, None], [], ["acgtacgtacgtacgtacgtacgtacgtacgtacgt"]]
+    data, offs, validity, goff = groups_to_arrow(groups)
+    for spill in (False, True):
+        got, ref = _both(engine, oracle, data, offs, goff, 17, 1, validity=validity, spill=spill)
+        assert list(np.diff(got.kmer_offsets)[:6]) == [0, 0, 0, 0, 0, 0] and got.kmer_offsets[-1] > 0
+    # k > 64 -> empty result, not an error (reference src/fracture.rs:212-215)
+    got = engine.count_prune(data, offs, goff, 65, 1, validity=validity, flags=EMIT_STATS)
+    assert got.k_eff == -1 and len(got.kmers_lo) == 0 and got.n_groups == len(groups)
+
+
+def test_int32_offsets_and_unaligned_slices(engine, oracle):
+    rng = np.random.default_rng(5)
+    groups = random_groups(rng, 40, max_reads=10, max_len=100, p_null=0.0)
+    data, offs, validity, goff = groups_to_arrow(groups)
+    ref = oracle.count_prune_batch(data, offs, goff, 17, 1, validity=validity)
+    got = engine.count_prune(data, offs.astype(np.int32), goff, 17, 1, validity=validity, flags=EMIT_STATS)
+    assert_batches_equal(got, ref)
+    # an Arrow slice: the data pointer is not 16-byte aligned and offsets do not start at 0
+    pad = np.concatenate([np.frombuffer(b"NNNNN", dtype=np.uint8), data])
+    got = engine.count_prune(pad, offs + 5, goff, 17, 1, validity=validity, flags=EMIT_STATS)
+    assert_batches_equal(got, ref)
+
+
+def test_utf8view_layout(engine, oracle):
+    """Polars String columns arrive as Arrow Utf8View: inline strings (<=12 bytes) and out-of-line strings
+    spread over two data buffers."""
+    rng = np.random.default_rng(9)
+    groups = random_groups(rng, 30, max_reads=10, max_len=60, tmpl_len=80, p_null=0.05)
+    flat = [r for g in groups for r in g]
+    goff = np.zeros(len(groups) + 1, dtype=np.int64)
+    np.cumsum([len(g) for g in groups], out=goff[1:])
+    bufs = [bytearray(), bytearray()]
+    views = np.zeros((len(flat), 16), dtype=np.uint8)
+    valid = np.ones(len(flat), dtype=bool)
+    for i, r in enumerate(flat):
+        if r is None:
+            valid[i] = False
+            continue
+        b = r.encode()
+        views[i, 0:4] = np.frombuffer(np.uint32(len(b)).tobytes(), dtype=np.uint8)
+        if len(b) <= 12:
+            views[i, 4:4 + len(b)] = np.frombuffer(b, dtype=np.uint8)
+        else:
+            which = i % 2
+            off = len(bufs[which])
+            bufs[which] += b
+            views[i, 4:8] = np.frombuffer(b[:4], dtype=np.uint8)
+            views[i, 8:12] = np.frombuffer(np.uint32(which).tobytes(), dtype=np.uint8)
+            views[i, 12:16] = np.frombuffer(np.uint32(off).tobytes(), dtype=np.uint8)
+    validity = None if valid.all() else np.packbits(valid, bitorder="little")
+    data, offs, v2, _ = groups_to_arrow(groups)
+    for k, mc in ((8, 1), (17, 2)):
+        ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=v2)
+        got = engine.count_prune_views(views, [np.frombuffer(bytes(b), dtype=np.uint8) for b in bufs], goff, k, mc,
+                                       validity=validity, flags=EMIT_STATS)
+        assert_batches_equal(got, ref, ctx=f"view k={k}")
+
+
+def test_count_saturation_and_long_reads(engine, oracle):
+    # one k-mer observed > 65535 times (u16 saturation); read longer than any staging tile
+    reads = ["A" * 70000, "ACGT" * 3000, "A" * 40 + "C" + "A" * 40]
+    data, offs, validity = oracle.strings_to_arrow(reads)
+    got, ref = _both(engine, oracle, data, offs, np.array([0, 3]), 16, 1, ctx="saturation")
+    assert got.counts.max() == 65535
+    got, ref = _both(engine, oracle, data, offs, np.array([0, 1, 2, 3]), 31, 2, ctx="saturation K=32")
+    # the all-T k-mer is the table's EMPTY sentinel for K=32 / K=64: must still be counted
+    reads = ["T" * 100, "T" * 40 + "G" + "T" * 70, "t" * 64]
+    data, offs, validity = oracle.strings_to_arrow(reads)
+    for k in (16, 32, 64):
+        for spill in (False, True):
+            _both(engine, oracle, data, offs, np.array([0, 2, 3]), k, 1, spill=spill, ctx=f"all-T k={k}")
+
+
+def test_groups_too_big_for_shared_memory_spill(engine, oracle):
+    """skewed groups (cfg3 shape): > 256 rows, > 16384 bases, or too many distinct k-mers go through the HBM tables;
+    the answer must not depend on the path taken."""
+    from rogtk_b200 import synth
+    rp = np.array([1, 2, 3, 40, 300, 7, 120, 600, 55, 1, 260, 90])
+    data, offs, goff = synth.synth_reads(synth.config_seed(3), 0, len(rp), rp, 150, 500)
+    for k in (11, 17, 33):
+        got, ref = _both(engine, oracle, data, offs, goff, k, 2, ctx=f"skew k={k}")
+        assert got.n_spilled_groups >= 3
+    # many distinct k-mers in few rows: 60 unrelated reads of 250 bases
+    rng = np.random.default_rng(11)
+    reads = ["".join("ACGT"[x] for x in rng.integers(0, 4, 250)) for _ in range(60)]
+    data, offs, validity = oracle.strings_to_arrow(reads)
+    got, ref = _both(engine, oracle, data, offs, np.array([0, 60]), 31, 1, ctx="distinct overflow")
+    assert got.n_spilled_groups == 1
+
+
+def test_device_generator_matches_numpy(engine):
+    from rogtk_b200 import synth
+    seed = synth.config_seed(2)
+    d_data, d_off, d_goff, nbytes = engine.synth_reads_device(seed, 3, 50, 7, 150, 500, 655)
+    data, offs, goff = synth.synth_reads(seed, 3, 50, 7, 150, 500, 655)
+    assert np.array_equal(engine.d2h(d_data, nbytes), data)
+    assert np.array_equal(engine.d2h(d_off, (50 * 7 + 1) * 8, np.int64), offs)
+    assert np.array_equal(engine.d2h(d_goff, 51 * 8, np.int64), goff)
+    for p in (d_data, d_off, d_goff):
+        engine.device_free(p)
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+def test_baseline_config_subsets(engine, oracle, cfg):
+    """First UMIs of BASELINE.json configs[0] (10k x 20 x 150, k=17, min_cov=2) and configs[1] (1M x 50 x 300, k=31)."""
+    from rogtk_b200 import synth
+    if cfg == "cfg1":
+        n, R, L, T, k = 1000, 20, 150, 500, 17
+    else:
+        n, R, L, T, k = 300, 50, 300, 1000, 31
+    data, offs, goff = synth.synth_reads(synth.config_seed(1 if cfg == "cfg1" else 2), 0, n, R, L, T)
+    got, ref = _both(engine, oracle, data, offs, goff, k, 2, csr=False, ctx=cfg)
+    assert got.k_eff == 32 and got.n_spilled_groups == 0
+    assert got.n_observations == n * R * (L - 31)
+    check_invariants(got, 2)
+    _both(engine, oracle, data, offs, goff, k, 1, csr=True, ctx=cfg + " mc=1")
+
+
+def test_device_resident_path_and_invariants_at_scale(engine, oracle):
+    """Inputs generated in HBM, outputs left in HBM (the `value` path of bench.py) at 20k UMIs of the cfg2 shape:
+    size-independent properties + a sampled comparison against the oracle."""
+    from rogtk_b200 import synth
+    seed = synth.config_seed(2)
+    n, R, L, T = 20000, 50, 300, 1000
+    d_data, d_off, d_goff, nbytes = engine.synth_reads_device(seed, 0, n, R, L, T, 655)
+    db = engine.count_prune_device(d_data, nbytes, d_off, n * R, d_goff, n, 31, 2, flags=EMIT_STATS)
+    assert db.n_observations == n * R * (L - 31) and db.n_spilled_groups == 0
+    got = db.to_host()
+    db.free()
+    check_invariants(got, 2)
+    assert np.array_equal(got.stats[:, 0], np.diff(got.kmer_offsets))
+    # second run gives the identical answer (no dependence on scheduling order)
+    db2 = engine.count_prune_device(d_data, nbytes, d_off, n * R, d_goff, n, 31, 2, flags=EMIT_STATS)
+    got2 = db2.to_host()
+    db2.free()
+    assert_batches_equal(got2, got)
+    # sampled oracle comparison: UMIs 0..199 and 19800..19999
+    for base in (0, n - 200):
+        data, offs, goff = synth.synth_reads(seed, base, 200, R, L, T)
+        ref = oracle.count_prune_batch(data, offs, goff, 31, 2)
+        a, b = int(got.kmer_offsets[base]), int(got.kmer_offsets[base + 200])
+        assert np.array_equal(got.kmer_offsets[base:base + 201] - a, ref.kmer_offsets)
+        assert np.array_equal(got.kmers_lo[a:b], ref.kmers_lo) and np.array_equal(got.exts[a:b], ref.exts)
+        assert np.array_equal(got.counts[a:b], ref.counts)
+    for p in (d_data, d_off, d_goff):
+        engine.device_free(p)
