@@ -113,7 +113,7 @@ def cpu_baseline(cfg, target_seconds=15.0, threads=0):
         b = dbg_oracle.count_prune_batch(data, offs, goff, cfg["k"], cfg["min_cov"], n_threads=cores)
         return time.perf_counter() - t0, b.n_observations
 
-    n0 = min(cfg["n_umis"], max(64, 32 * cores))
+    n0 = min(cfg["n_umis"], max(1024, 64 * cores))
     t, obs = run(n0)
     rate = obs / max(t, 1e-9)
     per_umi = obs / n0
@@ -159,7 +159,7 @@ def main():
         from oracle import dbg_oracle
         from rogtk_b200 import synth
         cores = dbg_oracle.max_threads()
-        n = min(cfg["n_umis"], max(256, 48 * cores))
+        n = min(cfg["n_umis"], max(2048, 96 * cores))
         data, offs, goff = synth.synth_reads(synth.config_seed(cfg["config_id"]), 0, n, cfg["reads"], cfg["read_len"],
                                              cfg["template"], cfg["err64k"])
         obs = 0
