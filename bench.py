@@ -52,10 +52,11 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.t_mark = 0.0
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -63,7 +64,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """start of the timed region: earlier samples are discarded"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -74,7 +79,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < self.t_mark:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -223,13 +230,14 @@ def main():
         db.free()
         return r
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # nvidia-smi needs ~1 s to produce its first line: start it before the warm-up
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local_rank)
     barrier()
     launches0 = eng.launch_count
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     ms_dev, ms_hot = 0.0, 0.0
     for _ in range(args.steps):

@@ -2,20 +2,13 @@
 // memory (ingest -> 2-bit pack -> rolling k-mers -> open-addressing table -> min-coverage compaction -> bucket sort
 // -> emit).  Replaces debruijn::filter::filter_kmers + CountFilter as called at reference src/fracture.rs:110-116.
 //
-// Table protocol (no shared-memory atomics on the common path): the CTA advances in rounds, every thread carrying at
-// most one observation (k-mer, exts) per round.
-//   P  probe (read only): first slot on the linear-probe path that holds the key or is EMPTY
-//   -- barrier A --
-//   C  claim: threads that stopped on EMPTY store their key (plain store, last writer wins); every thread stores its
-//      thread id into the tag byte of the slot's value word
-//   -- barrier B --
-//   V  verify: key differs  -> lost the slot, continue probing at the next slot next round
-//              key == mine, tag == mine -> sole elected owner this round: plain read-modify-write of count/exts
-//              key == mine, tag != mine -> a duplicate of this k-mer (or a stray tag) won: the observation is applied
-//                                          with a shared-memory atomic in the next round's C phase
-// Keys never change once verified, slots never return to EMPTY, so lookups stay consistent; counts are exact because
-// every observation is applied exactly once, either by the elected plain RMW (phase V) or atomically (phase C), and
-// the two phases are separated by barriers.
+// Table protocol: open addressing with linear probing in shared memory, keys claimed with one 64/128-bit
+// atomicCAS, values updated with one 32-bit atomicAdd (count in bits 8..31, exts in bits 0..7, so the add can never
+// carry into the exts and a group of <= 16384 bases cannot overflow 24 bits); the add returns the old word and an
+// atomicOr follows only when this observation brings a new exts bit.  Measured on B200 (tools/microbench_smem.cu,
+// profiles/r01_microbench_smem.txt): random-address shared atomicAdd sustains 16 ops/ns/SM, more than a plain
+// LDS+STS read-modify-write, so no barrier-synchronised election scheme is needed; warps run the whole counting
+// phase without a single __syncthreads.
 #pragma once
 #include <vector>
 
@@ -25,19 +18,30 @@
 
 namespace rogtk {
 
-constexpr int SM_NT = 256;            // threads per CTA == max rows per group on this path == tag range (8 bits)
+constexpr int SM_NT = 256;            // threads per CTA == max rows per group on this path
+constexpr int SM_NWARP = SM_NT / 32;
 constexpr int SM_MAX_BASES = 16384;   // bases staged per group (including <=15 bytes of alignment slack)
-constexpr int SM_PK_WORDS = SM_MAX_BASES / 16 + 4;
+constexpr int SM_PK_WORDS = SM_MAX_BASES / 16 + 8;   // 1 word of front pad, tail pad for window over-reads
+constexpr int SM_UNIT = 128;          // windows per work unit (one warp, 4 consecutive windows per lane)
+constexpr int SM_QCAP = 64;           // per-warp queue of collided observations (drained 32 at a time)
 constexpr int SM_TBITS = 13;          // 8192 slots
 constexpr int SM_TSIZE = 1 << SM_TBITS;
-constexpr int SM_LIMIT = SM_TSIZE * 3 / 4 - 8;   // max distinct k-mers per group on this path (sort scratch lives above them)
-constexpr int SM_SORT_BUCKETS = 2048;
-constexpr int SM_SORT_BITS = 11;
+constexpr int SM_SORT_BITS = 10;
+constexpr int SM_SORT_BUCKETS = 1 << SM_SORT_BITS;
+constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this -> HBM path (has a real sort)
+template <int W>
+constexpr int scratch_bytes()   // pk + per-warp queues; reused by the sort (histogram + order)
+{
+    return SM_PK_WORDS * 4 + SM_NWARP * SM_QCAP * (int)(sizeof(typename KeySlot<W>::T) + 4);
+}
+template <int W>
+constexpr int order_cap() { return (scratch_bytes<W>() - SM_SORT_BUCKETS * 4) / 2; }   // survivors sortable in shared memory
+static_assert(order_cap<1>() >= 2048, "sort scratch too small");
 
 template <int W>
 constexpr size_t smem_bytes()
 {
-    return (size_t)SM_TSIZE * sizeof(typename KeySlot<W>::T) + (size_t)SM_TSIZE * 4 + (size_t)SM_PK_WORDS * 4 +
+    return (size_t)SM_TSIZE * sizeof(typename KeySlot<W>::T) + (size_t)SM_TSIZE * 4 + (size_t)scratch_bytes<W>() +
            (size_t)(SM_NT + 1) * 4 * 2 + 40 * 4 + SM_NT + 64;
 }
 
@@ -59,14 +63,16 @@ struct SmemArgs {
     uint16_t *pool_counts;
     int32_t *deferred_ids;           // groups handed to the HBM-table path
     unsigned long long *n_deferred;
+    unsigned long long *phase_cycles;   // optional [8] per-phase SM cycles summed over CTAs (diagnostics)
 };
 
-__device__ __forceinline__ uint32_t hash32(const Key<1> &k)
+__device__ __forceinline__ uint32_t hash32(uint32_t lo, uint32_t hi)
 {
-    uint32_t h = (uint32_t)k.lo * 0x9E3779B1u + (uint32_t)(k.lo >> 32) * 0x85EBCA77u;
+    uint32_t h = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
     h ^= h >> 15;
     return h * 0x2C1B3C6Du;
 }
+__device__ __forceinline__ uint32_t hash32(const Key<1> &k) { return hash32((uint32_t)k.lo, (uint32_t)(k.lo >> 32)); }
 __device__ __forceinline__ uint32_t hash32(const Key<2> &k)
 {
     uint32_t h = (uint32_t)k.lo * 0x9E3779B1u + (uint32_t)(k.lo >> 32) * 0x85EBCA77u;
@@ -85,7 +91,11 @@ __device__ __forceinline__ uint64_t window64(const uint32_t *pk, uint32_t q)
     const uint32_t r0 = __funnelshift_l(x1, x0, s), r1 = __funnelshift_l(x2, x1, s);
     return ((uint64_t)r0 << 32) | r1;
 }
-__device__ __forceinline__ uint32_t base_of(const uint32_t *pk, uint32_t q) { return (pk[q >> 4] >> (30u - 2u * (q & 15u))) & 3u; }
+// base at index q; q == -1 (as uint32) reads the front pad word
+__device__ __forceinline__ uint32_t base_of(const uint32_t *pk, uint32_t q)
+{
+    return (pk[(int32_t)q >> 4] >> (30u - 2u * (q & 15u))) & 3u;
+}
 
 __device__ __forceinline__ void load_window(const uint32_t *pk, uint32_t q, int K, Key<1> &key)
 {
@@ -113,29 +123,6 @@ __device__ __forceinline__ uint32_t sort_bucket<2>(const Key<2> &k, int kbits)
     return sh >= 64 ? (uint32_t)(k.hi >> (sh - 64)) : (uint32_t)((k.hi << (64 - sh)) | (k.lo >> sh));
 }
 
-// saturating-u16 count increment + exts OR on a value word, keeping the tag byte
-__device__ __forceinline__ uint32_t val_apply(uint32_t v, uint32_t exts)
-{
-    uint32_t c = v & 0xffffu;
-    c += (c != 0xffffu);
-    return (v & 0xffff0000u) | c | (exts << 16);
-}
-__device__ __forceinline__ void val_apply_atomic(uint32_t *vp, uint32_t exts)
-{
-    uint32_t old = *reinterpret_cast<volatile uint32_t *>(vp);
-    if ((old & 0xffffu) < 0xfe00u) {   // < 256 concurrent adders cannot carry out of the count field
-        atomicAdd(vp, 1u);
-        if ((exts << 16) & ~old) atomicOr(vp, exts << 16);
-        return;
-    }
-    while (true) {
-        uint32_t nw = val_apply(old, exts);
-        uint32_t prev = atomicCAS(vp, old, nw);
-        if (prev == old) return;
-        old = prev;
-    }
-}
-
 // block-wide exclusive scan of one u32 per thread (SM_NT threads); ws = 9 words of shared scratch
 __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *total, uint32_t *ws)
 {
@@ -150,7 +137,7 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *total, 
     __syncthreads();
     uint32_t base = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < SM_NT / 32; w++) {
+    for (int w = 0; w < SM_NWARP; w++) {
         uint32_t s = ws[w];
         if (w < (int)warp) base += s;
         tot += s;
@@ -160,7 +147,119 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *total, 
     return base + x - v;
 }
 
+// ---- ingest helpers kept out of line: they run only for chunks at the edge of the data buffer / with a bad byte ------------
+__device__ __noinline__ uint4 load_chunk_guarded(const uint8_t *p, const uint8_t *lo, const uint8_t *hi)
+{
+    uint32_t wv[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
+    for (int t = 0; t < 16; t++) {
+        const uint8_t *pb = p + t;
+        if (pb >= lo && pb < hi) wv[t >> 2] = (wv[t >> 2] & ~(0xffu << (8 * (t & 3)))) | ((uint32_t)*pb << (8 * (t & 3)));
+    }
+    return make_uint4(wv[0], wv[1], wv[2], wv[3]);
+}
+// attribute every bad byte of a chunk to its read (reference src/fracture.rs:222 drops that read)
+__device__ __noinline__ void mark_bad_reads(uint4 v, uint32_t qbase, uint32_t slack, uint32_t span, const uint32_t *rstart, int nr,
+                                            uint8_t *bad)
+{
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    for (int t = 0; t < 16; t++) {
+        const uint32_t q = qbase + t;
+        if (q < slack || q >= span) continue;
+        if (base_ok((wv[t >> 2] >> (8 * (t & 3))) & 0xffu)) continue;
+        int lo = 0, hi = nr;   // last r with rstart[r] <= q
+        while (hi - lo > 1) {
+            int m = (lo + hi) >> 1;
+            if (rstart[m] <= q) lo = m; else hi = m;
+        }
+        bad[lo] = 1;
+    }
+}
+
+// ---- the table ------------------------------------------------------------------------------------------------------------------
+// count in bits 8..31, exts in bits 0..7: the add can never carry into the exts; the returned old word tells whether this
+// observation brings a new exts bit.
+__device__ __forceinline__ void val_add(uint32_t *vp, uint32_t ex)
+{
+    const uint32_t old = atomicAdd(vp, 256u);
+    if (ex & ~old) atomicOr(vp, ex);
+}
+
 template <int W>
+struct WarpQueue {   // collided observations of one warp, waiting for their next probe
+    typename KeySlot<W>::T *key;
+    uint32_t *hx;    // slot | exts << 16
+    uint32_t n;      // entries (warp-uniform)
+    int budget;      // drain steps left before the table is declared full (warp-uniform)
+};
+
+// One probe step for up to 32 queued observations (one per lane, full width).  Resolved ones are applied, the others are
+// pushed back.  Returns false when the probe bound is exceeded (table hopelessly full).
+template <int W>
+__device__ __forceinline__ void queue_drain_step(WarpQueue<W> &q, typename KeySlot<W>::T *tkey, uint32_t *tval, uint32_t tmask,
+                                                 uint32_t lane)
+{
+    using S = KeySlot<W>;
+    using KT = typename S::T;
+    const uint32_t take = q.n < 32u ? q.n : 32u;
+    const uint32_t base = q.n - take;
+    bool pend = false;
+    KT kp = S::empty();
+    uint32_t hx = 0;
+    if (lane < take) {
+        kp = q.key[base + lane];
+        hx = q.hx[base + lane];
+        uint32_t h = ((hx & 0xffffu) + 1u) & tmask;
+        KT cur = tkey[h];
+        if (cur == S::empty()) cur = atomicCAS(&tkey[h], S::empty(), kp);
+        if (cur == kp || cur == S::empty()) {
+            val_add(&tval[h], hx >> 16);
+        } else {
+            pend = true;
+            hx = (hx & 0xffff0000u) | h;
+        }
+    }
+    __syncwarp();
+    const uint32_t m = __ballot_sync(0xffffffffu, pend);
+    if (pend) {
+        const uint32_t i = base + __popc(m & ((1u << lane) - 1u));
+        q.key[i] = kp;
+        q.hx[i] = hx;
+    }
+    q.n = base + __popc(m);
+    __syncwarp();
+}
+
+template <int W>
+__device__ __forceinline__ void queue_push(WarpQueue<W> &q, bool pend, typename KeySlot<W>::T kp, uint32_t h, uint32_t ex,
+                                           typename KeySlot<W>::T *tkey, uint32_t *tval, uint32_t tmask, uint32_t lane)
+{
+    const uint32_t m = __ballot_sync(0xffffffffu, pend);
+    if (m == 0) return;
+    if (pend) {
+        const uint32_t i = q.n + __popc(m & ((1u << lane) - 1u));
+        q.key[i] = kp;
+        q.hx[i] = h | (ex << 16);
+    }
+    q.n += __popc(m);
+    __syncwarp();
+    // keep fewer than 32 entries queued, so that the next push (<= 32 entries) always fits in SM_QCAP
+    while (q.n >= 32u && q.budget > 0) {
+        queue_drain_step<W>(q, tkey, tval, tmask, lane);
+        q.budget--;
+    }
+    if (q.n >= 32u) q.n = 0;   // budget exhausted: the caller sees budget <= 0 and gives the group up
+}
+
+#define PHASE_MARK(idx)                                                  \
+    do {                                                                 \
+        if (a.phase_cycles && tid == 0) {                                \
+            const long long _t = clock64();                              \
+            atomicAdd(a.phase_cycles + (idx), (unsigned long long)(_t - t_phase)); \
+            t_phase = _t;                                                \
+        }                                                                \
+    } while (0)
+
+template <int W, bool K32>
 __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs a)
 {
     using S = KeySlot<W>;
@@ -168,17 +267,27 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     extern __shared__ __align__(16) uint8_t smem_raw[];
     KT *tkey = reinterpret_cast<KT *>(smem_raw);
     uint32_t *tval = reinterpret_cast<uint32_t *>(tkey + SM_TSIZE);
-    uint32_t *pk = tval + SM_TSIZE;
-    uint32_t *rstart = pk + SM_PK_WORDS;
-    uint32_t *cum = rstart + SM_NT + 1;
-    uint32_t *ws = cum + SM_NT + 1;                      // 40 words of scratch: [0..8] scan, [16..] misc
+    uint32_t *scratch = tval + SM_TSIZE;
+    uint32_t *pk = scratch + 1;                                                  // pk[-1] is a readable pad word
+    uint8_t *qbytes = reinterpret_cast<uint8_t *>(scratch + SM_PK_WORDS);        // per-warp queues (W=1: 8 B keys)
+    uint32_t *hist = scratch;                                                    // sort histogram (after counting)
+    uint16_t *order = reinterpret_cast<uint16_t *>(scratch + SM_SORT_BUCKETS);   // sort permutation (after counting)
+    uint32_t *rstart = scratch + scratch_bytes<W>() / 4;
+    uint32_t *ucum = rstart + SM_NT + 1;                 // work units before read r
+    uint32_t *ws = ucum + SM_NT + 1;                     // 40 words: [0..8] scan, [16..] misc
     uint8_t *bad = reinterpret_cast<uint8_t *>(ws + 40);
-    volatile uint32_t *misc = ws + 16;                   // [0],[1] ticket lo/hi  [2] special val  [3] abort flag  [4],[5] pool base
+    volatile uint32_t *misc = ws + 16;   // [0],[1] ticket [2] all-ones k-mer value [3] abort [4],[5] pool base [6] big bucket [7] unit counter
     const int tid = threadIdx.x;
-    const unsigned lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
     const int K = a.K, kbits = 2 * K;
     const uint32_t thr = a.min_cov > 1u ? a.min_cov : 1u;
     unsigned long long cta_obs = 0;
+    long long t_phase = clock64();
+    WarpQueue<W> wq;
+    wq.key = reinterpret_cast<KT *>(qbytes) + warp * SM_QCAP;
+    wq.hx = reinterpret_cast<uint32_t *>(reinterpret_cast<KT *>(qbytes) + SM_NWARP * SM_QCAP) + warp * SM_QCAP;
+    wq.n = 0;
+    wq.budget = 0;
 
     while (true) {
         __syncthreads();
@@ -188,6 +297,8 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             misc[1] = (uint32_t)(t >> 32);
             misc[2] = 0;
             misc[3] = 0;
+            misc[6] = 0;
+            misc[7] = 0;
         }
         __syncthreads();
         const int64_t g = (int64_t)(((unsigned long long)misc[1] << 32) | misc[0]);
@@ -212,6 +323,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         if (tid < nr) bad[tid] = col_valid(a.col, r0 + tid) ? 0 : 1;
         __syncthreads();
 
+        PHASE_MARK(0);
         // ---- ingest: 16-byte chunks -> one packed u32 (16 bases, first base in the top bits) --------------------------
         {
             const uint8_t *a0 = reinterpret_cast<const uint8_t *>(addr0 - slack);
@@ -227,14 +339,8 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                                      : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
                                      : "l"(p));
-                    } else {   // chunk straddles the buffer edge: guarded byte loads
-                        uint32_t wv[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
-                        for (int t = 0; t < 16; t++) {
-                            const uint8_t *pb = p + t;
-                            if (pb >= a.col.data && pb < a.data_end)
-                                wv[t >> 2] = (wv[t >> 2] & ~(0xffu << (8 * (t & 3)))) | ((uint32_t)*pb << (8 * (t & 3)));
-                        }
-                        v[i] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    } else {
+                        v[i] = load_chunk_guarded(p, a.col.data, a.data_end);
                     }
                 }
             }
@@ -244,43 +350,33 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                 if (c < nchunks) {
                     pk[c] = (pack4(v[i].x) << 24) | (pack4(v[i].y) << 16) | (pack4(v[i].z) << 8) | pack4(v[i].w);
                     const bool ok = valid4(v[i].x) & valid4(v[i].y) & valid4(v[i].z) & valid4(v[i].w);
-                    if (!ok) {   // attribute every bad byte to its read (reference src/fracture.rs:222 drops that read)
-                        const uint32_t wv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                        for (int t = 0; t < 16; t++) {
-                            const uint32_t q = 16u * c + t;
-                            if (q < slack || q >= span) continue;
-                            if (base_ok((wv[t >> 2] >> (8 * (t & 3))) & 0xffu)) continue;
-                            int lo = 0, hi = nr;   // last r with rstart[r] <= q
-                            while (hi - lo > 1) {
-                                int m = (lo + hi) >> 1;
-                                if (rstart[m] <= q) lo = m; else hi = m;
-                            }
-                            bad[lo] = 1;
-                        }
-                    }
+                    if (!ok) mark_bad_reads(v[i], 16u * c, slack, span, rstart, nr, bad);
                 }
             }
         }
         __syncthreads();
 
-        // ---- observations per read, prefix sums ---------------------------------------------------------------------------
-        uint32_t total;
+        PHASE_MARK(1);
+        // ---- windows per read -> work units of SM_UNIT windows, prefix sums ------------------------------------------------------
+        uint32_t total, nunits;
         {
             uint32_t nk = 0;
             if (tid < nr) {
                 const uint32_t len = rstart[tid + 1] - rstart[tid];
                 if (!bad[tid] && len >= (uint32_t)K) nk = len - K + 1;
             }
-            const uint32_t ex = block_scan_u32(nk, &total, ws);
-            cum[tid] = ex;
-            if (tid == 0) cum[SM_NT] = total;
+            block_scan_u32(nk, &total, ws);
+            const uint32_t ex = block_scan_u32((nk + SM_UNIT - 1) / SM_UNIT, &nunits, ws);
+            ucum[tid] = ex;
+            if (tid == 0) ucum[SM_NT] = nunits;
         }
-        if (total == 0) continue;   // (the loop-top barrier orders the cum[] writes before reuse)
+        if (total == 0) continue;   // (the loop-top barrier orders the shared writes before reuse)
 
         // ---- table sized to the group: power of two >= 2 * observations, at most SM_TSIZE -------------------------------------
         int tbits = 8;
         while (tbits < SM_TBITS && (1u << tbits) < 2u * total) tbits++;
         const uint32_t tsize = 1u << tbits, tmask = tsize - 1u;
+        const int tshift = 32 - tbits;
         {
             // keys = EMPTY (all ones), vals = 0
             uint4 *kq = reinterpret_cast<uint4 *>(tkey);
@@ -292,249 +388,208 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         }
         __syncthreads();
 
-        // ---- counting rounds ------------------------------------------------------------------------------------------------
-        const uint32_t per = (total + SM_NT - 1) / SM_NT;
-        uint32_t oi = (uint32_t)tid * per;                       // next observation index of this thread
-        const uint32_t oe = (oi + per < total) ? oi + per : total;
-        int r = 0;
-        uint32_t p = 0, nkr = 0, q = 0, len = 0;
-        bool fresh = true;
-        if (oi < oe) {   // last r with cum[r] <= oi and a non-empty read
-            int lo = 0, hi = nr;
-            while (hi - lo > 1) {
-                int m = (lo + hi) >> 1;
-                if (cum[m] <= oi) lo = m; else hi = m;
-            }
-            r = lo;
-            p = oi - cum[r];
-            nkr = cum[r + 1] - cum[r];
-            len = rstart[r + 1] - rstart[r];
-            q = rstart[r] + p;
-        }
-        Key<W> key = Key<W>::zero();
-        uint32_t ex = 0, nb = 0, prev_top = 0, h = 0;
-        bool have = false, dup = false, claim = false;
-        int occupied = 0, claimed_prev = 0;
-        bool aborted = false;
-        while (true) {
-            if (!have && oi < oe) {
-                // ---- fetch the next observation: rolling update inside a read, rebuild at read starts -------------------------
-                if (p == nkr) {
-                    do { r++; } while (cum[r + 1] == cum[r]);
-                    p = 0;
-                    nkr = cum[r + 1] - cum[r];
-                    len = rstart[r + 1] - rstart[r];
-                    q = rstart[r];
-                    fresh = true;
-                }
-                uint32_t left;
-                if (fresh) {
-                    load_window(pk, q, K, key);
-                    left = p ? (1u << base_of(pk, q - 1)) : 0u;
-                    fresh = false;
-                } else {
-                    key.push(nb, kbits);
-                    left = 1u << prev_top;
-                }
-                uint32_t right = 0;
-                if (p + K < len) {
-                    nb = base_of(pk, q + K);
-                    right = 16u << nb;
-                }
-                ex = left | right;
-                prev_top = key.top_base(kbits);
-                p++;
-                q++;
-                oi++;
-                if (S::pack(key) == S::empty()) {
-                    // the all-ones k-mer is the table's EMPTY marker: counted in a side word
-                    val_apply_atomic(const_cast<uint32_t *>(&misc[2]), ex);
-                } else {
-                    h = hash32(key) >> (32 - tbits);
-                    have = true;
-                }
-            }
-            // ---- P: probe ---------------------------------------------------------------------------------------------------
-            claim = false;
-            if (have && !dup) {
-                const KT kp = S::pack(key);
-                uint32_t guard = 0;
-                while (true) {
-                    const KT cur = tkey[h];
-                    if (cur == kp) break;
-                    if (cur == S::empty()) {
-                        claim = true;
-                        break;
-                    }
-                    h = (h + 1) & tmask;
-                    if (++guard > tsize) {   // cannot happen while occupied <= limit; never spin forever
-                        misc[3] = 1;
-                        have = false;
-                        break;
-                    }
-                }
-            }
-            occupied += __syncthreads_count(claimed_prev);   // barrier A
-            claimed_prev = 0;
-            if (occupied > SM_LIMIT || misc[3]) {
-                aborted = true;
-                break;
-            }
-            // ---- C: claim + tag, and deferred duplicates -------------------------------------------------------------------------
-            if (have) {
-                if (dup) {
-                    val_apply_atomic(&tval[h], ex);
-                    have = false;
-                    dup = false;
-                } else {
-                    if (claim) tkey[h] = S::pack(key);
-                    reinterpret_cast<uint8_t *>(&tval[h])[3] = (uint8_t)tid;
-                }
-            }
-            const int any = __syncthreads_or(have || (oi < oe));   // barrier B
-            // ---- V: verify ----------------------------------------------------------------------------------------------------------
-            if (have) {
-                const KT kp = S::pack(key);
-                const KT cur = claim ? tkey[h] : kp;
-                if (cur == kp) {
-                    claimed_prev = claim;   // duplicates that claimed together over-count: the occupancy bound stays safe
-                    const uint32_t v = tval[h];
-                    if ((v >> 24) == (uint32_t)tid) {
-                        tval[h] = val_apply(v, ex);
-                        have = false;
-                    } else {
-                        dup = true;
-                    }
-                } else {
-                    h = (h + 1) & tmask;
-                }
-            }
-            if (!any) break;
-        }
-        __syncthreads();
-        if (aborted) {   // too many distinct k-mers for a shared-memory table: HBM-table path
-            if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)g;
-            continue;
-        }
-
-        // ---- min-coverage prune + in-place compaction (4 slots per thread per pass; destinations never pass sources) -----------
-        uint32_t nS = 0;
-        for (uint32_t base = 0; base < tsize; base += 4 * SM_NT) {
-            KT k4[4];
-            uint32_t v4[4];
-            uint32_t cnt = 0;
-            bool keep[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const uint32_t slot = base + 4u * tid + t;
-                keep[t] = false;
-                if (slot < tsize) {
-                    k4[t] = tkey[slot];
-                    v4[t] = tval[slot];
-                    const uint32_t c = v4[t] & 0xffffu;
-                    keep[t] = (k4[t] != S::empty()) && c >= thr;
-                }
-                cnt += keep[t];
-            }
-            uint32_t tot;
-            uint32_t off = nS + block_scan_u32(cnt, &tot, ws);   // contains the barriers that order reads before writes
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                if (keep[t]) {
-                    tkey[off] = k4[t];
-                    tval[off] = v4[t];
-                    off++;
-                }
-            }
-            nS += tot;
-            __syncthreads();
-        }
+        PHASE_MARK(2);
+        // ---- counting: warps fetch units of SM_UNIT windows of one read; no block barriers ---------------------------------------------
         {
-            const uint32_t sv = misc[2];
-            if ((sv & 0xffffu) >= thr) {   // the all-ones k-mer survives
-                if (tid == 0) {
-                    tkey[nS] = S::empty();
-                    tval[nS] = sv;
+            wq.n = 0;
+            wq.budget = 64 + (int)(total >> 1);   // drain steps allowed per warp: far above any non-full table's need
+            uint32_t *special = const_cast<uint32_t *>(&misc[2]);
+            // first probe + claim of one observation; returns true when it must queue for further probing
+            auto first_probe = [&](KT kp, uint32_t h, uint32_t ex, KT cur) -> bool {
+                if (kp == S::empty()) {   // the all-ones k-mer is the EMPTY marker: counted in a side word
+                    val_add(special, ex);
+                    return false;
                 }
-                nS++;
+                if (cur == S::empty()) cur = atomicCAS(&tkey[h], S::empty(), kp);
+                if (cur == kp || cur == S::empty()) {
+                    val_add(&tval[h], ex);
+                    return false;
+                }
+                return true;
+            };
+            while (true) {
+                uint32_t unit = 0;
+                if (lane == 0) unit = atomicAdd(const_cast<uint32_t *>(&misc[7]), 1u);
+                unit = __shfl_sync(0xffffffffu, unit, 0);
+                if (unit >= nunits || misc[3] || wq.budget <= 0) break;
+                int lo = 0, hi = nr;   // read of this unit: last r with ucum[r] <= unit (reads without windows never match)
+                while (hi - lo > 1) {
+                    const int m = (lo + hi) >> 1;
+                    if (ucum[m] <= unit) lo = m; else hi = m;
+                }
+                const uint32_t rs = rstart[lo];
+                const uint32_t nk = rstart[lo + 1] - rs - (uint32_t)K + 1u;
+                const uint32_t p0 = (unit - ucum[lo]) * SM_UNIT;
+                const uint32_t rem = nk - p0;
+                if (K32 && rem >= (uint32_t)SM_UNIT) {
+                    // ---- full unit, K == 32: lane owns windows p0+4*lane .. +3; five packed words hold all their bases ------------
+                    const uint32_t p = p0 + 4u * lane;
+                    const uint32_t q = rs + p;
+                    const int32_t w = (int32_t)(q >> 4);
+                    const uint32_t s = 2u * (q & 15u);
+                    const uint32_t xm = pk[w - 1], x0 = pk[w], x1 = pk[w + 1], x2 = pk[w + 2], x3 = pk[w + 3];
+                    uint32_t kh[4], kl[4], ex[4], h[4];
+                    kh[0] = __funnelshift_l(x1, x0, s);
+                    kl[0] = __funnelshift_l(x2, x1, s);
+                    const uint32_t tail = __funnelshift_l(x3, x2, s);        // bases q+32 .. q+47
+                    const uint32_t lb0 = __funnelshift_l(x0, xm, s) & 3u;    // base q-1
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t nb = (tail >> (30 - 2 * u)) & 3u;     // base q+32+u: right neighbour of window u
+                        const uint32_t lb = u ? (kh[u - 1] >> 30) : lb0;     // left neighbour of window u
+                        const bool has_l = u ? true : (p != 0u);
+                        const bool has_r = (p + u + 1u) < nk;
+                        ex[u] = (has_l ? (1u << lb) : 0u) | (has_r ? (16u << nb) : 0u);
+                        h[u] = hash32(kl[u], kh[u]) >> tshift;
+                        if (u < 3) {
+                            kh[u + 1] = __funnelshift_l(kl[u], kh[u], 2);
+                            kl[u + 1] = (kl[u] << 2) | nb;
+                        }
+                    }
+                    KT cur[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) cur[u] = tkey[h[u]];
+                    bool pend[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
+                        pend[u] = first_probe(kp, h[u], ex[u], cur[u]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
+                        queue_push<W>(wq, pend[u], kp, h[u], ex[u], tkey, tval, tmask, lane);
+                    }
+                } else {
+                    // ---- generic: 32 windows per pass, one per lane ------------------------------------------------------------------
+                    const uint32_t cnt = rem < (uint32_t)SM_UNIT ? rem : (uint32_t)SM_UNIT;
+                    for (uint32_t pb = 0; pb < cnt; pb += 32u) {
+                        const uint32_t p = p0 + pb + lane;
+                        bool pend = false;
+                        KT kp = S::empty();
+                        uint32_t h = 0, ex = 0;
+                        if (p < nk) {
+                            const uint32_t q = rs + p;
+                            Key<W> key = Key<W>::zero();
+                            load_window(pk, q, K, key);
+                            const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
+                            // Exts of iter_kmer_exts with seq_exts = Exts::empty()
+                            ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
+                            h = hash32(key) >> tshift;
+                            kp = S::pack(key);
+                            pend = first_probe(kp, h, ex, tkey[h]);
+                        }
+                        __syncwarp();
+                        queue_push<W>(wq, pend, kp, h, ex, tkey, tval, tmask, lane);
+                    }
+                }
             }
+            // drain what is left of this warp's queue
+            while (wq.n && wq.budget > 0) {
+                queue_drain_step<W>(wq, tkey, tval, tmask, lane);
+                wq.budget--;
+            }
+            if (wq.budget <= 0) misc[3] = 1;   // never spin on a full table: the HBM path takes the group
         }
         __syncthreads();
-        if (nS == 0) {
-            cta_obs += total;
-            continue;
-        }
-        if (tid == 0) {
-            unsigned long long pb = atomicAdd(a.pool_cursor, (unsigned long long)nS);
-            misc[4] = (uint32_t)pb;
-            misc[5] = (uint32_t)(pb >> 32);
-        }
-        __syncthreads();
-        const int64_t pb = (int64_t)(((unsigned long long)misc[5] << 32) | misc[4]);
-        if (pb + (int64_t)nS > a.pool_cap) {   // survivor pool exhausted: let the HBM path (own pool) take the group
+        if (misc[3]) {   // too many distinct k-mers for a shared-memory table: HBM-table path
             if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)g;
             continue;
         }
 
-        // ---- ascending order: counting sort on the top SM_SORT_BITS bits, then fix the (tiny) buckets --------------------------------
-        uint32_t *hist = tval + nS;                                         // SM_SORT_BUCKETS words (nS <= SM_LIMIT)
-        uint16_t *order = reinterpret_cast<uint16_t *>(tkey + nS);          // nS entries
+        PHASE_MARK(3);
+        // ---- min-coverage prune + ascending order: counting sort on the top SM_SORT_BITS bits straight from the table --------------
         for (int j = tid; j < SM_SORT_BUCKETS; j += SM_NT) hist[j] = 0;
         __syncthreads();
-        for (uint32_t j = tid; j < nS; j += SM_NT) atomicAdd(&hist[sort_bucket<W>(S::unpack(tkey[j]), kbits)], 1u);
+        for (uint32_t slot = tid; slot < tsize; slot += SM_NT) {
+            if ((tval[slot] >> 8) >= thr) atomicAdd(&hist[sort_bucket<W>(S::unpack(tkey[slot]), kbits)], 1u);
+        }
+        const uint32_t sv = misc[2];
+        const bool special_survives = (sv >> 8) >= thr;
+        if (special_survives && tid == 0) atomicAdd(&hist[SM_SORT_BUCKETS - 1], 1u);   // all-ones sorts last
         __syncthreads();
+        uint32_t nS;
         {
             constexpr int PER = SM_SORT_BUCKETS / SM_NT;
-            uint32_t loc[PER], s = 0;
+            uint32_t loc[PER], s = 0, mx = 0;
 #pragma unroll
             for (int t = 0; t < PER; t++) {
                 loc[t] = hist[tid * PER + t];
                 s += loc[t];
+                mx = loc[t] > mx ? loc[t] : mx;
             }
-            uint32_t tot;
-            uint32_t e0 = block_scan_u32(s, &tot, ws);
+            if (mx > (uint32_t)SM_MAX_BUCKET) misc[6] = 1;
+            uint32_t e0 = block_scan_u32(s, &nS, ws);
 #pragma unroll
             for (int t = 0; t < PER; t++) {
                 hist[tid * PER + t] = e0;
                 e0 += loc[t];
             }
         }
-        __syncthreads();
-        for (uint32_t j = tid; j < nS; j += SM_NT) {
-            const uint32_t pos = atomicAdd(&hist[sort_bucket<W>(S::unpack(tkey[j]), kbits)], 1u);
-            order[pos] = (uint16_t)j;
+        if (tid == 0 && nS) {
+            unsigned long long pb = atomicAdd(a.pool_cursor, (unsigned long long)nS);
+            misc[4] = (uint32_t)pb;
+            misc[5] = (uint32_t)(pb >> 32);
         }
         __syncthreads();
-        for (int b = tid; b < SM_SORT_BUCKETS; b += SM_NT) {   // hist[b] is now the END of bucket b
+        if (nS == 0) {
+            cta_obs += total;
+            continue;
+        }
+        const int64_t pb = (int64_t)(((unsigned long long)misc[5] << 32) | misc[4]);
+        if (misc[6] || nS > (uint32_t)order_cap<W>() || pb + (int64_t)nS > a.pool_cap) {
+            // a sort bucket too large for the per-thread fix-up (low-complexity k-mers), more survivors than the shared
+            // sort scratch holds, or the survivor pool is exhausted: the HBM path takes the group (it owns a real sort)
+            if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)g;
+            continue;
+        }
+        PHASE_MARK(4);
+        // scatter slot indices to their bucket's range (bucket order == k-mer order up to in-bucket ties)
+        const uint16_t SPECIAL_SLOT = 0xffffu;   // stands for the all-ones k-mer kept in misc[2]
+        for (uint32_t slot = tid; slot < tsize; slot += SM_NT) {
+            if ((tval[slot] >> 8) >= thr) {
+                const uint32_t pos = atomicAdd(&hist[sort_bucket<W>(S::unpack(tkey[slot]), kbits)], 1u);
+                order[pos] = (uint16_t)slot;
+            }
+        }
+        if (special_survives && tid == 0) order[atomicAdd(&hist[SM_SORT_BUCKETS - 1], 1u)] = SPECIAL_SLOT;
+        __syncthreads();
+        // buckets with several survivors: insertion sort by k-mer (hist[b] is now the END of bucket b)
+        for (int b = tid; b < SM_SORT_BUCKETS; b += SM_NT) {
             const uint32_t s = b ? hist[b - 1] : 0u, e = hist[b];
-            for (uint32_t i = s + 1; i < e; i++) {             // insertion sort by key
-                const uint16_t oi2 = order[i];
-                const KT ki = tkey[oi2];
+            for (uint32_t i = s + 1; i < e; i++) {
+                const uint16_t oi = order[i];
+                const KT ki = (oi == SPECIAL_SLOT) ? S::empty() : tkey[oi];
                 uint32_t j = i;
-                while (j > s && tkey[order[j - 1]] > ki) {
-                    order[j] = order[j - 1];
+                while (j > s) {
+                    const uint16_t oj = order[j - 1];
+                    const KT kj = (oj == SPECIAL_SLOT) ? S::empty() : tkey[oj];
+                    if (!(kj > ki)) break;
+                    order[j] = oj;
                     j--;
                 }
-                order[j] = oi2;
+                order[j] = oi;
             }
         }
         __syncthreads();
-
+        PHASE_MARK(5);
         // ---- emit (coalesced) ------------------------------------------------------------------------------------------------------------
         for (uint32_t j = tid; j < nS; j += SM_NT) {
-            const uint32_t idx = order[j];
-            const Key<W> k = S::unpack(tkey[idx]);
-            const uint32_t v = tval[idx];
+            const uint16_t idx = order[j];
+            const Key<W> k = S::unpack(idx == SPECIAL_SLOT ? S::empty() : tkey[idx]);
+            const uint32_t v = (idx == SPECIAL_SLOT) ? sv : tval[idx];
             a.pool_lo[pb + j] = k.lo;
             if (W == 2) a.pool_hi[pb + j] = k.hi_word();
-            a.pool_exts[pb + j] = (uint8_t)(v >> 16);
-            a.pool_counts[pb + j] = (uint16_t)(v & 0xffffu);
+            a.pool_exts[pb + j] = (uint8_t)v;
+            a.pool_counts[pb + j] = (uint16_t)((v >> 8) > 65535u ? 65535u : (v >> 8));
         }
         if (tid == 0) {
             a.nsurv[g] = (int64_t)nS;
             a.pool_start[g] = pb;
         }
         cta_obs += total;
+        PHASE_MARK(6);
     }
     if (tid == 0 && cta_obs) atomicAdd(a.n_obs, cta_obs);
 }
@@ -568,17 +623,22 @@ struct SmemResult {
 
 inline void smem_path_configure()
 {
-    CK(cudaFuncSetAttribute(k_smem_count<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<1>()));
-    CK(cudaFuncSetAttribute(k_smem_count<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<2>()));
+    CK(cudaFuncSetAttribute(k_smem_count<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<1>()));
+    CK(cudaFuncSetAttribute(k_smem_count<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<1>()));
+    CK(cudaFuncSetAttribute(k_smem_count<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_smem_count<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<2>()));
+    CK(cudaFuncSetAttribute(k_smem_count<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_smem_count<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 }
 
 inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes, const ColView &col, const uint8_t *data_end,
                           const int64_t *d_group_offsets, int64_t n_groups, int K, uint32_t min_cov, unsigned long long *d_nobs,
-                          int64_t *d_nsurv, SmemResult &res, int64_t *launches, cudaEvent_t ev_a, cudaEvent_t ev_b)
+                          int64_t *d_nsurv, SmemResult &res, int64_t *launches, cudaEvent_t ev_a, cudaEvent_t ev_b,
+                          unsigned long long *phase_out /* host [8] or nullptr */)
 {
     const int W = K > 32 ? 2 : 1;
-    DevBuf ctr(64, st);
-    CK(cudaMemsetAsync(ctr.p, 0, 64, st));
+    DevBuf ctr(128, st);
+    CK(cudaMemsetAsync(ctr.p, 0, 128, st));
     unsigned long long *d_ctr = ctr.as<unsigned long long>();   // [0] ticket [1] pool cursor [2] n_deferred [3] obs upper bound
     k_obs_upper_bound<<<sm_count * 4, 256, 0, st>>>(col, K, d_ctr + 3);
     unsigned long long ub = 0;
@@ -625,18 +685,21 @@ inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes,
     a.pool_counts = p_counts;
     a.deferred_ids = d_ids;
     a.n_deferred = d_ctr + 2;
+    a.phase_cycles = phase_out ? d_ctr + 8 : nullptr;
     CK(cudaEventRecord(ev_a, st));
     if (W == 1) {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 2);
-        k_smem_count<1><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
+        if (K == 32) k_smem_count<1, true><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
+        else k_smem_count<1, false><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count);
-        k_smem_count<2><<<grid, SM_NT, smem_bytes<2>(), st>>>(a);
+        k_smem_count<2, false><<<grid, SM_NT, smem_bytes<2>(), st>>>(a);
     }
     CK(cudaEventRecord(ev_b, st));
     if (launches) *launches += 2;
     unsigned long long h_ctr[3];
     CK(cudaMemcpyAsync(h_ctr, d_ctr, 24, cudaMemcpyDeviceToHost, st));
+    if (phase_out) CK(cudaMemcpyAsync(phase_out, d_ctr + 8, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&res.ms_kernel, ev_a, ev_b));
     res.n_deferred = (int64_t)h_ctr[2];

@@ -40,6 +40,8 @@ struct rogtk_gpu_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     void *flush_buf = nullptr;
+    bool phase_enabled = false;
+    unsigned long long phase_cycles[8] = {};
     size_t flush_bytes = 0;
     // cache of pinned host blocks (size -> pointers) so steady-state calls do not pay cudaHostAlloc
     std::multimap<size_t, void *> pinned_free;
@@ -444,7 +446,8 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
     int64_t n_spill = n_groups;
     if (!(flags & ROGTK_FORCE_SPILL) && n_groups > 0) {
         run_smem_path(ctx->stream, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_end, in.group_offsets, n_groups, K,
-                      min_coverage, d_nobs, nsurv.as<int64_t>(), sm, &ctx->launches, ctx->ev[4], ctx->ev[5]);
+                      min_coverage, d_nobs, nsurv.as<int64_t>(), sm, &ctx->launches, ctx->ev[4], ctx->ev[5],
+                      ctx->phase_enabled ? ctx->phase_cycles : nullptr);
         d_spill_ids = sm.deferred_ids;
         n_spill = sm.n_deferred;
     }
@@ -686,6 +689,15 @@ extern "C" int rogtk_gpu_memcpy_d2h(rogtk_gpu_ctx *ctx, void *dst, const void *s
     return ROGTK_OK;
 }
 extern "C" int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint64_t *out8)
+{
+    if (!ctx) return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->phase_enabled = enable != 0;
+    if (out8) memcpy(out8, ctx->phase_cycles, sizeof(ctx->phase_cycles));
+    return ROGTK_OK;
+}
 
 extern "C" int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx)
 {

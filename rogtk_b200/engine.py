@@ -148,6 +148,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.rogtk_gpu_launch_count(self._ctx))
 
+    def phase_cycles(self, enable: bool = True) -> np.ndarray:
+        """diagnostics: per-phase SM cycles of the last batch inside k_smem_count (summed over CTAs)"""
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self._lib.rogtk_gpu_debug_phase_cycles(self._ctx, int(enable), out.ctypes.data))
+        return out
+
     def flush_l2(self):
         self._check(self._lib.rogtk_gpu_flush_l2(self._ctx))
 

@@ -29,6 +29,10 @@ __global__ void __launch_bounds__(NT, 2) k(uint32_t *out)
                          uint32_t v = v32[h]; v32[h] = v + 1; }                 // probe + tag + RMW (the protocol's mix)
         if (MODE == 6) { acc += (uint32_t)k64[h]; atomicAdd(&v32[h], 1u); }      // probe + atomic add
         if (MODE == 7) { unsigned m = __match_any_sync(0xffffffffu, h); acc += m; }
+        if (MODE == 8) { s ^= atomicAdd(&v32[h], 1u) & 0xff; }                      // dependent atomicAdd chain (latency)
+        if (MODE == 9) { s ^= v32[h] & 0xff; }                                      // dependent LDS chain (latency)
+        if (MODE == 10) { s ^= (uint32_t)atomicCAS(&k64[h], ~0ull, (unsigned long long)h) & 0xff; }   // dependent CAS chain
+        if (MODE == 11) { uint32_t v = v32[h]; unsigned long long kk = k64[h]; if ((uint32_t)kk != h) atomicAdd(&v32[h], 256u); if (v & 1) atomicOr(&v32[h], 2u); }
     }
     if (acc == 0x12345678u) out[0] = acc + v32[threadIdx.x];
 }
@@ -69,5 +73,9 @@ int main()
     run<5>("LDS.64 + tag STS.8 + RMW", sms);
     run<6>("LDS.64 + atomicAdd", sms);
     run<7>("match_any u32", sms);
+    run<8>("dependent atomicAdd chain", sms);
+    run<9>("dependent LDS chain", sms);
+    run<10>("dependent CAS.64 chain", sms);
+    run<11>("LDS.64+LDS.32 then RED add/or", sms);
     return 0;
 }
