@@ -18,12 +18,14 @@
 
 namespace rogtk {
 
-constexpr int SM_NT = 256;            // threads per CTA == max rows per group on this path
+constexpr int SM_NT = 384;            // threads per CTA
+constexpr int SM_MAXR = 256;          // max rows per group on this path
 constexpr int SM_NWARP = SM_NT / 32;
 constexpr int SM_MAX_BASES = 16384;   // bases staged per group (including <=15 bytes of alignment slack)
 constexpr int SM_PK_WORDS = SM_MAX_BASES / 16 + 8;   // 1 word of front pad, tail pad for window over-reads
 constexpr int SM_UNIT = 128;          // windows per work unit (one warp, 4 consecutive windows per lane)
 constexpr int SM_QCAP = 64;           // per-warp queue of collided observations (drained 32 at a time)
+constexpr int SM_MAX_UNITS = SM_MAX_BASES / SM_UNIT + SM_MAXR;   // work units of one group
 constexpr int SM_TBITS = 13;          // 8192 slots
 constexpr int SM_TSIZE = 1 << SM_TBITS;
 constexpr int SM_SORT_BITS = 10;
@@ -42,7 +44,7 @@ template <int W>
 constexpr size_t smem_bytes()
 {
     return (size_t)SM_TSIZE * sizeof(typename KeySlot<W>::T) + (size_t)SM_TSIZE * 4 + (size_t)scratch_bytes<W>() +
-           (size_t)(SM_NT + 1) * 4 * 2 + 40 * 4 + SM_NT + 64;
+           (size_t)(SM_MAXR + 1) * 4 * 2 + 40 * 4 + SM_MAXR + SM_MAX_UNITS * 2 + 64;
 }
 
 struct SmemArgs {
@@ -273,9 +275,10 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     uint32_t *hist = scratch;                                                    // sort histogram (after counting)
     uint16_t *order = reinterpret_cast<uint16_t *>(scratch + SM_SORT_BUCKETS);   // sort permutation (after counting)
     uint32_t *rstart = scratch + scratch_bytes<W>() / 4;
-    uint32_t *ucum = rstart + SM_NT + 1;                 // work units before read r
-    uint32_t *ws = ucum + SM_NT + 1;                     // 40 words: [0..8] scan, [16..] misc
+    uint32_t *ucum = rstart + SM_MAXR + 1;               // work units before read r
+    uint32_t *ws = ucum + SM_MAXR + 1;                     // 40 words: [0..8] scan, [16..] misc
     uint8_t *bad = reinterpret_cast<uint8_t *>(ws + 40);
+    uint16_t *unit_read = reinterpret_cast<uint16_t *>(bad + SM_MAXR);   // read index of every work unit
     volatile uint32_t *misc = ws + 16;   // [0],[1] ticket [2] all-ones k-mer value [3] abort [4],[5] pool base [6] big bucket [7] unit counter
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.col.data + b0);
         const uint32_t slack = (uint32_t)(addr0 & 15u);
         const int64_t span64 = (b1 - b0) + slack;
-        if (nrows > SM_NT || span64 > SM_MAX_BASES) {   // too many rows / bases for this path
+        if (nrows > SM_MAXR || span64 > SM_MAX_BASES) {   // too many rows / bases for this path
             if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)g;
             continue;
         }
@@ -367,8 +370,9 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             }
             block_scan_u32(nk, &total, ws);
             const uint32_t ex = block_scan_u32((nk + SM_UNIT - 1) / SM_UNIT, &nunits, ws);
-            ucum[tid] = ex;
-            if (tid == 0) ucum[SM_NT] = nunits;
+            if (tid < SM_MAXR) ucum[tid] = ex;
+            if (tid == 0) ucum[SM_MAXR] = nunits;
+            for (uint32_t j = 0; j < (nk + SM_UNIT - 1) / SM_UNIT; j++) unit_read[ex + j] = (uint16_t)tid;
         }
         if (total == 0) continue;   // (the loop-top barrier orders the shared writes before reuse)
 
@@ -412,11 +416,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                 if (lane == 0) unit = atomicAdd(const_cast<uint32_t *>(&misc[7]), 1u);
                 unit = __shfl_sync(0xffffffffu, unit, 0);
                 if (unit >= nunits || misc[3] || wq.budget <= 0) break;
-                int lo = 0, hi = nr;   // read of this unit: last r with ucum[r] <= unit (reads without windows never match)
-                while (hi - lo > 1) {
-                    const int m = (lo + hi) >> 1;
-                    if (ucum[m] <= unit) lo = m; else hi = m;
-                }
+                const int lo = unit_read[unit];   // read of this unit
                 const uint32_t rs = rstart[lo];
                 const uint32_t nk = rstart[lo + 1] - rs - (uint32_t)K + 1u;
                 const uint32_t p0 = (unit - ucum[lo]) * SM_UNIT;
@@ -485,12 +485,32 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                     }
                 }
             }
-            // drain what is left of this warp's queue
-            while (wq.n && wq.budget > 0) {
-                queue_drain_step<W>(wq, tkey, tval, tmask, lane);
-                wq.budget--;
-            }
             if (wq.budget <= 0) misc[3] = 1;   // never spin on a full table: the HBM path takes the group
+            if (lane == 0) ws[24 + warp] = wq.n;   // leftovers (< 32 per warp) are finished by the whole CTA below
+        }
+        __syncthreads();
+        if (!misc[3]) {
+            // every thread takes at most one leftover observation and probes until it lands
+            const uint32_t wsrc = (uint32_t)tid >> 5, isrc = (uint32_t)tid & 31u;   // thread t <- entry isrc of warp wsrc
+            if (wsrc < (uint32_t)SM_NWARP && isrc < ws[24 + wsrc]) {
+                const KT kp = (reinterpret_cast<KT *>(qbytes) + wsrc * SM_QCAP)[isrc];
+                const uint32_t hx = (reinterpret_cast<uint32_t *>(reinterpret_cast<KT *>(qbytes) + SM_NWARP * SM_QCAP) + wsrc * SM_QCAP)[isrc];
+                uint32_t h = hx & 0xffffu;
+                uint32_t guard = 0;
+                while (true) {
+                    h = (h + 1) & tmask;
+                    KT cur = tkey[h];
+                    if (cur == S::empty()) cur = atomicCAS(&tkey[h], S::empty(), kp);
+                    if (cur == kp || cur == S::empty()) {
+                        val_add(&tval[h], hx >> 16);
+                        break;
+                    }
+                    if (++guard > tsize) {
+                        misc[3] = 1;
+                        break;
+                    }
+                }
+            }
         }
         __syncthreads();
         if (misc[3]) {   // too many distinct k-mers for a shared-memory table: HBM-table path
@@ -511,11 +531,12 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         __syncthreads();
         uint32_t nS;
         {
-            constexpr int PER = SM_SORT_BUCKETS / SM_NT;
+            constexpr int PER = (SM_SORT_BUCKETS + SM_NT - 1) / SM_NT;
             uint32_t loc[PER], s = 0, mx = 0;
 #pragma unroll
             for (int t = 0; t < PER; t++) {
-                loc[t] = hist[tid * PER + t];
+                const int b = tid * PER + t;
+                loc[t] = b < SM_SORT_BUCKETS ? hist[b] : 0u;
                 s += loc[t];
                 mx = loc[t] > mx ? loc[t] : mx;
             }
@@ -523,7 +544,8 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             uint32_t e0 = block_scan_u32(s, &nS, ws);
 #pragma unroll
             for (int t = 0; t < PER; t++) {
-                hist[tid * PER + t] = e0;
+                const int b = tid * PER + t;
+                if (b < SM_SORT_BUCKETS) hist[b] = e0;
                 e0 += loc[t];
             }
         }
