@@ -166,7 +166,7 @@ def main():
         from oracle import dbg_oracle
         from rogtk_b200 import synth
         cores = dbg_oracle.max_threads()
-        n = min(cfg["n_umis"], max(2048, 96 * cores))
+        n = min(cfg["n_umis"], max(8192, 1024 * cores))
         data, offs, goff = synth.synth_reads(synth.config_seed(cfg["config_id"]), 0, n, cfg["reads"], cfg["read_len"],
                                              cfg["template"], cfg["err64k"])
         obs = 0
