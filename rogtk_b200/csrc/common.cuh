@@ -18,6 +18,7 @@ struct ColView {
     const uint8_t *validity;  // bitmap or nullptr
     int64_t validity_bit_offset;
     int64_t n_rows;
+    int64_t row_begin;  // first row of this view (offsets / validity are indexed with absolute rows)
     int off64;  // 1: int64 offsets
 };
 

@@ -51,7 +51,8 @@ constexpr size_t smem_bytes()
 
 struct SmemArgs {
     ColView col;
-    const uint8_t *data_end;         // one past the last readable byte of col.data
+    const uint8_t *data_begin;       // first readable byte of the data buffer (col.data may be a virtual base below it)
+    const uint8_t *data_end;         // one past the last readable byte
     const int64_t *group_offsets;
     int64_t n_groups;
     int K;
@@ -369,12 +370,12 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                 v[i] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
                 if (c < nchunks) {
                     const uint8_t *p = a0 + 16 * c;
-                    if (p >= a.col.data && p + 16 <= a.data_end) {
+                    if (p >= a.data_begin && p + 16 <= a.data_end) {
                         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                                      : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
                                      : "l"(p));
                     } else {
-                        v[i] = load_chunk_guarded(p, a.col.data, a.data_end);
+                        v[i] = load_chunk_guarded(p, a.data_begin, a.data_end);
                     }
                 }
             }
@@ -689,7 +690,8 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
 __global__ void k_obs_upper_bound(ColView col, int K, unsigned long long *out)
 {
     unsigned long long s = 0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < col.n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t r = col.row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < col.row_begin + col.n_rows;
+         r += (int64_t)gridDim.x * blockDim.x) {
         int64_t len = col_off(col, r + 1) - col_off(col, r);
         if (len >= K) s += (unsigned long long)(len - K + 1);
     }
@@ -722,7 +724,8 @@ inline void smem_path_configure()
     CK(cudaFuncSetAttribute(k_smem_count<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 }
 
-inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes, const ColView &col, const uint8_t *data_end,
+inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes, const ColView &col, const uint8_t *data_begin,
+                          const uint8_t *data_end,
                           const int64_t *d_group_offsets, int64_t n_groups, int K, uint32_t min_cov, unsigned long long *d_nobs,
                           int64_t *d_nsurv, SmemResult &res, int64_t *launches, cudaEvent_t ev_a, cudaEvent_t ev_b,
                           unsigned long long *phase_out /* host [8] or nullptr */)
@@ -760,6 +763,7 @@ inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes,
 
     SmemArgs a{};
     a.col = col;
+    a.data_begin = data_begin;
     a.data_end = data_end;
     a.group_offsets = d_group_offsets;
     a.n_groups = n_groups;

@@ -273,6 +273,12 @@ __global__ void k_spill_extract(SpillArgs a)
 }
 
 // sorted records -> structure-of-arrays output for the listed groups
+__global__ void k_add_i64(int64_t *p, int64_t n, int64_t v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += v;
+}
+
 __global__ void k_gather_i64(const int64_t *src, const int32_t *ids, int64_t list_base, int64_t n, int64_t *dst)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

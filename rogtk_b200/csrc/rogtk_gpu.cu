@@ -32,6 +32,8 @@ struct rogtk_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t out_stream = nullptr;
+    size_t chunk_bytes = (size_t)256 << 20;   // read bytes per chunk of the overlapped host->host path
     cudaEvent_t ev[6] = {};
     size_t workspace_bytes = 0;
     std::mutex mu;
@@ -249,6 +251,8 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         ctx->smem_optin = prop.sharedMemPerBlockOptin;
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+        if (const char *e = getenv("ROGTK_CHUNK_BYTES")) ctx->chunk_bytes = (size_t)std::max(4096ll, atoll(e));
         for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
@@ -278,6 +282,7 @@ extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     delete ctx;
 }
 
@@ -320,6 +325,7 @@ namespace {
 struct Staged {   // device-resident contiguous column
     ColView col{};
     const int64_t *group_offsets = nullptr;
+    const uint8_t *data_begin = nullptr;   // first / one-past-last readable byte of the data buffer
     const uint8_t *data_end = nullptr;
     std::vector<DevBuf> keep;
 };
@@ -347,6 +353,7 @@ void stage_input(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         s.col.off64 = o64;
         s.col.offsets = to_device(ctx, s, c->offsets_or_views, (size_t)(n + 1) * (o64 ? 8 : 4), on_device);
         s.col.data = (const uint8_t *)to_device(ctx, s, c->data[0], (size_t)c->data_len[0], on_device);
+        s.data_begin = s.col.data;
         s.data_end = s.col.data + c->data_len[0];
         return;
     }
@@ -373,6 +380,7 @@ void stage_input(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     s.col.off64 = 1;
     s.col.offsets = offs;
     s.col.data = data;
+    s.data_begin = data;
     s.data_end = data + total;
 }
 
@@ -399,6 +407,306 @@ void fill_empty_batch(rogtk_gpu_ctx *ctx, int64_t n_groups, bool out_dev, uint32
             own->ptrs.push_back(q);
         }
     }
+}
+
+struct DeviceResult {   // dense, group-ordered result of one pipeline run, still in HBM
+    DevBuf off, lo, hi, exts, counts, stats, rowptr, cols;
+    int64_t n_kmers = 0, n_edges = 0, n_obs = 0, n_spill = 0;
+    float ms_hot = 0.f;
+};
+
+// The device pipeline on ctx->stream: count (shared-memory path, then HBM-table path for deferred groups), scan, gather,
+// optional statistics / CSR.  Records ctx->ev[0] (start), ev[1]/ev[2] (counting), ev[3] (end); returns without a final sync.
+void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K, uint32_t min_coverage, uint32_t flags,
+                  DeviceResult &r)
+{
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    DevBuf nsurv((size_t)(n_groups + 1) * 8, st), misc(64, st);
+    CK(cudaMemsetAsync(nsurv.p, 0, nsurv.bytes, st));
+    CK(cudaMemsetAsync(misc.p, 0, 64, st));
+    unsigned long long *d_nobs = misc.as<unsigned long long>();
+
+    // ---- counting -------------------------------------------------------------------------------------------
+    CK(cudaEventRecord(ctx->ev[1], st));
+    SmemResult sm;            // survivors of the shared-memory path (pool, per-group start) + deferred groups
+    std::vector<SpillWave> waves;
+    const int32_t *d_spill_ids = nullptr;
+    int64_t n_spill = n_groups;
+    if (!(flags & ROGTK_FORCE_SPILL) && n_groups > 0) {
+        run_smem_path(ctx->stream, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_begin, in.data_end, in.group_offsets,
+                      n_groups, K, min_coverage, d_nobs, nsurv.as<int64_t>(), sm, &ctx->launches, ctx->ev[4], ctx->ev[5],
+                      ctx->phase_enabled ? ctx->phase_cycles : nullptr);
+        d_spill_ids = sm.deferred_ids;
+        n_spill = sm.n_deferred;
+    }
+    if (n_spill > 0) {
+        if (K <= 32)
+            run_spill<1>(ctx, in.col, in.group_offsets, d_spill_ids, n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), waves);
+        else
+            run_spill<2>(ctx, in.col, in.group_offsets, d_spill_ids, n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), waves);
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- dense, group-ordered output ----------------------------------------------------------------------------
+    DevBuf scratch(scan_scratch_bytes(n_groups), st);
+    r.off.alloc((size_t)(n_groups + 1) * 8, st);
+    exclusive_scan<int64_t>(nsurv.as<int64_t>(), n_groups, r.off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
+    int64_t n_kmers = 0;
+    unsigned long long h_nobs = 0;
+    CK(cudaMemcpyAsync(&n_kmers, r.off.as<int64_t>() + n_groups, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_nobs, d_nobs, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const size_t nk = (size_t)std::max<int64_t>(n_kmers, 1);
+    r.lo.alloc(nk * 8, st);
+    if (K > 32) r.hi.alloc(nk * 8, st);
+    r.exts.alloc(nk, st);
+    r.counts.alloc(nk * 2, st);
+    uint64_t *p_hi = K > 32 ? r.hi.as<uint64_t>() : nullptr;
+    if (sm.n_pool_groups > 0) {
+        k_gather_pool<<<ctx->sm_count * 8, 256, 0, st>>>(n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi,
+                                                         sm.pool_exts, sm.pool_counts, r.lo.as<uint64_t>(), p_hi,
+                                                         r.exts.as<uint8_t>(), r.counts.as<uint16_t>());
+        ctx->launches++;
+    }
+    for (auto &wv : waves) {
+        if (wv.n_recs == 0) continue;
+        k_spill_scatter<<<blocks_for(wv.n_recs, 256), 256, 0, st>>>(wv.recs.as<SpillRec>(), wv.n_recs, d_spill_ids, wv.list_base,
+                                                                    wv.rec_off.as<int64_t>(), r.off.as<int64_t>(),
+                                                                    r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(),
+                                                                    r.counts.as<uint16_t>());
+        ctx->launches++;
+    }
+
+    // ---- optional node statistics and successor CSR ---------------------------------------------------------------------
+    int64_t n_edges = 0;
+    if (flags & ROGTK_EMIT_STATS) {
+        r.stats.alloc((size_t)n_groups * 12 + 16, st);
+        if (n_groups > 0) {
+            k_stats<<<ctx->sm_count * 8, 256, 0, st>>>(n_groups, r.off.as<int64_t>(), r.exts.as<uint8_t>(), r.stats.as<uint32_t>());
+            ctx->launches++;
+        }
+    }
+    if (flags & ROGTK_EMIT_CSR) {
+        DevBuf deg(nk * 4, st), scr(scan_scratch_bytes(n_kmers), st);
+        r.rowptr.alloc((size_t)(n_kmers + 1) * 8, st);
+        if (n_kmers > 0) {
+            k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, r.off.as<int64_t>(), r.lo.as<uint64_t>(), p_hi,
+                                                            r.exts.as<uint8_t>(), K, deg.as<int32_t>(), nullptr, nullptr);
+            ctx->launches++;
+        }
+        exclusive_scan<int32_t>(deg.as<int32_t>(), n_kmers, r.rowptr.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+        CK(cudaMemcpyAsync(&n_edges, r.rowptr.as<int64_t>() + n_kmers, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        r.cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
+        if (n_kmers > 0) {
+            k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, r.off.as<int64_t>(), r.lo.as<uint64_t>(), p_hi,
+                                                            r.exts.as<uint8_t>(), K, nullptr, r.rowptr.as<int64_t>(),
+                                                            r.cols.as<int32_t>());
+            ctx->launches++;
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    r.n_kmers = n_kmers;
+    r.n_edges = n_edges;
+    r.n_obs = (int64_t)h_nobs;
+    r.n_spill = n_spill;
+    r.ms_hot = sm.ms_kernel;
+}
+
+// growable pinned host array of the final result
+struct HostArr {
+    uint8_t *p = nullptr;
+    size_t cap = 0;   // bytes
+};
+void host_reserve(rogtk_gpu_ctx *ctx, HostArr &a, size_t need, size_t used, cudaStream_t drain)
+{
+    if (need <= a.cap) return;
+    size_t ncap = std::max(need + need / 4 + 4096, a.cap + a.cap / 2);
+    uint8_t *np_ = (uint8_t *)pinned_get(ctx, ncap);
+    ncap = ctx->pinned_size[np_];
+    if (a.p) {
+        CK(cudaStreamSynchronize(drain));   // copies into the old block must have landed
+        if (used) memcpy(np_, a.p, used);
+        pinned_put(ctx, a.p);
+    }
+    a.p = np_;
+    a.cap = ncap;
+}
+
+// Host Arrow buffers in, host arrays out, for batches much larger than ctx->chunk_bytes: the groups are cut into chunks of
+// ~chunk_bytes of read data; H2D of chunk c+1 and D2H of chunk c-1 run on their own streams while chunk c is being counted.
+void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group_offsets, int64_t n_groups, int K,
+                 uint32_t min_coverage, uint32_t flags, rogtk_graph_batch *out, BatchOwner *own)
+{
+    const bool o64 = c->layout == ROGTK_UTF8_I64;
+    const int osz = o64 ? 8 : 4;
+    auto off_at = [&](int64_t row) -> int64_t {
+        return o64 ? ((const int64_t *)c->offsets_or_views)[row] : (int64_t)((const int32_t *)c->offsets_or_views)[row];
+    };
+    // chunk boundaries (whole groups)
+    std::vector<int64_t> cut{0};
+    {
+        int64_t start_byte = off_at(group_offsets[0]);
+        for (int64_t g = 0; g < n_groups; g++) {
+            const int64_t end_byte = off_at(group_offsets[g + 1]);
+            if (end_byte - start_byte >= (int64_t)ctx->chunk_bytes && g + 1 < n_groups) {
+                cut.push_back(g + 1);
+                start_byte = end_byte;
+            }
+        }
+        cut.push_back(n_groups);
+    }
+    const int n_chunks = (int)cut.size() - 1;
+    cudaStream_t s_in = ctx->copy_stream, s_comp = ctx->stream, s_out = ctx->out_stream;
+    struct InSet {
+        DevBuf data, offs, goff, valid;
+        cudaEvent_t ready = nullptr, consumed = nullptr;
+        Staged st;
+    } sets[2];
+    for (auto &x : sets) {
+        CK(cudaEventCreateWithFlags(&x.ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&x.consumed, cudaEventDisableTiming));
+    }
+    cudaEvent_t comp_done;
+    CK(cudaEventCreateWithFlags(&comp_done, cudaEventDisableTiming));
+    struct Guard {
+        InSet *s; cudaEvent_t e;
+        ~Guard() { for (int i = 0; i < 2; i++) { cudaEventDestroy(s[i].ready); cudaEventDestroy(s[i].consumed); } cudaEventDestroy(e); }
+    } guard{sets, comp_done};
+
+    auto stage_chunk = [&](int ci) {
+        InSet &x = sets[ci & 1];
+        const int64_t g0 = cut[ci], g1 = cut[ci + 1];
+        const int64_t r0 = group_offsets[g0], r1 = group_offsets[g1];
+        const int64_t b0 = off_at(r0), b1 = off_at(r1);
+        CK(cudaStreamWaitEvent(s_in, x.consumed, 0));   // the compute that last read this set has finished
+        const size_t pad = (size_t)(b0 & 15);           // keep the 16-byte phase of the bytes so that aligned chunks stay inside
+        x.data.alloc(pad + (size_t)(b1 - b0) + 32, s_in);
+        x.offs.alloc((size_t)(r1 - r0 + 1) * osz, s_in);
+        x.goff.alloc((size_t)(g1 - g0 + 1) * 8, s_in);
+        if (b1 > b0) CK(cudaMemcpyAsync(x.data.as<uint8_t>() + pad, c->data[0] + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s_in));
+        CK(cudaMemcpyAsync(x.offs.p, (const uint8_t *)c->offsets_or_views + (size_t)r0 * osz, (size_t)(r1 - r0 + 1) * osz,
+                           cudaMemcpyHostToDevice, s_in));
+        CK(cudaMemcpyAsync(x.goff.p, group_offsets + g0, (size_t)(g1 - g0 + 1) * 8, cudaMemcpyHostToDevice, s_in));
+        Staged &s = x.st;
+        s = Staged();
+        s.col.n_rows = r1 - r0;
+        s.col.row_begin = r0;
+        s.col.off64 = o64;
+        // "virtual base" pointers: the kernels keep indexing with absolute rows / byte offsets
+        s.col.offsets = reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(x.offs.p) - (uintptr_t)r0 * osz);
+        s.col.data = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(x.data.p) + pad - (uintptr_t)b0);
+        s.data_begin = x.data.as<uint8_t>();
+        s.data_end = x.data.as<uint8_t>() + pad + (size_t)(b1 - b0);
+        s.group_offsets = x.goff.as<int64_t>();
+        s.col.validity = nullptr;
+        s.col.validity_bit_offset = c->validity_bit_offset;
+        if (c->validity) {
+            const int64_t bit0 = r0 + c->validity_bit_offset, bit1 = r1 + c->validity_bit_offset;
+            const int64_t by0 = bit0 >> 3, by1 = (bit1 + 7) >> 3;
+            x.valid.alloc((size_t)(by1 - by0) + 8, s_in);
+            if (by1 > by0) CK(cudaMemcpyAsync(x.valid.p, c->validity + by0, (size_t)(by1 - by0), cudaMemcpyHostToDevice, s_in));
+            s.col.validity = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(x.valid.p) - (uintptr_t)by0);
+        }
+        CK(cudaEventRecord(x.ready, s_in));
+    };
+
+    HostArr h_off, h_lo, h_hi, h_exts, h_counts, h_stats, h_rowptr, h_cols;
+    host_reserve(ctx, h_off, (size_t)(n_groups + 1) * 8, 0, s_out);
+    if (flags & ROGTK_EMIT_STATS) host_reserve(ctx, h_stats, (size_t)n_groups * 12 + 16, 0, s_out);
+    int64_t base_k = 0, base_e = 0, n_obs = 0, n_spill = 0;
+    float ms_total = 0, ms_count = 0, ms_hot = 0;
+    const int64_t total_bytes = std::max<int64_t>(1, off_at(group_offsets[n_groups]) - off_at(group_offsets[0]));
+    std::vector<DeviceResult> inflight(2);
+
+    stage_chunk(0);
+    for (int ci = 0; ci < n_chunks; ci++) {
+        if (ci + 1 < n_chunks) stage_chunk(ci + 1);
+        InSet &x = sets[ci & 1];
+        const int64_t g0 = cut[ci], g1 = cut[ci + 1], ng = g1 - g0;
+        CK(cudaStreamWaitEvent(s_comp, x.ready, 0));
+        DeviceResult &r = inflight[ci & 1];
+        // the previous result held in this slot has been copied out: its buffers are released in s_out order below
+        r = DeviceResult();
+        run_pipeline(ctx, x.st, ng, K, min_coverage, flags, r);
+        // shift the chunk-local offsets to their global base (in place, on the compute stream)
+        if (base_k) k_add_i64<<<blocks_for(ng + 1, 256), 256, 0, s_comp>>>(r.off.as<int64_t>(), ng + 1, base_k);
+        if ((flags & ROGTK_EMIT_CSR) && base_e)
+            k_add_i64<<<blocks_for(r.n_kmers + 1, 256), 256, 0, s_comp>>>(r.rowptr.as<int64_t>(), r.n_kmers + 1, base_e);
+        CK(cudaEventRecord(comp_done, s_comp));
+        CK(cudaEventRecord(x.consumed, s_comp));
+        // capacity of the final host arrays: after the first chunk extrapolate from bytes processed
+        const int64_t done_bytes = std::max<int64_t>(1, off_at(group_offsets[g1]) - off_at(group_offsets[0]));
+        const double scale = (double)total_bytes / (double)done_bytes;
+        const size_t est_k = (size_t)((double)(base_k + r.n_kmers) * scale * 1.05) + 4096;
+        const size_t est_e = (size_t)((double)(base_e + r.n_edges) * scale * 1.05) + 4096;
+        const size_t need_k = (size_t)(base_k + r.n_kmers);
+        host_reserve(ctx, h_lo, std::max(need_k, ci == 0 ? est_k : need_k) * 8, (size_t)base_k * 8, s_out);
+        if (K > 32) host_reserve(ctx, h_hi, std::max(need_k, ci == 0 ? est_k : need_k) * 8, (size_t)base_k * 8, s_out);
+        host_reserve(ctx, h_exts, std::max(need_k, ci == 0 ? est_k : need_k), (size_t)base_k, s_out);
+        host_reserve(ctx, h_counts, std::max(need_k, ci == 0 ? est_k : need_k) * 2, (size_t)base_k * 2, s_out);
+        if (flags & ROGTK_EMIT_CSR) {
+            host_reserve(ctx, h_rowptr, (std::max(need_k, ci == 0 ? est_k : need_k) + 1) * 8, (size_t)(base_k + 1) * 8, s_out);
+            const size_t need_e = (size_t)(base_e + r.n_edges);
+            host_reserve(ctx, h_cols, std::max(need_e, ci == 0 ? est_e : need_e) * 4 + 16, (size_t)base_e * 4, s_out);
+        }
+        // D2H on its own stream
+        CK(cudaStreamWaitEvent(s_out, comp_done, 0));
+        auto pull = [&](HostArr &h, size_t dst_off, DevBuf &d, size_t bytes) {
+            if (bytes) CK(cudaMemcpyAsync(h.p + dst_off, d.p, bytes, cudaMemcpyDeviceToHost, s_out));
+            d.st = s_out;   // released after the copy, in s_out order
+        };
+        pull(h_off, (size_t)g0 * 8, r.off, (size_t)(ng + 1) * 8);
+        pull(h_lo, (size_t)base_k * 8, r.lo, (size_t)r.n_kmers * 8);
+        if (K > 32) pull(h_hi, (size_t)base_k * 8, r.hi, (size_t)r.n_kmers * 8);
+        pull(h_exts, (size_t)base_k, r.exts, (size_t)r.n_kmers);
+        pull(h_counts, (size_t)base_k * 2, r.counts, (size_t)r.n_kmers * 2);
+        if (flags & ROGTK_EMIT_STATS) pull(h_stats, (size_t)g0 * 12, r.stats, (size_t)ng * 12);
+        if (flags & ROGTK_EMIT_CSR) {
+            pull(h_rowptr, (size_t)base_k * 8, r.rowptr, (size_t)(r.n_kmers + 1) * 8);
+            pull(h_cols, (size_t)base_e * 4, r.cols, (size_t)r.n_edges * 4);
+        }
+        r.off.release(); r.lo.release(); r.hi.release(); r.exts.release(); r.counts.release();
+        r.stats.release(); r.rowptr.release(); r.cols.release();
+        // timings of this chunk (waits for its compute; the next chunk's input copy is already in flight)
+        CK(cudaEventSynchronize(ctx->ev[3]));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+        ms_total += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+        ms_count += ms;
+        ms_hot += r.ms_hot;
+        base_k += r.n_kmers;
+        base_e += r.n_edges;
+        n_obs += r.n_obs;
+        n_spill += r.n_spill;
+    }
+    CK(cudaStreamSynchronize(s_out));
+    CK(cudaStreamSynchronize(s_in));
+    for (auto &x : sets) { x.data.release(); x.offs.release(); x.goff.release(); x.valid.release(); }
+    out->n_kmers = base_k;
+    out->n_edges = base_e;
+    out->n_observations = n_obs;
+    out->n_spilled_groups = n_spill;
+    auto adopt = [&](HostArr &h) -> void * {
+        if (h.p) own->ptrs.push_back(h.p);
+        return h.p;
+    };
+    out->kmer_offsets = (int64_t *)adopt(h_off);
+    out->kmers_lo = (uint64_t *)adopt(h_lo);
+    out->kmers_hi = K > 32 ? (uint64_t *)adopt(h_hi) : nullptr;
+    out->exts = (uint8_t *)adopt(h_exts);
+    out->counts = (uint16_t *)adopt(h_counts);
+    if (flags & ROGTK_EMIT_STATS) out->stats = (uint32_t *)adopt(h_stats);
+    if (flags & ROGTK_EMIT_CSR) {
+        out->csr_row_ptr = (int64_t *)adopt(h_rowptr);
+        out->csr_col = (int32_t *)adopt(h_cols);
+    }
+    out->ms_total = ms_total;
+    out->ms_count = ms_count;
+    out->ms_hot_kernel = ms_hot;
+    CK(cudaGetLastError());
 }
 
 int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets, int64_t n_groups, int64_t k,
@@ -429,98 +737,23 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
         return ROGTK_OK;
     }
 
+    // host input + host output of a large offsets-layout column: chunked, copies overlapped with compute
+    if (!in_dev && !out_dev && (reads->layout == ROGTK_UTF8_I32 || reads->layout == ROGTK_UTF8_I64) && reads->n_buffers == 1 &&
+        reads->data && reads->data_len && n_groups > 1 && reads->data_len[0] > (int64_t)ctx->chunk_bytes + (ctx->chunk_bytes >> 1)) {
+        run_chunked(ctx, reads, group_offsets, n_groups, K, min_coverage, flags, out, own);
+        return ROGTK_OK;
+    }
+
     Staged in;
     stage_input(ctx, reads, group_offsets, n_groups, in_dev, in);
-
-    CK(cudaEventRecord(ctx->ev[0], st));
-    DevBuf nsurv((size_t)(n_groups + 1) * 8, st), misc(64, st);
-    CK(cudaMemsetAsync(nsurv.p, 0, nsurv.bytes, st));
-    CK(cudaMemsetAsync(misc.p, 0, 64, st));
-    unsigned long long *d_nobs = misc.as<unsigned long long>();
-
-    // ---- counting -------------------------------------------------------------------------------------------
-    CK(cudaEventRecord(ctx->ev[1], st));
-    SmemResult sm;            // survivors of the shared-memory path (pool, per-group start) + deferred groups
-    std::vector<SpillWave> waves;
-    const int32_t *d_spill_ids = nullptr;
-    int64_t n_spill = n_groups;
-    if (!(flags & ROGTK_FORCE_SPILL) && n_groups > 0) {
-        run_smem_path(ctx->stream, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_end, in.group_offsets, n_groups, K,
-                      min_coverage, d_nobs, nsurv.as<int64_t>(), sm, &ctx->launches, ctx->ev[4], ctx->ev[5],
-                      ctx->phase_enabled ? ctx->phase_cycles : nullptr);
-        d_spill_ids = sm.deferred_ids;
-        n_spill = sm.n_deferred;
-    }
-    if (n_spill > 0) {
-        if (K <= 32)
-            run_spill<1>(ctx, in.col, in.group_offsets, d_spill_ids, n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), waves);
-        else
-            run_spill<2>(ctx, in.col, in.group_offsets, d_spill_ids, n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), waves);
-    }
-    CK(cudaEventRecord(ctx->ev[2], st));
-
-    // ---- dense, group-ordered output ----------------------------------------------------------------------------
-    DevBuf d_off((size_t)(n_groups + 1) * 8, st), scratch(scan_scratch_bytes(n_groups), st);
-    exclusive_scan<int64_t>(nsurv.as<int64_t>(), n_groups, d_off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
-    int64_t n_kmers = 0;
-    unsigned long long h_nobs = 0;
-    CK(cudaMemcpyAsync(&n_kmers, d_off.as<int64_t>() + n_groups, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&h_nobs, d_nobs, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const size_t nk = (size_t)std::max<int64_t>(n_kmers, 1);
-    DevBuf o_lo(nk * 8, st), o_hi(K > 32 ? nk * 8 : 0, st), o_exts(nk, st), o_counts(nk * 2, st);
-    uint64_t *p_hi = K > 32 ? o_hi.as<uint64_t>() : nullptr;
-    if (sm.n_pool_groups > 0) {
-        k_gather_pool<<<ctx->sm_count * 8, 256, 0, st>>>(n_groups, sm.pool_start, d_off.as<int64_t>(), sm.pool_lo, sm.pool_hi,
-                                                         sm.pool_exts, sm.pool_counts, o_lo.as<uint64_t>(), p_hi,
-                                                         o_exts.as<uint8_t>(), o_counts.as<uint16_t>());
-        ctx->launches++;
-    }
-    for (auto &wv : waves) {
-        if (wv.n_recs == 0) continue;
-        k_spill_scatter<<<blocks_for(wv.n_recs, 256), 256, 0, st>>>(wv.recs.as<SpillRec>(), wv.n_recs, d_spill_ids, wv.list_base,
-                                                                    wv.rec_off.as<int64_t>(), d_off.as<int64_t>(),
-                                                                    o_lo.as<uint64_t>(), p_hi, o_exts.as<uint8_t>(),
-                                                                    o_counts.as<uint16_t>());
-        ctx->launches++;
-    }
-    out->n_spilled_groups = n_spill;
-
-    // ---- optional node statistics and successor CSR ---------------------------------------------------------------------
-    DevBuf d_stats, d_rowptr, d_cols;
-    int64_t n_edges = 0;
-    if (flags & ROGTK_EMIT_STATS) {
-        d_stats.alloc((size_t)n_groups * 12 + 16, st);
-        if (n_groups > 0) {
-            k_stats<<<ctx->sm_count * 8, 256, 0, st>>>(n_groups, d_off.as<int64_t>(), o_exts.as<uint8_t>(), d_stats.as<uint32_t>());
-            ctx->launches++;
-        }
-    }
-    if (flags & ROGTK_EMIT_CSR) {
-        DevBuf deg(nk * 4, st), scr(scan_scratch_bytes(n_kmers), st);
-        d_rowptr.alloc((size_t)(n_kmers + 1) * 8, st);
-        if (n_kmers > 0) {
-            k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, d_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi,
-                                                            o_exts.as<uint8_t>(), K, deg.as<int32_t>(), nullptr, nullptr);
-            ctx->launches++;
-        }
-        exclusive_scan<int32_t>(deg.as<int32_t>(), n_kmers, d_rowptr.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
-        CK(cudaMemcpyAsync(&n_edges, d_rowptr.as<int64_t>() + n_kmers, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        d_cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
-        if (n_kmers > 0) {
-            k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, d_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi,
-                                                            o_exts.as<uint8_t>(), K, nullptr, d_rowptr.as<int64_t>(),
-                                                            d_cols.as<int32_t>());
-            ctx->launches++;
-        }
-    }
-    CK(cudaEventRecord(ctx->ev[3], st));
+    DeviceResult r;
+    run_pipeline(ctx, in, n_groups, K, min_coverage, flags, r);
 
     // ---- hand over ------------------------------------------------------------------------------------------------------
-    out->n_kmers = n_kmers;
-    out->n_edges = n_edges;
-    out->n_observations = (int64_t)h_nobs;
+    out->n_kmers = r.n_kmers;
+    out->n_edges = r.n_edges;
+    out->n_observations = r.n_obs;
+    out->n_spilled_groups = r.n_spill;
     auto give = [&](DevBuf &b, size_t bytes) -> void * {
         if (!b.p) return nullptr;
         if (out_dev) {
@@ -533,15 +766,15 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
         if (bytes) CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, st));
         return h;
     };
-    out->kmer_offsets = (int64_t *)give(d_off, (size_t)(n_groups + 1) * 8);
-    out->kmers_lo = (uint64_t *)give(o_lo, (size_t)n_kmers * 8);
-    out->kmers_hi = K > 32 ? (uint64_t *)give(o_hi, (size_t)n_kmers * 8) : nullptr;
-    out->exts = (uint8_t *)give(o_exts, (size_t)n_kmers);
-    out->counts = (uint16_t *)give(o_counts, (size_t)n_kmers * 2);
-    if (flags & ROGTK_EMIT_STATS) out->stats = (uint32_t *)give(d_stats, (size_t)n_groups * 12);
+    out->kmer_offsets = (int64_t *)give(r.off, (size_t)(n_groups + 1) * 8);
+    out->kmers_lo = (uint64_t *)give(r.lo, (size_t)r.n_kmers * 8);
+    out->kmers_hi = K > 32 ? (uint64_t *)give(r.hi, (size_t)r.n_kmers * 8) : nullptr;
+    out->exts = (uint8_t *)give(r.exts, (size_t)r.n_kmers);
+    out->counts = (uint16_t *)give(r.counts, (size_t)r.n_kmers * 2);
+    if (flags & ROGTK_EMIT_STATS) out->stats = (uint32_t *)give(r.stats, (size_t)n_groups * 12);
     if (flags & ROGTK_EMIT_CSR) {
-        out->csr_row_ptr = (int64_t *)give(d_rowptr, (size_t)(n_kmers + 1) * 8);
-        out->csr_col = (int32_t *)give(d_cols, (size_t)n_edges * 4);
+        out->csr_row_ptr = (int64_t *)give(r.rowptr, (size_t)(r.n_kmers + 1) * 8);
+        out->csr_col = (int32_t *)give(r.cols, (size_t)r.n_edges * 4);
     }
     CK(cudaStreamSynchronize(st));
     float ms = 0;
@@ -549,7 +782,7 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
     out->ms_total = ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
     out->ms_count = ms;
-    out->ms_hot_kernel = sm.ms_kernel;
+    out->ms_hot_kernel = r.ms_hot;
     CK(cudaGetLastError());
     return ROGTK_OK;
 }

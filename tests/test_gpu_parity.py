@@ -195,3 +195,29 @@ def test_device_resident_path_and_invariants_at_scale(engine, oracle):
         assert np.array_equal(got.counts[a:b], ref.counts)
     for p in (d_data, d_off, d_goff):
         engine.device_free(p)
+
+
+def test_chunked_overlapped_host_path(oracle, monkeypatch):
+    """Large host batches are cut into chunks whose H2D / compute / D2H overlap (rogtk_gpu.cu run_chunked).  Force tiny chunks
+    and compare every output array, including CSR and statistics whose indices must be re-based across chunks."""
+    import rogtk_b200
+    from rogtk_b200 import synth
+    monkeypatch.setenv("ROGTK_CHUNK_BYTES", "65536")
+    eng = rogtk_b200.Engine(device=0)
+    try:
+        rng = np.random.default_rng(77)
+        groups = random_groups(rng, 900, max_reads=12, max_len=140, tmpl_len=200)
+        data, offs, validity, goff = groups_to_arrow(groups)
+        assert data.size > 3 * 65536
+        for k, mc, o32 in ((17, 2, False), (31, 1, True), (40, 1, False)):
+            o = offs.astype(np.int32) if o32 else offs
+            got = eng.count_prune(data, o, goff, k, mc, validity=validity, flags=EMIT_STATS | EMIT_CSR)
+            ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity, emit_csr=True)
+            assert_batches_equal(got, ref, check_csr=True, ctx=f"chunked k={k}")
+        # BASELINE configs[1] shape, 400 UMIs = 6 MB -> ~90 chunks
+        data, offs, goff = synth.synth_reads(synth.config_seed(2), 0, 400, 50, 300, 1000)
+        got = eng.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)
+        ref = oracle.count_prune_batch(data, offs, goff, 31, 2)
+        assert_batches_equal(got, ref, ctx="chunked cfg2")
+    finally:
+        eng.close()
