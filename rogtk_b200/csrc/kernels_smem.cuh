@@ -32,15 +32,12 @@ constexpr int SM_TSIZE = 1 << SM_TBITS;
 constexpr int SM_SORT_BITS = 10;
 constexpr int SM_SORT_BUCKETS = 1 << SM_SORT_BITS;
 constexpr int SM_POOL_CHUNK = 32768;   // survivors a CTA reserves from the pool at a time
-constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this -> HBM path (has a real sort)
+constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this -> bitonic kernel
 template <int W>
 constexpr int scratch_bytes()   // pk + per-warp queues; reused by the sort (histogram + order)
 {
     return SM_PK_WORDS * 4 + SM_NWARP * SM_QCAP * (int)(sizeof(typename KeySlot<W>::T) + 4);
 }
-template <int W>
-constexpr int order_cap() { return (scratch_bytes<W>() - SM_SORT_BUCKETS * 4) / 2; }   // survivors sortable in shared memory
-static_assert(order_cap<1>() >= 2048, "sort scratch too small");
 
 template <int W>
 constexpr size_t smem_bytes()
@@ -273,8 +270,6 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     uint32_t *scratch = tval + SM_TSIZE;
     uint32_t *pk = scratch + 1;                                                  // pk[-1] is a readable pad word
     uint8_t *qbytes = reinterpret_cast<uint8_t *>(scratch + SM_PK_WORDS);        // per-warp queues (W=1: 8 B keys)
-    uint32_t *hist = scratch;                                                    // sort histogram (after counting)
-    uint16_t *order = reinterpret_cast<uint16_t *>(scratch + SM_SORT_BUCKETS);   // sort permutation (after counting)
     uint32_t *rstart = scratch + scratch_bytes<W>() / 4;
     uint32_t *ucum = rstart + SM_MAXR + 1;               // work units before read r
     uint32_t *ws = ucum + SM_MAXR + 1;                     // 64 words: [0..11] scan, [16..31] misc, [40..51] queue leftovers
@@ -283,7 +278,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     volatile uint32_t *misc = ws + 16;   // [0],[1] group [2] all-ones k-mer value [3] abort [4],[5] pool base [6] big bucket [7] unit counter [8..15] r0,r1,b0,b1
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
-    const int K = a.K, kbits = 2 * K;
+    const int K = a.K;
     const uint32_t thr = a.min_cov > 1u ? a.min_cov : 1u;
     unsigned long long cta_obs = 0;
     long long t_phase = clock64();
@@ -563,125 +558,64 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         }
 
         PHASE_MARK(3);
-        // ---- min-coverage prune + ascending order: counting sort on the top SM_SORT_BITS bits straight from the table --------------
-        for (int j = tid; j < SM_SORT_BUCKETS; j += SM_NT) hist[j] = 0;
-        __syncthreads();
-        {
-            const uint4 *tval4 = reinterpret_cast<const uint4 *>(tval);
-            for (uint32_t j = tid; j < tsize / 4; j += SM_NT) {
-                const uint4 vv = tval4[j];
-                const uint32_t c[4] = {vv.x >> 8, vv.y >> 8, vv.z >> 8, vv.w >> 8};
-                if ((c[0] >= thr) | (c[1] >= thr) | (c[2] >= thr) | (c[3] >= thr)) {
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (c[t] >= thr) atomicAdd(&hist[sort_bucket<W>(S::unpack(tkey[4 * j + t]), kbits)], 1u);
-                }
-            }
+        // ---- min-coverage prune: survivors go to the pool unsorted; k_sort_small / k_sort_big order them while building the
+        //      dense output, at far higher occupancy than this kernel's 2 CTAs/SM -----------------------------------------------
+        const uint4 *tval4 = reinterpret_cast<const uint4 *>(tval);
+        uint32_t cnt = 0;
+        for (uint32_t j = tid; j < tsize / 4; j += SM_NT) {
+            const uint4 vv = tval4[j];
+            cnt += ((vv.x >> 8) >= thr) + ((vv.y >> 8) >= thr) + ((vv.z >> 8) >= thr) + ((vv.w >> 8) >= thr);
         }
         const uint32_t sv = misc[2];
         const bool special_survives = (sv >> 8) >= thr;
-        if (special_survives && tid == 0) atomicAdd(&hist[SM_SORT_BUCKETS - 1], 1u);   // all-ones sorts last
-        __syncthreads();
         uint32_t nS;
-        {
-            constexpr int PER = (SM_SORT_BUCKETS + SM_NT - 1) / SM_NT;
-            uint32_t loc[PER], s = 0, mx = 0;
-#pragma unroll
-            for (int t = 0; t < PER; t++) {
-                const int b = tid * PER + t;
-                loc[t] = b < SM_SORT_BUCKETS ? hist[b] : 0u;
-                s += loc[t];
-                mx = loc[t] > mx ? loc[t] : mx;
-            }
-            if (mx > (uint32_t)SM_MAX_BUCKET) misc[6] = 1;
-            uint32_t e0 = block_scan_u32(s, &nS, ws);
-#pragma unroll
-            for (int t = 0; t < PER; t++) {
-                const int b = tid * PER + t;
-                if (b < SM_SORT_BUCKETS) hist[b] = e0;
-                e0 += loc[t];
-            }
-        }
-        if (tid == 0 && nS) {
-            if (cta_pool_pos + (int64_t)nS > cta_pool_end) {   // one global atomic per ~SM_POOL_CHUNK survivors, not per group
-                const unsigned long long chunk = nS > (uint32_t)SM_POOL_CHUNK ? nS : (uint32_t)SM_POOL_CHUNK;
+        uint32_t rank = block_scan_u32(cnt, &nS, ws);   // this thread's first position among the survivors
+        const uint32_t n_out = nS + (special_survives ? 1u : 0u);
+        if (tid == 0 && n_out) {
+            if (cta_pool_pos + (int64_t)n_out > cta_pool_end) {   // one global atomic per ~SM_POOL_CHUNK survivors, not per group
+                const unsigned long long chunk = n_out > (uint32_t)SM_POOL_CHUNK ? n_out : (uint32_t)SM_POOL_CHUNK;
                 cta_pool_pos = (int64_t)atomicAdd(a.pool_cursor, chunk);
                 cta_pool_end = cta_pool_pos + (int64_t)chunk;
             }
-            const unsigned long long pb = (unsigned long long)cta_pool_pos;
-            cta_pool_pos += nS;
-            misc[4] = (uint32_t)pb;
-            misc[5] = (uint32_t)(pb >> 32);
+            const unsigned long long pb0 = (unsigned long long)cta_pool_pos;
+            cta_pool_pos += n_out;
+            misc[4] = (uint32_t)pb0;
+            misc[5] = (uint32_t)(pb0 >> 32);
         }
         __syncthreads();
-        if (nS == 0) {
+        if (n_out == 0) {
             cta_obs += total;
             continue;
         }
         const int64_t pb = (int64_t)(((unsigned long long)misc[5] << 32) | misc[4]);
-        if (misc[6] || nS > (uint32_t)order_cap<W>() || pb + (int64_t)nS > a.pool_cap) {
-            // a sort bucket too large for the per-thread fix-up (low-complexity k-mers), more survivors than the shared
-            // sort scratch holds, or the survivor pool is exhausted: the HBM path takes the group (it owns a real sort)
+        if (pb + (int64_t)n_out > a.pool_cap) {   // survivor pool exhausted: the HBM path (own pool) takes the group
             if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)g;
             continue;
         }
         PHASE_MARK(4);
-        // scatter slot indices to their bucket's range (bucket order == k-mer order up to in-bucket ties)
-        const uint16_t SPECIAL_SLOT = 0xffffu;   // stands for the all-ones k-mer kept in misc[2]
-        {
-            const uint4 *tval4 = reinterpret_cast<const uint4 *>(tval);
-            for (uint32_t j = tid; j < tsize / 4; j += SM_NT) {
-                const uint4 vv = tval4[j];
-                const uint32_t c[4] = {vv.x >> 8, vv.y >> 8, vv.z >> 8, vv.w >> 8};
-                if ((c[0] >= thr) | (c[1] >= thr) | (c[2] >= thr) | (c[3] >= thr)) {
+        auto emit = [&](int64_t pos, KT kq, uint32_t v) {
+            const Key<W> k = S::unpack(kq);
+            a.pool_lo[pos] = k.lo;
+            if (W == 2) a.pool_hi[pos] = k.hi_word();
+            a.pool_exts[pos] = (uint8_t)v;
+            a.pool_counts[pos] = (uint16_t)((v >> 8) > 65535u ? 65535u : (v >> 8));
+        };
+        for (uint32_t j = tid; j < tsize / 4; j += SM_NT) {
+            const uint4 vv = tval4[j];
+            const uint32_t c[4] = {vv.x, vv.y, vv.z, vv.w};
+            if (((c[0] >> 8) >= thr) | ((c[1] >> 8) >= thr) | ((c[2] >> 8) >= thr) | ((c[3] >> 8) >= thr)) {
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        if (c[t] >= thr) {
-                            const uint32_t slot = 4 * j + t;
-                            const uint32_t pos = atomicAdd(&hist[sort_bucket<W>(S::unpack(tkey[slot]), kbits)], 1u);
-                            order[pos] = (uint16_t)slot;
-                        }
-                    }
-                }
+                for (int t = 0; t < 4; t++)
+                    if ((c[t] >> 8) >= thr) emit(pb + (int64_t)(rank++), tkey[4 * j + t], c[t]);
             }
         }
-        if (special_survives && tid == 0) order[atomicAdd(&hist[SM_SORT_BUCKETS - 1], 1u)] = SPECIAL_SLOT;
-        __syncthreads();
-        // buckets with several survivors: insertion sort by k-mer (hist[b] is now the END of bucket b)
-        for (int b = tid; b < SM_SORT_BUCKETS; b += SM_NT) {
-            const uint32_t s = b ? hist[b - 1] : 0u, e = hist[b];
-            for (uint32_t i = s + 1; i < e; i++) {
-                const uint16_t oi = order[i];
-                const KT ki = (oi == SPECIAL_SLOT) ? S::empty() : tkey[oi];
-                uint32_t j = i;
-                while (j > s) {
-                    const uint16_t oj = order[j - 1];
-                    const KT kj = (oj == SPECIAL_SLOT) ? S::empty() : tkey[oj];
-                    if (!(kj > ki)) break;
-                    order[j] = oj;
-                    j--;
-                }
-                order[j] = oi;
-            }
-        }
-        __syncthreads();
-        PHASE_MARK(5);
-        // ---- emit (coalesced) ------------------------------------------------------------------------------------------------------------
-        for (uint32_t j = tid; j < nS; j += SM_NT) {
-            const uint16_t idx = order[j];
-            const Key<W> k = S::unpack(idx == SPECIAL_SLOT ? S::empty() : tkey[idx]);
-            const uint32_t v = (idx == SPECIAL_SLOT) ? sv : tval[idx];
-            a.pool_lo[pb + j] = k.lo;
-            if (W == 2) a.pool_hi[pb + j] = k.hi_word();
-            a.pool_exts[pb + j] = (uint8_t)v;
-            a.pool_counts[pb + j] = (uint16_t)((v >> 8) > 65535u ? 65535u : (v >> 8));
-        }
+        if (special_survives && tid == 0) emit(pb + (int64_t)nS, S::empty(), sv);
         if (tid == 0) {
-            a.nsurv[g] = (int64_t)nS;
+            a.nsurv[g] = (int64_t)n_out;
             a.pool_start[g] = pb;
         }
         cta_obs += total;
-        PHASE_MARK(6);
+        PHASE_MARK(5);
     }
     if (tid == 0 && cta_obs) atomicAdd(a.n_obs, cta_obs);
 }
@@ -697,6 +631,221 @@ __global__ void k_obs_upper_bound(ColView col, int K, unsigned long long *out)
     }
     for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// -----------------------------------------------------------------------------------------------------------------------------
+// Ordering + dense output.  filter_kmers emits every group's survivors in ascending k-mer order; the counting
+// kernel leaves them unsorted in the pool.  k_sort_small orders one group per CTA pass in 32 KB of shared memory (counting
+// sort on the top 10 k-mer bits + insertion sort inside the tiny buckets) and writes the dense, group-ordered arrays;
+// groups with more than sort_small_max() survivors or a crowded bucket go to k_sort_big (bitonic sort in shared memory).
+// -----------------------------------------------------------------------------------------------------------------------------
+constexpr int SORT_NT = 128;
+template <int W>
+constexpr int sort_small_max() { return W == 2 ? 1536 : 2048; }   // static shared memory stays under 48 KB
+constexpr int SORT_BIG_NT = 256;
+constexpr int SORT_BIG_MAX = SM_TSIZE;   // a shared-memory table never yields more survivors than it has slots
+
+struct SortArgs {
+    int64_t n_groups;
+    const int64_t *pool_start;     // -1: group not in the pool (deferred to the HBM path)
+    const int64_t *kmer_offsets;   // dense output offsets
+    const uint64_t *p_lo, *p_hi;
+    const uint8_t *p_exts;
+    const uint16_t *p_counts;
+    uint64_t *o_lo, *o_hi;
+    uint8_t *o_exts;
+    uint16_t *o_counts;
+    int32_t *big_ids;              // groups left to k_sort_big
+    unsigned long long *n_big;
+    int kbits;
+};
+
+template <int W>
+__global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a)
+{
+    constexpr int SORT_SMALL_MAX = sort_small_max<W>();
+    __shared__ uint64_t s_lo[SORT_SMALL_MAX];
+    __shared__ uint64_t s_hi[W == 2 ? SORT_SMALL_MAX : 1];
+    __shared__ uint32_t s_val[SORT_SMALL_MAX];      // exts | count << 8
+    __shared__ uint32_t s_hist[SM_SORT_BUCKETS];
+    __shared__ uint16_t s_order[SORT_SMALL_MAX];
+    __shared__ uint32_t s_ws[8];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    for (int64_t g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+        const int64_t ps = a.pool_start[g];
+        if (ps < 0) continue;
+        const int64_t o = a.kmer_offsets[g];
+        const int n = (int)(a.kmer_offsets[g + 1] - o);
+        if (n == 0) continue;
+        if (n > SORT_SMALL_MAX) {
+            if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)g;
+            continue;
+        }
+        __syncthreads();   // previous group's shared data no longer in use
+        if (tid == 0) s_flag = 0;
+        for (int j = tid; j < SM_SORT_BUCKETS; j += SORT_NT) s_hist[j] = 0;
+        for (int j = tid; j < n; j += SORT_NT) {
+            s_lo[j] = a.p_lo[ps + j];
+            if (W == 2) s_hi[j] = a.p_hi[ps + j];
+            s_val[j] = (uint32_t)a.p_exts[ps + j] | ((uint32_t)a.p_counts[ps + j] << 8);
+        }
+        __syncthreads();
+        auto bucket_of = [&](int j) -> uint32_t {
+            if (W == 2) return sort_bucket<2>(Key<2>{s_lo[j], s_hi[j]}, a.kbits);
+            return sort_bucket<1>(Key<1>{s_lo[j]}, a.kbits);
+        };
+        for (int j = tid; j < n; j += SORT_NT) atomicAdd(&s_hist[bucket_of(j)], 1u);
+        __syncthreads();
+        {   // exclusive scan of the bucket sizes (8 per thread)
+            constexpr int PER = SM_SORT_BUCKETS / SORT_NT;
+            uint32_t loc[PER], s = 0, mx = 0;
+#pragma unroll
+            for (int t = 0; t < PER; t++) {
+                loc[t] = s_hist[tid * PER + t];
+                s += loc[t];
+                mx = loc[t] > mx ? loc[t] : mx;
+            }
+            if (mx > (uint32_t)SM_MAX_BUCKET) s_flag = 1;
+            uint32_t x = s;
+            const unsigned lane = tid & 31u, warp = tid >> 5;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (unsigned)d) x += y;
+            }
+            if (lane == 31) s_ws[warp] = x;
+            __syncthreads();
+            uint32_t base = 0;
+            for (unsigned w = 0; w < warp; w++) base += s_ws[w];
+            uint32_t e0 = base + x - s;
+#pragma unroll
+            for (int t = 0; t < PER; t++) {
+                s_hist[tid * PER + t] = e0;
+                e0 += loc[t];
+            }
+        }
+        __syncthreads();
+        if (s_flag) {   // a crowded bucket (low-complexity k-mers): bitonic kernel
+            if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)g;
+            continue;
+        }
+        for (int j = tid; j < n; j += SORT_NT) s_order[atomicAdd(&s_hist[bucket_of(j)], 1u)] = (uint16_t)j;
+        __syncthreads();
+        for (int b = tid; b < SM_SORT_BUCKETS; b += SORT_NT) {   // s_hist[b] is now the END of bucket b
+            const uint32_t s = b ? s_hist[b - 1] : 0u, e = s_hist[b];
+            for (uint32_t i = s + 1; i < e; i++) {
+                const uint16_t oi = s_order[i];
+                const uint64_t li = s_lo[oi], hi_i = (W == 2) ? s_hi[oi] : 0ull;
+                uint32_t j = i;
+                while (j > s) {
+                    const uint16_t oj = s_order[j - 1];
+                    const uint64_t lj = s_lo[oj], hj = (W == 2) ? s_hi[oj] : 0ull;
+                    if (!(hj > hi_i || (hj == hi_i && lj > li))) break;
+                    s_order[j] = oj;
+                    j--;
+                }
+                s_order[j] = oi;
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += SORT_NT) {
+            const int idx = s_order[j];
+            a.o_lo[o + j] = s_lo[idx];
+            if (W == 2) a.o_hi[o + j] = s_hi[idx];
+            const uint32_t v = s_val[idx];
+            a.o_exts[o + j] = (uint8_t)v;
+            a.o_counts[o + j] = (uint16_t)(v >> 8);
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(SORT_BIG_NT) k_sort_big(SortArgs a, int64_t n_big)
+{
+    extern __shared__ __align__(16) uint8_t sraw[];
+    uint64_t *s_lo = reinterpret_cast<uint64_t *>(sraw);
+    uint64_t *s_hi = s_lo + SORT_BIG_MAX;                                    // only touched when W == 2
+    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_lo + (W == 2 ? 2 : 1) * SORT_BIG_MAX);
+    const int tid = threadIdx.x;
+    for (int64_t i = blockIdx.x; i < n_big; i += gridDim.x) {
+        const int64_t g = a.big_ids[i];
+        const int64_t ps = a.pool_start[g], o = a.kmer_offsets[g];
+        const int n = (int)(a.kmer_offsets[g + 1] - o);
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        __syncthreads();
+        for (int j = tid; j < np2; j += SORT_BIG_NT) {
+            const bool in = j < n;
+            s_lo[j] = in ? a.p_lo[ps + j] : ~0ull;
+            if (W == 2) s_hi[j] = in ? a.p_hi[ps + j] : ~0ull;
+            // padding sorts after every real entry: real k-mers equal to the all-ones key keep val != 0xffffffff
+            s_val[j] = in ? ((uint32_t)a.p_exts[ps + j] | ((uint32_t)a.p_counts[ps + j] << 8)) : 0xffffffffu;
+        }
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < np2; t += SORT_BIG_NT) {
+                    const int p = t ^ j;
+                    if (p > t) {
+                        const bool up = (t & k) == 0;
+                        const uint64_t la = s_lo[t], lb = s_lo[p];
+                        const uint64_t ha = (W == 2) ? s_hi[t] : 0ull, hb = (W == 2) ? s_hi[p] : 0ull;
+                        const uint32_t va = s_val[t], vb = s_val[p];
+                        // order by (hi, lo, padding flag)
+                        const bool a_gt_b = ha > hb || (ha == hb && (la > lb || (la == lb && va == 0xffffffffu && vb != 0xffffffffu)));
+                        if (a_gt_b == up) {
+                            s_lo[t] = lb; s_lo[p] = la;
+                            if (W == 2) { s_hi[t] = hb; s_hi[p] = ha; }
+                            s_val[t] = vb; s_val[p] = va;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int j = tid; j < n; j += SORT_BIG_NT) {
+            a.o_lo[o + j] = s_lo[j];
+            if (W == 2) a.o_hi[o + j] = s_hi[j];
+            const uint32_t v = s_val[j];
+            a.o_exts[o + j] = (uint8_t)v;
+            a.o_counts[o + j] = (uint16_t)(v >> 8);
+        }
+    }
+}
+
+template <int W>
+constexpr size_t sort_big_smem() { return (size_t)SORT_BIG_MAX * (8 * W + 4); }
+
+// host launcher: pool (unsorted, completion order) -> dense, group-ordered, k-mer-ascending arrays
+inline void run_sort_gather(cudaStream_t st, int sm_count, int K, int64_t n_groups, const int64_t *pool_start, const int64_t *kmer_offsets,
+                            const uint64_t *p_lo, const uint64_t *p_hi, const uint8_t *p_exts, const uint16_t *p_counts, uint64_t *o_lo,
+                            uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts, int64_t *launches)
+{
+    DevBuf big((size_t)n_groups * 4 + 16, st), ctr(16, st);
+    CK(cudaMemsetAsync(ctr.p, 0, 16, st));
+    SortArgs a{};
+    a.n_groups = n_groups;
+    a.pool_start = pool_start;
+    a.kmer_offsets = kmer_offsets;
+    a.p_lo = p_lo; a.p_hi = p_hi; a.p_exts = p_exts; a.p_counts = p_counts;
+    a.o_lo = o_lo; a.o_hi = o_hi; a.o_exts = o_exts; a.o_counts = o_counts;
+    a.big_ids = big.as<int32_t>();
+    a.n_big = ctr.as<unsigned long long>();
+    a.kbits = 2 * K;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 16);
+    if (K > 32) k_sort_small<2><<<grid, SORT_NT, 0, st>>>(a);
+    else k_sort_small<1><<<grid, SORT_NT, 0, st>>>(a);
+    unsigned long long n_big = 0;
+    CK(cudaMemcpyAsync(&n_big, ctr.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (launches) *launches += 1;
+    if (n_big) {
+        const unsigned g2 = (unsigned)std::min<int64_t>((int64_t)n_big, (int64_t)sm_count * 2);
+        if (K > 32) k_sort_big<2><<<g2, SORT_BIG_NT, sort_big_smem<2>(), st>>>(a, (int64_t)n_big);
+        else k_sort_big<1><<<g2, SORT_BIG_NT, sort_big_smem<1>(), st>>>(a, (int64_t)n_big);
+        if (launches) *launches += 1;
+    }
 }
 
 // -----------------------------------------------------------------------------------------------------------------------------
@@ -721,6 +870,8 @@ inline void smem_path_configure()
     CK(cudaFuncSetAttribute(k_smem_count<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_smem_count<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<2>()));
     CK(cudaFuncSetAttribute(k_smem_count<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_sort_big<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<1>()));
+    CK(cudaFuncSetAttribute(k_sort_big<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<2>()));
     CK(cudaFuncSetAttribute(k_smem_count<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 }
 

@@ -463,12 +463,9 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     r.exts.alloc(nk, st);
     r.counts.alloc(nk * 2, st);
     uint64_t *p_hi = K > 32 ? r.hi.as<uint64_t>() : nullptr;
-    if (sm.n_pool_groups > 0) {
-        k_gather_pool<<<ctx->sm_count * 8, 256, 0, st>>>(n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi,
-                                                         sm.pool_exts, sm.pool_counts, r.lo.as<uint64_t>(), p_hi,
-                                                         r.exts.as<uint8_t>(), r.counts.as<uint16_t>());
-        ctx->launches++;
-    }
+    if (sm.n_pool_groups > 0)
+        run_sort_gather(st, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
+                        sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches);
     for (auto &wv : waves) {
         if (wv.n_recs == 0) continue;
         k_spill_scatter<<<blocks_for(wv.n_recs, 256), 256, 0, st>>>(wv.recs.as<SpillRec>(), wv.n_recs, d_spill_ids, wv.list_base,

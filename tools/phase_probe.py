@@ -12,7 +12,7 @@ for it in range(3):
     db = eng.count_prune_device(d_data, nbytes, d_off, n * 50, d_goff, n, 31, 2)
     ms = (db.ms_total, db.ms_hot_kernel); db.free()
     pc = eng.phase_cycles(True).astype(np.float64)
-    names = ["meta", "ingest", "prefix+clear", "count", "hist+scan", "scatter", "fix", "-"]
+    names = ["meta", "ingest", "prefix+clear", "count", "prune+reserve", "compact", "-", "-"]
     tot = pc.sum()
     print(f"run {it}: ms_total={ms[0]:.3f} ms_kernel={ms[1]:.3f}  cycles/UMI: " +
           "  ".join(f"{nm}={c / n:.0f}" for nm, c in zip(names, pc) if nm != "-") + f"  total={tot / n:.0f}")
