@@ -641,7 +641,7 @@ __global__ void k_obs_upper_bound(ColView col, int K, unsigned long long *out)
 // -----------------------------------------------------------------------------------------------------------------------------
 constexpr int SORT_NT = 128;
 template <int W>
-constexpr int sort_small_max() { return W == 2 ? 1536 : 2048; }   // static shared memory stays under 48 KB
+constexpr int sort_small_max() { return W == 2 ? 1408 : 2048; }   // static shared memory stays under 48 KB
 constexpr int SORT_BIG_NT = 256;
 constexpr int SORT_BIG_MAX = SM_TSIZE;   // a shared-memory table never yields more survivors than it has slots
 
@@ -669,6 +669,7 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a)
     __shared__ uint32_t s_val[SORT_SMALL_MAX];      // exts | count << 8
     __shared__ uint32_t s_hist[SM_SORT_BUCKETS];
     __shared__ uint16_t s_order[SORT_SMALL_MAX];
+    __shared__ uint16_t s_fin[SORT_SMALL_MAX];
     __shared__ uint32_t s_ws[8];
     __shared__ int s_flag;
     const int tid = threadIdx.x;
@@ -732,25 +733,25 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a)
         }
         for (int j = tid; j < n; j += SORT_NT) s_order[atomicAdd(&s_hist[bucket_of(j)], 1u)] = (uint16_t)j;
         __syncthreads();
-        for (int b = tid; b < SM_SORT_BUCKETS; b += SORT_NT) {   // s_hist[b] is now the END of bucket b
+        // s_hist[b] is now the END of bucket b.  Every survivor ranks itself inside its (tiny) bucket: final position =
+        // bucket start + number of bucket members with a smaller k-mer (k-mers are distinct).
+        for (int j = tid; j < n; j += SORT_NT) {
+            const uint32_t b = bucket_of(j);
             const uint32_t s = b ? s_hist[b - 1] : 0u, e = s_hist[b];
-            for (uint32_t i = s + 1; i < e; i++) {
-                const uint16_t oi = s_order[i];
-                const uint64_t li = s_lo[oi], hi_i = (W == 2) ? s_hi[oi] : 0ull;
-                uint32_t j = i;
-                while (j > s) {
-                    const uint16_t oj = s_order[j - 1];
-                    const uint64_t lj = s_lo[oj], hj = (W == 2) ? s_hi[oj] : 0ull;
-                    if (!(hj > hi_i || (hj == hi_i && lj > li))) break;
-                    s_order[j] = oj;
-                    j--;
+            uint32_t r = s;
+            if (e - s > 1u) {
+                const uint64_t lj = s_lo[j], hj = (W == 2) ? s_hi[j] : 0ull;
+                for (uint32_t i = s; i < e; i++) {
+                    const uint16_t oi = s_order[i];
+                    const uint64_t li = s_lo[oi], hi_i = (W == 2) ? s_hi[oi] : 0ull;
+                    r += (hi_i < hj || (hi_i == hj && li < lj)) ? 1u : 0u;
                 }
-                s_order[j] = oi;
             }
+            s_fin[r] = (uint16_t)j;
         }
         __syncthreads();
         for (int j = tid; j < n; j += SORT_NT) {
-            const int idx = s_order[j];
+            const int idx = s_fin[j];
             a.o_lo[o + j] = s_lo[idx];
             if (W == 2) a.o_hi[o + j] = s_hi[idx];
             const uint32_t v = s_val[idx];
