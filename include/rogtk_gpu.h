@@ -120,6 +120,22 @@ int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, c
                                 rogtk_graph_batch *out);
 void rogtk_gpu_free_batch(rogtk_gpu_ctx *ctx, rogtk_graph_batch *batch);
 
+/* ---- global k-mer spectrum: one group spanning the reads of every rank (BASELINE configs[4]) -----------------------
+ * The reference has no multi-process analogue: it is the un-grouped call of the same expression (one filter_kmers over all
+ * reads).  Protocol per rank:
+ *   1. rogtk_gpu_count_prune_batch(reads of this rank, group_offsets = {0, n_rows}, min_coverage = 1, OUTPUT_ON_DEVICE)
+ *      -> ascending distinct k-mers of the local reads with partial (u16-saturated) counts and exts
+ *   2. rogtk_gpu_spectrum_split: where the ascending list changes owner (owner = range of first-4-base buckets)
+ *   3. all-to-all of the four arrays (NCCL; done by the host, e.g. torch.distributed.all_to_all_single)
+ *   4. rogtk_gpu_spectrum_merge: sum partial counts (saturating), OR exts, apply min_coverage, ascending output (one group)
+ * Rank-ordered concatenation of the results equals the single-process answer. */
+int rogtk_gpu_spectrum_owner(uint64_t kmer_lo, uint64_t kmer_hi, int k_eff, int n_ranks);
+int rogtk_gpu_spectrum_split(rogtk_gpu_ctx *ctx, const uint64_t *d_kmers_lo, const uint64_t *d_kmers_hi, int64_t n, int k_eff,
+                             int n_ranks, int64_t *h_bounds /* [n_ranks+1] host */);
+int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_kmers_lo, const uint64_t *d_kmers_hi, const uint16_t *d_counts,
+                             const uint8_t *d_exts, int64_t n, int k_eff, uint32_t min_coverage, uint32_t flags,
+                             rogtk_graph_batch *out);
+
 /* ---- bench / test utilities (not part of the reference surface) ------------------------------------------------ */
 /* Synthetic reads of SURVEY 8(d) generated directly in HBM: n_umis groups x reads_per_umi reads of read_len bases
  * drawn from a per-UMI random template of template_len bases with iid substitution errors (err_per_64k / 65536).

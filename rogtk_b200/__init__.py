@@ -2,6 +2,6 @@
 rogtk's `assemble_sequences` Polars expression, reference src/fracture.rs:105-158)."""
 from .engine import DeviceBatch, Engine, GraphBatch, RogtkGpuError, estimate_k, k_eff, shard_of  # noqa: F401
 from . import _ffi as ffi  # noqa: F401
-from . import synth  # noqa: F401
+from . import sharding, spectrum, synth  # noqa: F401
 
-__all__ = ["Engine", "GraphBatch", "DeviceBatch", "RogtkGpuError", "k_eff", "estimate_k", "shard_of", "ffi", "synth"]
+__all__ = ["Engine", "GraphBatch", "DeviceBatch", "RogtkGpuError", "k_eff", "estimate_k", "shard_of", "ffi", "synth", "sharding", "spectrum"]

@@ -138,6 +138,82 @@ __global__ void k_csr(int64_t n_kmers, int64_t n_groups, const int64_t *kmer_off
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// global k-mer spectrum (one group spanning every rank).  Distinct k-mers are owned by the rank whose
+// range of first-4-base buckets (the reference's bucket()) contains them, so the rank-ordered concatenation of
+// the per-rank results is globally ascending like filter_kmers' bucket order.
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int spectrum_owner(uint64_t lo, uint64_t hi, int kbits, int n_ranks)
+{
+    uint32_t b;   // first 4 bases = top 8 bits of the k-mer (k-mers shorter than 4 bases: left-aligned)
+    if (kbits > 64) b = (uint32_t)(hi >> (kbits - 64 - 8 >= 0 ? kbits - 72 : 0)) & 0xffu;
+    else if (kbits >= 8) b = (uint32_t)(lo >> (kbits - 8)) & 0xffu;
+    else b = (uint32_t)(lo << (8 - kbits)) & 0xffu;
+    if (kbits > 64 && kbits < 72) b = (uint32_t)(((hi << (72 - kbits)) | (lo >> (kbits - 8))) & 0xffu);
+    return (int)((b * (uint32_t)n_ranks) >> 8);
+}
+
+// bounds[d] = index of the first k-mer (ascending input) owned by a rank >= d, d in [0, n_ranks]
+__global__ void k_spectrum_bounds(const uint64_t *lo, const uint64_t *hi, int64_t n, int kbits, int n_ranks, int64_t *bounds)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d > n_ranks) return;
+    int64_t a = 0, b = n;
+    while (a < b) {
+        const int64_t m = (a + b) >> 1;
+        if (spectrum_owner(lo[m], hi ? hi[m] : 0ull, kbits, n_ranks) < d) a = m + 1; else b = m;
+    }
+    bounds[d] = a;
+}
+
+struct SpecRec {   // (k-mer, partial count, exts) received from one source rank
+    uint64_t hi, lo;
+    uint32_t val;   // count (low 16, saturated) | exts << 16
+    uint32_t pad;
+};
+struct SpecRecLess {
+    __device__ __forceinline__ bool operator()(const SpecRec &a, const SpecRec &b) const
+    {
+        return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+    }
+};
+__global__ void k_spec_pack(const uint64_t *lo, const uint64_t *hi, const uint16_t *counts, const uint8_t *exts, int64_t n, SpecRec *r)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    r[i] = SpecRec{hi ? hi[i] : 0ull, lo[i], (uint32_t)counts[i] | ((uint32_t)exts[i] << 16), 0u};
+}
+// equal k-mers are adjacent after the sort: the first of each run sums the partial counts (saturating u16) and ORs the exts
+__global__ void k_spec_reduce(SpecRec *r, int64_t n, uint32_t min_cov, int32_t *keep)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SpecRec me = r[i];
+    int k = 0;
+    if (i == 0 || r[i - 1].hi != me.hi || r[i - 1].lo != me.lo) {
+        uint32_t c = me.val & 0xffffu, e = me.val >> 16;
+        for (int64_t j = i + 1; j < n && r[j].hi == me.hi && r[j].lo == me.lo; j++) {
+            c += r[j].val & 0xffffu;
+            e |= r[j].val >> 16;
+        }
+        if (c > 65535u) c = 65535u;
+        r[i].val = c | (e << 16);
+        k = (c >= min_cov && c > 0u) ? 1 : 0;
+    }
+    keep[i] = k;
+}
+__global__ void k_spec_emit(const SpecRec *r, int64_t n, const int32_t *keep, const int64_t *pos, uint64_t *o_lo, uint64_t *o_hi,
+                            uint8_t *o_exts, uint16_t *o_counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const int64_t d = pos[i];
+    o_lo[d] = r[i].lo;
+    if (o_hi) o_hi[d] = r[i].hi;
+    o_exts[d] = (uint8_t)(r[i].val >> 16);
+    o_counts[d] = (uint16_t)(r[i].val & 0xffffu);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // synthetic reads: per UMI u (global index) s_u = splitmix_out(seed, u);
 //   template base i      = (splitmix_out(s_u, i>>5) >> 2*(i&31)) & 3
 //   read r start         = splitmix_out(s_u, 2^20 + 4096 r) mod (T-L+1)

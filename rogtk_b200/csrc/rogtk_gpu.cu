@@ -836,6 +836,129 @@ extern "C" int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strco
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// global k-mer spectrum
+// -----------------------------------------------------------------------------------------------------------------
+extern "C" int rogtk_gpu_spectrum_owner(uint64_t kmer_lo, uint64_t kmer_hi, int k_eff, int n_ranks)
+{
+    if (k_eff < 1 || k_eff > 64 || n_ranks < 1 || n_ranks > 256) return -1;
+    return spectrum_owner(kmer_lo, kmer_hi, 2 * k_eff, n_ranks);
+}
+
+extern "C" int rogtk_gpu_spectrum_split(rogtk_gpu_ctx *ctx, const uint64_t *d_lo, const uint64_t *d_hi, int64_t n, int k_eff,
+                                        int n_ranks, int64_t *h_bounds)
+{
+    if (!ctx || !h_bounds || n < 0 || k_eff < 1 || k_eff > 64 || n_ranks < 1 || n_ranks > 256 || (n > 0 && !d_lo))
+        return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    try {
+        CK(cudaSetDevice(ctx->device));
+        DevBuf b((size_t)(n_ranks + 1) * 8, ctx->stream);
+        k_spectrum_bounds<<<blocks_for(n_ranks + 1, 128), 128, 0, ctx->stream>>>(d_lo, k_eff > 32 ? d_hi : nullptr, n, 2 * k_eff, n_ranks,
+                                                                               b.as<int64_t>());
+        ctx->launches++;
+        CK(cudaMemcpyAsync(h_bounds, b.p, (size_t)(n_ranks + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } catch (const CudaFail &f) {
+        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
+        cudaGetLastError();
+        return ROGTK_ERR_CUDA;
+    }
+    return ROGTK_OK;
+}
+
+extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo, const uint64_t *d_hi, const uint16_t *d_counts,
+                                        const uint8_t *d_exts, int64_t n, int k_eff, uint32_t min_coverage, uint32_t flags,
+                                        rogtk_graph_batch *out)
+{
+    if (!ctx || !out || n < 0 || k_eff < 1 || k_eff > 64 || (n > 0 && (!d_lo || !d_counts || !d_exts)) || (k_eff > 32 && n > 0 && !d_hi))
+        return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    memset(out, 0, sizeof(*out));
+    BatchOwner *own = new BatchOwner();
+    const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
+    own->on_device = out_dev;
+    out->_owner = own;
+    int rc = ROGTK_OK;
+    try {
+        CK(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        CK(cudaEventRecord(ctx->ev[0], st));
+        const size_t nn = (size_t)std::max<int64_t>(n, 1);
+        DevBuf recs(nn * sizeof(SpecRec), st), keep(nn * 4, st), pos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st);
+        int64_t n_out = 0;
+        if (n > 0) {
+            k_spec_pack<<<blocks_for(n, 256), 256, 0, st>>>(d_lo, k_eff > 32 ? d_hi : nullptr, d_counts, d_exts, n, recs.as<SpecRec>());
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, recs.as<SpecRec>(), n, SpecRecLess(), st));
+            DevBuf tmp(tmp_bytes, st);
+            CK(cub::DeviceMergeSort::SortKeys(tmp.p, tmp_bytes, recs.as<SpecRec>(), n, SpecRecLess(), st));
+            k_spec_reduce<<<blocks_for(n, 256), 256, 0, st>>>(recs.as<SpecRec>(), n, min_coverage, keep.as<int32_t>());
+            exclusive_scan<int32_t>(keep.as<int32_t>(), n, pos.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+            CK(cudaMemcpyAsync(&n_out, pos.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ctx->launches += 5;
+        }
+        const size_t no = (size_t)std::max<int64_t>(n_out, 1);
+        DevBuf o_lo(no * 8, st), o_hi(k_eff > 32 ? no * 8 : 0, st), o_exts(no, st), o_counts(no * 2, st), o_off(16, st), o_stats(16, st);
+        if (n > 0) {
+            k_spec_emit<<<blocks_for(n, 256), 256, 0, st>>>(recs.as<SpecRec>(), n, keep.as<int32_t>(), pos.as<int64_t>(), o_lo.as<uint64_t>(),
+                                                            k_eff > 32 ? o_hi.as<uint64_t>() : nullptr, o_exts.as<uint8_t>(),
+                                                            o_counts.as<uint16_t>());
+            ctx->launches++;
+        }
+        const int64_t h_off[2] = {0, n_out};
+        CK(cudaMemcpyAsync(o_off.p, h_off, 16, cudaMemcpyHostToDevice, st));
+        if (flags & ROGTK_EMIT_STATS) {
+            k_stats<<<1, 256, 0, st>>>(1, o_off.as<int64_t>(), o_exts.as<uint8_t>(), o_stats.as<uint32_t>());
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(ctx->ev[3], st));
+        out->n_groups = 1;
+        out->n_kmers = n_out;
+        out->k_eff = k_eff;
+        out->on_device = out_dev ? 1 : 0;
+        auto give = [&](DevBuf &b, size_t bytes) -> void * {
+            if (out_dev) {
+                void *p = b.detach();
+                own->ptrs.push_back(p);
+                return p;
+            }
+            void *h = pinned_get(ctx, bytes);
+            own->ptrs.push_back(h);
+            if (bytes) CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, st));
+            return h;
+        };
+        out->kmer_offsets = (int64_t *)give(o_off, 16);
+        out->kmers_lo = (uint64_t *)give(o_lo, (size_t)n_out * 8);
+        out->kmers_hi = k_eff > 32 ? (uint64_t *)give(o_hi, (size_t)n_out * 8) : nullptr;
+        out->exts = (uint8_t *)give(o_exts, (size_t)n_out);
+        out->counts = (uint16_t *)give(o_counts, (size_t)n_out * 2);
+        if (flags & ROGTK_EMIT_STATS) out->stats = (uint32_t *)give(o_stats, 12);
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+        out->ms_total = ms;
+        CK(cudaGetLastError());
+    } catch (const CudaFail &f) {
+        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
+        rc = (f.e == cudaErrorMemoryAllocation) ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
+        cudaGetLastError();
+    } catch (...) {
+        set_error(ctx, "unexpected internal error");
+        rc = ROGTK_ERR_INTERNAL;
+    }
+    if (rc != ROGTK_OK) {
+        for (void *p : own->ptrs) {
+            if (own->on_device) cudaFreeAsync(p, ctx->stream);
+            else pinned_put(ctx, p);
+        }
+        delete own;
+        memset(out, 0, sizeof(*out));
+    }
+    return rc;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // bench / test utilities
 // -----------------------------------------------------------------------------------------------------------------
 extern "C" int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t reads_per_umi,

@@ -282,3 +282,40 @@ class Engine:
         return DeviceBatch(k_eff=int(c.k_eff), n_groups=int(c.n_groups), n_kmers=int(c.n_kmers), n_edges=int(c.n_edges),
                            n_observations=int(c.n_observations), ms_total=float(c.ms_total), ms_count=float(c.ms_count),
                            ms_hot_kernel=float(c.ms_hot_kernel), n_spilled_groups=int(c.n_spilled_groups), _c=c, _engine=self)
+
+
+    def count_prune_to_device(self, data: np.ndarray, offsets: np.ndarray, group_offsets: np.ndarray, k: int, min_coverage: int,
+                              validity: np.ndarray | None = None, flags: int = 0) -> DeviceBatch:
+        """Host Arrow buffers in, result left in HBM (used by the global-spectrum mode before the all-to-all)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        group_offsets = np.ascontiguousarray(group_offsets, dtype=np.int64)
+        if validity is not None:
+            validity = np.ascontiguousarray(validity, dtype=np.uint8)
+        dptr = (ctypes.c_void_p * 1)(data.ctypes.data if data.size else None)
+        dlen = (ctypes.c_int64 * 1)(data.size)
+        col = _ffi.StrCol(layout=_ffi.UTF8_I64, n_buffers=1, n_rows=len(offsets) - 1,
+                          validity=validity.ctypes.data if validity is not None else None, validity_bit_offset=0,
+                          offsets_or_views=offsets.ctypes.data, data=dptr, data_len=dlen)
+        c = self._call(col, group_offsets.ctypes.data, len(group_offsets) - 1, k, min_coverage,
+                       (flags | _ffi.OUTPUT_ON_DEVICE) & ~_ffi.INPUT_ON_DEVICE)
+        return DeviceBatch(k_eff=int(c.k_eff), n_groups=int(c.n_groups), n_kmers=int(c.n_kmers), n_edges=int(c.n_edges),
+                           n_observations=int(c.n_observations), ms_total=float(c.ms_total), ms_count=float(c.ms_count),
+                           ms_hot_kernel=float(c.ms_hot_kernel), n_spilled_groups=int(c.n_spilled_groups), _c=c, _engine=self)
+
+    # ---- global k-mer spectrum (one group spanning every rank) -------------------------------------------------------------
+    def spectrum_split(self, d_lo: int, d_hi: int | None, n: int, k_eff_: int, n_ranks: int) -> np.ndarray:
+        """bounds[d] = first index of the ascending device list owned by a rank >= d (owner = first-4-base bucket range)."""
+        b = np.zeros(n_ranks + 1, dtype=np.int64)
+        self._check(self._lib.rogtk_gpu_spectrum_split(self._ctx, ctypes.c_void_p(d_lo), ctypes.c_void_p(d_hi or 0), int(n),
+                                                       int(k_eff_), int(n_ranks), b.ctypes.data))
+        return b
+
+    def spectrum_merge(self, d_lo: int, d_hi: int | None, d_counts: int, d_exts: int, n: int, k_eff_: int, min_coverage: int,
+                       flags: int = 0) -> GraphBatch:
+        """Merge (k-mer, partial count, exts) triples received from all ranks: one ascending group with count >= min_coverage."""
+        out = _ffi.GraphBatchC()
+        self._check(self._lib.rogtk_gpu_spectrum_merge(self._ctx, ctypes.c_void_p(d_lo), ctypes.c_void_p(d_hi or 0),
+                                                       ctypes.c_void_p(d_counts), ctypes.c_void_p(d_exts), int(n), int(k_eff_),
+                                                       int(min_coverage), int(flags) & ~_ffi.OUTPUT_ON_DEVICE, ctypes.byref(out)))
+        return self._to_numpy(out)

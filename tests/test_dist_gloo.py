@@ -78,3 +78,54 @@ def test_two_rank_sharding_gloo(tmp_path, oracle):
     ids = np.arange(500, dtype=np.uint64) * 7919
     for w in (2, 4, 8):
         assert np.array_equal(sharding.shard_ids(ids, w), [rogtk_b200.shard_of(int(i), w) for i in ids])
+
+
+def _spectrum_worker(rank, world, port, tmpdir):
+    """Protocol of the global k-mer-spectrum mode (rogtk_b200/spectrum.py) with the oracle standing in for the GPU engine:
+    local distinct k-mers (min_cov=1) -> split by owner -> all-to-all -> merge (saturating sum, OR) -> min_coverage."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import rogtk_b200
+    from oracle import dbg_oracle
+    from rogtk_b200 import synth
+    from rogtk_b200.spectrum import _exchange
+    data, offs, _ = synth.synth_reads(synth.config_seed(5), 0, 30, 20, 100, 300)
+    n_rows, L = len(offs) - 1, 100
+    rows = np.arange(rank, n_rows, world)
+    d = data.reshape(n_rows, L)[rows].reshape(-1)
+    o = np.arange(len(rows) + 1, dtype=np.int64) * L
+    k, mc = 21, 2
+    loc = dbg_oracle.count_prune_batch(d, o, np.array([0, len(rows)]), k, 1)
+    owner = np.array([rogtk_b200.ffi.load().rogtk_gpu_spectrum_owner(int(x), 0, loc.k_eff, world) for x in loc.kmers_lo])
+    assert np.all(np.diff(owner) >= 0)
+    send_counts = [int((owner == r).sum()) for r in range(world)]
+    r_lo, _ = _exchange(torch.from_numpy(loc.kmers_lo.view(np.int64)), send_counts, None, "cpu")
+    r_ct, _ = _exchange(torch.from_numpy(loc.counts.view(np.int16)), send_counts, None, "cpu")
+    r_ex, _ = _exchange(torch.from_numpy(loc.exts), send_counts, None, "cpu")
+    lo, ct, ex = r_lo.numpy().view(np.uint64), r_ct.numpy().view(np.uint16).astype(np.int64), r_ex.numpy()
+    order = np.argsort(lo, kind="stable")
+    lo, ct, ex = lo[order], ct[order], ex[order]
+    ulo, start = np.unique(lo, return_index=True)
+    csum = np.minimum(65535, np.add.reduceat(ct, start)) if len(lo) else ct
+    eor = np.bitwise_or.reduceat(ex, start) if len(lo) else ex
+    keep = csum >= mc
+    np.savez(os.path.join(tmpdir, f"s{rank}.npz"), lo=ulo[keep], ct=csum[keep].astype(np.uint16), ex=eor[keep])
+    dist.destroy_process_group()
+
+
+def test_global_spectrum_protocol_gloo(tmp_path, oracle):
+    import torch.multiprocessing as mp
+    from rogtk_b200 import synth
+    world, port = 2, _free_port()
+    mp.spawn(_spectrum_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    data, offs, _ = synth.synth_reads(synth.config_seed(5), 0, 30, 20, 100, 300)
+    ref = oracle.count_prune_batch(data, offs, np.array([0, len(offs) - 1]), 21, 2)
+    parts = [np.load(tmp_path / f"s{r}.npz") for r in range(world)]
+    assert all(len(p["lo"]) > 0 for p in parts)
+    assert np.array_equal(np.concatenate([p["lo"] for p in parts]), ref.kmers_lo)      # rank order == ascending order
+    assert np.array_equal(np.concatenate([p["ct"] for p in parts]), ref.counts)
+    assert np.array_equal(np.concatenate([p["ex"] for p in parts]), ref.exts)

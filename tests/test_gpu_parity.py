@@ -221,3 +221,50 @@ def test_chunked_overlapped_host_path(oracle, monkeypatch):
         assert_batches_equal(got, ref, ctx="chunked cfg2")
     finally:
         eng.close()
+
+
+def test_global_spectrum_single_rank_and_emulated_sources(engine, oracle):
+    """Global k-mer-spectrum mode: the merge of per-source partial (k-mer, count, exts) lists must equal one
+    un-grouped filter_kmers call.  Sources are emulated on one GPU: every "rank" counts its stripe of the reads, the lists are
+    split by owner and concatenated per owner exactly as the all-to-all would deliver them."""
+    import torch
+    from rogtk_b200 import spectrum, synth
+    data, offs, _ = synth.synth_reads(synth.config_seed(5), 0, 40, 25, 150, 500)   # 1000 reads from 40 templates
+    n_rows = len(offs) - 1
+    for k, mc in ((31, 2), (13, 1), (40, 2)):
+        ref = oracle.count_prune_batch(data, offs, np.array([0, n_rows]), k, mc)
+        # single rank
+        got = spectrum.global_spectrum(engine, data, offs, k, mc, flags=EMIT_STATS)
+        assert_batches_equal(got, ref, ctx=f"spectrum 1 rank k={k}")
+        # 3 emulated ranks, reads striped round-robin
+        world = 3
+        parts = []
+        for r in range(world):
+            rows = np.arange(r, n_rows, world)
+            d = np.concatenate([data[offs[i]:offs[i + 1]] for i in rows])
+            o = np.concatenate([[0], np.cumsum(offs[rows + 1] - offs[rows])]).astype(np.int64)
+            b = engine.count_prune(d, o, np.array([0, len(rows)]), k, 1)
+            owner = np.array([engine._lib.rogtk_gpu_spectrum_owner(int(b.kmers_lo[i]), int(b.kmers_hi[i]) if b.kmers_hi is not None else 0,
+                                                                   b.k_eff, world) for i in range(len(b.kmers_lo))])
+            assert np.all(np.diff(owner) >= 0)            # owners are monotone in the ascending list
+            parts.append((b, owner))
+        pieces = []
+        for dst in range(world):
+            sel = [(b, owner == dst) for b, owner in parts]
+            lo = np.concatenate([b.kmers_lo[m] for b, m in sel])
+            hi = np.concatenate([b.kmers_hi[m] for b, m in sel]) if ref.kmers_hi is not None else None
+            ct = np.concatenate([b.counts[m] for b, m in sel])
+            ex = np.concatenate([b.exts[m] for b, m in sel])
+            t_lo = torch.from_numpy(lo.view(np.int64)).cuda()
+            t_hi = torch.from_numpy(hi.view(np.int64)).cuda() if hi is not None else None
+            t_ct = torch.from_numpy(ct.view(np.int16)).cuda()
+            t_ex = torch.from_numpy(ex).cuda()
+            torch.cuda.synchronize()
+            pieces.append(engine.spectrum_merge(t_lo.data_ptr() if len(lo) else 0, t_hi.data_ptr() if t_hi is not None and len(lo) else 0,
+                                                t_ct.data_ptr() if len(lo) else 0, t_ex.data_ptr() if len(lo) else 0, len(lo),
+                                                ref.k_eff, mc))
+        assert np.array_equal(np.concatenate([p.kmers_lo for p in pieces]), ref.kmers_lo)
+        if ref.kmers_hi is not None:
+            assert np.array_equal(np.concatenate([p.kmers_hi for p in pieces]), ref.kmers_hi)
+        assert np.array_equal(np.concatenate([p.exts for p in pieces]), ref.exts)
+        assert np.array_equal(np.concatenate([p.counts for p in pieces]), ref.counts)
