@@ -120,6 +120,13 @@ int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, c
                                 rogtk_graph_batch *out);
 void rogtk_gpu_free_batch(rogtk_gpu_ctx *ctx, rogtk_graph_batch *batch);
 
+/* ---- threshold re-use -------------------------------------------------------------------------------------------
+ * `in` is a device-resident batch (ROGTK_OUTPUT_ON_DEVICE) counted at min_coverage <= min_coverage2.  Produces the batch the
+ * hot path would return for min_coverage2 without touching the reads again: what sweep_assembly_params_expr
+ * (src/expressions.rs:901-941) and optimize_assembly's W/E moves (src/fracture_opt.rs:163-218) need per extra threshold. */
+int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, uint32_t min_coverage2, uint32_t flags,
+                          rogtk_graph_batch *out);
+
 /* ---- global k-mer spectrum: one group spanning the reads of every rank (BASELINE configs[4]) -----------------------
  * The reference has no multi-process analogue: it is the un-grouped call of the same expression (one filter_kmers over all
  * reads).  Protocol per rank:

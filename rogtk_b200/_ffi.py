@@ -33,7 +33,7 @@ SYMBOLS = [
     "rogtk_gpu_k_eff", "rogtk_gpu_estimate_k", "rogtk_gpu_shard_of", "rogtk_gpu_count_prune_batch", "rogtk_gpu_free_batch",
     "rogtk_gpu_synth_reads", "rogtk_gpu_device_alloc", "rogtk_gpu_device_free", "rogtk_gpu_pinned_alloc",
     "rogtk_gpu_pinned_free", "rogtk_gpu_memcpy_h2d", "rogtk_gpu_memcpy_d2h", "rogtk_gpu_launch_count", "rogtk_gpu_flush_l2", "rogtk_gpu_debug_phase_cycles",
-    "rogtk_gpu_spectrum_owner", "rogtk_gpu_spectrum_split", "rogtk_gpu_spectrum_merge",
+    "rogtk_gpu_spectrum_owner", "rogtk_gpu_spectrum_split", "rogtk_gpu_spectrum_merge", "rogtk_gpu_rethreshold",
 ]
 
 
@@ -129,6 +129,8 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_spectrum_split.restype = ctypes.c_int
     lib.rogtk_gpu_spectrum_merge.argtypes = [vp, vp, vp, vp, vp, i64, ctypes.c_int, u32, u32, ctypes.POINTER(GraphBatchC)]
     lib.rogtk_gpu_spectrum_merge.restype = ctypes.c_int
+    lib.rogtk_gpu_rethreshold.argtypes = [vp, ctypes.POINTER(GraphBatchC), u32, u32, ctypes.POINTER(GraphBatchC)]
+    lib.rogtk_gpu_rethreshold.restype = ctypes.c_int
     lib.rogtk_gpu_flush_l2.argtypes = [vp]
     lib.rogtk_gpu_flush_l2.restype = ctypes.c_int
     _lib = lib

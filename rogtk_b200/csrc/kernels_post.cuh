@@ -138,6 +138,35 @@ __global__ void k_csr(int64_t n_kmers, int64_t n_groups, const int64_t *kmer_off
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// threshold re-use: the reference re-counts all reads for every (k, min_coverage) cell of
+// sweep_assembly_params_expr (src/expressions.rs:901-941) and every probe of optimize_assembly (src/fracture_opt.rs:243-263),
+// although only K_eff and the threshold matter.  Pruning is a pure filter on the counts (exts are never censored),
+// so a batch counted once at a low threshold yields every higher threshold exactly.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_thr_flags(const uint16_t *counts, int64_t n, uint32_t thr, int32_t *keep)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = (uint32_t)counts[i] >= thr ? 1 : 0;
+}
+__global__ void k_thr_offsets(const int64_t *old_off, int64_t n_groups, const int64_t *pos, int64_t *new_off)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g <= n_groups) new_off[g] = pos[old_off[g]];
+}
+__global__ void k_thr_compact(int64_t n, const int32_t *keep, const int64_t *pos, const uint64_t *lo, const uint64_t *hi,
+                              const uint8_t *exts, const uint16_t *counts, uint64_t *o_lo, uint64_t *o_hi, uint8_t *o_exts,
+                              uint16_t *o_counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const int64_t d = pos[i];
+    o_lo[d] = lo[i];
+    if (o_hi) o_hi[d] = hi[i];
+    o_exts[d] = exts[i];
+    o_counts[d] = counts[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // global k-mer spectrum (one group spanning every rank).  Distinct k-mers are owned by the rank whose
 // range of first-4-base buckets (the reference's bucket()) contains them, so the rank-ordered concatenation of
 // the per-rank results is globally ascending like filter_kmers' bucket order.

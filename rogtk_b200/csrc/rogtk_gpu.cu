@@ -836,6 +836,115 @@ extern "C" int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strco
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// threshold re-use
+// -----------------------------------------------------------------------------------------------------------------
+extern "C" int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, uint32_t min_coverage2, uint32_t flags,
+                                     rogtk_graph_batch *out)
+{
+    if (!ctx || !in || !out || !in->on_device || in->n_groups < 0 || in->n_kmers < 0) return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    memset(out, 0, sizeof(*out));
+    BatchOwner *own = new BatchOwner();
+    const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
+    own->on_device = out_dev;
+    out->_owner = own;
+    int rc = ROGTK_OK;
+    try {
+        CK(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        CK(cudaEventRecord(ctx->ev[0], st));
+        const int64_t n = in->n_kmers, ng = in->n_groups;
+        const int K = in->k_eff;
+        const uint32_t thr = min_coverage2 > 1u ? min_coverage2 : 1u;
+        const size_t nn = (size_t)std::max<int64_t>(n, 1);
+        DevBuf keep(nn * 4, st), pos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st), n_off((size_t)(ng + 1) * 8, st);
+        if (n > 0) k_thr_flags<<<blocks_for(n, 256), 256, 0, st>>>(in->counts, n, thr, keep.as<int32_t>());
+        exclusive_scan<int32_t>(keep.as<int32_t>(), n, pos.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+        int64_t n_out = 0;
+        CK(cudaMemcpyAsync(&n_out, pos.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+        k_thr_offsets<<<blocks_for(ng + 1, 256), 256, 0, st>>>(in->kmer_offsets, ng, pos.as<int64_t>(), n_off.as<int64_t>());
+        CK(cudaStreamSynchronize(st));
+        const size_t no = (size_t)std::max<int64_t>(n_out, 1);
+        DevBuf o_lo(no * 8, st), o_hi(K > 32 ? no * 8 : 0, st), o_exts(no, st), o_counts(no * 2, st), d_stats, d_rowptr, d_cols;
+        uint64_t *p_hi = K > 32 ? o_hi.as<uint64_t>() : nullptr;
+        if (n > 0)
+            k_thr_compact<<<blocks_for(n, 256), 256, 0, st>>>(n, keep.as<int32_t>(), pos.as<int64_t>(), in->kmers_lo, in->kmers_hi, in->exts,
+                                                              in->counts, o_lo.as<uint64_t>(), p_hi, o_exts.as<uint8_t>(),
+                                                              o_counts.as<uint16_t>());
+        ctx->launches += 3;
+        int64_t n_edges = 0;
+        if (flags & ROGTK_EMIT_STATS) {
+            d_stats.alloc((size_t)ng * 12 + 16, st);
+            if (ng > 0) k_stats<<<ctx->sm_count * 8, 256, 0, st>>>(ng, n_off.as<int64_t>(), o_exts.as<uint8_t>(), d_stats.as<uint32_t>());
+        }
+        if (flags & ROGTK_EMIT_CSR) {
+            DevBuf deg(no * 4, st), scr2(scan_scratch_bytes(n_out), st);
+            d_rowptr.alloc((size_t)(n_out + 1) * 8, st);
+            if (n_out > 0)
+                k_csr<<<blocks_for(n_out, 256), 256, 0, st>>>(n_out, ng, n_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi, o_exts.as<uint8_t>(), K,
+                                                              deg.as<int32_t>(), nullptr, nullptr);
+            exclusive_scan<int32_t>(deg.as<int32_t>(), n_out, d_rowptr.as<int64_t>(), scr2.as<int64_t>(), st, &ctx->launches);
+            CK(cudaMemcpyAsync(&n_edges, d_rowptr.as<int64_t>() + n_out, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            d_cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
+            if (n_out > 0)
+                k_csr<<<blocks_for(n_out, 256), 256, 0, st>>>(n_out, ng, n_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi, o_exts.as<uint8_t>(), K,
+                                                              nullptr, d_rowptr.as<int64_t>(), d_cols.as<int32_t>());
+        }
+        CK(cudaEventRecord(ctx->ev[3], st));
+        out->n_groups = ng;
+        out->n_kmers = n_out;
+        out->n_edges = n_edges;
+        out->n_observations = in->n_observations;
+        out->k_eff = K;
+        out->on_device = out_dev ? 1 : 0;
+        auto give = [&](DevBuf &b, size_t bytes) -> void * {
+            if (!b.p) return nullptr;
+            if (out_dev) {
+                void *p = b.detach();
+                own->ptrs.push_back(p);
+                return p;
+            }
+            void *h = pinned_get(ctx, bytes);
+            own->ptrs.push_back(h);
+            if (bytes) CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, st));
+            return h;
+        };
+        out->kmer_offsets = (int64_t *)give(n_off, (size_t)(ng + 1) * 8);
+        out->kmers_lo = (uint64_t *)give(o_lo, (size_t)n_out * 8);
+        out->kmers_hi = K > 32 ? (uint64_t *)give(o_hi, (size_t)n_out * 8) : nullptr;
+        out->exts = (uint8_t *)give(o_exts, (size_t)n_out);
+        out->counts = (uint16_t *)give(o_counts, (size_t)n_out * 2);
+        if (flags & ROGTK_EMIT_STATS) out->stats = (uint32_t *)give(d_stats, (size_t)ng * 12);
+        if (flags & ROGTK_EMIT_CSR) {
+            out->csr_row_ptr = (int64_t *)give(d_rowptr, (size_t)(n_out + 1) * 8);
+            out->csr_col = (int32_t *)give(d_cols, (size_t)n_edges * 4);
+        }
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+        out->ms_total = ms;
+        CK(cudaGetLastError());
+    } catch (const CudaFail &f) {
+        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
+        rc = (f.e == cudaErrorMemoryAllocation) ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
+        cudaGetLastError();
+    } catch (...) {
+        set_error(ctx, "unexpected internal error");
+        rc = ROGTK_ERR_INTERNAL;
+    }
+    if (rc != ROGTK_OK) {
+        for (void *p : own->ptrs) {
+            if (own->on_device) cudaFreeAsync(p, ctx->stream);
+            else pinned_put(ctx, p);
+        }
+        delete own;
+        memset(out, 0, sizeof(*out));
+    }
+    return rc;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // global k-mer spectrum
 // -----------------------------------------------------------------------------------------------------------------
 extern "C" int rogtk_gpu_spectrum_owner(uint64_t kmer_lo, uint64_t kmer_hi, int k_eff, int n_ranks)

@@ -319,3 +319,12 @@ class Engine:
                                                        ctypes.c_void_p(d_counts), ctypes.c_void_p(d_exts), int(n), int(k_eff_),
                                                        int(min_coverage), int(flags) & ~_ffi.OUTPUT_ON_DEVICE, ctypes.byref(out)))
         return self._to_numpy(out)
+
+    # ---- threshold re-use -------------------------------------------------------------------------------------------
+    def rethreshold(self, batch: DeviceBatch, min_coverage: int, flags: int = 0) -> GraphBatch:
+        """The batch the hot path would return for a higher min_coverage, from a device-resident batch counted once at a lower
+        one (sweep_assembly_params / optimize_assembly re-count all reads per cell in the reference)."""
+        out = _ffi.GraphBatchC()
+        self._check(self._lib.rogtk_gpu_rethreshold(self._ctx, ctypes.byref(batch._c), int(min_coverage),
+                                                    int(flags) & ~_ffi.OUTPUT_ON_DEVICE, ctypes.byref(out)))
+        return self._to_numpy(out)

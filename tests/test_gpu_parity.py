@@ -268,3 +268,36 @@ def test_global_spectrum_single_rank_and_emulated_sources(engine, oracle):
             assert np.array_equal(np.concatenate([p.kmers_hi for p in pieces]), ref.kmers_hi)
         assert np.array_equal(np.concatenate([p.exts for p in pieces]), ref.exts)
         assert np.array_equal(np.concatenate([p.counts for p in pieces]), ref.counts)
+
+
+def test_threshold_reuse_matches_recount(engine, oracle):
+    """one count at min_coverage=1 serves every higher threshold of the sweep / optimise drivers
+    (reference src/expressions.rs:901-941, src/fracture_opt.rs:163-218) bit-for-bit."""
+    rng = np.random.default_rng(123)
+    groups = random_groups(rng, 80, max_reads=30, max_len=150, tmpl_len=200, err=0.03)
+    data, offs, validity, goff = groups_to_arrow(groups)
+    for k in (12, 31, 50):
+        base = engine.count_prune_to_device(data, offs, goff, k, 1, validity=validity)
+        try:
+            for mc in (1, 2, 3, 5, 9, 70000):
+                got = engine.rethreshold(base, mc, flags=EMIT_STATS | EMIT_CSR)
+                ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity, emit_csr=True)
+                assert_batches_equal(got, ref, check_csr=True, ctx=f"rethreshold k={k} mc={mc}")
+        finally:
+            base.free()
+
+
+def test_low_complexity_groups_crowded_sort_buckets(engine, oracle):
+    """Many surviving k-mers sharing their leading bases (homopolymer-rich reads) overflow the counting-sort buckets of
+    k_sort_small and must take the bitonic kernel; order and content must not change."""
+    rng = np.random.default_rng(2024)
+    groups = []
+    for g in range(12):
+        reads = []
+        for _ in range(40):
+            tail = "".join("ACGT"[x] for x in rng.integers(0, 4, 40))
+            reads.append("A" * int(rng.integers(30, 60)) + tail + "A" * int(rng.integers(5, 40)) + tail[:20])
+        groups.append(reads)
+    data, offs, validity, goff = groups_to_arrow(groups)
+    for k, mc in ((31, 1), (16, 1), (40, 1), (31, 2)):
+        _both(engine, oracle, data, offs, goff, k, mc, validity=validity, ctx=f"low complexity k={k} mc={mc}")
