@@ -107,25 +107,32 @@ def algorithmic_bytes(n_groups, n_reads, n_bytes, n_kmers, key_bytes=8):
     return n_bytes + 8 * (n_reads + n_groups) + n_kmers * (key_bytes + 3) + 8 * n_groups
 
 
-def cpu_baseline(cfg, target_seconds=15.0, threads=0):
-    """Time the oracle (C restatement of the reference algorithm, one group per OpenMP task) on a bounded sample."""
+def cpu_baseline(cfg, host=None, target_seconds=15.0, threads=0):
+    """Time the oracle (C restatement of the reference algorithm, one group per OpenMP task) on a bounded sample of the
+    workload: a prefix of the host copy of the bench input when there is one (host = (data, offsets, group_offsets) numpy
+    views), else a numpy-generated prefix."""
     from oracle import dbg_oracle
     from rogtk_b200 import synth
     seed = synth.config_seed(cfg["config_id"])
     cores = dbg_oracle.max_threads() if threads <= 0 else threads
+    R, L = cfg["reads"], cfg["read_len"]
 
     def run(n):
-        data, offs, goff = synth.synth_reads(seed, 0, n, cfg["reads"], cfg["read_len"], cfg["template"], cfg["err64k"])
+        if host is not None:
+            data, offs, goff = host[0][:n * R * L], host[1][:n * R + 1], host[2][:n + 1]
+        else:
+            data, offs, goff = synth.synth_reads_chunked(seed, 0, n, R, L, cfg["template"], cfg["err64k"])
         t0 = time.perf_counter()
         b = dbg_oracle.count_prune_batch(data, offs, goff, cfg["k"], cfg["min_cov"], n_threads=cores)
         return time.perf_counter() - t0, b.n_observations
 
-    n0 = min(cfg["n_umis"], max(1024, 64 * cores))
+    n0 = min(cfg["n_umis"], max(4096, 512 * cores))
     t, obs = run(n0)
     rate = obs / max(t, 1e-9)
     per_umi = obs / n0
     n = int(min(cfg["n_umis"], max(n0, rate * target_seconds / per_umi)))
-    n = min(n, 60000)   # bound host memory for the sample (<= ~1 GB of reads)
+    if host is None:
+        n = min(n, 60000)   # bound generation time / memory when the sample has to be generated on the host
     t, obs = run(n)
     return {"value": obs / t, "unit": "obs/s", "cores": cores, "kind": "port",
             "sample": f"first {n} UMIs of {cfg['name']} ({obs} observations, {t:.2f} s); C restatement of the reference "
@@ -166,9 +173,9 @@ def main():
         from oracle import dbg_oracle
         from rogtk_b200 import synth
         cores = dbg_oracle.max_threads()
-        n = min(cfg["n_umis"], max(8192, 1024 * cores))
-        data, offs, goff = synth.synth_reads(synth.config_seed(cfg["config_id"]), 0, n, cfg["reads"], cfg["read_len"],
-                                             cfg["template"], cfg["err64k"])
+        n = min(cfg["n_umis"], max(8192, 4096 * cores))
+        data, offs, goff = synth.synth_reads_chunked(synth.config_seed(cfg["config_id"]), 0, n, cfg["reads"], cfg["read_len"],
+                                                     cfg["template"], cfg["err64k"])
         obs = 0
         for _ in range(max(1, min(args.warmup, 1))):
             obs = dbg_oracle.count_prune_batch(data, offs, goff, cfg["k"], cfg["min_cov"], n_threads=cores).n_observations
@@ -258,12 +265,17 @@ def main():
     peak, peak_src = load_peaks()
     alg = algorithmic_bytes(n_umis, n_reads, n_bytes, n_kmers)
     achieved = alg / (ms_hot_avg * 1e-3) / 1e9 if ms_hot_avg > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM traffic of k_smem_count from the committed ncu --set full capture (profiles/r01_ncu_k_smem_count_full.txt:
+    # dram__bytes_read.sum 309.33 MB + dram__bytes_write.sum 154.50 MB for a 20 000-UMI launch of this workload shape),
+    # scaled to this launch's UMI count; only quoted for the shape it was measured on.
+    traffic = (309.33376e6 + 154.495488e6) / 20000.0 * n_umis if cfg["name"] == "cfg2" else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k_smem_count<1>", "kernel_ms": ms_hot_avg, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                 "pipeline_frac": alg / (ms_dev_max * 1e-3) / 1e9 / peak}
 
     # ---- e2e: host (pinned) Arrow buffers -> C ABI -> host arrays; H2D + D2H inside the timed region -------------------
     e2e = None
+    cpu = None
     if not args.no_e2e:
         import ctypes
         h_data = eng.pinned_alloc(n_bytes + 16)
@@ -301,11 +313,17 @@ def main():
         e2e = {"value": obs_all / dt, "unit": "obs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
                "api": "rogtk_gpu_count_prune_batch (C ABI via ctypes), pinned host Arrow buffers in, pinned host arrays out"}
+        host_views = None
+        if rank == 0 and args.gpus == 1 and not args.no_cpu:
+            def view(ptr, n, dt):
+                ct = np.ctypeslib.as_ctypes_type(np.dtype(dt))
+                return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,))
+            host_views = (view(h_data, n_bytes, np.uint8), view(h_off, n_reads + 1, np.int64), view(h_goff, n_umis + 1, np.int64))
+            cpu = cpu_baseline(cfg, host=host_views)
         for p in (h_data, h_off, h_goff):
             eng.pinned_free(p)
 
-    cpu = None
-    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+    if cpu is None and rank == 0 and args.gpus == 1 and not args.no_cpu:
         cpu = cpu_baseline(cfg)
 
     if rank == 0:

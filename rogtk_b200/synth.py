@@ -63,3 +63,15 @@ def skewed_reads_per_umi(seed: int, n_umis: int, max_reads: int = 5000) -> np.nd
     """cfg3: reads/UMI = floor(exp(U(0, ln max_reads))) clamped to [1, max_reads] (log-uniform skew)."""
     u = (_sm(np.uint64(seed ^ 0x5EED), np.arange(n_umis, dtype=np.uint64)) >> np.uint64(11)).astype(np.float64) / float(1 << 53)
     return np.clip(np.floor(np.exp(u * np.log(max_reads))), 1, max_reads).astype(np.int64)
+
+
+def synth_reads_chunked(seed: int, umi_base: int, n_umis: int, reads_per_umi: int, read_len: int, template_len: int,
+                        err_per_64k: int = 655, chunk: int = 4096):
+    """synth_reads for large n_umis with bounded temporary memory (fixed reads_per_umi)."""
+    parts = []
+    for a in range(0, n_umis, chunk):
+        b = min(n_umis, a + chunk)
+        parts.append(synth_reads(seed, umi_base + a, b - a, reads_per_umi, read_len, template_len, err_per_64k)[0])
+    data = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+    n_reads = n_umis * reads_per_umi
+    return data, np.arange(n_reads + 1, dtype=np.int64) * read_len, np.arange(n_umis + 1, dtype=np.int64) * reads_per_umi
