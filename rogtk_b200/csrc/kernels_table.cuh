@@ -65,7 +65,9 @@ struct SpillArgs {
     int64_t pool_cap;
     int64_t *nsurv;                // [n_groups] survivors per group (global index)
     int *overflow;                 // set when the record pool is too small
-    int count_only;                // extraction dry run: only bump pool_cursor
+    int count_only;                // pass 1: only count survivors per warp
+    int64_t *warp_count;           // [n_extract_warps] pass 1 output
+    const int64_t *warp_base;      // [n_extract_warps + 1] exclusive scan of warp_count (pass 2 input)
 };
 
 // per listed group: rows and table capacity (power of two >= 1.5x the observation upper bound)
@@ -203,76 +205,93 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32) k_spill_insert(SpillArgs a)
     }
 }
 
-// one thread per slot: survivors -> record pool, per-group survivor counts
+// Survivors -> record pool, per-group survivor counts.  Every warp owns SPILL_EXTRACT_SLOTS consecutive slots.  Pass 1
+// (count_only) writes the number of survivors of each warp; after an exclusive scan pass 2 writes the records at
+// warp_base + running rank: no global cursor (a single cursor serialised ~15 M same-address atomics and made this kernel
+// 10 ms for 7 GB of table, profiles/r01 notes), deterministic pool order.
+constexpr int SPILL_EXTRACT_NT = 256;
+constexpr int SPILL_EXTRACT_SLOTS = 2048;   // per warp
 template <int W>
-__global__ void k_spill_extract(SpillArgs a)
+__global__ void __launch_bounds__(SPILL_EXTRACT_NT) k_spill_extract(SpillArgs a)
 {
     using S = KeySlot<W>;
     const int64_t total = a.slot_off[a.n_list];
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = false;
-    SpillRec rec;
-    int64_t g = 0;
-    if (slot < total) {
+    const unsigned lane = lane_id();
+    const int64_t gw = (int64_t)blockIdx.x * (SPILL_EXTRACT_NT / 32) + (threadIdx.x >> 5);
+    const int64_t w0 = gw * SPILL_EXTRACT_SLOTS;
+    if (w0 >= total) return;
+    int64_t i0 = 0;   // listed group of the warp's first slot
+    if (lane == 0) {
         int64_t lo = 0, hi = a.n_list;
         while (hi - lo > 1) {
             int64_t m = (lo + hi) >> 1;
-            if (a.slot_off[m] <= slot) lo = m; else hi = m;
+            if (a.slot_off[m] <= w0) lo = m; else hi = m;
         }
-        const int64_t i = lo;
-        g = a.ids ? a.ids[a.list_base + i] : a.list_base + i;
-        const typename S::T kp = reinterpret_cast<const typename S::T *>(a.keys)[slot];
-        if (kp != S::empty()) {
-            uint32_t v = a.vals[slot];
-            uint32_t c = v & TV_COUNT_MASK;
-            if (c > 65535u) c = 65535u;
-            if (c >= a.min_cov && c > 0) {
-                Key<W> k = S::unpack(kp);
-                rec.hi = k.hi_word();
-                rec.lo = k.lo;
-                rec.grank = (uint32_t)(a.list_base + i);
-                rec.val = c | ((v >> 24) << 16);
-                keep = true;
-            }
-        }
-        // the all-ones k-mer lives outside the table; emitted by the thread of the group's first slot
-        if (slot == a.slot_off[i]) {
-            uint32_t v = a.special[i];
-            uint32_t c = v & TV_COUNT_MASK;
-            if (c > 65535u) c = 65535u;
-            if (c >= a.min_cov && c > 0) {
-                unsigned long long pos = atomicAdd(a.pool_cursor, 1ull);
-                if (a.count_only) {
-                } else if ((int64_t)pos < a.pool_cap) {
-                    SpillRec r2;
-                    const int kbits = 2 * a.K;
-                    r2.lo = kbits >= 64 ? ~0ull : ((1ull << kbits) - 1ull);
-                    r2.hi = kbits >= 128 ? ~0ull : (kbits > 64 ? ((1ull << (kbits - 64)) - 1ull) : 0ull);
-                    r2.grank = (uint32_t)(a.list_base + i);
-                    r2.val = c | ((v >> 24) << 16);
-                    a.pool[pos] = r2;
-                } else {
-                    *a.overflow = 1;
+        i0 = lo;
+    }
+    i0 = __shfl_sync(0xffffffffu, i0, 0);
+    int64_t running = a.count_only ? 0 : a.warp_base[gw];
+    const int kbits = 2 * a.K;
+    for (int64_t slot = w0 + lane; slot - lane < w0 + SPILL_EXTRACT_SLOTS && slot - lane < total; slot += 32) {
+        bool keep = false, keep_special = false;
+        SpillRec rec{}, rec2{};
+        int64_t g = -1;
+        if (slot < total) {
+            int64_t i = i0;
+            while (i + 1 < a.n_list && a.slot_off[i + 1] <= slot) i++;
+            g = a.ids ? a.ids[a.list_base + i] : a.list_base + i;
+            const typename S::T kp = reinterpret_cast<const typename S::T *>(a.keys)[slot];
+            if (kp != S::empty()) {
+                const uint32_t v = a.vals[slot];
+                uint32_t c = v & TV_COUNT_MASK;
+                if (c > 65535u) c = 65535u;
+                if (c >= a.min_cov && c > 0) {
+                    const Key<W> k = S::unpack(kp);
+                    rec.hi = k.hi_word();
+                    rec.lo = k.lo;
+                    rec.grank = (uint32_t)(a.list_base + i);
+                    rec.val = c | ((v >> 24) << 16);
+                    keep = true;
                 }
-                if (!a.count_only) atomicAdd(reinterpret_cast<unsigned long long *>(a.nsurv + g), 1ull);
+            }
+            // the all-ones k-mer lives outside the table; emitted by the thread of the group's first slot
+            if (slot == a.slot_off[i]) {
+                const uint32_t v = a.special[i];
+                uint32_t c = v & TV_COUNT_MASK;
+                if (c > 65535u) c = 65535u;
+                if (c >= a.min_cov && c > 0) {
+                    rec2.lo = kbits >= 64 ? ~0ull : ((1ull << kbits) - 1ull);
+                    rec2.hi = kbits >= 128 ? ~0ull : (kbits > 64 ? ((1ull << (kbits - 64)) - 1ull) : 0ull);
+                    rec2.grank = (uint32_t)(a.list_base + i);
+                    rec2.val = c | ((v >> 24) << 16);
+                    keep_special = true;
+                }
+            }
+            if (lane == 31) i0 = i;   // the next 32 slots start in this group or later
+        }
+        i0 = __shfl_sync(0xffffffffu, i0, 31);
+        const unsigned m = __ballot_sync(0xffffffffu, keep), m2 = __ballot_sync(0xffffffffu, keep_special);
+        const unsigned n_new = __popc(m) + __popc(m2);
+        if (n_new == 0) continue;
+        if (!a.count_only) {
+            if (keep) a.pool[running + __popc(m & ((1u << lane) - 1u))] = rec;
+            if (keep_special) a.pool[running + __popc(m) + __popc(m2 & ((1u << lane) - 1u))] = rec2;
+            // survivors per group: one add per warp step when all its survivors share a group (the common case)
+            const int leader = m ? __ffs(m) - 1 : __ffs(m2) - 1;
+            const int64_t g_lead = __shfl_sync(0xffffffffu, g, leader);
+            const bool uniform = __all_sync(0xffffffffu, (!keep && !keep_special) || g == g_lead);
+            if (uniform) {
+                if ((int)lane == leader) atomicAdd(reinterpret_cast<unsigned long long *>(a.nsurv + g_lead), (unsigned long long)n_new);
+            } else {
+                if (keep) atomicAdd(reinterpret_cast<unsigned long long *>(a.nsurv + g), 1ull);
+                if (keep_special) atomicAdd(reinterpret_cast<unsigned long long *>(a.nsurv + g), 1ull);
             }
         }
+        running += n_new;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
-        const unsigned lane = lane_id();
-        unsigned long long base = 0;
-        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(a.pool_cursor, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (keep && !a.count_only) {
-            unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-            if ((int64_t)pos < a.pool_cap) a.pool[pos] = rec; else *a.overflow = 1;
-            atomicAdd(reinterpret_cast<unsigned long long *>(a.nsurv + g), 1ull);
-        }
-    }
+    if (a.count_only && lane == 0) a.warp_count[gw] = running;
 }
 
-// sorted records -> structure-of-arrays output for the listed groups
 __global__ void k_add_i64(int64_t *p, int64_t n, int64_t v)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

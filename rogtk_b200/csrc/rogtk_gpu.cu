@@ -170,26 +170,26 @@ void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_of
             k_spill_insert<W><<<grid, SPILL_WARPS * 32, 0, st>>>(a);
             ctx->launches++;
         }
-        // pass 1: count the wave's survivors so that the record pool is sized exactly
-        DevBuf cnt(8, st);
-        CK(cudaMemsetAsync(cnt.p, 0, 8, st));
-        {
-            SpillArgs c = a;
-            c.count_only = 1;
-            c.pool_cursor = cnt.as<unsigned long long>();
-            k_spill_extract<W><<<blocks_for(total_slots, 256), 256, 0, st>>>(c);
-            ctx->launches++;
-        }
-        unsigned long long h_cnt = 0;
-        CK(cudaMemcpyAsync(&h_cnt, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+        // pass 1: survivors per extraction warp -> exclusive scan -> exact pool size and every warp's first record
+        const int64_t n_xw = (total_slots + SPILL_EXTRACT_SLOTS - 1) / SPILL_EXTRACT_SLOTS;
+        const unsigned x_grid = blocks_for(n_xw, SPILL_EXTRACT_NT / 32);
+        DevBuf wcount((size_t)std::max<int64_t>(n_xw, 1) * 8, st), wbase((size_t)(n_xw + 1) * 8, st), wscr(scan_scratch_bytes(n_xw), st);
+        CK(cudaMemsetAsync(wcount.p, 0, wcount.bytes, st));
+        a.warp_count = wcount.as<int64_t>();
+        a.warp_base = wbase.as<int64_t>();
+        a.count_only = 1;
+        k_spill_extract<W><<<x_grid, SPILL_EXTRACT_NT, 0, st>>>(a);
+        exclusive_scan<int64_t>(wcount.as<int64_t>(), n_xw, wbase.as<int64_t>(), wscr.as<int64_t>(), st, &ctx->launches);
+        int64_t h_cnt = 0;
+        CK(cudaMemcpyAsync(&h_cnt, wbase.as<int64_t>() + n_xw, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        wv.n_recs = (int64_t)h_cnt;
+        wv.n_recs = h_cnt;
         wv.recs.alloc((size_t)std::max<int64_t>(1, wv.n_recs) * sizeof(SpillRec), st);
         a.pool = wv.recs.as<SpillRec>();
         a.pool_cap = wv.n_recs;
-        CK(cudaMemsetAsync(cursor.p, 0, 16, st));
-        k_spill_extract<W><<<blocks_for(total_slots, 256), 256, 0, st>>>(a);
-        ctx->launches++;
+        a.count_only = 0;
+        k_spill_extract<W><<<x_grid, SPILL_EXTRACT_NT, 0, st>>>(a);
+        ctx->launches += 2;
         if (wv.n_recs > 1) {
             size_t tmp_bytes = 0;
             CK(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, wv.recs.as<SpillRec>(), wv.n_recs, SpillRecLess(), st));
