@@ -8,6 +8,27 @@
 namespace rogtk {
 
 // ---------------------------------------------------------------------------------------------------------------
+// input validation: a malformed column must come back as ROGTK_ERR_INVALID_ARG, never as an out-of-bounds access
+// err bits: 1 offsets decrease / negative, 2 offsets exceed the data buffer, 4 group_offsets not monotone / out of range
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_validate(ColView col, int64_t data_len, const int64_t *group_offsets, int64_t n_groups, int *err)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int e = 0;
+    for (int64_t r = t; r < col.n_rows; r += stride) {
+        const int64_t a = col_off(col, col.row_begin + r), b = col_off(col, col.row_begin + r + 1);
+        if (a < 0 || b < a) e |= 1;
+        if (b > data_len) e |= 2;
+    }
+    for (int64_t g = t; g < n_groups; g += stride) {
+        const int64_t a = group_offsets[g], b = group_offsets[g + 1];
+        if (a < col.row_begin || b < a || b > col.row_begin + col.n_rows) e |= 4;
+    }
+    if (e) atomicOr(err, e);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Arrow Utf8View -> contiguous (LargeUtf8-like) column
 // view = { u32 len; if len<=12: 12 inline bytes; else u32 prefix, u32 buffer_index, u32 offset }
 // ---------------------------------------------------------------------------------------------------------------

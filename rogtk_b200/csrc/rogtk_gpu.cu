@@ -426,6 +426,22 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     CK(cudaMemsetAsync(nsurv.p, 0, nsurv.bytes, st));
     CK(cudaMemsetAsync(misc.p, 0, 64, st));
     unsigned long long *d_nobs = misc.as<unsigned long long>();
+    {   // reject malformed offsets before any kernel dereferences them
+        int *d_err = reinterpret_cast<int *>(misc.as<unsigned long long>() + 4);
+        const int64_t data_len = (int64_t)(in.data_end - in.col.data);   // virtual-base aware: offsets are absolute
+        k_validate<<<ctx->sm_count * 4, 256, 0, st>>>(in.col, data_len, in.group_offsets, n_groups, d_err);
+        ctx->launches++;
+        int h_err = 0;
+        CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_err) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "malformed input:%s%s%s", (h_err & 1) ? " string offsets not monotone;" : "",
+                     (h_err & 2) ? " string offsets exceed the data buffer;" : "",
+                     (h_err & 4) ? " group_offsets not monotone or outside the rows;" : "");
+            throw ArgFail{ROGTK_ERR_INVALID_ARG, msg};
+        }
+    }
 
     // ---- counting -------------------------------------------------------------------------------------------
     CK(cudaEventRecord(ctx->ev[1], st));
@@ -734,6 +750,15 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
         return ROGTK_OK;
     }
 
+    if (!in_dev && n_groups > 0) {   // host-visible group offsets: reject nonsense before the host itself indexes with them
+        int64_t prev = group_offsets[0];
+        bool ok = prev >= 0;
+        for (int64_t g = 1; g <= n_groups && ok; g++) {
+            ok = group_offsets[g] >= prev;
+            prev = group_offsets[g];
+        }
+        if (!ok || prev > reads->n_rows) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: group_offsets not monotone or outside the rows;"};
+    }
     // host input + host output of a large offsets-layout column: chunked, copies overlapped with compute
     if (!in_dev && !out_dev && (reads->layout == ROGTK_UTF8_I32 || reads->layout == ROGTK_UTF8_I64) && reads->n_buffers == 1 &&
         reads->data && reads->data_len && n_groups > 1 && reads->data_len[0] > (int64_t)ctx->chunk_bytes + (ctx->chunk_bytes >> 1)) {

@@ -301,3 +301,23 @@ def test_low_complexity_groups_crowded_sort_buckets(engine, oracle):
     data, offs, validity, goff = groups_to_arrow(groups)
     for k, mc in ((31, 1), (16, 1), (40, 1), (31, 2)):
         _both(engine, oracle, data, offs, goff, k, mc, validity=validity, ctx=f"low complexity k={k} mc={mc}")
+
+
+def test_malformed_input_is_rejected_not_faulted(engine):
+    """Bad offsets / group offsets come back as ROGTK_ERR_INVALID_ARG; the context stays usable."""
+    import rogtk_b200
+    data = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT", dtype=np.uint8)
+    good_off = np.array([0, 20, 40], dtype=np.int64)
+    cases = [
+        (np.array([0, 30, 20], dtype=np.int64), np.array([0, 2])),      # offsets decrease
+        (np.array([0, 20, 4000], dtype=np.int64), np.array([0, 2])),    # offsets beyond the data buffer
+        (good_off, np.array([0, 5])),                                    # group beyond the rows
+        (good_off, np.array([0, 2, 1])),                                 # group offsets decrease
+        (np.array([-5, 20, 40], dtype=np.int64), np.array([0, 2])),     # negative offset
+    ]
+    for offs, goff in cases:
+        with pytest.raises(rogtk_b200.RogtkGpuError) as ei:
+            engine.count_prune(data, offs, goff, 17, 1)
+        assert ei.value.code == -1
+    got = engine.count_prune(data, good_off, np.array([0, 2]), 8, 1)
+    assert got.n_observations == 26
