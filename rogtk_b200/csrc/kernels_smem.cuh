@@ -494,10 +494,38 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                         pend[u] = first_probe(kp, h[u], ex[u], cur[u]);
                     }
                     __syncwarp();
+                    // collided observations of the four windows -> queue, with one warp scan when they fit at once
+                    const uint32_t c = (uint32_t)pend[0] + pend[1] + pend[2] + pend[3];
+                    uint32_t incl = c;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
-                        queue_push<W>(wq, pend[u], kp, h[u], ex[u], tkey, tval, tmask, lane);
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= (uint32_t)d) incl += y;
+                    }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                    if (tot != 0u && wq.n + tot <= (uint32_t)SM_QCAP) {
+                        uint32_t i = wq.n + incl - c;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (pend[u]) {
+                                wq.key[i] = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
+                                wq.hx[i] = h[u] | (ex[u] << 16);
+                                i++;
+                            }
+                        }
+                        wq.n += tot;
+                        __syncwarp();
+                        while (wq.n >= 32u && wq.budget > 0) {
+                            queue_drain_step<W>(wq, tkey, tval, tmask, lane);
+                            wq.budget--;
+                        }
+                        if (wq.n >= 32u) wq.n = 0;   // budget exhausted (checked by the caller)
+                    } else if (tot != 0u) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
+                            queue_push<W>(wq, pend[u], kp, h[u], ex[u], tkey, tval, tmask, lane);
+                        }
                     }
                 } else {
                     // ---- generic: 32 windows per pass, one per lane ------------------------------------------------------------------
