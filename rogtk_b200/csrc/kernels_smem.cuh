@@ -66,7 +66,6 @@ struct SmemArgs {
     int32_t *deferred_ids;           // groups handed to the HBM-table path
     unsigned long long *n_deferred;
     unsigned long long *phase_cycles;   // optional [8] per-phase SM cycles summed over CTAs (diagnostics)
-    int cas_first;                      // tuning knob: probe with the CAS itself instead of LDS + CAS
 };
 
 // multiplicative hash, slot = top bits.  On the synthetic shapes it probes 1.32 slots per observation vs 1.31 for a
@@ -449,14 +448,20 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                 const uint32_t nk = rstart[lo + 1] - rs - (uint32_t)K + 1u;
                 const uint32_t p0 = (unit - ucum[lo]) * SM_UNIT;
                 const uint32_t rem = nk - p0;
-                if (K32 && rem >= (uint32_t)SM_UNIT) {
-                    // ---- full unit, K == 32: lane owns windows p0+4*lane .. +3; five packed words hold all their bases ------------
-                    const uint32_t p = p0 + 4u * lane;
+                const uint32_t ulen = rem < (uint32_t)SM_UNIT ? rem : (uint32_t)SM_UNIT;   // windows of this unit
+                // The 4-windows-per-lane path costs the same for any number of windows, the generic path costs one pass per 32
+                // windows: short read tails (269 = 128 + 128 + 13) take the generic path, everything else the wide one.
+                if (K32 && ulen > 48u) {
+                    // ---- K == 32: lane owns R <= 4 consecutive windows p0+R*lane ..; five packed words hold all their bases ---------
+                    const uint32_t R = (ulen + 31u) >> 5;
+                    const uint32_t j0 = R * lane;                        // first window of this lane inside the unit
+                    const uint32_t p = p0 + (j0 < ulen ? j0 : 0u);       // idle lanes read the unit's first words (in bounds)
                     const uint32_t q = rs + p;
                     const int32_t w = (int32_t)(q >> 4);
                     const uint32_t s = 2u * (q & 15u);
                     const uint32_t xm = pk[w - 1], x0 = pk[w], x1 = pk[w + 1], x2 = pk[w + 2], x3 = pk[w + 3];
                     uint32_t kh[4], kl[4], ex[4], h[4];
+                    bool act[4];
                     kh[0] = __funnelshift_l(x1, x0, s);
                     kl[0] = __funnelshift_l(x2, x1, s);
                     const uint32_t tail = __funnelshift_l(x3, x2, s);        // bases q+32 .. q+47
@@ -467,6 +472,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                         const uint32_t lb = u ? (kh[u - 1] >> 30) : lb0;     // left neighbour of window u
                         const bool has_l = u ? true : (p != 0u);
                         const bool has_r = (p + u + 1u) < nk;
+                        act[u] = (uint32_t)u < R && j0 + (uint32_t)u < ulen;
                         ex[u] = (has_l ? (1u << lb) : 0u) | (has_r ? (16u << nb) : 0u);
                         h[u] = hash32(kl[u], kh[u]) >> tshift;
                         if (u < 3) {
@@ -475,23 +481,13 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                         }
                     }
                     KT cur[4];
-                    if (a.cas_first) {
-                        // probe with the claim itself: returns EMPTY (claimed), the key (hit) or another key (collision).
-                        // The all-ones k-mer would "claim" an EMPTY slot without changing it, so it is diverted first.
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
-                            cur[u] = (kp == S::empty()) ? kp : atomicCAS(&tkey[h[u]], S::empty(), kp);
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; u++) cur[u] = tkey[h[u]];
-                    }
+                    for (int u = 0; u < 4; u++) cur[u] = act[u] ? tkey[h[u]] : S::empty();
                     bool pend[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
-                        pend[u] = first_probe(kp, h[u], ex[u], cur[u]);
+                        pend[u] = act[u] ? first_probe(kp, h[u], ex[u], cur[u]) : false;
                     }
                     __syncwarp();
                     // collided observations of the four windows -> queue, with one warp scan when they fit at once
@@ -529,13 +525,12 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                     }
                 } else {
                     // ---- generic: 32 windows per pass, one per lane ------------------------------------------------------------------
-                    const uint32_t cnt = rem < (uint32_t)SM_UNIT ? rem : (uint32_t)SM_UNIT;
-                    for (uint32_t pb = 0; pb < cnt; pb += 32u) {
+                    for (uint32_t pb = 0; pb < ulen; pb += 32u) {
                         const uint32_t p = p0 + pb + lane;
                         bool pend = false;
                         KT kp = S::empty();
                         uint32_t h = 0, ex = 0;
-                        if (p < nk) {
+                        if (pb + lane < ulen) {
                             const uint32_t q = rs + p;
                             Key<W> key = Key<W>::zero();
                             load_window(pk, q, K, key);
@@ -962,10 +957,6 @@ inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes,
     a.deferred_ids = d_ids;
     a.n_deferred = d_ctr + 2;
     a.phase_cycles = phase_out ? d_ctr + 8 : nullptr;
-    {
-        const char *e = getenv("ROGTK_CAS_FIRST");
-        a.cas_first = e ? atoi(e) : 0;
-    }
     CK(cudaEventRecord(ev_a, st));
     if (W == 1) {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 2);
