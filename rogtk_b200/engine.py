@@ -328,3 +328,46 @@ class Engine:
         self._check(self._lib.rogtk_gpu_rethreshold(self._ctx, ctypes.byref(batch._c), int(min_coverage),
                                                     int(flags) & ~_ffi.OUTPUT_ON_DEVICE, ctypes.byref(out)))
         return self._to_numpy(out)
+
+    # ---- Arrow-native entry: one call per frame ----------------------------------------------------------------------
+    def count_prune_arrow(self, reads, k: int, min_coverage: int, flags: int = 0) -> GraphBatch:
+        """`reads` is a pyarrow List/LargeList of String/LargeString/StringView (one row per UMI group: what
+        `df.group_by("umi").agg(pl.col("seq"))` hands to a batched plugin call), or a ChunkedArray of those.  The list
+        offsets are the group offsets; the child string buffers go to the C ABI without re-encoding.  Null lists are empty
+        groups, null strings are dropped (reference src/expressions.rs:737-740)."""
+        import pyarrow as pa
+        if isinstance(reads, pa.ChunkedArray):
+            reads = reads.combine_chunks() if reads.num_chunks != 1 else reads.chunk(0)
+        if not (pa.types.is_list(reads.type) or pa.types.is_large_list(reads.type)):
+            raise TypeError("expected a List(String) / LargeList(String) array (one row per group)")
+        n_groups = len(reads)
+        odt = np.int64 if pa.types.is_large_list(reads.type) else np.int32
+        lbufs = reads.buffers()
+        goff = np.frombuffer(lbufs[1], dtype=odt)[reads.offset:reads.offset + n_groups + 1].astype(np.int64)
+        if reads.null_count:   # a null list is an empty group
+            valid = np.unpackbits(np.frombuffer(lbufs[0], dtype=np.uint8), bitorder="little")[reads.offset:reads.offset + n_groups]
+            lens = np.diff(goff) * valid
+            # rows of null lists are skipped by collapsing their range; keep absolute row indices monotone
+            keep_rows = np.repeat(valid.astype(bool), np.diff(goff))
+            child = reads.values.slice(int(goff[0]), int(goff[-1] - goff[0])).filter(pa.array(keep_rows))
+            goff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        else:
+            child = reads.values
+        ct = child.type
+        bufs = child.buffers()
+        validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None
+        if pa.types.is_string(ct) or pa.types.is_large_string(ct) or pa.types.is_binary(ct) or pa.types.is_large_binary(ct):
+            sdt = np.int64 if (pa.types.is_large_string(ct) or pa.types.is_large_binary(ct)) else np.int32
+            offs = np.frombuffer(bufs[1], dtype=sdt)[child.offset:child.offset + len(child) + 1]
+            data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None else np.zeros(0, np.uint8)
+            return self.count_prune(data, offs, goff, k, min_coverage, validity=validity, validity_bit_offset=child.offset,
+                                    flags=flags)
+        if hasattr(pa.types, "is_string_view") and (pa.types.is_string_view(ct) or pa.types.is_binary_view(ct)):
+            if child.offset or validity is not None and child.offset:
+                child = pa.concat_arrays([child])   # re-base a sliced view array
+                bufs = child.buffers()
+                validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None
+            views = np.frombuffer(bufs[1], dtype=np.uint8)[:len(child) * 16].reshape(-1, 16)
+            data_bufs = [np.frombuffer(b, dtype=np.uint8) for b in bufs[2:] if b is not None]
+            return self.count_prune_views(views, data_bufs, goff, k, min_coverage, validity=validity, flags=flags)
+        raise TypeError(f"unsupported child type {ct}")

@@ -321,3 +321,27 @@ def test_malformed_input_is_rejected_not_faulted(engine):
         assert ei.value.code == -1
     got = engine.count_prune(data, good_off, np.array([0, 2]), 8, 1)
     assert got.n_observations == 26
+
+
+def test_arrow_list_of_strings_entry(engine, oracle):
+    """a List(String) column (one row per UMI) goes through in one call; list offsets are the group offsets.
+    Covers String, LargeString and StringView children, null strings, null lists and a sliced array."""
+    import pyarrow as pa
+    rng = np.random.default_rng(31)
+    groups = random_groups(rng, 50, max_reads=9, max_len=90, tmpl_len=120, p_null=0.06)
+    data, offs, validity, goff = groups_to_arrow(groups)
+    ref = oracle.count_prune_batch(data, offs, goff, 17, 1, validity=validity)
+    for child_t, list_ctor in ((pa.string(), pa.list_), (pa.large_string(), pa.large_list), (pa.string_view(), pa.list_)):
+        arr = pa.array(groups, type=list_ctor(child_t))
+        got = engine.count_prune_arrow(arr, 17, 1, flags=EMIT_STATS)
+        assert_batches_equal(got, ref, ctx=f"arrow {child_t}")
+    # a sliced list array and a null list
+    arr = pa.array(groups, type=pa.list_(pa.string())).slice(7, 30)
+    d2, o2, v2, g2 = groups_to_arrow(groups[7:37])
+    assert_batches_equal(engine.count_prune_arrow(arr, 31, 2, flags=EMIT_STATS), oracle.count_prune_batch(d2, o2, g2, 31, 2, validity=v2),
+                         ctx="arrow slice")
+    with_null = list(groups[:10]) + [None] + list(groups[10:20])
+    arr = pa.array(with_null, type=pa.list_(pa.string()))
+    d3, o3, v3, g3 = groups_to_arrow(groups[:10] + [[]] + groups[10:20])
+    assert_batches_equal(engine.count_prune_arrow(arr, 17, 1, flags=EMIT_STATS), oracle.count_prune_batch(d3, o3, g3, 17, 1, validity=v3),
+                         ctx="arrow null list")
