@@ -197,6 +197,9 @@ def main():
     # ------------------------------------------------------------------------------------------------ our arm
     dist = None
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -278,6 +281,17 @@ def main():
     cpu = None
     if not args.no_e2e:
         import ctypes
+        # host memory is shared by all ranks of the node: the e2e leg takes the first e_umis UMIs of the rank's shard, as many
+        # as fit in 40 % of the available host memory divided by the ranks (pinned input + pinned result, ~27 KB per UMI)
+        try:
+            with open("/proc/meminfo") as f:
+                avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable"))
+        except Exception:
+            avail = 64 << 30
+        per_umi = R * L + 8 * R + 8 + 12 * 1100
+        e_umis = int(min(n_umis, max(1000, 0.4 * avail / world / per_umi)))
+        full_umis, full_reads, full_bytes = n_umis, n_reads, n_bytes
+        n_umis, n_reads, n_bytes = e_umis, e_umis * R, e_umis * R * L
         h_data = eng.pinned_alloc(n_bytes + 16)
         h_off = eng.pinned_alloc((n_reads + 1) * 8)
         h_goff = eng.pinned_alloc((n_umis + 1) * 8)
@@ -310,8 +324,9 @@ def main():
         dt = max_over_ranks(dt)
         h2d = n_bytes + (n_reads + 1) * 8 + (n_umis + 1) * 8
         d2h = nk * 11 + (n_umis + 1) * 8
-        e2e = {"value": obs_all / dt, "unit": "obs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+        e2e_obs = sum_over_ranks(float(n_reads * (L - 31)))
+        e2e = {"value": e2e_obs / dt, "unit": "obs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "umis_per_rank": n_umis,
                "api": "rogtk_gpu_count_prune_batch (C ABI via ctypes), pinned host Arrow buffers in, pinned host arrays out"}
         host_views = None
         if rank == 0 and args.gpus == 1 and not args.no_cpu:
@@ -322,6 +337,7 @@ def main():
             cpu = cpu_baseline(cfg, host=host_views)
         for p in (h_data, h_off, h_goff):
             eng.pinned_free(p)
+        n_umis, n_reads, n_bytes = full_umis, full_reads, full_bytes
 
     if cpu is None and rank == 0 and args.gpus == 1 and not args.no_cpu:
         cpu = cpu_baseline(cfg)

@@ -278,6 +278,10 @@ extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->pinned_size) cudaFreeHost(kv.first);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    {   // hand the stream-ordered pool's cached memory back to the device
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
