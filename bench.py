@@ -114,7 +114,9 @@ def cpu_baseline(cfg, host=None, target_seconds=15.0, threads=0):
     from oracle import dbg_oracle
     from rogtk_b200 import synth
     seed = synth.config_seed(cfg["config_id"])
-    cores = dbg_oracle.max_threads() if threads <= 0 else threads
+    if threads <= 0:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else dbg_oracle.max_threads()
+    cores = threads
     R, L = cfg["reads"], cfg["read_len"]
 
     def run(n):
@@ -172,8 +174,9 @@ def main():
         # oracle port of its algorithm on the host cores, each step a bounded sample of the same workload.
         from oracle import dbg_oracle
         from rogtk_b200 import synth
-        cores = dbg_oracle.max_threads()
-        n = min(cfg["n_umis"], max(8192, 4096 * cores))
+        # every host core the process may use (torchrun exports OMP_NUM_THREADS=1, which is not what this arm measures)
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        n = min(cfg["n_umis"], 65536, max(8192, 2048 * cores))
         data, offs, goff = synth.synth_reads_chunked(synth.config_seed(cfg["config_id"]), 0, n, cfg["reads"], cfg["read_len"],
                                                      cfg["template"], cfg["err64k"])
         obs = 0
@@ -203,7 +206,19 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL writes its version banner to stdout when the communicator is created; stdout must carry ONE JSON line, so the
+        # process-level stdout is pointed at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if dist is not None:
