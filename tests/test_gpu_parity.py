@@ -345,3 +345,51 @@ def test_arrow_list_of_strings_entry(engine, oracle):
     d3, o3, v3, g3 = groups_to_arrow(groups[:10] + [[]] + groups[10:20])
     assert_batches_equal(engine.count_prune_arrow(arr, 17, 1, flags=EMIT_STATS), oracle.count_prune_batch(d3, o3, g3, 17, 1, validity=v3),
                          ctx="arrow null list")
+
+
+def test_concurrent_contexts_from_host_threads(oracle):
+    """Polars calls the plugin concurrently from its rayon workers (SURVEY 8b "Threading"): one context per host thread must
+    give independent, correct results; a shared context must serialise safely."""
+    import threading
+    import rogtk_b200
+    rng = np.random.default_rng(99)
+    jobs = []
+    for t in range(4):
+        groups = random_groups(rng, 120, max_reads=12, max_len=120, tmpl_len=160)
+        data, offs, validity, goff = groups_to_arrow(groups)
+        jobs.append((data, offs, validity, goff, oracle.count_prune_batch(data, offs, goff, 31, 2, validity=validity)))
+    results, errors = [None] * 4, []
+    shared = rogtk_b200.Engine(device=0)
+
+    def work(i, own_ctx):
+        try:
+            eng = rogtk_b200.Engine(device=0) if own_ctx else shared
+            d, o, v, g, _ = jobs[i]
+            for _ in range(5):
+                results[i] = eng.count_prune(d, o, g, 31, 2, validity=v, flags=EMIT_STATS)
+            if own_ctx:
+                eng.close()
+        except Exception as e:   # pragma: no cover
+            errors.append(e)
+
+    for own_ctx in (True, False):
+        th = [threading.Thread(target=work, args=(i, own_ctx)) for i in range(4)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errors, errors
+        for i in range(4):
+            assert_batches_equal(results[i], jobs[i][4], ctx=f"thread {i} own_ctx={own_ctx}")
+    shared.close()
+
+
+def test_many_tiny_groups(engine, oracle):
+    """100 k groups of 1-3 short reads (the low end of the skewed config): per-group bookkeeping, empty groups included."""
+    rng = np.random.default_rng(5150)
+    n = 100_000
+    reads_per = rng.integers(0, 4, size=n)
+    lens = rng.integers(20, 60, size=int(reads_per.sum()))
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    data = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(offs[-1]))]
+    goff = np.concatenate([[0], np.cumsum(reads_per)]).astype(np.int64)
+    for k, mc in ((17, 1), (31, 1), (12, 2)):
+        _both(engine, oracle, data, offs, goff, k, mc, csr=False, ctx=f"tiny groups k={k}")
