@@ -483,15 +483,37 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                     KT cur[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) cur[u] = act[u] ? tkey[h[u]] : S::empty();
-                    bool pend[4];
+                    // the all-ones k-mer is the table's EMPTY marker: divert it to the side word first (one warp vote, rarely taken)
+                    {
+                        bool sp = false;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) sp |= act[u] && (kh[u] & kl[u]) == 0xffffffffu;
+                        if (__any_sync(0xffffffffu, sp)) {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (act[u] && (kh[u] & kl[u]) == 0xffffffffu) {
+                                    val_add(special, ex[u]);
+                                    act[u] = false;
+                                }
+                            }
+                        }
+                    }
+                    uint32_t pm = 0;   // bit u: window u collided and must queue
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
-                        pend[u] = act[u] ? first_probe(kp, h[u], ex[u], cur[u]) : false;
+                        KT c = cur[u];
+                        if (act[u] && c == S::empty()) c = atomicCAS(&tkey[h[u]], S::empty(), kp);
+                        const bool ok = (c == kp) | (c == S::empty());   // hit, or the claim went through
+                        if (act[u] && ok) val_add(&tval[h[u]], ex[u]);
+                        pm |= (act[u] && !ok) ? (1u << u) : 0u;
                     }
                     __syncwarp();
+                    bool pend[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) pend[u] = (pm >> u) & 1u;
                     // collided observations of the four windows -> queue, with one warp scan when they fit at once
-                    const uint32_t c = (uint32_t)pend[0] + pend[1] + pend[2] + pend[3];
+                    const uint32_t c = (uint32_t)__popc(pm);
                     uint32_t incl = c;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
