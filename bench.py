@@ -284,9 +284,9 @@ def main():
     alg = algorithmic_bytes(n_umis, n_reads, n_bytes, n_kmers)
     achieved = alg / (ms_hot_avg * 1e-3) / 1e9 if ms_hot_avg > 0 else 0.0
     # DRAM traffic of k_smem_count from the committed ncu --set full capture (profiles/r01_ncu_k_smem_count_full.txt:
-    # dram__bytes_read.sum 309.33 MB + dram__bytes_write.sum 154.50 MB for a 20 000-UMI launch of this workload shape),
+    # dram__bytes_read.sum 308.67 MB + dram__bytes_write.sum 156.22 MB for a 20 000-UMI launch of this workload shape),
     # scaled to this launch's UMI count; only quoted for the shape it was measured on.
-    traffic = (309.33376e6 + 154.495488e6) / 20000.0 * n_umis if cfg["name"] == "cfg2" else None
+    traffic = (308.670464e6 + 156.22144e6) / 20000.0 * n_umis if cfg["name"] == "cfg2" else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k_smem_count<1>", "kernel_ms": ms_hot_avg, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                 "pipeline_frac": alg / (ms_dev_max * 1e-3) / 1e9 / peak}
