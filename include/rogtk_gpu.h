@@ -161,7 +161,7 @@ int rogtk_gpu_memcpy_d2h(rogtk_gpu_ctx *ctx, void *dst, const void *src, size_t 
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx);
 /* diagnostics: enable per-phase clock64 accounting inside k_smem_count and read the cycles of the last batch
- * (0 meta, 1 ingest, 2 prefix+clear, 3 count, 4 histogram+scan, 5 scatter, 6 bucket fix-up), summed over CTAs */
+ * (0 meta, 1 ingest, 2 prefix+clear, 3 count, 4 prune+reserve, 5 compact), summed over CTAs */
 int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint64_t *out8);
 /* write a >L2 scratch buffer (L2 flush between timed iterations) */
 int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx);

@@ -1,5 +1,4 @@
-// kernels_post.cuh -- kernels either side of the counting step: Utf8View gather (ingest), final assembly of the
-// dense per-group output, node statistics (reference src/fracture.rs:124-141) and the successor CSR that stands in
+// kernels_post.cuh -- kernels either side of the counting step: input validation, Utf8View gather (ingest), node statistics (reference src/fracture.rs:124-141) and the successor CSR that stands in
 // for BaseGraph::finish()'s neighbour lookup (reference src/fracture.rs:343-348), plus the synthetic
 // read generator used by bench.py / tests.
 #pragma once
@@ -64,29 +63,8 @@ __global__ void k_view_gather(const View16 *views, int64_t n_rows, const uint8_t
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// final assembly
+// per-group outputs derived from the dense result
 // ---------------------------------------------------------------------------------------------------------------
-// shared-memory path survivors sit in a pool in completion order; copy group g's run to its dense position.
-// one warp per group (runs are ~1k entries), grid-stride.
-__global__ void k_gather_pool(int64_t n_groups, const int64_t *pool_start /* -1: not in pool */, const int64_t *kmer_offsets,
-                              const uint64_t *p_lo, const uint64_t *p_hi, const uint8_t *p_exts, const uint16_t *p_counts,
-                              uint64_t *o_lo, uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts)
-{
-    const unsigned lane = lane_id();
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += nw) {
-        const int64_t ps = pool_start[g];
-        if (ps < 0) continue;
-        const int64_t o = kmer_offsets[g], n = kmer_offsets[g + 1] - o;
-        for (int64_t j = lane; j < n; j += 32) {
-            o_lo[o + j] = p_lo[ps + j];
-            if (o_hi) o_hi[o + j] = p_hi[ps + j];
-            o_exts[o + j] = p_exts[ps + j];
-            o_counts[o + j] = p_counts[ps + j];
-        }
-    }
-}
-
 // node / terminal / isolated counts per group (reference src/fracture.rs:124-141); one warp per group
 __global__ void k_stats(int64_t n_groups, const int64_t *kmer_offsets, const uint8_t *exts, uint32_t *stats)
 {

@@ -1,6 +1,7 @@
 // kernels_smem.cuh -- the hot kernel: one CTA builds one UMI group's pruned de Bruijn node set entirely in shared
-// memory (ingest -> 2-bit pack -> rolling k-mers -> open-addressing table -> min-coverage compaction -> bucket sort
-// -> emit).  Replaces debruijn::filter::filter_kmers + CountFilter as called at reference src/fracture.rs:110-116.
+// memory (ingest -> 2-bit pack -> k-mer windows -> open-addressing table -> min-coverage compaction into a pool), plus
+// the per-group ordering kernels that turn the pool into the dense, ascending output.  Together they replace
+// debruijn::filter::filter_kmers + CountFilter as called at reference src/fracture.rs:110-116.
 //
 // Table protocol: open addressing with linear probing in shared memory, keys claimed with one 64/128-bit
 // atomicCAS, values updated with one 32-bit atomicAdd (count in bits 8..31, exts in bits 0..7, so the add can never

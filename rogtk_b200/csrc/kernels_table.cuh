@@ -61,10 +61,8 @@ struct SpillArgs {
     unsigned long long *n_obs;     // global accumulator
     // extraction
     SpillRec *pool;
-    unsigned long long *pool_cursor;
     int64_t pool_cap;
     int64_t *nsurv;                // [n_groups] survivors per group (global index)
-    int *overflow;                 // set when the record pool is too small
     int count_only;                // pass 1: only count survivors per warp
     int64_t *warp_count;           // [n_extract_warps] pass 1 output
     const int64_t *warp_base;      // [n_extract_warps + 1] exclusive scan of warp_count (pass 2 input)

@@ -142,11 +142,10 @@ void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_of
         CK(cudaStreamSynchronize(st));
         const int64_t total_rows = h_tot[0], total_slots = h_tot[1];
         DevBuf keys((size_t)total_slots * sizeof(typename KeySlot<W>::T), st), vals((size_t)total_slots * 4, st),
-            special((size_t)nl * 4, st), cursor(16, st);
+            special((size_t)nl * 4, st);
         CK(cudaMemsetAsync(keys.p, 0xff, keys.bytes, st));
         CK(cudaMemsetAsync(vals.p, 0, vals.bytes, st));
         CK(cudaMemsetAsync(special.p, 0, special.bytes, st));
-        CK(cudaMemsetAsync(cursor.p, 0, 16, st));
         SpillArgs a{};
         a.col = col;
         a.group_offsets = d_group_offsets;
@@ -162,8 +161,6 @@ void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_of
         a.min_cov = min_cov;
         a.n_obs = d_nobs;
         a.nsurv = d_nsurv;
-        a.pool_cursor = cursor.as<unsigned long long>();
-        a.overflow = reinterpret_cast<int *>(cursor.as<unsigned long long>() + 1);
         if (total_rows > 0) {
             const int64_t want_blocks = (total_rows + SPILL_WARPS - 1) / SPILL_WARPS;
             const unsigned grid = (unsigned)std::min<int64_t>(want_blocks, (int64_t)ctx->sm_count * 16);
@@ -732,6 +729,9 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
     if (!reads || !out || n_groups < 0 || (n_groups > 0 && !group_offsets) || reads->n_rows < 0)
         throw ArgFail{ROGTK_ERR_INVALID_ARG, "null or negative argument"};
     if (n_groups >= (int64_t)1 << 31) throw ArgFail{ROGTK_ERR_UNSUPPORTED, "more than 2^31 groups per batch"};
+    if (n_groups > 0 && !reads->offsets_or_views) throw ArgFail{ROGTK_ERR_INVALID_ARG, "null offsets / views buffer"};
+    if (reads->layout != ROGTK_UTF8_VIEW && reads->n_rows > 0 && (!reads->data || !reads->data_len || reads->n_buffers != 1))
+        throw ArgFail{ROGTK_ERR_INVALID_ARG, "offset layouts need exactly one data buffer"};
     memset(out, 0, sizeof(*out));
     const bool in_dev = flags & ROGTK_INPUT_ON_DEVICE, out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
     int K;
@@ -870,7 +870,9 @@ extern "C" int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strco
 extern "C" int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, uint32_t min_coverage2, uint32_t flags,
                                      rogtk_graph_batch *out)
 {
-    if (!ctx || !in || !out || !in->on_device || in->n_groups < 0 || in->n_kmers < 0) return ROGTK_ERR_INVALID_ARG;
+    if (!ctx || !in || !out || !in->on_device || in->n_groups < 0 || in->n_kmers < 0 || !in->kmer_offsets ||
+        (in->n_kmers > 0 && (!in->kmers_lo || !in->exts || !in->counts)) || (in->k_eff > 32 && in->n_kmers > 0 && !in->kmers_hi))
+        return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     memset(out, 0, sizeof(*out));
     BatchOwner *own = new BatchOwner();
