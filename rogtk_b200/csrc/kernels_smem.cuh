@@ -865,7 +865,7 @@ template <int W>
 constexpr size_t sort_big_smem() { return (size_t)SORT_BIG_MAX * (8 * W + 4); }
 
 // host launcher: pool (unsorted, completion order) -> dense, group-ordered, k-mer-ascending arrays
-inline void run_sort_gather(cudaStream_t st, int sm_count, int K, int64_t n_groups, const int64_t *pool_start, const int64_t *kmer_offsets,
+inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, int K, int64_t n_groups, const int64_t *pool_start, const int64_t *kmer_offsets,
                             const uint64_t *p_lo, const uint64_t *p_hi, const uint8_t *p_exts, const uint16_t *p_counts, uint64_t *o_lo,
                             uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts, int64_t *launches)
 {
@@ -884,8 +884,9 @@ inline void run_sort_gather(cudaStream_t st, int sm_count, int K, int64_t n_grou
     if (K > 32) k_sort_small<2><<<grid, SORT_NT, 0, st>>>(a);
     else k_sort_small<1><<<grid, SORT_NT, 0, st>>>(a);
     unsigned long long n_big = 0;
-    CK(cudaMemcpyAsync(&n_big, ctr.p, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    Peek pk(peek_slot, st, launches);
+    pk.add(ctr.p, 8, &n_big);
+    pk.sync();
     if (launches) *launches += 1;
     if (n_big) {
         const unsigned g2 = (unsigned)std::min<int64_t>((int64_t)n_big, (int64_t)sm_count * 2);
@@ -922,7 +923,7 @@ inline void smem_path_configure()
     CK(cudaFuncSetAttribute(k_smem_count<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 }
 
-inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes, const ColView &col, const uint8_t *data_begin,
+inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, size_t workspace_bytes, const ColView &col, const uint8_t *data_begin,
                           const uint8_t *data_end,
                           const int64_t *d_group_offsets, int64_t n_groups, int K, uint32_t min_cov, unsigned long long *d_nobs,
                           int64_t *d_nsurv, SmemResult &res, int64_t *launches, cudaEvent_t ev_a, cudaEvent_t ev_b,
@@ -934,8 +935,9 @@ inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes,
     unsigned long long *d_ctr = ctr.as<unsigned long long>();   // [0] ticket [1] pool cursor [2] n_deferred [3] obs upper bound
     k_obs_upper_bound<<<sm_count * 4, 256, 0, st>>>(col, K, d_ctr + 3);
     unsigned long long ub = 0;
-    CK(cudaMemcpyAsync(&ub, d_ctr + 3, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    Peek pk(peek_slot, st, launches);
+    pk.add(d_ctr + 3, 8, &ub);
+    pk.sync();
     // a k-mer needs min_cov observations to survive, so survivors <= observations / min_cov
     const size_t entry = (W == 2 ? 19 : 11);
     int64_t pool_cap = (int64_t)(ub / (min_cov > 1 ? min_cov : 1)) + 1;
@@ -992,9 +994,9 @@ inline void run_smem_path(cudaStream_t st, int sm_count, size_t workspace_bytes,
     CK(cudaEventRecord(ev_b, st));
     if (launches) *launches += 2;
     unsigned long long h_ctr[3];
-    CK(cudaMemcpyAsync(h_ctr, d_ctr, 24, cudaMemcpyDeviceToHost, st));
-    if (phase_out) CK(cudaMemcpyAsync(phase_out, d_ctr + 8, 64, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    pk.add(d_ctr, 24, h_ctr);
+    if (phase_out) pk.add(d_ctr + 8, 64, phase_out);
+    pk.sync();
     CK(cudaEventElapsedTime(&res.ms_kernel, ev_a, ev_b));
     res.n_deferred = (int64_t)h_ctr[2];
     res.n_pool_groups = n_groups - res.n_deferred;

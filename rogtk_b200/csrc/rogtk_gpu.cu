@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -39,6 +40,7 @@ struct rogtk_gpu_ctx {
     std::mutex mu;
     std::string last_error;
     int64_t launches = 0;
+    uint8_t *peek_slot = nullptr;   // mapped pinned words the counter reads land in (host_util.cuh: Peek)
     int sm_count = 148;
     size_t smem_optin = 0;
     void *flush_buf = nullptr;
@@ -137,9 +139,10 @@ void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_of
         exclusive_scan<int64_t>(rows.as<int64_t>() + i0, nl, row_off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
         exclusive_scan<int64_t>(caps.as<int64_t>() + i0, nl, slot_off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
         int64_t h_tot[2];
-        CK(cudaMemcpyAsync(&h_tot[0], row_off.as<int64_t>() + nl, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&h_tot[1], slot_off.as<int64_t>() + nl, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        Peek pk(ctx->peek_slot, st, &ctx->launches);
+        pk.add(row_off.as<int64_t>() + nl, 8, &h_tot[0]);
+        pk.add(slot_off.as<int64_t>() + nl, 8, &h_tot[1]);
+        pk.sync();
         const int64_t total_rows = h_tot[0], total_slots = h_tot[1];
         DevBuf keys((size_t)total_slots * sizeof(typename KeySlot<W>::T), st), vals((size_t)total_slots * 4, st),
             special((size_t)nl * 4, st);
@@ -178,8 +181,9 @@ void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_of
         k_spill_extract<W><<<x_grid, SPILL_EXTRACT_NT, 0, st>>>(a);
         exclusive_scan<int64_t>(wcount.as<int64_t>(), n_xw, wbase.as<int64_t>(), wscr.as<int64_t>(), st, &ctx->launches);
         int64_t h_cnt = 0;
-        CK(cudaMemcpyAsync(&h_cnt, wbase.as<int64_t>() + n_xw, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        Peek pk2(ctx->peek_slot, st, &ctx->launches);
+        pk2.add(wbase.as<int64_t>() + n_xw, 8, &h_cnt);
+        pk2.sync();
         wv.n_recs = h_cnt;
         wv.recs.alloc((size_t)std::max<int64_t>(1, wv.n_recs) * sizeof(SpillRec), st);
         a.pool = wv.recs.as<SpillRec>();
@@ -251,6 +255,7 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         CK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
         if (const char *e = getenv("ROGTK_CHUNK_BYTES")) ctx->chunk_bytes = (size_t)std::max(4096ll, atoll(e));
         for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
+        CK(cudaHostAlloc((void **)&ctx->peek_slot, Peek::SLOT_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         ctx->workspace_bytes = workspace_bytes ? workspace_bytes : free_b / 4;
@@ -275,6 +280,7 @@ extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->pinned_size) cudaFreeHost(kv.first);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->peek_slot) cudaFreeHost(ctx->peek_slot);
     {   // hand the stream-ordered pool's cached memory back to the device
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
@@ -433,8 +439,9 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
         k_validate<<<ctx->sm_count * 4, 256, 0, st>>>(in.col, data_len, in.group_offsets, n_groups, d_err);
         ctx->launches++;
         int h_err = 0;
-        CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        Peek pk(ctx->peek_slot, st, &ctx->launches);
+        pk.add(d_err, 4, &h_err);
+        pk.sync();
         if (h_err) {
             char msg[160];
             snprintf(msg, sizeof(msg), "malformed input:%s%s%s", (h_err & 1) ? " string offsets not monotone;" : "",
@@ -451,7 +458,7 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     const int32_t *d_spill_ids = nullptr;
     int64_t n_spill = n_groups;
     if (!(flags & ROGTK_FORCE_SPILL) && n_groups > 0) {
-        run_smem_path(ctx->stream, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_begin, in.data_end, in.group_offsets,
+        run_smem_path(ctx->stream, ctx->peek_slot, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_begin, in.data_end, in.group_offsets,
                       n_groups, K, min_coverage, d_nobs, nsurv.as<int64_t>(), sm, &ctx->launches, ctx->ev[4], ctx->ev[5],
                       ctx->phase_enabled ? ctx->phase_cycles : nullptr);
         d_spill_ids = sm.deferred_ids;
@@ -471,9 +478,10 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     exclusive_scan<int64_t>(nsurv.as<int64_t>(), n_groups, r.off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
     int64_t n_kmers = 0;
     unsigned long long h_nobs = 0;
-    CK(cudaMemcpyAsync(&n_kmers, r.off.as<int64_t>() + n_groups, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&h_nobs, d_nobs, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    Peek pk(ctx->peek_slot, st, &ctx->launches);
+    pk.add(r.off.as<int64_t>() + n_groups, 8, &n_kmers);
+    pk.add(d_nobs, 8, &h_nobs);
+    pk.sync();
     const size_t nk = (size_t)std::max<int64_t>(n_kmers, 1);
     r.lo.alloc(nk * 8, st);
     if (K > 32) r.hi.alloc(nk * 8, st);
@@ -481,7 +489,7 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     r.counts.alloc(nk * 2, st);
     uint64_t *p_hi = K > 32 ? r.hi.as<uint64_t>() : nullptr;
     if (sm.n_pool_groups > 0)
-        run_sort_gather(st, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
+        run_sort_gather(st, ctx->peek_slot, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
                         sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches);
     for (auto &wv : waves) {
         if (wv.n_recs == 0) continue;
@@ -510,8 +518,8 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
             ctx->launches++;
         }
         exclusive_scan<int32_t>(deg.as<int32_t>(), n_kmers, r.rowptr.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
-        CK(cudaMemcpyAsync(&n_edges, r.rowptr.as<int64_t>() + n_kmers, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        pk.add(r.rowptr.as<int64_t>() + n_kmers, 8, &n_edges);
+        pk.sync();
         r.cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
         if (n_kmers > 0) {
             k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, r.off.as<int64_t>(), r.lo.as<uint64_t>(), p_hi,
@@ -589,6 +597,22 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         ~Guard() { for (int i = 0; i < 2; i++) { cudaEventDestroy(s[i].ready); cudaEventDestroy(s[i].consumed); } cudaEventDestroy(e); }
     } guard{sets, comp_done};
 
+    // ROGTK_TRACE=1: per-chunk timeline (H2D / count / D2H begin and end, ms from the first copy) on stderr
+    const bool trace = getenv("ROGTK_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto tmark = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(e, s));
+        tev.push_back(e);
+    };
+    std::vector<double> host_ms;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto hmark = [&]() {
+        if (trace) host_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+    };
+
     auto stage_chunk = [&](int ci) {
         InSet &x = sets[ci & 1];
         const int64_t g0 = cut[ci], g1 = cut[ci + 1];
@@ -599,6 +623,8 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         x.data.alloc(pad + (size_t)(b1 - b0) + 32, s_in);
         x.offs.alloc((size_t)(r1 - r0 + 1) * osz, s_in);
         x.goff.alloc((size_t)(g1 - g0 + 1) * 8, s_in);
+        hmark();
+        tmark(s_in);
         if (b1 > b0) CK(cudaMemcpyAsync(x.data.as<uint8_t>() + pad, c->data[0] + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s_in));
         CK(cudaMemcpyAsync(x.offs.p, (const uint8_t *)c->offsets_or_views + (size_t)r0 * osz, (size_t)(r1 - r0 + 1) * osz,
                            cudaMemcpyHostToDevice, s_in));
@@ -624,6 +650,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
             s.col.validity = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(x.valid.p) - (uintptr_t)by0);
         }
         CK(cudaEventRecord(x.ready, s_in));
+        tmark(s_in);
     };
 
     HostArr h_off, h_lo, h_hi, h_exts, h_counts, h_stats, h_rowptr, h_cols;
@@ -643,6 +670,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         DeviceResult &r = inflight[ci & 1];
         // the previous result held in this slot has been copied out: its buffers are released in s_out order below
         r = DeviceResult();
+        tmark(s_comp);
         run_pipeline(ctx, x.st, ng, K, min_coverage, flags, r);
         // shift the chunk-local offsets to their global base (in place, on the compute stream)
         if (base_k) k_add_i64<<<blocks_for(ng + 1, 256), 256, 0, s_comp>>>(r.off.as<int64_t>(), ng + 1, base_k);
@@ -650,6 +678,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
             k_add_i64<<<blocks_for(r.n_kmers + 1, 256), 256, 0, s_comp>>>(r.rowptr.as<int64_t>(), r.n_kmers + 1, base_e);
         CK(cudaEventRecord(comp_done, s_comp));
         CK(cudaEventRecord(x.consumed, s_comp));
+        tmark(s_comp);
         // capacity of the final host arrays: after the first chunk extrapolate from bytes processed
         const int64_t done_bytes = std::max<int64_t>(1, off_at(group_offsets[g1]) - off_at(group_offsets[0]));
         const double scale = (double)total_bytes / (double)done_bytes;
@@ -667,6 +696,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         }
         // D2H on its own stream
         CK(cudaStreamWaitEvent(s_out, comp_done, 0));
+        tmark(s_out);
         auto pull = [&](HostArr &h, size_t dst_off, DevBuf &d, size_t bytes) {
             if (bytes) CK(cudaMemcpyAsync(h.p + dst_off, d.p, bytes, cudaMemcpyDeviceToHost, s_out));
             d.st = s_out;   // released after the copy, in s_out order
@@ -681,6 +711,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
             pull(h_rowptr, (size_t)base_k * 8, r.rowptr, (size_t)(r.n_kmers + 1) * 8);
             pull(h_cols, (size_t)base_e * 4, r.cols, (size_t)r.n_edges * 4);
         }
+        tmark(s_out);
         r.off.release(); r.lo.release(); r.hi.release(); r.exts.release(); r.counts.release();
         r.stats.release(); r.rowptr.release(); r.cols.release();
         // timings of this chunk (waits for its compute; the next chunk's input copy is already in flight)
@@ -698,6 +729,20 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     }
     CK(cudaStreamSynchronize(s_out));
     CK(cudaStreamSynchronize(s_in));
+    if (trace) {
+        // event order: chunk 0 H2D (2), then per chunk ci: [H2D of ci+1 (2) if any], count (2), D2H (2)
+        auto at = [&](size_t i) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); return ms; };
+        size_t i = 2, hi = 1;
+        std::vector<float> h0(n_chunks), h1(n_chunks);
+        h0[0] = at(0); h1[0] = at(1);
+        for (int ci = 0; ci < n_chunks; ci++) {
+            if (ci + 1 < n_chunks) { h0[ci + 1] = at(i); h1[ci + 1] = at(i + 1); i += 2; hi++; }
+            fprintf(stderr, "chunk %3d  h2d %8.2f-%8.2f  count %8.2f-%8.2f  d2h %8.2f-%8.2f  staged@host %8.2f\n", ci, h0[ci], h1[ci],
+                    at(i), at(i + 1), at(i + 2), at(i + 3), host_ms[ci]);
+            i += 4;
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+    }
     for (auto &x : sets) { x.data.release(); x.offs.release(); x.goff.release(); x.valid.release(); }
     out->n_kmers = base_k;
     out->n_edges = base_e;
