@@ -51,6 +51,7 @@ extern "C" {
 #define ROGTK_INPUT_ON_DEVICE (1u << 3)  /* all rogtk_strcol / group_offsets pointers are device pointers */
 #define ROGTK_OUTPUT_ON_DEVICE (1u << 4) /* leave the result arrays in device memory */
 #define ROGTK_FORCE_SPILL (1u << 5)      /* testing: bypass the shared-memory tables, use the HBM tables only */
+#define ROGTK_NO_MULTIPASS (1u << 6)     /* testing: groups beyond one shared-memory table go straight to the HBM tables */
 
 typedef struct rogtk_gpu_ctx rogtk_gpu_ctx;
 
@@ -86,7 +87,7 @@ typedef struct rogtk_graph_batch {
     float ms_total;          /* device time of the whole pipeline (CUDA events on the context stream) */
     float ms_count;          /* device time of the counting phase (shared-memory path + HBM-table path) */
     float ms_hot_kernel;     /* device time of the k_smem_count launch alone (the dominant kernel; roofline numerator) */
-    float _pad0;
+    int32_t n_multipass_groups; /* groups counted in several shared-memory passes (more distinct k-mers / bases than one table holds) */
     int64_t n_spilled_groups;/* groups that went through the HBM-table path */
     void *_owner;            /* internal */
 } rogtk_graph_batch;

@@ -26,6 +26,7 @@ EXACT_K = 1 << 2
 INPUT_ON_DEVICE = 1 << 3
 OUTPUT_ON_DEVICE = 1 << 4
 FORCE_SPILL = 1 << 5
+NO_MULTIPASS = 1 << 6
 
 # every symbol include/rogtk_gpu.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
@@ -69,7 +70,7 @@ class GraphBatchC(ctypes.Structure):
         ("ms_total", ctypes.c_float),
         ("ms_count", ctypes.c_float),
         ("ms_hot_kernel", ctypes.c_float),
-        ("_pad0", ctypes.c_float),
+        ("n_multipass_groups", ctypes.c_int32),
         ("n_spilled_groups", ctypes.c_int64),
         ("_owner", ctypes.c_void_p),
     ]

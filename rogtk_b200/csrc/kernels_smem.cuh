@@ -34,6 +34,19 @@ constexpr int SM_SORT_BITS = 10;
 constexpr int SM_SORT_BUCKETS = 1 << SM_SORT_BITS;
 constexpr int SM_POOL_CHUNK = 32768;   // survivors a CTA reserves from the pool at a time
 constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this -> bitonic kernel
+// Multi-pass variant for groups that do not fit one table / one staged span (MULTI = true): the k-mer space is cut into
+// 2^lg equal ranges by the top bits of the k-mer; pass p re-reads the group's reads in slabs of <= SM_MAX_BASES bases and
+// counts only the k-mers of range p, so every pass needs a table for about 1/2^lg of the distinct k-mers and its survivors
+// form one ascending segment of the group's output.
+constexpr int SM_PMAX_LG = 4;                 // up to 16 passes
+constexpr int SM_PMAX = 1 << SM_PMAX_LG;
+constexpr int64_t SM_PASS_OBS = 12288;        // bases per pass the first attempt plans for (doubles the passes on overflow)
+
+struct SegRec {          // survivors of one pass of a multi-pass group
+    int64_t pool_start;
+    int32_t n;
+    int32_t prefix;      // survivors of the earlier passes of the group
+};
 template <int W>
 constexpr int scratch_bytes()   // pk + per-warp queues; reused by the sort (histogram + order)
 {
@@ -67,7 +80,21 @@ struct SmemArgs {
     int32_t *deferred_ids;           // groups handed to the HBM-table path
     unsigned long long *n_deferred;
     unsigned long long *phase_cycles;   // optional [8] per-phase SM cycles summed over CTAs (diagnostics)
+    // MULTI only: the groups to process (tickets index this list), one SegRec per (list entry, pass), passes used per entry
+    const int32_t *group_list;
+    int64_t n_list;
+    SegRec *segs;                    // [n_list * SM_PMAX]
+    int32_t *seg_count;              // [n_list], 0 = the group was not finished here
 };
+
+// top `lg` bits of a k-mer of kbits bits (lg <= kbits)
+__device__ __forceinline__ uint32_t key_part(const Key<1> &k, int kbits, int lg) { return lg ? (uint32_t)(k.lo >> (kbits - lg)) : 0u; }
+__device__ __forceinline__ uint32_t key_part(const Key<2> &k, int kbits, int lg)
+{
+    if (!lg) return 0u;
+    const int sh = kbits - lg;   // >= 60 here (kbits > 64, lg <= 4)
+    return sh >= 64 ? (uint32_t)(k.hi >> (sh - 64)) : (uint32_t)((k.hi << (64 - sh)) | (k.lo >> sh));
+}
 
 // multiplicative hash, slot = top bits.  On the synthetic shapes it probes 1.32 slots per observation vs 1.31 for a
 // two-round mixer, for half the instructions.
@@ -259,7 +286,7 @@ __device__ __forceinline__ void queue_push(WarpQueue<W> &q, bool pend, typename 
         }                                                                \
     } while (0)
 
-template <int W, bool K32>
+template <int W, bool K32, bool MULTI>
 __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs a)
 {
     using S = KeySlot<W>;
@@ -272,14 +299,15 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     uint8_t *qbytes = reinterpret_cast<uint8_t *>(scratch + SM_PK_WORDS);        // per-warp queues (W=1: 8 B keys)
     uint32_t *rstart = scratch + scratch_bytes<W>() / 4;
     uint32_t *ucum = rstart + SM_MAXR + 1;               // work units before read r
-    uint32_t *ws = ucum + SM_MAXR + 1;                     // 64 words: [0..11] scan, [16..31] misc, [40..51] queue leftovers
+    uint32_t *ws = ucum + SM_MAXR + 1;                     // 64 words: [0..11] scan, [16..31] misc, [32..33] group id (MULTI), [40..51] queue leftovers
     uint8_t *bad = reinterpret_cast<uint8_t *>(ws + 64);
     uint16_t *unit_read = reinterpret_cast<uint16_t *>(bad + SM_MAXR);   // read index of every work unit
-    volatile uint32_t *misc = ws + 16;   // [0],[1] group [2] all-ones k-mer value [3] abort [4],[5] pool base [6] big bucket [7] unit counter [8..15] r0,r1,b0,b1
+    volatile uint32_t *misc = ws + 16;   // [0],[1] ticket [2] all-ones k-mer value [3] abort [4],[5] pool base [6] big bucket [7] unit counter [8..15] r0,r1,b0,b1
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
     const int K = a.K;
     const uint32_t thr = a.min_cov > 1u ? a.min_cov : 1u;
+    const int64_t n_items = MULTI ? a.n_list : a.n_groups;
     unsigned long long cta_obs = 0;
     long long t_phase = clock64();
     WarpQueue<W> wq;
@@ -291,18 +319,19 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     // thread 0 runs one group ahead: ticket, row range and byte range of the next group are fetched while the current one is
     // being counted, so their global-memory latencies are off the critical path.
     unsigned long long pf_g = 0;
-    int64_t pf_r0 = 0, pf_r1 = 0, pf_b0 = 0, pf_b1 = 0;
+    int64_t pf_gid = 0, pf_r0 = 0, pf_r1 = 0, pf_b0 = 0, pf_b1 = 0;
     int pf_stage = 0;   // 0: have pf_g   1: + row range   2: + byte range
     int64_t cta_pool_pos = 0, cta_pool_end = 0;   // this CTA's chunk of the survivor pool (thread 0)
     if (tid == 0) pf_g = atomicAdd(a.ticket, 1ull);
     auto pf_advance = [&]() {   // thread 0 only
-        if ((int64_t)pf_g >= a.n_groups) {
+        if ((int64_t)pf_g >= n_items) {
             pf_stage = 2;
             return;
         }
         if (pf_stage == 0) {
-            pf_r0 = a.group_offsets[pf_g];
-            pf_r1 = a.group_offsets[pf_g + 1];
+            pf_gid = MULTI ? (int64_t)a.group_list[pf_g] : (int64_t)pf_g;
+            pf_r0 = a.group_offsets[pf_gid];
+            pf_r1 = a.group_offsets[pf_gid + 1];
             pf_stage = 1;
         } else if (pf_stage == 1) {
             pf_b0 = col_off(a.col, pf_r0);
@@ -310,47 +339,112 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             pf_stage = 2;
         }
     };
+    auto defer = [&](int64_t gid) {   // hand a group to the next path
+        if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)gid;
+    };
+
+    // the group being worked on; MULTI keeps it over several iterations of the loop (one slab of one pass each)
+    int64_t item = 0, g = 0, r0 = 0, r1 = 0, b0 = 0, b1 = 0;
+    bool in_group = false;             // MULTI: a group is in progress
+    int lgP = 0, pass = 0;             // MULTI: 2^lgP passes, current pass
+    int64_t srow = 0;                  // MULTI: first row of the next slab
+    uint32_t gprefix = 0, gobs = 0;    // MULTI: survivors of the finished passes, observations of the group
 
     while (true) {
         __syncthreads();
-        if (tid == 0) {
-            while (pf_stage < 2) pf_advance();
-            misc[0] = (uint32_t)pf_g;
-            misc[1] = (uint32_t)(pf_g >> 32);
-            misc[2] = 0;
-            misc[3] = 0;
-            misc[6] = 0;
-            misc[7] = 0;
-            misc[8] = (uint32_t)pf_r0;  misc[9] = (uint32_t)((uint64_t)pf_r0 >> 32);
-            misc[10] = (uint32_t)pf_r1; misc[11] = (uint32_t)((uint64_t)pf_r1 >> 32);
-            misc[12] = (uint32_t)pf_b0; misc[13] = (uint32_t)((uint64_t)pf_b0 >> 32);
-            misc[14] = (uint32_t)pf_b1; misc[15] = (uint32_t)((uint64_t)pf_b1 >> 32);
+        if (!MULTI || !in_group) {
+            if (tid == 0) {
+                while (pf_stage < 2) pf_advance();
+                misc[0] = (uint32_t)pf_g;
+                misc[1] = (uint32_t)(pf_g >> 32);
+                misc[2] = 0;
+                misc[3] = 0;
+                misc[6] = 0;
+                misc[7] = 0;
+                misc[8] = (uint32_t)pf_r0;  misc[9] = (uint32_t)((uint64_t)pf_r0 >> 32);
+                misc[10] = (uint32_t)pf_r1; misc[11] = (uint32_t)((uint64_t)pf_r1 >> 32);
+                misc[12] = (uint32_t)pf_b0; misc[13] = (uint32_t)((uint64_t)pf_b0 >> 32);
+                misc[14] = (uint32_t)pf_b1; misc[15] = (uint32_t)((uint64_t)pf_b1 >> 32);
+                if (MULTI) {
+                    ws[32] = (uint32_t)pf_gid;
+                    ws[33] = (uint32_t)((uint64_t)pf_gid >> 32);
+                }
+            }
+            __syncthreads();
+            item = (int64_t)(((unsigned long long)misc[1] << 32) | misc[0]);
+            if (item >= n_items) break;
+            g = MULTI ? (int64_t)(((uint64_t)ws[33] << 32) | ws[32]) : item;
+            r0 = (int64_t)(((uint64_t)misc[9] << 32) | misc[8]);
+            r1 = (int64_t)(((uint64_t)misc[11] << 32) | misc[10]);
+            b0 = (int64_t)(((uint64_t)misc[13] << 32) | misc[12]);
+            b1 = (int64_t)(((uint64_t)misc[15] << 32) | misc[14]);
+            if (tid == 0) {   // take the next ticket now; its metadata follows at later points of this iteration
+                pf_g = atomicAdd(a.ticket, 1ull);
+                pf_stage = 0;
+            }
+            if (r1 - r0 <= 0) continue;
+            if (b1 <= b0) continue;
+            if (MULTI) {
+                const int64_t ub = b1 - b0;   // every observation starts at its own base
+                if (ub > SM_PASS_OBS * SM_PMAX) {   // too much work for one CTA: HBM-table path
+                    defer(g);
+                    continue;
+                }
+                lgP = 0;
+                if (2 * K > 12)   // at most 4^K <= 4096 distinct k-mers otherwise: one table always holds them
+                    while (lgP < SM_PMAX_LG && ub > (SM_PASS_OBS << lgP)) lgP++;
+                in_group = true;
+                pass = 0;
+                srow = r0;
+                gprefix = 0;
+                gobs = 0;
+            }
         }
-        __syncthreads();
-        const int64_t g = (int64_t)(((unsigned long long)misc[1] << 32) | misc[0]);
-        if (g >= a.n_groups) break;
-        const int64_t r0 = (int64_t)(((uint64_t)misc[9] << 32) | misc[8]), r1 = (int64_t)(((uint64_t)misc[11] << 32) | misc[10]);
-        const int64_t b0 = (int64_t)(((uint64_t)misc[13] << 32) | misc[12]), b1 = (int64_t)(((uint64_t)misc[15] << 32) | misc[14]);
-        if (tid == 0) {   // take the next ticket now; its metadata follows at later points of this iteration
-            pf_g = atomicAdd(a.ticket, 1ull);
-            pf_stage = 0;
+
+        // ---- the rows staged in this iteration: the whole group, or (MULTI) the next slab of it -----------------------
+        int64_t s0 = r0, s1 = r1, sb0 = b0, sb1 = b1;
+        if (MULTI) {
+            s0 = srow;
+            sb0 = col_off(a.col, s0);
+            const uint32_t slk = (uint32_t)(reinterpret_cast<uintptr_t>(a.col.data + sb0) & 15u);
+            bool fits = false;   // rows s0 .. s0+tid fit one slab (monotone in tid: the offsets are validated as monotone)
+            if (tid < SM_MAXR && s0 + tid + 1 <= r1) fits = col_off(a.col, s0 + tid + 1) - sb0 + (int64_t)slk <= (int64_t)SM_MAX_BASES;
+            const int cnt = __syncthreads_count(fits);
+            if (cnt == 0) {   // a single read longer than a slab
+                defer(g);
+                in_group = false;
+                continue;
+            }
+            s1 = s0 + cnt;
+            sb1 = col_off(a.col, s1);
+            if (tid == 0) {
+                misc[7] = 0;
+                if (s0 == r0) {
+                    misc[2] = 0;
+                    misc[3] = 0;
+                }
+            }
+            if (s0 == r0) {   // a pass starts: empty table of full size
+                uint4 *kq = reinterpret_cast<uint4 *>(tkey);
+                for (int j = tid; j < (int)(SM_TSIZE * sizeof(KT) / 16); j += SM_NT) kq[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                uint4 *vq = reinterpret_cast<uint4 *>(tval);
+                for (int j = tid; j < SM_TSIZE / 4; j += SM_NT) vq[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
-        const int64_t nrows = r1 - r0;
-        if (nrows <= 0) continue;
-        if (b1 <= b0) continue;
-        const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.col.data + b0);
+        const int64_t nrows = s1 - s0;
+        const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.col.data + sb0);
         const uint32_t slack = (uint32_t)(addr0 & 15u);
-        const int64_t span64 = (b1 - b0) + slack;
-        if (nrows > SM_MAXR || span64 > SM_MAX_BASES) {   // too many rows / bases for this path
-            if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)g;
+        const int64_t span64 = (sb1 - sb0) + slack;
+        if (!MULTI && (nrows > SM_MAXR || span64 > SM_MAX_BASES)) {   // too many rows / bases for one staged span
+            defer(g);
             continue;
         }
         const uint32_t span = (uint32_t)span64;
         const int nr = (int)nrows;
 
         // ---- per-read base offsets inside the staged span, null rows ----------------------------------------------
-        for (int r = tid; r <= nr; r += SM_NT) rstart[r] = (uint32_t)(col_off(a.col, r0 + r) - b0) + slack;
-        if (tid < nr) bad[tid] = col_valid(a.col, r0 + tid) ? 0 : 1;
+        for (int r = tid; r <= nr; r += SM_NT) rstart[r] = (uint32_t)(col_off(a.col, s0 + r) - sb0) + slack;
+        if (tid < nr) bad[tid] = col_valid(a.col, s0 + tid) ? 0 : 1;
         __syncthreads();
 
         PHASE_MARK(0);
@@ -401,14 +495,15 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             if (tid == 0) ucum[SM_MAXR] = nunits;
             for (uint32_t j = 0; j < (nk + SM_UNIT - 1) / SM_UNIT; j++) unit_read[ex + j] = (uint16_t)tid;
         }
-        if (total == 0) continue;   // (the loop-top barrier orders the shared writes before reuse)
+        if (!MULTI && total == 0) continue;   // (the loop-top barrier orders the shared writes before reuse)
 
-        // ---- table sized to the group: power of two >= 2 * observations, at most SM_TSIZE -------------------------------------
-        int tbits = 8;
-        while (tbits < SM_TBITS && (1u << tbits) < 2u * total) tbits++;
+        // ---- table sized to the group: power of two >= 2 * observations, at most SM_TSIZE (MULTI: always SM_TSIZE) ---------------
+        int tbits = MULTI ? SM_TBITS : 8;
+        if (!MULTI)
+            while (tbits < SM_TBITS && (1u << tbits) < 2u * total) tbits++;
         const uint32_t tsize = 1u << tbits, tmask = tsize - 1u;
         const int tshift = 32 - tbits;
-        {
+        if (!MULTI) {
             // keys = EMPTY (all ones), vals = 0
             uint4 *kq = reinterpret_cast<uint4 *>(tkey);
             const int nkq = (int)(tsize * sizeof(KT) / 16);
@@ -422,7 +517,10 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         PHASE_MARK(2);
         // ---- counting: warps fetch units of SM_UNIT windows of one read; no block barriers ---------------------------------------------
         if (tid == 0 && pf_stage == 0) pf_advance();   // next group's row range (its ticket has long arrived)
-        {
+        // MULTI: this pass takes the k-mers whose top lgP bits equal `pass`
+        const uint32_t pmask32 = (MULTI && lgP) ? (~0u << (32 - lgP)) : 0u;
+        const uint32_t pval32 = (MULTI && lgP) ? ((uint32_t)pass << (32 - lgP)) : 0u;
+        if (total != 0) {
             wq.n = 0;
             wq.budget = 64 + (int)(total >> 1);   // drain steps allowed per warp: far above any non-full table's need
             uint32_t *special = const_cast<uint32_t *>(&misc[2]);
@@ -474,6 +572,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                         const bool has_l = u ? true : (p != 0u);
                         const bool has_r = (p + u + 1u) < nk;
                         act[u] = (uint32_t)u < R && j0 + (uint32_t)u < ulen;
+                        if (MULTI) act[u] = act[u] && (kh[u] & pmask32) == pval32;
                         ex[u] = (has_l ? (1u << lb) : 0u) | (has_r ? (16u << nb) : 0u);
                         h[u] = hash32(kl[u], kh[u]) >> tshift;
                         if (u < 3) {
@@ -481,9 +580,12 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                             kl[u + 1] = (kl[u] << 2) | nb;
                         }
                     }
+                    const bool sparse = MULTI && lgP != 0;   // few windows of the unit belong to this pass
                     KT cur[4];
+                    if (!sparse) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) cur[u] = act[u] ? tkey[h[u]] : S::empty();
+                        for (int u = 0; u < 4; u++) cur[u] = act[u] ? tkey[h[u]] : S::empty();
+                    }
                     // the all-ones k-mer is the table's EMPTY marker: divert it to the side word first (one warp vote, rarely taken)
                     {
                         bool sp = false;
@@ -499,15 +601,25 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                             }
                         }
                     }
-                    uint32_t pm = 0;   // bit u: window u collided and must queue
+                    uint32_t pm = 0;   // bit u: window u must queue (it collided, or the pass is sparse)
+                    if (!sparse) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
-                        KT c = cur[u];
-                        if (act[u] && c == S::empty()) c = atomicCAS(&tkey[h[u]], S::empty(), kp);
-                        const bool ok = (c == kp) | (c == S::empty());   // hit, or the claim went through
-                        if (act[u] && ok) val_add(&tval[h[u]], ex[u]);
-                        pm |= (act[u] && !ok) ? (1u << u) : 0u;
+                        for (int u = 0; u < 4; u++) {
+                            const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
+                            KT c = cur[u];
+                            if (act[u] && c == S::empty()) c = atomicCAS(&tkey[h[u]], S::empty(), kp);
+                            const bool ok = (c == kp) | (c == S::empty());   // hit, or the claim went through
+                            if (act[u] && ok) val_add(&tval[h[u]], ex[u]);
+                            pm |= (act[u] && !ok) ? (1u << u) : 0u;
+                        }
+                    } else {
+                        // probing inline would run the insert code for a fraction of the lanes: the windows of this pass are
+                        // queued instead (as if their probe of slot h-1 had failed) and the queue is drained 32 wide
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            pm |= act[u] ? (1u << u) : 0u;
+                            h[u] = (h[u] - 1u) & tmask;
+                        }
                     }
                     __syncwarp();
                     bool pend[4];
@@ -557,12 +669,19 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                             const uint32_t q = rs + p;
                             Key<W> key = Key<W>::zero();
                             load_window(pk, q, K, key);
-                            const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
-                            // Exts of iter_kmer_exts with seq_exts = Exts::empty()
-                            ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
-                            h = hash32(key) >> tshift;
-                            kp = S::pack(key);
-                            pend = first_probe(kp, h, ex, tkey[h]);
+                            if (!MULTI || key_part(key, 2 * K, lgP) == (uint32_t)pass) {
+                                const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
+                                // Exts of iter_kmer_exts with seq_exts = Exts::empty()
+                                ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
+                                h = hash32(key) >> tshift;
+                                kp = S::pack(key);
+                                if (MULTI && lgP != 0 && !(kp == S::empty())) {   // sparse pass: queue, drain 32 wide
+                                    pend = true;
+                                    h = (h - 1u) & tmask;
+                                } else {
+                                    pend = first_probe(kp, h, ex, tkey[h]);
+                                }
+                            }
                         }
                         __syncwarp();
                         queue_push<W>(wq, pend, kp, h, ex, tkey, tval, tmask, lane);
@@ -574,7 +693,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             if (lane == 0) ws[40 + warp] = wq.n;   // leftovers (< 32 per warp) are finished by the whole CTA below
         }
         __syncthreads();
-        if (!misc[3]) {
+        if (total != 0 && !misc[3]) {
             // every thread takes at most one leftover observation and probes until it lands
             const uint32_t wsrc = (uint32_t)tid >> 5, isrc = (uint32_t)tid & 31u;   // thread t <- entry isrc of warp wsrc
             if (wsrc < (uint32_t)SM_NWARP && isrc < ws[40 + wsrc]) {
@@ -598,9 +717,23 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             }
         }
         __syncthreads();
-        if (misc[3]) {   // too many distinct k-mers for a shared-memory table: HBM-table path
-            if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)g;
+        if (misc[3]) {   // too many distinct k-mers for a shared-memory table
+            if (MULTI && lgP < SM_PMAX_LG && lgP < 2 * K) {   // start the group over with twice the passes
+                lgP++;
+                pass = 0;
+                srow = r0;
+                gprefix = 0;
+                gobs = 0;
+                continue;
+            }
+            defer(g);   // HBM-table path
+            in_group = false;
             continue;
+        }
+        if (MULTI) {
+            if (pass == 0) gobs += total;
+            srow = s1;
+            if (srow < r1) continue;   // next slab of this pass
         }
 
         PHASE_MARK(3);
@@ -629,13 +762,15 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             misc[5] = (uint32_t)(pb0 >> 32);
         }
         __syncthreads();
-        if (n_out == 0) {
+        if (!MULTI && n_out == 0) {
             cta_obs += total;
             continue;
         }
         const int64_t pb = (int64_t)(((unsigned long long)misc[5] << 32) | misc[4]);
-        if (pb + (int64_t)n_out > a.pool_cap) {   // survivor pool exhausted: the HBM path (own pool) takes the group
-            if (tid == 0) a.deferred_ids[atomicAdd(a.n_deferred, 1ull)] = (int32_t)g;
+        if (n_out != 0 && (pb + (int64_t)n_out > a.pool_cap || n_out > (uint32_t)SM_TSIZE)) {
+            // survivor pool exhausted (or a segment the ordering kernel cannot hold): the HBM path (own pool) takes the group
+            defer(g);
+            in_group = false;
             continue;
         }
         PHASE_MARK(4);
@@ -646,21 +781,38 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             a.pool_exts[pos] = (uint8_t)v;
             a.pool_counts[pos] = (uint16_t)((v >> 8) > 65535u ? 65535u : (v >> 8));
         };
-        for (uint32_t j = tid; j < tsize / 4; j += SM_NT) {
-            const uint4 vv = tval4[j];
-            const uint32_t c[4] = {vv.x, vv.y, vv.z, vv.w};
-            if (((c[0] >> 8) >= thr) | ((c[1] >> 8) >= thr) | ((c[2] >> 8) >= thr) | ((c[3] >> 8) >= thr)) {
+        if (n_out != 0) {
+            for (uint32_t j = tid; j < tsize / 4; j += SM_NT) {
+                const uint4 vv = tval4[j];
+                const uint32_t c[4] = {vv.x, vv.y, vv.z, vv.w};
+                if (((c[0] >> 8) >= thr) | ((c[1] >> 8) >= thr) | ((c[2] >> 8) >= thr) | ((c[3] >> 8) >= thr)) {
 #pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if ((c[t] >> 8) >= thr) emit(pb + (int64_t)(rank++), tkey[4 * j + t], c[t]);
+                    for (int t = 0; t < 4; t++)
+                        if ((c[t] >> 8) >= thr) emit(pb + (int64_t)(rank++), tkey[4 * j + t], c[t]);
+                }
+            }
+            if (special_survives && tid == 0) emit(pb + (int64_t)nS, S::empty(), sv);
+        }
+        if (!MULTI) {
+            if (tid == 0) {
+                a.nsurv[g] = (int64_t)n_out;
+                a.pool_start[g] = pb;
+            }
+            cta_obs += total;
+        } else {
+            if (tid == 0) a.segs[item * SM_PMAX + pass] = SegRec{pb, (int32_t)n_out, (int32_t)gprefix};
+            gprefix += n_out;
+            pass++;
+            srow = r0;
+            if (pass == (1 << lgP)) {   // group complete; its pool_start stays -1, the segments carry the survivors
+                if (tid == 0) {
+                    a.seg_count[item] = pass;
+                    a.nsurv[g] = (int64_t)gprefix;
+                }
+                cta_obs += gobs;
+                in_group = false;
             }
         }
-        if (special_survives && tid == 0) emit(pb + (int64_t)nS, S::empty(), sv);
-        if (tid == 0) {
-            a.nsurv[g] = (int64_t)n_out;
-            a.pool_start[g] = pb;
-        }
-        cta_obs += total;
         PHASE_MARK(5);
     }
     if (tid == 0 && cta_obs) atomicAdd(a.n_obs, cta_obs);
@@ -704,10 +856,16 @@ struct SortArgs {
     int32_t *big_ids;              // groups left to k_sort_big
     unsigned long long *n_big;
     int kbits;
+    // segments of multi-pass groups (k_sort_big<W, true>): item i = pass i % SM_PMAX of list entry i / SM_PMAX
+    const SegRec *segs;
+    const int32_t *seg_count;
+    const int32_t *seg_list;
 };
 
-template <int W>
-__global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a)
+// SEG = false: work items are groups.  SEG = true: segments of multi-pass groups (item i = pass i % SM_PMAX of list entry
+// i / SM_PMAX); the k-mers of a segment share their top lg bits, so the buckets are taken from the bits below them.
+template <int W, bool SEG>
+__global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_items)
 {
     constexpr int SORT_SMALL_MAX = sort_small_max<W>();
     __shared__ uint64_t s_lo[SORT_SMALL_MAX];
@@ -719,14 +877,27 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a)
     __shared__ uint32_t s_ws[8];
     __shared__ int s_flag;
     const int tid = threadIdx.x;
-    for (int64_t g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
-        const int64_t ps = a.pool_start[g];
-        if (ps < 0) continue;
-        const int64_t o = a.kmer_offsets[g];
-        const int n = (int)(a.kmer_offsets[g + 1] - o);
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        int64_t ps, o;
+        int n, kb = a.kbits;
+        if (SEG) {
+            const int64_t e = it / SM_PMAX;
+            const int np = a.seg_count[e];
+            if ((int)(it % SM_PMAX) >= np) continue;
+            const SegRec r = a.segs[it];
+            ps = r.pool_start;
+            o = a.kmer_offsets[a.seg_list[e]] + r.prefix;
+            n = r.n;
+            kb -= 31 - __clz(np);   // np = 2^lg passes: the top lg bits are the same for the whole segment
+        } else {
+            ps = a.pool_start[it];
+            if (ps < 0) continue;
+            o = a.kmer_offsets[it];
+            n = (int)(a.kmer_offsets[it + 1] - o);
+        }
         if (n == 0) continue;
         if (n > SORT_SMALL_MAX) {
-            if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)g;
+            if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)it;
             continue;
         }
         __syncthreads();   // previous group's shared data no longer in use
@@ -739,8 +910,8 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a)
         }
         __syncthreads();
         auto bucket_of = [&](int j) -> uint32_t {
-            if (W == 2) return sort_bucket<2>(Key<2>{s_lo[j], s_hi[j]}, a.kbits);
-            return sort_bucket<1>(Key<1>{s_lo[j]}, a.kbits);
+            if (W == 2) return sort_bucket<2>(Key<2>{s_lo[j], s_hi[j]}, kb) & (uint32_t)(SM_SORT_BUCKETS - 1);
+            return sort_bucket<1>(Key<1>{s_lo[j]}, kb) & (uint32_t)(SM_SORT_BUCKETS - 1);
         };
         for (int j = tid; j < n; j += SORT_NT) atomicAdd(&s_hist[bucket_of(j)], 1u);
         __syncthreads();
@@ -774,7 +945,7 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a)
         }
         __syncthreads();
         if (s_flag) {   // a crowded bucket (low-complexity k-mers): bitonic kernel
-            if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)g;
+            if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)it;
             continue;
         }
         for (int j = tid; j < n; j += SORT_NT) s_order[atomicAdd(&s_hist[bucket_of(j)], 1u)] = (uint16_t)j;
@@ -807,7 +978,9 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a)
     }
 }
 
-template <int W>
+// SEG = false: one work item per group listed in big_ids.  SEG = true: big_ids lists segments of multi-pass groups; the
+// segments of a group hold ascending k-mer ranges, so ordering each one in place orders the group.
+template <int W, bool SEG>
 __global__ void __launch_bounds__(SORT_BIG_NT) k_sort_big(SortArgs a, int64_t n_big)
 {
     extern __shared__ __align__(16) uint8_t sraw[];
@@ -816,9 +989,20 @@ __global__ void __launch_bounds__(SORT_BIG_NT) k_sort_big(SortArgs a, int64_t n_
     uint32_t *s_val = reinterpret_cast<uint32_t *>(s_lo + (W == 2 ? 2 : 1) * SORT_BIG_MAX);
     const int tid = threadIdx.x;
     for (int64_t i = blockIdx.x; i < n_big; i += gridDim.x) {
-        const int64_t g = a.big_ids[i];
-        const int64_t ps = a.pool_start[g], o = a.kmer_offsets[g];
-        const int n = (int)(a.kmer_offsets[g + 1] - o);
+        int64_t ps, o;
+        int n;
+        if (SEG) {
+            const int64_t it = a.big_ids[i];
+            const SegRec r = a.segs[it];
+            ps = r.pool_start;
+            o = a.kmer_offsets[a.seg_list[it / SM_PMAX]] + r.prefix;
+            n = r.n;
+        } else {
+            const int64_t g = a.big_ids[i];
+            ps = a.pool_start[g];
+            o = a.kmer_offsets[g];
+            n = (int)(a.kmer_offsets[g + 1] - o);
+        }
         int np2 = 1;
         while (np2 < n) np2 <<= 1;
         __syncthreads();
@@ -867,7 +1051,8 @@ constexpr size_t sort_big_smem() { return (size_t)SORT_BIG_MAX * (8 * W + 4); }
 // host launcher: pool (unsorted, completion order) -> dense, group-ordered, k-mer-ascending arrays
 inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, int K, int64_t n_groups, const int64_t *pool_start, const int64_t *kmer_offsets,
                             const uint64_t *p_lo, const uint64_t *p_hi, const uint8_t *p_exts, const uint16_t *p_counts, uint64_t *o_lo,
-                            uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts, int64_t *launches)
+                            uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts, int64_t *launches, const SegRec *segs = nullptr,
+                            const int32_t *seg_count = nullptr, const int32_t *seg_list = nullptr, int64_t n_seg_groups = 0)
 {
     DevBuf big((size_t)n_groups * 4 + 16, st), ctr(16, st);
     CK(cudaMemsetAsync(ctr.p, 0, 16, st));
@@ -881,17 +1066,38 @@ inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, i
     a.n_big = ctr.as<unsigned long long>();
     a.kbits = 2 * K;
     const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 16);
-    if (K > 32) k_sort_small<2><<<grid, SORT_NT, 0, st>>>(a);
-    else k_sort_small<1><<<grid, SORT_NT, 0, st>>>(a);
-    unsigned long long n_big = 0;
-    Peek pk(peek_slot, st, launches);
-    pk.add(ctr.p, 8, &n_big);
-    pk.sync();
+    if (K > 32) k_sort_small<2, false><<<grid, SORT_NT, 0, st>>>(a, n_groups);
+    else k_sort_small<1, false><<<grid, SORT_NT, 0, st>>>(a, n_groups);
     if (launches) *launches += 1;
-    if (n_big) {
-        const unsigned g2 = (unsigned)std::min<int64_t>((int64_t)n_big, (int64_t)sm_count * 2);
-        if (K > 32) k_sort_big<2><<<g2, SORT_BIG_NT, sort_big_smem<2>(), st>>>(a, (int64_t)n_big);
-        else k_sort_big<1><<<g2, SORT_BIG_NT, sort_big_smem<1>(), st>>>(a, (int64_t)n_big);
+    // segments of the multi-pass groups: same counting sort, items = (list entry, pass)
+    const int64_t n_seg_items = n_seg_groups * SM_PMAX;
+    DevBuf big_seg((size_t)n_seg_items * 4 + 16, st);
+    SortArgs b = a;
+    if (n_seg_groups > 0) {
+        b.segs = segs;
+        b.seg_count = seg_count;
+        b.seg_list = seg_list;
+        b.big_ids = big_seg.as<int32_t>();
+        b.n_big = ctr.as<unsigned long long>() + 1;
+        const unsigned g3 = (unsigned)std::min<int64_t>(n_seg_items, (int64_t)sm_count * 16);
+        if (K > 32) k_sort_small<2, true><<<g3, SORT_NT, 0, st>>>(b, n_seg_items);
+        else k_sort_small<1, true><<<g3, SORT_NT, 0, st>>>(b, n_seg_items);
+        if (launches) *launches += 1;
+    }
+    unsigned long long n_big[2] = {0, 0};
+    Peek pk(peek_slot, st, launches);
+    pk.add(ctr.p, 16, n_big);
+    pk.sync();
+    if (n_big[0]) {
+        const unsigned g2 = (unsigned)std::min<int64_t>((int64_t)n_big[0], (int64_t)sm_count * 2);
+        if (K > 32) k_sort_big<2, false><<<g2, SORT_BIG_NT, sort_big_smem<2>(), st>>>(a, (int64_t)n_big[0]);
+        else k_sort_big<1, false><<<g2, SORT_BIG_NT, sort_big_smem<1>(), st>>>(a, (int64_t)n_big[0]);
+        if (launches) *launches += 1;
+    }
+    if (n_big[1]) {
+        const unsigned g2 = (unsigned)std::min<int64_t>((int64_t)n_big[1], (int64_t)sm_count * 2);
+        if (K > 32) k_sort_big<2, true><<<g2, SORT_BIG_NT, sort_big_smem<2>(), st>>>(b, (int64_t)n_big[1]);
+        else k_sort_big<1, true><<<g2, SORT_BIG_NT, sort_big_smem<1>(), st>>>(b, (int64_t)n_big[1]);
         if (launches) *launches += 1;
     }
 }
@@ -909,25 +1115,36 @@ struct SmemResult {
     const uint16_t *pool_counts = nullptr;
     std::vector<DevBuf> keep;
     float ms_kernel = 0.f;
+    // multi-pass groups: list entries, their segments (SM_PMAX per entry) and passes used
+    int64_t n_seg_groups = 0;
+    const int32_t *seg_list = nullptr;
+    const SegRec *segs = nullptr;
+    const int32_t *seg_count = nullptr;
 };
 
 inline void smem_path_configure()
 {
-    CK(cudaFuncSetAttribute(k_smem_count<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<1>()));
-    CK(cudaFuncSetAttribute(k_smem_count<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<1>()));
-    CK(cudaFuncSetAttribute(k_smem_count<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK(cudaFuncSetAttribute(k_smem_count<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<2>()));
-    CK(cudaFuncSetAttribute(k_smem_count<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK(cudaFuncSetAttribute(k_sort_big<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<1>()));
-    CK(cudaFuncSetAttribute(k_sort_big<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<2>()));
-    CK(cudaFuncSetAttribute(k_smem_count<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    auto cfg = [](auto kernel, size_t bytes) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    };
+    cfg(k_smem_count<1, true, false>, smem_bytes<1>());
+    cfg(k_smem_count<1, false, false>, smem_bytes<1>());
+    cfg(k_smem_count<2, false, false>, smem_bytes<2>());
+    cfg(k_smem_count<1, true, true>, smem_bytes<1>());
+    cfg(k_smem_count<1, false, true>, smem_bytes<1>());
+    cfg(k_smem_count<2, false, true>, smem_bytes<2>());
+    CK(cudaFuncSetAttribute(k_sort_big<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<1>()));
+    CK(cudaFuncSetAttribute(k_sort_big<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<2>()));
+    CK(cudaFuncSetAttribute(k_sort_big<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<1>()));
+    CK(cudaFuncSetAttribute(k_sort_big<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<2>()));
 }
 
 inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, size_t workspace_bytes, const ColView &col, const uint8_t *data_begin,
                           const uint8_t *data_end,
                           const int64_t *d_group_offsets, int64_t n_groups, int K, uint32_t min_cov, unsigned long long *d_nobs,
                           int64_t *d_nsurv, SmemResult &res, int64_t *launches, cudaEvent_t ev_a, cudaEvent_t ev_b,
-                          unsigned long long *phase_out /* host [8] or nullptr */)
+                          unsigned long long *phase_out /* host [8] or nullptr */, bool multipass = true)
 {
     const int W = K > 32 ? 2 : 1;
     DevBuf ctr(128, st);
@@ -985,11 +1202,11 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     CK(cudaEventRecord(ev_a, st));
     if (W == 1) {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 2);
-        if (K == 32) k_smem_count<1, true><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
-        else k_smem_count<1, false><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
+        if (K == 32) k_smem_count<1, true, false><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
+        else k_smem_count<1, false, false><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count);
-        k_smem_count<2, false><<<grid, SM_NT, smem_bytes<2>(), st>>>(a);
+        k_smem_count<2, false, false><<<grid, SM_NT, smem_bytes<2>(), st>>>(a);
     }
     CK(cudaEventRecord(ev_b, st));
     if (launches) *launches += 2;
@@ -999,8 +1216,46 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     pk.sync();
     CK(cudaEventElapsedTime(&res.ms_kernel, ev_a, ev_b));
     res.n_deferred = (int64_t)h_ctr[2];
-    res.n_pool_groups = n_groups - res.n_deferred;
     res.deferred_ids = d_ids;
+    if (res.n_deferred > 0 && multipass) {
+        // second launch: the deferred groups, several passes over slabs of their reads; what it cannot finish either
+        // (very large groups, single reads longer than a slab) is listed again for the HBM-table path
+        const int64_t n_a = res.n_deferred;
+        res.keep.emplace_back((size_t)n_a * 4, st);
+        int32_t *d_ids2 = res.keep.back().as<int32_t>();
+        res.keep.emplace_back((size_t)n_a * SM_PMAX * sizeof(SegRec), st);
+        SegRec *d_segs = res.keep.back().as<SegRec>();
+        res.keep.emplace_back((size_t)n_a * 4, st);
+        int32_t *d_segc = res.keep.back().as<int32_t>();
+        CK(cudaMemsetAsync(d_segc, 0, (size_t)n_a * 4, st));
+        a.group_list = d_ids;
+        a.n_list = n_a;
+        a.segs = d_segs;
+        a.seg_count = d_segc;
+        a.ticket = d_ctr + 4;
+        a.deferred_ids = d_ids2;
+        a.n_deferred = d_ctr + 5;
+        a.phase_cycles = nullptr;
+        if (W == 1) {
+            const unsigned grid = (unsigned)std::min<int64_t>(n_a, (int64_t)sm_count * 2);
+            if (K == 32) k_smem_count<1, true, true><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
+            else k_smem_count<1, false, true><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
+        } else {
+            const unsigned grid = (unsigned)std::min<int64_t>(n_a, (int64_t)sm_count);
+            k_smem_count<2, false, true><<<grid, SM_NT, smem_bytes<2>(), st>>>(a);
+        }
+        if (launches) *launches += 1;
+        unsigned long long n_b = 0;
+        pk.add(d_ctr + 5, 8, &n_b);
+        pk.sync();
+        res.n_seg_groups = n_a;
+        res.seg_list = d_ids;
+        res.segs = d_segs;
+        res.seg_count = d_segc;
+        res.deferred_ids = d_ids2;
+        res.n_deferred = (int64_t)n_b;
+    }
+    res.n_pool_groups = n_groups - res.n_deferred;
     res.pool_start = p_start;
     res.pool_lo = p_lo;
     res.pool_hi = p_hi;

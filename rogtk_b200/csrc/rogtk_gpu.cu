@@ -418,7 +418,7 @@ void fill_empty_batch(rogtk_gpu_ctx *ctx, int64_t n_groups, bool out_dev, uint32
 
 struct DeviceResult {   // dense, group-ordered result of one pipeline run, still in HBM
     DevBuf off, lo, hi, exts, counts, stats, rowptr, cols;
-    int64_t n_kmers = 0, n_edges = 0, n_obs = 0, n_spill = 0;
+    int64_t n_kmers = 0, n_edges = 0, n_obs = 0, n_spill = 0, n_multi = 0;
     float ms_hot = 0.f;
 };
 
@@ -460,7 +460,7 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     if (!(flags & ROGTK_FORCE_SPILL) && n_groups > 0) {
         run_smem_path(ctx->stream, ctx->peek_slot, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_begin, in.data_end, in.group_offsets,
                       n_groups, K, min_coverage, d_nobs, nsurv.as<int64_t>(), sm, &ctx->launches, ctx->ev[4], ctx->ev[5],
-                      ctx->phase_enabled ? ctx->phase_cycles : nullptr);
+                      ctx->phase_enabled ? ctx->phase_cycles : nullptr, !(flags & ROGTK_NO_MULTIPASS));
         d_spill_ids = sm.deferred_ids;
         n_spill = sm.n_deferred;
     }
@@ -490,7 +490,8 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     uint64_t *p_hi = K > 32 ? r.hi.as<uint64_t>() : nullptr;
     if (sm.n_pool_groups > 0)
         run_sort_gather(st, ctx->peek_slot, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
-                        sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches);
+                        sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches,
+                        sm.segs, sm.seg_count, sm.seg_list, sm.n_seg_groups);
     for (auto &wv : waves) {
         if (wv.n_recs == 0) continue;
         k_spill_scatter<<<blocks_for(wv.n_recs, 256), 256, 0, st>>>(wv.recs.as<SpillRec>(), wv.n_recs, d_spill_ids, wv.list_base,
@@ -533,6 +534,7 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     r.n_edges = n_edges;
     r.n_obs = (int64_t)h_nobs;
     r.n_spill = n_spill;
+    r.n_multi = sm.n_seg_groups - (sm.n_seg_groups ? sm.n_deferred : 0);
     r.ms_hot = sm.ms_kernel;
 }
 
@@ -656,7 +658,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     HostArr h_off, h_lo, h_hi, h_exts, h_counts, h_stats, h_rowptr, h_cols;
     host_reserve(ctx, h_off, (size_t)(n_groups + 1) * 8, 0, s_out);
     if (flags & ROGTK_EMIT_STATS) host_reserve(ctx, h_stats, (size_t)n_groups * 12 + 16, 0, s_out);
-    int64_t base_k = 0, base_e = 0, n_obs = 0, n_spill = 0;
+    int64_t base_k = 0, base_e = 0, n_obs = 0, n_spill = 0, n_multi = 0;
     float ms_total = 0, ms_count = 0, ms_hot = 0;
     const int64_t total_bytes = std::max<int64_t>(1, off_at(group_offsets[n_groups]) - off_at(group_offsets[0]));
     std::vector<DeviceResult> inflight(2);
@@ -726,6 +728,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         base_e += r.n_edges;
         n_obs += r.n_obs;
         n_spill += r.n_spill;
+        n_multi += r.n_multi;
     }
     CK(cudaStreamSynchronize(s_out));
     CK(cudaStreamSynchronize(s_in));
@@ -748,6 +751,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     out->n_edges = base_e;
     out->n_observations = n_obs;
     out->n_spilled_groups = n_spill;
+    out->n_multipass_groups = (int32_t)n_multi;
     auto adopt = [&](HostArr &h) -> void * {
         if (h.p) own->ptrs.push_back(h.p);
         return h.p;
@@ -825,6 +829,7 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
     out->n_edges = r.n_edges;
     out->n_observations = r.n_obs;
     out->n_spilled_groups = r.n_spill;
+    out->n_multipass_groups = (int32_t)r.n_multi;
     auto give = [&](DevBuf &b, size_t bytes) -> void * {
         if (!b.p) return nullptr;
         if (out_dev) {

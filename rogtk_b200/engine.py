@@ -42,6 +42,7 @@ class GraphBatch:
     ms_count: float = 0.0
     ms_hot_kernel: float = 0.0
     n_spilled_groups: int = 0
+    n_multipass_groups: int = 0
 
     @property
     def n_groups(self) -> int:
@@ -65,6 +66,7 @@ class DeviceBatch:
     ms_count: float
     ms_hot_kernel: float
     n_spilled_groups: int
+    n_multipass_groups: int
     _c: _ffi.GraphBatchC
     _engine: "Engine"
 
@@ -92,7 +94,7 @@ class DeviceBatch:
             csr_row_ptr=pull(c.csr_row_ptr, self.n_kmers + 1, np.int64) if c.csr_row_ptr else None,
             csr_col=pull(c.csr_col, self.n_edges, np.int32) if c.csr_col else None,
             ms_total=self.ms_total, ms_count=self.ms_count, ms_hot_kernel=self.ms_hot_kernel,
-            n_spilled_groups=self.n_spilled_groups)
+            n_spilled_groups=self.n_spilled_groups, n_multipass_groups=self.n_multipass_groups)
 
 
 def k_eff(k: int) -> int:
@@ -224,7 +226,7 @@ class Engine:
             csr_row_ptr=arr(c.csr_row_ptr, nk + 1, np.int64) if c.csr_row_ptr else None,
             csr_col=arr(c.csr_col, int(c.n_edges), np.int32) if c.csr_row_ptr else None,
             ms_total=float(c.ms_total), ms_count=float(c.ms_count), ms_hot_kernel=float(c.ms_hot_kernel),
-            n_spilled_groups=int(c.n_spilled_groups))
+            n_spilled_groups=int(c.n_spilled_groups), n_multipass_groups=int(c.n_multipass_groups))
         self._lib.rogtk_gpu_free_batch(self._ctx, ctypes.byref(c))
         return res
 
@@ -281,7 +283,8 @@ class Engine:
                        flags | _ffi.INPUT_ON_DEVICE | _ffi.OUTPUT_ON_DEVICE)
         return DeviceBatch(k_eff=int(c.k_eff), n_groups=int(c.n_groups), n_kmers=int(c.n_kmers), n_edges=int(c.n_edges),
                            n_observations=int(c.n_observations), ms_total=float(c.ms_total), ms_count=float(c.ms_count),
-                           ms_hot_kernel=float(c.ms_hot_kernel), n_spilled_groups=int(c.n_spilled_groups), _c=c, _engine=self)
+                           ms_hot_kernel=float(c.ms_hot_kernel), n_spilled_groups=int(c.n_spilled_groups),
+                           n_multipass_groups=int(c.n_multipass_groups), _c=c, _engine=self)
 
 
     def count_prune_to_device(self, data: np.ndarray, offsets: np.ndarray, group_offsets: np.ndarray, k: int, min_coverage: int,
@@ -301,7 +304,8 @@ class Engine:
                        (flags | _ffi.OUTPUT_ON_DEVICE) & ~_ffi.INPUT_ON_DEVICE)
         return DeviceBatch(k_eff=int(c.k_eff), n_groups=int(c.n_groups), n_kmers=int(c.n_kmers), n_edges=int(c.n_edges),
                            n_observations=int(c.n_observations), ms_total=float(c.ms_total), ms_count=float(c.ms_count),
-                           ms_hot_kernel=float(c.ms_hot_kernel), n_spilled_groups=int(c.n_spilled_groups), _c=c, _engine=self)
+                           ms_hot_kernel=float(c.ms_hot_kernel), n_spilled_groups=int(c.n_spilled_groups),
+                           n_multipass_groups=int(c.n_multipass_groups), _c=c, _engine=self)
 
     # ---- global k-mer spectrum (one group spanning every rank) -------------------------------------------------------------
     def spectrum_split(self, d_lo: int, d_hi: int | None, n: int, k_eff_: int, n_ranks: int) -> np.ndarray:

@@ -7,11 +7,11 @@ from util import assert_batches_equal, check_invariants, groups_to_arrow, load_g
 
 pytestmark = pytest.mark.gpu
 
-EMIT_CSR, EMIT_STATS, EXACT_K, FORCE_SPILL = 1, 2, 4, 32
+EMIT_CSR, EMIT_STATS, EXACT_K, FORCE_SPILL, NO_MULTIPASS = 1, 2, 4, 32, 64
 
 
-def _both(engine, oracle, data, offs, goff, k, mc, validity=None, exact=False, spill=False, csr=True, ctx=""):
-    flags = EMIT_STATS | (EMIT_CSR if csr else 0) | (EXACT_K if exact else 0) | (FORCE_SPILL if spill else 0)
+def _both(engine, oracle, data, offs, goff, k, mc, validity=None, exact=False, spill=False, csr=True, ctx="", extra_flags=0):
+    flags = EMIT_STATS | (EMIT_CSR if csr else 0) | (EXACT_K if exact else 0) | (FORCE_SPILL if spill else 0) | extra_flags
     got = engine.count_prune(data, offs, goff, k, mc, validity=validity, flags=flags)
     ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity, exact_k=exact, emit_csr=csr)
     assert_batches_equal(got, ref, check_csr=csr, ctx=ctx)
@@ -122,21 +122,67 @@ def test_count_saturation_and_long_reads(engine, oracle):
             _both(engine, oracle, data, offs, np.array([0, 2, 3]), k, 1, spill=spill, ctx=f"all-T k={k}")
 
 
-def test_groups_too_big_for_shared_memory_spill(engine, oracle):
-    """skewed groups (cfg3 shape): > 256 rows, > 16384 bases, or too many distinct k-mers go through the HBM tables;
+def test_groups_too_big_for_one_table(engine, oracle):
+    """skewed groups (cfg3 shape): > 256 rows, > 16384 bases, or too many distinct k-mers for one shared-memory table are
+    counted in several passes over slabs of their reads, or (ROGTK_NO_MULTIPASS / very large groups) through the HBM tables;
     the answer must not depend on the path taken."""
     from rogtk_b200 import synth
     rp = np.array([1, 2, 3, 40, 300, 7, 120, 600, 55, 1, 260, 90])
     data, offs, goff = synth.synth_reads(synth.config_seed(3), 0, len(rp), rp, 150, 500)
     for k in (11, 17, 33):
         got, ref = _both(engine, oracle, data, offs, goff, k, 2, ctx=f"skew k={k}")
-        assert got.n_spilled_groups >= 3
+        assert got.n_multipass_groups >= 3 and got.n_spilled_groups == 0
+        got, ref = _both(engine, oracle, data, offs, goff, k, 2, ctx=f"skew k={k} hbm", extra_flags=NO_MULTIPASS)
+        assert got.n_spilled_groups >= 3 and got.n_multipass_groups == 0
     # many distinct k-mers in few rows: 60 unrelated reads of 250 bases
     rng = np.random.default_rng(11)
     reads = ["".join("ACGT"[x] for x in rng.integers(0, 4, 250)) for _ in range(60)]
     data, offs, validity = oracle.strings_to_arrow(reads)
     got, ref = _both(engine, oracle, data, offs, np.array([0, 60]), 31, 1, ctx="distinct overflow")
+    assert got.n_multipass_groups == 1 and got.n_spilled_groups == 0
+    got, ref = _both(engine, oracle, data, offs, np.array([0, 60]), 31, 1, ctx="distinct overflow hbm", extra_flags=NO_MULTIPASS)
     assert got.n_spilled_groups == 1
+
+
+@pytest.mark.parametrize("k,exact", [(31, False), (16, False), (47, False), (33, True), (6, True), (1, True)])
+def test_multipass_groups(engine, oracle, k, exact):
+    """mid-size groups: 60..600 reads of 300 bp around a 1000 bp template (1..16 passes), a group of unrelated reads (every pass
+    near its table limit), null / invalid / short reads inside slabs, and a group beyond the multi-pass limit (HBM tables)."""
+    from rogtk_b200 import synth
+    rp = np.array([60, 5, 130, 280, 0, 600, 90, 700])
+    data, offs, goff = synth.synth_reads(synth.config_seed(2), 7, len(rp), rp, 300, 1000)
+    for mc in (1, 2, 3):
+        got, ref = _both(engine, oracle, data, offs, goff, k, mc, exact=exact, csr=(mc == 2), ctx=f"multipass k={k} mc={mc}")
+        assert got.n_multipass_groups >= 4
+        assert got.n_spilled_groups == 1           # 700 x 300 bases is beyond 16 passes
+    rng = np.random.default_rng(k)
+    groups = []
+    # unrelated reads: ~ as many distinct k-mers as observations
+    groups.append(["".join("ACGT"[x] for x in rng.integers(0, 4, 200)) for _ in range(300)])
+    # dirty slabs: nulls, empties, non-ACGT bytes, lower case, reads shorter than k, one long read
+    tmpl = "".join("ACGT"[x] for x in rng.integers(0, 4, 3000))
+    dirty = []
+    for i in range(400):
+        s = int(rng.integers(0, 2700))
+        r = tmpl[s:s + int(rng.integers(1, 300))]
+        u = rng.random()
+        if u < 0.05:
+            r = None
+        elif u < 0.10:
+            r = ""
+        elif u < 0.15:
+            r = r[:len(r) // 2] + "N" + r[len(r) // 2 + 1:]
+        elif u < 0.25:
+            r = r.lower()
+        dirty.append(r)
+    dirty.insert(200, tmpl)
+    groups.append(dirty)
+    # low-complexity group: every k-mer of the group falls into very few ranges
+    groups.append(["A" * 250 + "C" * 50, "T" * 300, "ACAC" * 75] * 40)
+    d2, o2, v2, g2 = groups_to_arrow(groups)
+    for mc in (1, 2):
+        got, ref = _both(engine, oracle, d2, o2, g2, k, mc, validity=v2, exact=exact, ctx=f"multipass dirty k={k} mc={mc}")
+        assert got.n_multipass_groups >= 2
 
 
 def test_device_generator_matches_numpy(engine):
