@@ -35,12 +35,11 @@ constexpr int SM_SORT_BUCKETS = 1 << SM_SORT_BITS;
 constexpr int SM_POOL_CHUNK = 32768;   // survivors a CTA reserves from the pool at a time
 constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this -> bitonic kernel
 // Multi-pass variant for groups that do not fit one table / one staged span (MULTI = true): the k-mer space is cut into
-// 2^lg equal ranges by the top bits of the k-mer; pass p re-reads the group's reads in slabs of <= SM_MAX_BASES bases and
-// counts only the k-mers of range p, so every pass needs a table for about 1/2^lg of the distinct k-mers and its survivors
-// form one ascending segment of the group's output.
-constexpr int SM_PMAX_LG = 4;                 // up to 16 passes
-constexpr int SM_PMAX = 1 << SM_PMAX_LG;
-constexpr int64_t SM_PASS_OBS = 12288;        // bases per pass the first attempt plans for (doubles the passes on overflow)
+// P equal ranges (range of a k-mer = floor(top 32 bits * P / 2^32)); pass p re-reads the group's reads in slabs of
+// <= SM_MAX_BASES bases and counts only the k-mers of range p, so every pass needs a table for about 1/P of the distinct
+// k-mers and its survivors form one ascending segment of the group's output.
+constexpr int SM_PMAX = 16;                   // passes per group at most
+constexpr int64_t SM_PASS_OBS = 16384;        // bases per pass the first attempt plans for (doubles the passes on overflow)
 
 struct SegRec {          // survivors of one pass of a multi-pass group
     int64_t pool_start;
@@ -87,13 +86,22 @@ struct SmemArgs {
     int32_t *seg_count;              // [n_list], 0 = the group was not finished here
 };
 
-// top `lg` bits of a k-mer of kbits bits (lg <= kbits)
-__device__ __forceinline__ uint32_t key_part(const Key<1> &k, int kbits, int lg) { return lg ? (uint32_t)(k.lo >> (kbits - lg)) : 0u; }
-__device__ __forceinline__ uint32_t key_part(const Key<2> &k, int kbits, int lg)
+// top 32 bits of a k-mer of kbits bits (shorter k-mers are left-aligned)
+__device__ __forceinline__ uint32_t key_top32(const Key<1> &k, int kbits)
 {
-    if (!lg) return 0u;
-    const int sh = kbits - lg;   // >= 60 here (kbits > 64, lg <= 4)
+    return kbits >= 32 ? (uint32_t)(k.lo >> (kbits - 32)) : (uint32_t)k.lo << (32 - kbits);
+}
+__device__ __forceinline__ uint32_t key_top32(const Key<2> &k, int kbits)
+{
+    const int sh = kbits - 32;   // 34 .. 96
     return sh >= 64 ? (uint32_t)(k.hi >> (sh - 64)) : (uint32_t)((k.hi << (64 - sh)) | (k.lo >> sh));
+}
+// range (pass) of a k-mer among P equal ranges of the k-mer space; monotone in the k-mer
+__device__ __forceinline__ uint32_t pass_of(uint32_t top32, uint32_t P) { return __umulhi(top32, P); }
+// first top-32 value of range p: smallest x with floor(x * P / 2^32) == p
+__device__ __forceinline__ uint32_t pass_first(uint32_t p, uint32_t P)
+{
+    return (uint32_t)((((uint64_t)p << 32) + P - 1u) / P);
 }
 
 // multiplicative hash, slot = top bits.  On the synthetic shapes it probes 1.32 slots per observation vs 1.31 for a
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     // the group being worked on; MULTI keeps it over several iterations of the loop (one slab of one pass each)
     int64_t item = 0, g = 0, r0 = 0, r1 = 0, b0 = 0, b1 = 0;
     bool in_group = false;             // MULTI: a group is in progress
-    int lgP = 0, pass = 0;             // MULTI: 2^lgP passes, current pass
+    int P = 1, pass = 0;               // MULTI: number of passes, current pass
     int64_t srow = 0;                  // MULTI: first row of the next slab
     uint32_t gprefix = 0, gobs = 0;    // MULTI: survivors of the finished passes, observations of the group
 
@@ -390,9 +398,8 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                     defer(g);
                     continue;
                 }
-                lgP = 0;
-                if (2 * K > 12)   // at most 4^K <= 4096 distinct k-mers otherwise: one table always holds them
-                    while (lgP < SM_PMAX_LG && ub > (SM_PASS_OBS << lgP)) lgP++;
+                P = 1;
+                if (2 * K > 12) P = (int)((ub + SM_PASS_OBS - 1) / SM_PASS_OBS);   // <= 4^K <= 4096 distinct k-mers otherwise
                 in_group = true;
                 pass = 0;
                 srow = r0;
@@ -517,9 +524,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         PHASE_MARK(2);
         // ---- counting: warps fetch units of SM_UNIT windows of one read; no block barriers ---------------------------------------------
         if (tid == 0 && pf_stage == 0) pf_advance();   // next group's row range (its ticket has long arrived)
-        // MULTI: this pass takes the k-mers whose top lgP bits equal `pass`
-        const uint32_t pmask32 = (MULTI && lgP) ? (~0u << (32 - lgP)) : 0u;
-        const uint32_t pval32 = (MULTI && lgP) ? ((uint32_t)pass << (32 - lgP)) : 0u;
+        // MULTI: this pass takes the k-mers of range `pass` (pass_of)
         if (total != 0) {
             wq.n = 0;
             wq.budget = 64 + (int)(total >> 1);   // drain steps allowed per warp: far above any non-full table's need
@@ -572,7 +577,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                         const bool has_l = u ? true : (p != 0u);
                         const bool has_r = (p + u + 1u) < nk;
                         act[u] = (uint32_t)u < R && j0 + (uint32_t)u < ulen;
-                        if (MULTI) act[u] = act[u] && (kh[u] & pmask32) == pval32;
+                        if (MULTI) act[u] = act[u] && pass_of(kh[u], (uint32_t)P) == (uint32_t)pass;
                         ex[u] = (has_l ? (1u << lb) : 0u) | (has_r ? (16u << nb) : 0u);
                         h[u] = hash32(kl[u], kh[u]) >> tshift;
                         if (u < 3) {
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                             kl[u + 1] = (kl[u] << 2) | nb;
                         }
                     }
-                    const bool sparse = MULTI && lgP != 0;   // few windows of the unit belong to this pass
+                    const bool sparse = MULTI && P > 1;   // few windows of the unit belong to this pass
                     KT cur[4];
                     if (!sparse) {
 #pragma unroll
@@ -669,13 +674,13 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                             const uint32_t q = rs + p;
                             Key<W> key = Key<W>::zero();
                             load_window(pk, q, K, key);
-                            if (!MULTI || key_part(key, 2 * K, lgP) == (uint32_t)pass) {
+                            if (!MULTI || pass_of(key_top32(key, 2 * K), (uint32_t)P) == (uint32_t)pass) {
                                 const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
                                 // Exts of iter_kmer_exts with seq_exts = Exts::empty()
                                 ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
                                 h = hash32(key) >> tshift;
                                 kp = S::pack(key);
-                                if (MULTI && lgP != 0 && !(kp == S::empty())) {   // sparse pass: queue, drain 32 wide
+                                if (MULTI && P > 1 && !(kp == S::empty())) {   // sparse pass: queue, drain 32 wide
                                     pend = true;
                                     h = (h - 1u) & tmask;
                                 } else {
@@ -718,8 +723,8 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         }
         __syncthreads();
         if (misc[3]) {   // too many distinct k-mers for a shared-memory table
-            if (MULTI && lgP < SM_PMAX_LG && lgP < 2 * K) {   // start the group over with twice the passes
-                lgP++;
+            if (MULTI && P < SM_PMAX && 2 * K > 12) {   // start the group over with twice the passes
+                P = 2 * P < SM_PMAX ? 2 * P : SM_PMAX;
                 pass = 0;
                 srow = r0;
                 gprefix = 0;
@@ -804,7 +809,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             gprefix += n_out;
             pass++;
             srow = r0;
-            if (pass == (1 << lgP)) {   // group complete; its pool_start stays -1, the segments carry the survivors
+            if (pass == P) {   // group complete; its pool_start stays -1, the segments carry the survivors
                 if (tid == 0) {
                     a.seg_count[item] = pass;
                     a.nsurv[g] = (int64_t)gprefix;
@@ -863,7 +868,7 @@ struct SortArgs {
 };
 
 // SEG = false: work items are groups.  SEG = true: segments of multi-pass groups (item i = pass i % SM_PMAX of list entry
-// i / SM_PMAX); the k-mers of a segment share their top lg bits, so the buckets are taken from the bits below them.
+// i / SM_PMAX); the k-mers of a segment lie in 1/P of the k-mer space, so the buckets subdivide that range.
 template <int W, bool SEG>
 __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_items)
 {
@@ -879,7 +884,9 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
     const int tid = threadIdx.x;
     for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
         int64_t ps, o;
-        int n, kb = a.kbits;
+        int n;
+        const int kb = a.kbits;
+        uint32_t seg_np = 1, seg_first = 0;   // SEG: passes of the group, first top-32 value of this segment's k-mer range
         if (SEG) {
             const int64_t e = it / SM_PMAX;
             const int np = a.seg_count[e];
@@ -888,7 +895,8 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
             ps = r.pool_start;
             o = a.kmer_offsets[a.seg_list[e]] + r.prefix;
             n = r.n;
-            kb -= 31 - __clz(np);   // np = 2^lg passes: the top lg bits are the same for the whole segment
+            seg_np = (uint32_t)np;
+            seg_first = pass_first((uint32_t)(it % SM_PMAX), seg_np);
         } else {
             ps = a.pool_start[it];
             if (ps < 0) continue;
@@ -910,8 +918,13 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
         }
         __syncthreads();
         auto bucket_of = [&](int j) -> uint32_t {
-            if (W == 2) return sort_bucket<2>(Key<2>{s_lo[j], s_hi[j]}, kb) & (uint32_t)(SM_SORT_BUCKETS - 1);
-            return sort_bucket<1>(Key<1>{s_lo[j]}, kb) & (uint32_t)(SM_SORT_BUCKETS - 1);
+            if (SEG) {   // position inside the segment's k-mer range, scaled to the bucket count (monotone in the k-mer)
+                const uint32_t t = W == 2 ? key_top32(Key<2>{s_lo[j], s_hi[j]}, kb) : key_top32(Key<1>{s_lo[j]}, kb);
+                const uint64_t b = ((uint64_t)(t - seg_first) * seg_np) >> (32 - SM_SORT_BITS);
+                return b < (uint64_t)SM_SORT_BUCKETS ? (uint32_t)b : (uint32_t)(SM_SORT_BUCKETS - 1);
+            }
+            if (W == 2) return sort_bucket<2>(Key<2>{s_lo[j], s_hi[j]}, kb);
+            return sort_bucket<1>(Key<1>{s_lo[j]}, kb);
         };
         for (int j = tid; j < n; j += SORT_NT) atomicAdd(&s_hist[bucket_of(j)], 1u);
         __syncthreads();

@@ -149,12 +149,12 @@ def test_multipass_groups(engine, oracle, k, exact):
     """mid-size groups: 60..600 reads of 300 bp around a 1000 bp template (1..16 passes), a group of unrelated reads (every pass
     near its table limit), null / invalid / short reads inside slabs, and a group beyond the multi-pass limit (HBM tables)."""
     from rogtk_b200 import synth
-    rp = np.array([60, 5, 130, 280, 0, 600, 90, 700])
+    rp = np.array([60, 5, 130, 280, 0, 600, 90, 1000])
     data, offs, goff = synth.synth_reads(synth.config_seed(2), 7, len(rp), rp, 300, 1000)
     for mc in (1, 2, 3):
         got, ref = _both(engine, oracle, data, offs, goff, k, mc, exact=exact, csr=(mc == 2), ctx=f"multipass k={k} mc={mc}")
         assert got.n_multipass_groups >= 4
-        assert got.n_spilled_groups == 1           # 700 x 300 bases is beyond 16 passes
+        assert got.n_spilled_groups == 1           # 1000 x 300 bases is beyond 16 passes
     rng = np.random.default_rng(k)
     groups = []
     # unrelated reads: ~ as many distinct k-mers as observations
