@@ -316,13 +316,19 @@ class Engine:
         return b
 
     def spectrum_merge(self, d_lo: int, d_hi: int | None, d_counts: int, d_exts: int, n: int, k_eff_: int, min_coverage: int,
-                       flags: int = 0) -> GraphBatch:
-        """Merge (k-mer, partial count, exts) triples received from all ranks: one ascending group with count >= min_coverage."""
+                       flags: int = 0, on_device: bool = False):
+        """Merge (k-mer, partial count, exts) triples received from all ranks: one ascending group with count >= min_coverage.
+        on_device=True leaves the result in HBM (DeviceBatch): the carry between the rounds of a chunked global spectrum."""
         out = _ffi.GraphBatchC()
+        f = (int(flags) | _ffi.OUTPUT_ON_DEVICE) if on_device else (int(flags) & ~_ffi.OUTPUT_ON_DEVICE)
         self._check(self._lib.rogtk_gpu_spectrum_merge(self._ctx, ctypes.c_void_p(d_lo), ctypes.c_void_p(d_hi or 0),
                                                        ctypes.c_void_p(d_counts), ctypes.c_void_p(d_exts), int(n), int(k_eff_),
-                                                       int(min_coverage), int(flags) & ~_ffi.OUTPUT_ON_DEVICE, ctypes.byref(out)))
-        return self._to_numpy(out)
+                                                       int(min_coverage), f, ctypes.byref(out)))
+        if not on_device:
+            return self._to_numpy(out)
+        return DeviceBatch(k_eff=int(out.k_eff), n_groups=int(out.n_groups), n_kmers=int(out.n_kmers), n_edges=int(out.n_edges),
+                           n_observations=int(out.n_observations), ms_total=float(out.ms_total), ms_count=float(out.ms_count),
+                           ms_hot_kernel=float(out.ms_hot_kernel), n_spilled_groups=0, n_multipass_groups=0, _c=out, _engine=self)
 
     # ---- threshold re-use (SURVEY 8f-1) -------------------------------------------------------------------------------------------
     def rethreshold(self, batch: DeviceBatch, min_coverage: int, flags: int = 0) -> GraphBatch:

@@ -58,44 +58,88 @@ def _exchange(send, send_counts, group, device):
 
 
 def global_spectrum(engine: Engine, data: np.ndarray, offsets: np.ndarray, k: int, min_coverage: int, group=None,
-                    validity: np.ndarray | None = None, flags: int = 0) -> GraphBatch:
+                    validity: np.ndarray | None = None, flags: int = 0, chunk_rows: int | None = None) -> GraphBatch:
     """This rank's share of the global spectrum of all ranks' reads.  `group` is a torch.distributed process group
-    (None = default group; if torch.distributed is not initialised the call is the single-rank form)."""
+    (None = default group; if torch.distributed is not initialised the call is the single-rank form).
+
+    `chunk_rows` bounds the reads counted at a time: the local table of a round is sized by the round's reads, not by the
+    whole input, and the rank's share of the spectrum (distinct k-mers it owns, counts saturating at 65535, exts) is carried in
+    HBM from round to round; min_coverage is applied in the last round only.  Every rank runs the same number of rounds."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    multi = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if multi else 1
+    nccl = multi and dist.get_backend(group) == "nccl"
     device = torch.device("cuda", engine.device)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n_rows = len(offsets) - 1
-    local = engine.count_prune_to_device(data, offsets, np.array([0, n_rows], dtype=np.int64), k, 1, validity=validity,
-                                         flags=flags & _ffi.EXACT_K)
+    step = n_rows if not chunk_rows or chunk_rows <= 0 else int(chunk_rows)
+    rounds = max(1, -(-n_rows // max(step, 1)))
+    if world > 1:
+        t = torch.tensor([rounds], dtype=torch.int64, device=device if nccl else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        rounds = int(t.item())
+    if validity is not None and rounds > 1:
+        raise ValueError("chunk_rows with a validity bitmap is not supported: drop the null rows first")
+
+    carry = None        # device-resident share of the spectrum after the previous rounds (C batch, min_coverage 1)
+    carry_t = None      # torch views of it
+    n_obs = 0
+    K = None
     try:
-        K = local.k_eff
-        if K < 0:   # k > 64: empty result (reference src/fracture.rs:212-215)
-            return local.to_host()
-        c, n = local._c, local.n_kmers
-        bounds = engine.spectrum_split(c.kmers_lo, c.kmers_hi, n, K, world)
-        send_counts = [int(bounds[d + 1] - bounds[d]) for d in range(world)]
-        lo = _as_tensor(c.kmers_lo, n, "<i8", torch.int64, device)
-        hi = _as_tensor(c.kmers_hi, n, "<i8", torch.int64, device) if K > 32 else None
-        cnt = _as_tensor(c.counts, n, "<i2", torch.int16, device)
-        ext = _as_tensor(c.exts, n, "|u1", torch.uint8, device)
-        if world > 1:
-            r_lo, _ = _exchange(lo, send_counts, group, device)
-            r_hi = _exchange(hi, send_counts, group, device)[0] if hi is not None else None
-            r_cnt, _ = _exchange(cnt, send_counts, group, device)
-            r_ext, _ = _exchange(ext, send_counts, group, device)
-        else:
-            r_lo, r_hi, r_cnt, r_ext = lo, hi, cnt, ext
-        torch.cuda.synchronize(device)
-        n_obs = local.n_observations
-        if world > 1:   # observations of the whole job (a size, not data)
-            t = torch.tensor([n_obs], dtype=torch.int64, device=device if dist.get_backend(group) == "nccl" else "cpu")
-            dist.all_reduce(t, group=group)
-            n_obs = int(t.item())
-        res = engine.spectrum_merge(r_lo.data_ptr() if r_lo.numel() else 0, r_hi.data_ptr() if r_hi is not None and r_hi.numel() else 0,
-                                     r_cnt.data_ptr() if r_cnt.numel() else 0, r_ext.data_ptr() if r_ext.numel() else 0,
-                                     int(r_lo.numel()), K, min_coverage, flags=flags & _ffi.EMIT_STATS)
-        res.n_observations = n_obs
-        return res
+        for r in range(rounds):
+            a, b = min(n_rows, r * step), min(n_rows, (r + 1) * step)
+            d = data[offsets[a]:offsets[b]]
+            o = offsets[a:b + 1] - offsets[a]
+            local = engine.count_prune_to_device(d, o, np.array([0, b - a], dtype=np.int64), k, 1,
+                                                 validity=validity if rounds == 1 else None, flags=flags & _ffi.EXACT_K)
+            try:
+                K = local.k_eff
+                if K < 0:   # k > 64: empty result (reference src/fracture.rs:212-215)
+                    return local.to_host()
+                n_obs += local.n_observations
+                c, n = local._c, local.n_kmers
+                bounds = engine.spectrum_split(c.kmers_lo, c.kmers_hi, n, K, world)
+                send_counts = [int(bounds[i + 1] - bounds[i]) for i in range(world)]
+                lo = _as_tensor(c.kmers_lo, n, "<i8", torch.int64, device)
+                hi = _as_tensor(c.kmers_hi, n, "<i8", torch.int64, device) if K > 32 else None
+                cnt = _as_tensor(c.counts, n, "<i2", torch.int16, device)
+                ext = _as_tensor(c.exts, n, "|u1", torch.uint8, device)
+                if world > 1:
+                    r_lo, _ = _exchange(lo, send_counts, group, device)
+                    r_hi = _exchange(hi, send_counts, group, device)[0] if hi is not None else None
+                    r_cnt, _ = _exchange(cnt, send_counts, group, device)
+                    r_ext, _ = _exchange(ext, send_counts, group, device)
+                else:
+                    r_lo, r_hi, r_cnt, r_ext = lo, hi, cnt, ext
+                if carry_t is not None:   # what this rank owns so far joins the merge as one more source
+                    r_lo = torch.cat([carry_t[0], r_lo])
+                    r_hi = torch.cat([carry_t[1], r_hi]) if r_hi is not None else None
+                    r_cnt = torch.cat([carry_t[2], r_cnt])
+                    r_ext = torch.cat([carry_t[3], r_ext])
+                torch.cuda.synchronize(device)
+                last = r == rounds - 1
+                ptr = lambda t_: t_.data_ptr() if t_ is not None and t_.numel() else 0
+                merged = engine.spectrum_merge(ptr(r_lo), ptr(r_hi), ptr(r_cnt), ptr(r_ext), int(r_lo.numel()), K,
+                                               min_coverage if last else 1, flags=flags & _ffi.EMIT_STATS if last else 0,
+                                               on_device=not last)
+            finally:
+                local.free()
+            if carry is not None:
+                carry.free()
+                carry, carry_t = None, None
+            if last:
+                if world > 1:   # observations of the whole job (a size, not data)
+                    t = torch.tensor([n_obs], dtype=torch.int64, device=device if nccl else "cpu")
+                    dist.all_reduce(t, group=group)
+                    n_obs = int(t.item())
+                merged.n_observations = n_obs
+                return merged
+            carry = merged
+            cc, m = carry._c, carry.n_kmers
+            carry_t = (_as_tensor(cc.kmers_lo, m, "<i8", torch.int64, device),
+                       _as_tensor(cc.kmers_hi, m, "<i8", torch.int64, device) if K > 32 else None,
+                       _as_tensor(cc.counts, m, "<i2", torch.int16, device), _as_tensor(cc.exts, m, "|u1", torch.uint8, device))
     finally:
-        local.free()
+        if carry is not None:
+            carry.free()

@@ -282,6 +282,9 @@ def test_global_spectrum_single_rank_and_emulated_sources(engine, oracle):
         # single rank
         got = spectrum.global_spectrum(engine, data, offs, k, mc, flags=EMIT_STATS)
         assert_batches_equal(got, ref, ctx=f"spectrum 1 rank k={k}")
+        # the same in rounds of 130 reads: the share of the spectrum is carried in HBM between the rounds
+        got = spectrum.global_spectrum(engine, data, offs, k, mc, flags=EMIT_STATS, chunk_rows=130)
+        assert_batches_equal(got, ref, ctx=f"spectrum 1 rank, 8 rounds, k={k}")
         # 3 emulated ranks, reads striped round-robin
         world = 3
         parts = []
