@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
     const int K = a.K;
-    const uint32_t thr = a.min_cov > 1u ? a.min_cov : 1u;
+    // CountFilter compares the SATURATED u16 count: nothing can reach a min_coverage above 65535
+    const uint32_t thr = a.min_cov > 65535u ? 0xffffffffu : (a.min_cov > 1u ? a.min_cov : 1u);
     const int64_t n_items = MULTI ? a.n_list : a.n_groups;
     unsigned long long cta_obs = 0;
     long long t_phase = clock64();

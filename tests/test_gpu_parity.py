@@ -183,6 +183,13 @@ def test_multipass_groups(engine, oracle, k, exact):
     for mc in (1, 2):
         got, ref = _both(engine, oracle, d2, o2, g2, k, mc, validity=v2, exact=exact, ctx=f"multipass dirty k={k} mc={mc}")
         assert got.n_multipass_groups >= 2
+    if k == 31:
+        # the threshold is compared with the saturated u16 count: 900 x 219 observations of the all-A 32-mer
+        d3, o3, v3, g3 = groups_to_arrow([["A" * 250] * 900])
+        got, _ = _both(engine, oracle, d3, o3, g3, k, 65535, ctx="saturated count meets min_coverage 65535")
+        assert got.n_multipass_groups == 1 and len(got.kmers_lo) == 1 and got.counts[0] == 65535
+        got, _ = _both(engine, oracle, d3, o3, g3, k, 65536, ctx="saturated count below min_coverage 65536")
+        assert len(got.kmers_lo) == 0
 
 
 def test_device_generator_matches_numpy(engine):
