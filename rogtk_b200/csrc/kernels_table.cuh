@@ -68,26 +68,36 @@ struct SpillArgs {
     const int64_t *warp_base;      // [n_extract_warps + 1] exclusive scan of warp_count (pass 2 input)
 };
 
-// per listed group: rows and table capacity (power of two >= 1.5x the observation upper bound)
-__global__ void k_spill_plan(ColView col, const int64_t *group_offsets, const int32_t *ids, int64_t n_list,
-                             int64_t list_base, int K, int64_t *rows, int64_t *caps)
+// per listed group: rows and table capacity (power of two >= 1.5x the observation upper bound).  A warp sums the rows of
+// an entry; gridDim.y warps-worth of blocks share the rows of very large entries (one global-spectrum group has every row).
+__global__ void k_spill_plan_obs(ColView col, const int64_t *group_offsets, const int32_t *ids, int64_t n_list,
+                                 int64_t list_base, int K, unsigned long long *ub /* [n_list], zeroed */)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_list) return;
-    int64_t g = ids ? ids[list_base + i] : list_base + i;
-    int64_t r0 = group_offsets[g], r1 = group_offsets[g + 1];
-    int64_t ub = 0;
-    int64_t prev = col_off(col, r0);
-    for (int64_t r = r0; r < r1; r++) {
-        int64_t nxt = col_off(col, r + 1);
-        int64_t len = nxt - prev;
-        prev = nxt;
-        if (len >= K) ub += len - K + 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n_list; i += n_warps) {
+        const int64_t g = ids ? ids[list_base + i] : list_base + i;
+        const int64_t r0 = group_offsets[g], r1 = group_offsets[g + 1];
+        unsigned long long s = 0;
+        for (int64_t r = r0 + (int64_t)blockIdx.y * 32 + lane; r < r1; r += (int64_t)gridDim.y * 32) {
+            const int64_t len = col_off(col, r + 1) - col_off(col, r);
+            if (len >= K) s += (unsigned long long)(len - K + 1);
+        }
+        for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0 && s) atomicAdd(ub + i, s);
     }
-    int64_t want = ub + (ub >> 1) + 8;
+}
+__global__ void k_spill_plan_caps(const int64_t *group_offsets, const int32_t *ids, int64_t n_list, int64_t list_base,
+                                  const unsigned long long *ub, int64_t *rows, int64_t *caps)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    const int64_t g = ids ? ids[list_base + i] : list_base + i;
+    const int64_t u = (int64_t)ub[i];
+    const int64_t want = u + (u >> 1) + 8;
     int64_t cap = 16;
     while (cap < want) cap <<= 1;
-    rows[i] = r1 - r0;
+    rows[i] = group_offsets[g + 1] - group_offsets[g];
     caps[i] = cap;
 }
 

@@ -5,6 +5,8 @@
 #include "../../include/rogtk_gpu.h"
 
 #include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda/std/tuple>
 
 #include <algorithm>
 #include <cmath>
@@ -93,6 +95,60 @@ struct BatchOwner {
 
 inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
 
+// ---- record ordering: LSD radix sort (cub, library call off the hot path) over exactly the key bits in use ---------------------
+struct SpillKey1 {   // K <= 32: (group rank, k-mer)
+    __host__ __device__ ::cuda::std::tuple<uint32_t &, uint64_t &> operator()(SpillRec &r) const { return {r.grank, r.lo}; }
+};
+struct SpillKey2 {   // K > 32: (group rank, hi, lo)
+    __host__ __device__ ::cuda::std::tuple<uint32_t &, uint64_t &, uint64_t &> operator()(SpillRec &r) const { return {r.grank, r.hi, r.lo}; }
+};
+struct SpecKey1 {
+    __host__ __device__ ::cuda::std::tuple<uint64_t &> operator()(SpecRec &r) const { return {r.lo}; }
+};
+struct SpecKey2 {
+    __host__ __device__ ::cuda::std::tuple<uint64_t &, uint64_t &> operator()(SpecRec &r) const { return {r.hi, r.lo}; }
+};
+// orders n records by (group rank, k-mer); the result is in `recs` (which may be replaced by a new buffer).  One listed group
+// (a giant UMI group, the global-spectrum local count): LSD radix sort over the k-mer's 2K bits.  Several groups: the key
+// would be 74..160 bits of a 24-byte record, where the comparison merge sort measured faster (600 groups x 7.6 k records).
+template <int W>
+void sort_spill_records(cudaStream_t st, DevBuf &recs, int64_t n, int K, int64_t n_ranks)
+{
+    size_t tmp_bytes = 0;
+    if (n_ranks > 1) {
+        CK(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, recs.as<SpillRec>(), n, SpillRecLess(), st));
+        DevBuf tmp(tmp_bytes, st);
+        CK(cub::DeviceMergeSort::SortKeys(tmp.p, tmp_bytes, recs.as<SpillRec>(), n, SpillRecLess(), st));
+        return;
+    }
+    DevBuf sorted((size_t)n * sizeof(SpillRec), st);
+    const SpillRec *in = recs.as<SpillRec>();
+    SpillRec *out = sorted.as<SpillRec>();
+    if (W == 1) {
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, in, out, n, SpillKey1(), 0, 2 * K, st));
+        DevBuf tmp(tmp_bytes, st);
+        CK(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, in, out, n, SpillKey1(), 0, 2 * K, st));
+    } else {
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, in, out, n, SpillKey2(), 0, 2 * K, st));
+        DevBuf tmp(tmp_bytes, st);
+        CK(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, in, out, n, SpillKey2(), 0, 2 * K, st));
+    }
+    recs = std::move(sorted);
+}
+inline void sort_spec_records(cudaStream_t st, const SpecRec *in, SpecRec *out, int64_t n, int K)
+{
+    size_t tmp_bytes = 0;
+    if (K <= 32) {
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, in, out, n, SpecKey1(), 0, 2 * K, st));
+        DevBuf tmp(tmp_bytes, st);
+        CK(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, in, out, n, SpecKey1(), 0, 2 * K, st));
+    } else {
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, in, out, n, SpecKey2(), 0, 2 * K, st));
+        DevBuf tmp(tmp_bytes, st);
+        CK(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, in, out, n, SpecKey2(), 0, 2 * K, st));
+    }
+}
+
 int k_eff_host(int64_t k)
 {
     if (k < 0) return -1;
@@ -118,10 +174,19 @@ void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_of
     cudaStream_t st = ctx->stream;
     if (n_list_total == 0) return;
     // capacities of every listed group -> host decides the waves
-    DevBuf rows(n_list_total * 8, st), caps(n_list_total * 8, st);
-    k_spill_plan<<<blocks_for(n_list_total, 256), 256, 0, st>>>(col, d_group_offsets, d_ids, n_list_total, 0, K,
-                                                                rows.as<int64_t>(), caps.as<int64_t>());
-    ctx->launches++;
+    DevBuf rows(n_list_total * 8, st), caps(n_list_total * 8, st), ub(n_list_total * 8, st);
+    CK(cudaMemsetAsync(ub.p, 0, ub.bytes, st));
+    {
+        // a warp per listed group; when the list is short its rows are shared by up to 1024 warps (gridDim.y)
+        const int64_t per_entry = std::max<int64_t>(1, col.n_rows / std::max<int64_t>(1, n_list_total));
+        const unsigned gy = (unsigned)std::min<int64_t>(1024, std::max<int64_t>(1, per_entry / 2048));
+        const unsigned gx = (unsigned)std::min<int64_t>(blocks_for(n_list_total * 32, 256), (int64_t)ctx->sm_count * 32);
+        k_spill_plan_obs<<<dim3(gx, gy), 256, 0, st>>>(col, d_group_offsets, d_ids, n_list_total, 0, K, ub.as<unsigned long long>());
+        k_spill_plan_caps<<<blocks_for(n_list_total, 256), 256, 0, st>>>(d_group_offsets, d_ids, n_list_total, 0,
+                                                                          ub.as<unsigned long long>(), rows.as<int64_t>(),
+                                                                          caps.as<int64_t>());
+        ctx->launches += 2;
+    }
     std::vector<int64_t> h_caps((size_t)n_list_total);
     CK(cudaMemcpyAsync(h_caps.data(), caps.p, n_list_total * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -192,10 +257,7 @@ void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_of
         k_spill_extract<W><<<x_grid, SPILL_EXTRACT_NT, 0, st>>>(a);
         ctx->launches += 2;
         if (wv.n_recs > 1) {
-            size_t tmp_bytes = 0;
-            CK(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, wv.recs.as<SpillRec>(), wv.n_recs, SpillRecLess(), st));
-            DevBuf tmp(tmp_bytes, st);
-            CK(cub::DeviceMergeSort::SortKeys(tmp.p, tmp_bytes, wv.recs.as<SpillRec>(), wv.n_recs, SpillRecLess(), st));
+            sort_spill_records<W>(st, wv.recs, wv.n_recs, K, n_list_total);
             ctx->launches += 3;
         }
         // survivors per listed group -> record offsets of the wave
@@ -1078,10 +1140,11 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
         int64_t n_out = 0;
         if (n > 0) {
             k_spec_pack<<<blocks_for(n, 256), 256, 0, st>>>(d_lo, k_eff > 32 ? d_hi : nullptr, d_counts, d_exts, n, recs.as<SpecRec>());
-            size_t tmp_bytes = 0;
-            CK(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, recs.as<SpecRec>(), n, SpecRecLess(), st));
-            DevBuf tmp(tmp_bytes, st);
-            CK(cub::DeviceMergeSort::SortKeys(tmp.p, tmp_bytes, recs.as<SpecRec>(), n, SpecRecLess(), st));
+            {
+                DevBuf sorted(nn * sizeof(SpecRec), st);
+                sort_spec_records(st, recs.as<SpecRec>(), sorted.as<SpecRec>(), n, k_eff);
+                recs = std::move(sorted);
+            }
             k_spec_reduce<<<blocks_for(n, 256), 256, 0, st>>>(recs.as<SpecRec>(), n, min_coverage, keep.as<int32_t>());
             exclusive_scan<int32_t>(keep.as<int32_t>(), n, pos.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
             CK(cudaMemcpyAsync(&n_out, pos.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
