@@ -38,7 +38,7 @@ constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond 
 // P equal ranges (range of a k-mer = floor(top 32 bits * P / 2^32)); pass p re-reads the group's reads in slabs of
 // <= SM_MAX_BASES bases and counts only the k-mers of range p, so every pass needs a table for about 1/P of the distinct
 // k-mers and its survivors form one ascending segment of the group's output.
-constexpr int SM_PMAX = 16;                   // passes per group at most
+constexpr int SM_PMAX = 8;                    // passes per group at most (larger groups: one CTA would become the tail of the launch)
 constexpr int64_t SM_PASS_OBS = 16384;        // bases per pass the first attempt plans for (doubles the passes on overflow)
 
 struct SegRec {          // survivors of one pass of a multi-pass group

@@ -146,15 +146,15 @@ def test_groups_too_big_for_one_table(engine, oracle):
 
 @pytest.mark.parametrize("k,exact", [(31, False), (16, False), (47, False), (33, True), (6, True), (1, True)])
 def test_multipass_groups(engine, oracle, k, exact):
-    """mid-size groups: 60..600 reads of 300 bp around a 1000 bp template (1..16 passes), a group of unrelated reads (every pass
+    """mid-size groups: 60..430 reads of 300 bp around a 1000 bp template (1..8 passes), a group of unrelated reads (every pass
     near its table limit), null / invalid / short reads inside slabs, and a group beyond the multi-pass limit (HBM tables)."""
     from rogtk_b200 import synth
-    rp = np.array([60, 5, 130, 280, 0, 600, 90, 1000])
+    rp = np.array([60, 5, 130, 280, 0, 430, 90, 600])
     data, offs, goff = synth.synth_reads(synth.config_seed(2), 7, len(rp), rp, 300, 1000)
     for mc in (1, 2, 3):
         got, ref = _both(engine, oracle, data, offs, goff, k, mc, exact=exact, csr=(mc == 2), ctx=f"multipass k={k} mc={mc}")
         assert got.n_multipass_groups >= 4
-        assert got.n_spilled_groups == 1           # 1000 x 300 bases is beyond 16 passes
+        assert got.n_spilled_groups == 1           # 600 x 300 bases is beyond 8 passes
     rng = np.random.default_rng(k)
     groups = []
     # unrelated reads: ~ as many distinct k-mers as observations
@@ -184,8 +184,8 @@ def test_multipass_groups(engine, oracle, k, exact):
         got, ref = _both(engine, oracle, d2, o2, g2, k, mc, validity=v2, exact=exact, ctx=f"multipass dirty k={k} mc={mc}")
         assert got.n_multipass_groups >= 2
     if k == 31:
-        # the threshold is compared with the saturated u16 count: 900 x 219 observations of the all-A 32-mer
-        d3, o3, v3, g3 = groups_to_arrow([["A" * 250] * 900])
+        # the threshold is compared with the saturated u16 count: 500 x 219 observations of the all-A 32-mer
+        d3, o3, v3, g3 = groups_to_arrow([["A" * 250] * 500])
         got, _ = _both(engine, oracle, d3, o3, g3, k, 65535, ctx="saturated count meets min_coverage 65535")
         assert got.n_multipass_groups == 1 and len(got.kmers_lo) == 1 and got.counts[0] == 65535
         got, _ = _both(engine, oracle, d3, o3, g3, k, 65536, ctx="saturated count below min_coverage 65536")
