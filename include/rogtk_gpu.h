@@ -128,6 +128,39 @@ void rogtk_gpu_free_batch(rogtk_gpu_ctx *ctx, rogtk_graph_batch *batch);
 int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, uint32_t min_coverage2, uint32_t flags,
                           rogtk_graph_batch *out);
 
+/* ---- unitig compaction + contig selection ------------------------------------------------------------------------
+ * The `Compression` assembly method: replaces compress_graph(true, SimpleCompress(saturating_add), graph, None) and the
+ * contig loop of reference src/fracture.rs:351-383, and the plugin's min_length filter + longest-contig choice
+ * (src/fracture.rs:258-277; only_largest is hard-wired to true by the expression, src/expressions.rs:742-751).
+ * `in` is a device-resident batch of the hot path.  Per group the SET of unitigs (sequence, saturating-summed count, exts)
+ * equals the reference's; their ORDER is by ascending first k-mer here (the reference lists them in boomphf slot order), and a
+ * pure cycle is cut at its smallest k-mer.  largest_flags marks the groups where that matters for the plugin's single answer:
+ * bit 0 = several contigs share the maximal length (the reference's max_by_key keeps the last one in ITS order), bit 1 = the
+ * chosen contig is a pure cycle (its rotation depends on the reference's start node).  For every other group the sequence
+ * of unitig `largest[g]` is byte-for-byte what assemble_sequences_expr returns. */
+typedef struct rogtk_contig_batch {
+    int64_t n_groups;
+    int64_t n_unitigs;       /* unitigs of all groups */
+    int64_t n_bases;         /* bytes in seq */
+    int32_t k_eff;
+    int32_t on_device;
+    int64_t *unitig_offsets; /* [n_groups+1] unitigs of group g: [unitig_offsets[g], unitig_offsets[g+1]) */
+    int64_t *seq_offsets;    /* [n_unitigs+1] bytes of unitig u in seq (Arrow LargeUtf8 layout) */
+    uint8_t *seq;            /* ASCII A/C/G/T */
+    uint16_t *counts;        /* [n_unitigs] saturating sum of the node counts (src/fracture.rs:361) */
+    uint8_t *exts;           /* [n_unitigs] left nibble of the first node, right nibble of the last (after fix_exts) */
+    uint8_t *cyclic;         /* [n_unitigs] 1 = pure cycle */
+    int64_t *largest;        /* [n_groups] unitig the plugin returns for the group (>= min_length, longest), or -1 */
+    uint8_t *largest_flags;  /* [n_groups] bit 0: tie in length, bit 1: cyclic */
+    float ms_total;          /* device time (CUDA events on the context stream) */
+    float _pad0;
+    void *_owner;            /* internal */
+} rogtk_contig_batch;
+
+int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_length, uint32_t flags,
+                               rogtk_contig_batch *out);
+void rogtk_gpu_free_contigs(rogtk_gpu_ctx *ctx, rogtk_contig_batch *batch);
+
 /* ---- global k-mer spectrum: one group spanning the reads of every rank (BASELINE configs[4]) -----------------------
  * The reference has no multi-process analogue: it is the un-grouped call of the same expression (one filter_kmers over all
  * reads).  Protocol per rank:

@@ -308,6 +308,59 @@ def compress_unitigs(nodes, K: int):
     return set(contigs)
 
 
+def compress_unitigs_full(nodes, K: int):
+    """compress_unitigs with the data the reference keeps per compressed node: {contig: (count, exts, cyclic)} where count is
+    the saturating-u16 fold of the node counts (src/fracture.rs:361), exts = (left nibble of the first node, right nibble of
+    the last, after fix_exts) and cyclic marks a pure cycle (cut at its smallest k-mer here; the reference cuts
+    it at whichever member comes first in boomphf order)."""
+    present = {km: (e, c) for km, e, c in nodes}
+
+    def fixed(km):
+        e, _ = present[km]
+        f = 0
+        for b in range(4):
+            if e & (1 << b) and ("ACGT"[b] + km[:-1]) in present:
+                f |= 1 << b
+            if e & (16 << b) and (km[1:] + "ACGT"[b]) in present:
+                f |= 16 << b
+        return f
+
+    fx = {km: fixed(km) for km in present}
+
+    def right(km):
+        nib = fx[km] >> 4
+        if bin(nib).count("1") != 1:
+            return None
+        nxt = km[1:] + "ACGT"[nib.bit_length() - 1]
+        if nxt == km or bin(fx[nxt] & 15).count("1") != 1:
+            return None
+        return nxt
+
+    link = {km: right(km) for km in present}
+    has_in = {n for n in link.values() if n is not None}
+    out, used = {}, set()
+
+    def walk(head, cyclic):
+        path, cur = [head], head
+        used.add(head)
+        while link[cur] is not None and link[cur] not in used:
+            cur = link[cur]
+            path.append(cur)
+            used.add(cur)
+        cnt = 0
+        for p in path:
+            cnt = min(65535, cnt + present[p][1])
+        out[path[0] + "".join(p[-1] for p in path[1:])] = (cnt, (fx[path[0]] & 15) | (fx[path[-1]] & 0xf0), cyclic)
+
+    for km in sorted(present):
+        if km not in has_in:
+            walk(km, False)
+    for km in sorted(present):
+        if km not in used:
+            walk(km, True)
+    return out
+
+
 def shortest_path_contig(nodes, K: int, start_anchor: str, end_anchor: str):
     """reference src/djfind.rs:257-304 on the uncompressed node graph: nodes whose k-mer string starts with
     start_anchor / ends with end_anchor (djfind.rs:124-154), edge weight -ln(mean coverage) (:113-114),

@@ -35,6 +35,7 @@ SYMBOLS = [
     "rogtk_gpu_synth_reads", "rogtk_gpu_device_alloc", "rogtk_gpu_device_free", "rogtk_gpu_pinned_alloc",
     "rogtk_gpu_pinned_free", "rogtk_gpu_memcpy_h2d", "rogtk_gpu_memcpy_d2h", "rogtk_gpu_launch_count", "rogtk_gpu_flush_l2", "rogtk_gpu_debug_phase_cycles",
     "rogtk_gpu_spectrum_owner", "rogtk_gpu_spectrum_split", "rogtk_gpu_spectrum_merge", "rogtk_gpu_rethreshold",
+    "rogtk_gpu_compress_unitigs", "rogtk_gpu_free_contigs",
 ]
 
 
@@ -72,6 +73,27 @@ class GraphBatchC(ctypes.Structure):
         ("ms_hot_kernel", ctypes.c_float),
         ("n_multipass_groups", ctypes.c_int32),
         ("n_spilled_groups", ctypes.c_int64),
+        ("_owner", ctypes.c_void_p),
+    ]
+
+
+class ContigBatchC(ctypes.Structure):
+    _fields_ = [
+        ("n_groups", ctypes.c_int64),
+        ("n_unitigs", ctypes.c_int64),
+        ("n_bases", ctypes.c_int64),
+        ("k_eff", ctypes.c_int32),
+        ("on_device", ctypes.c_int32),
+        ("unitig_offsets", ctypes.c_void_p),
+        ("seq_offsets", ctypes.c_void_p),
+        ("seq", ctypes.c_void_p),
+        ("counts", ctypes.c_void_p),
+        ("exts", ctypes.c_void_p),
+        ("cyclic", ctypes.c_void_p),
+        ("largest", ctypes.c_void_p),
+        ("largest_flags", ctypes.c_void_p),
+        ("ms_total", ctypes.c_float),
+        ("_pad0", ctypes.c_float),
         ("_owner", ctypes.c_void_p),
     ]
 
@@ -132,6 +154,9 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_spectrum_merge.restype = ctypes.c_int
     lib.rogtk_gpu_rethreshold.argtypes = [vp, ctypes.POINTER(GraphBatchC), u32, u32, ctypes.POINTER(GraphBatchC)]
     lib.rogtk_gpu_rethreshold.restype = ctypes.c_int
+    lib.rogtk_gpu_compress_unitigs.argtypes = [vp, ctypes.POINTER(GraphBatchC), i64, u32, ctypes.POINTER(ContigBatchC)]
+    lib.rogtk_gpu_compress_unitigs.restype = ctypes.c_int
+    lib.rogtk_gpu_free_contigs.argtypes = [vp, ctypes.POINTER(ContigBatchC)]
     lib.rogtk_gpu_flush_l2.argtypes = [vp]
     lib.rogtk_gpu_flush_l2.restype = ctypes.c_int
     _lib = lib

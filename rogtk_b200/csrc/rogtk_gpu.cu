@@ -24,6 +24,7 @@
 #include "kernels_post.cuh"
 #include "kernels_smem.cuh"
 #include "kernels_table.cuh"
+#include "kernels_unitig.cuh"
 #include "scan.cuh"
 
 using namespace rogtk;
@@ -1209,6 +1210,137 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
         memset(out, 0, sizeof(*out));
     }
     return rc;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// unitig compaction + contig selection
+// -----------------------------------------------------------------------------------------------------------------
+extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_length, uint32_t flags,
+                                          rogtk_contig_batch *out)
+{
+    if (!ctx || !in || !out || !in->on_device || in->n_groups < 0 || in->n_kmers < 0 || !in->kmer_offsets || in->k_eff > 64 ||
+        (in->n_kmers > 0 && (!in->kmers_lo || !in->exts || !in->counts || in->k_eff < 1)) ||
+        (in->k_eff > 32 && in->n_kmers > 0 && !in->kmers_hi))
+        return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    memset(out, 0, sizeof(*out));
+    BatchOwner *own = new BatchOwner();
+    const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
+    own->on_device = out_dev;
+    out->_owner = own;
+    int rc = ROGTK_OK;
+    try {
+        CK(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        CK(cudaEventRecord(ctx->ev[0], st));
+        const int64_t n = in->n_kmers, ng = in->n_groups;
+        const int K = in->k_eff;
+        const size_t nn = (size_t)std::max<int64_t>(n, 1);
+        DevBuf fx(nn, st), nxt(nn * 4, st), fl(nn, st), hlen(nn * 4, st), hcnt(nn * 2, st), hext(nn, st), is_head(nn * 4, st),
+            upos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st), uoff((size_t)(ng + 1) * 8, st);
+        CK(cudaMemsetAsync(fl.p, 0, nn, st));
+        UnitigArgs a{};
+        a.n = n; a.n_groups = ng; a.offsets = in->kmer_offsets;
+        a.lo = in->kmers_lo; a.hi = K > 32 ? in->kmers_hi : nullptr; a.exts = in->exts; a.counts = in->counts; a.K = K;
+        a.fx = fx.as<uint8_t>(); a.nxt = nxt.as<int32_t>(); a.flags = fl.as<uint8_t>(); a.hlen = hlen.as<int32_t>();
+        a.hcnt = hcnt.as<uint16_t>(); a.hext = hext.as<uint8_t>();
+        if (n > 0) {
+            const unsigned gb = blocks_for(n, 256);
+            k_unitig_links<<<gb, 256, 0, st>>>(a);
+            k_unitig_next<<<gb, 256, 0, st>>>(a);
+            k_unitig_heads<<<gb, 256, 0, st>>>(a);
+            k_unitig_cycles<<<gb, 256, 0, st>>>(a);
+            k_unitig_headflags<<<gb, 256, 0, st>>>(a.flags, n, is_head.as<int32_t>());
+            ctx->launches += 5;
+        }
+        exclusive_scan<int32_t>(is_head.as<int32_t>(), n, upos.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+        k_thr_offsets<<<blocks_for(ng + 1, 256), 256, 0, st>>>(in->kmer_offsets, ng, upos.as<int64_t>(), uoff.as<int64_t>());
+        int64_t nu = 0;
+        Peek pk(ctx->peek_slot, st, &ctx->launches);
+        pk.add(upos.as<int64_t>() + n, 8, &nu);
+        pk.sync();
+        const size_t nun = (size_t)std::max<int64_t>(nu, 1);
+        DevBuf uhead(nun * 8, st), ulen(nun * 4, st), ucnt(nun * 2, st), uext(nun, st), ucyc(nun, st), soff((nun + 1) * 8, st),
+            scr2(scan_scratch_bytes(nu), st), largest((size_t)std::max<int64_t>(ng, 1) * 8, st), lflags((size_t)std::max<int64_t>(ng, 1), st);
+        if (n > 0)
+            k_unitig_compact<<<blocks_for(n, 256), 256, 0, st>>>(a, upos.as<int64_t>(), uhead.as<int64_t>(), ulen.as<int32_t>(),
+                                                                 ucnt.as<uint16_t>(), uext.as<uint8_t>(), ucyc.as<uint8_t>());
+        exclusive_scan<int32_t>(ulen.as<int32_t>(), nu, soff.as<int64_t>(), scr2.as<int64_t>(), st, &ctx->launches);
+        int64_t nb = 0;
+        pk.add(soff.as<int64_t>() + nu, 8, &nb);
+        pk.sync();
+        DevBuf seq((size_t)std::max<int64_t>(nb, 1) + 8, st);
+        if (nu > 0)
+            k_unitig_emit<<<blocks_for(nu, 128), 128, 0, st>>>(a, nu, uhead.as<int64_t>(), ulen.as<int32_t>(), soff.as<int64_t>(),
+                                                               seq.as<uint8_t>());
+        if (ng > 0)
+            k_unitig_largest<<<blocks_for(ng, 256), 256, 0, st>>>(ng, uoff.as<int64_t>(), ulen.as<int32_t>(), ucyc.as<uint8_t>(),
+                                                                  min_length, largest.as<int64_t>(), lflags.as<uint8_t>());
+        ctx->launches += 4;
+        CK(cudaEventRecord(ctx->ev[3], st));
+        out->n_groups = ng;
+        out->n_unitigs = nu;
+        out->n_bases = nb;
+        out->k_eff = K;
+        out->on_device = out_dev ? 1 : 0;
+        auto give = [&](DevBuf &b, size_t bytes) -> void * {
+            if (out_dev) {
+                void *p = b.detach();
+                own->ptrs.push_back(p);
+                return p;
+            }
+            void *h = pinned_get(ctx, bytes);
+            own->ptrs.push_back(h);
+            if (bytes) CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, st));
+            return h;
+        };
+        out->unitig_offsets = (int64_t *)give(uoff, (size_t)(ng + 1) * 8);
+        out->seq_offsets = (int64_t *)give(soff, (size_t)(nu + 1) * 8);
+        out->seq = (uint8_t *)give(seq, (size_t)nb);
+        out->counts = (uint16_t *)give(ucnt, (size_t)nu * 2);
+        out->exts = (uint8_t *)give(uext, (size_t)nu);
+        out->cyclic = (uint8_t *)give(ucyc, (size_t)nu);
+        out->largest = (int64_t *)give(largest, (size_t)ng * 8);
+        out->largest_flags = (uint8_t *)give(lflags, (size_t)ng);
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+        out->ms_total = ms;
+        CK(cudaGetLastError());
+    } catch (const CudaFail &f) {
+        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
+        rc = (f.e == cudaErrorMemoryAllocation) ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
+        cudaGetLastError();
+    } catch (const ArgFail &f) {
+        set_error(ctx, "%s", f.msg.c_str());
+        rc = f.code > 0 ? f.code : ROGTK_ERR_INTERNAL;
+    } catch (...) {
+        set_error(ctx, "unexpected internal error");
+        rc = ROGTK_ERR_INTERNAL;
+    }
+    if (rc != ROGTK_OK) {
+        for (void *p : own->ptrs) {
+            if (own->on_device) cudaFreeAsync(p, ctx->stream);
+            else pinned_put(ctx, p);
+        }
+        delete own;
+        memset(out, 0, sizeof(*out));
+    }
+    return rc;
+}
+
+extern "C" void rogtk_gpu_free_contigs(rogtk_gpu_ctx *ctx, rogtk_contig_batch *b)
+{
+    if (!ctx || !b || !b->_owner) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BatchOwner *own = reinterpret_cast<BatchOwner *>(b->_owner);
+    cudaSetDevice(ctx->device);
+    for (void *p : own->ptrs) {
+        if (own->on_device) cudaFreeAsync(p, ctx->stream);
+        else pinned_put(ctx, p);
+    }
+    delete own;
+    memset(b, 0, sizeof(*b));
 }
 
 // -----------------------------------------------------------------------------------------------------------------

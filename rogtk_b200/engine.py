@@ -97,6 +97,39 @@ class DeviceBatch:
             n_spilled_groups=self.n_spilled_groups, n_multipass_groups=self.n_multipass_groups)
 
 
+@dataclass
+class ContigBatch:
+    """Unitigs of every group (reference src/fracture.rs:351-383) and the plugin's per-group answer
+    (min_length filter + longest contig, src/fracture.rs:258-277).  Unitigs of a group are listed by ascending first k-mer."""
+    k_eff: int
+    unitig_offsets: np.ndarray   # int64 [n_groups+1]
+    seq_offsets: np.ndarray      # int64 [n_unitigs+1]
+    seq: np.ndarray              # uint8 ASCII
+    counts: np.ndarray           # uint16 saturating sum of node counts
+    exts: np.ndarray             # uint8
+    cyclic: np.ndarray           # uint8
+    largest: np.ndarray          # int64 [n_groups], -1 = no contig of at least min_length
+    largest_flags: np.ndarray    # uint8 [n_groups]: bit 0 tie in length, bit 1 cyclic
+    ms_total: float = 0.0
+
+    @property
+    def n_groups(self) -> int:
+        return len(self.unitig_offsets) - 1
+
+    def unitig(self, u: int) -> str:
+        return self.seq[int(self.seq_offsets[u]):int(self.seq_offsets[u + 1])].tobytes().decode("ascii")
+
+    def group(self, g: int):
+        """[(sequence, count, exts, cyclic)] of group g."""
+        a, b = int(self.unitig_offsets[g]), int(self.unitig_offsets[g + 1])
+        return [(self.unitig(u), int(self.counts[u]), int(self.exts[u]), bool(self.cyclic[u])) for u in range(a, b)]
+
+    def assembled(self, g: int):
+        """What assemble_sequences_expr returns for the group (one contig, '' if none), and the ambiguity flags."""
+        u = int(self.largest[g])
+        return (self.unitig(u) if u >= 0 else ""), int(self.largest_flags[g])
+
+
 def k_eff(k: int) -> int:
     """reference src/fracture.rs:246-256: K = 4/8/16/32/64, the smallest >= k; -1 when k > 64."""
     return int(_ffi.load().rogtk_gpu_k_eff(int(k)))
@@ -338,6 +371,44 @@ class Engine:
         self._check(self._lib.rogtk_gpu_rethreshold(self._ctx, ctypes.byref(batch._c), int(min_coverage),
                                                     int(flags) & ~_ffi.OUTPUT_ON_DEVICE, ctypes.byref(out)))
         return self._to_numpy(out)
+
+    # ---- unitig compaction + contig selection ------------------------------------------------------------------------
+    def compress_unitigs(self, batch: DeviceBatch, min_length: int = 0) -> ContigBatch:
+        """Unitigs (maximal non-branching paths, saturating-summed counts) of a device-resident batch and, per group, the
+        contig assemble_sequences_expr(method="compression") returns (longest with at least min_length bases)."""
+        out = _ffi.ContigBatchC()
+        self._check(self._lib.rogtk_gpu_compress_unitigs(self._ctx, ctypes.byref(batch._c), int(min_length), 0, ctypes.byref(out)))
+
+        def arr(ptr, n, dt):
+            if n == 0 or not ptr:
+                return np.zeros(0, dtype=dt)
+            ct = np.ctypeslib.as_ctypes_type(np.dtype(dt))
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,)).copy()
+
+        ng, nu, nb = int(out.n_groups), int(out.n_unitigs), int(out.n_bases)
+        res = ContigBatch(k_eff=int(out.k_eff), unitig_offsets=arr(out.unitig_offsets, ng + 1, np.int64),
+                          seq_offsets=arr(out.seq_offsets, nu + 1, np.int64), seq=arr(out.seq, nb, np.uint8),
+                          counts=arr(out.counts, nu, np.uint16), exts=arr(out.exts, nu, np.uint8), cyclic=arr(out.cyclic, nu, np.uint8),
+                          largest=arr(out.largest, ng, np.int64), largest_flags=arr(out.largest_flags, ng, np.uint8),
+                          ms_total=float(out.ms_total))
+        self._lib.rogtk_gpu_free_contigs(self._ctx, ctypes.byref(out))
+        return res
+
+    def assemble(self, data: np.ndarray, offsets: np.ndarray, group_offsets: np.ndarray, k: int, min_coverage: int,
+                 min_length: int = 0, validity: np.ndarray | None = None) -> ContigBatch:
+        """reads -> pruned de Bruijn nodes -> unitigs -> the plugin's contig per group, all on the device
+        (assemble_sequences_expr with method="compression", reference src/expressions.rs:695-762)."""
+        db = self.count_prune_to_device(data, offsets, group_offsets, k, min_coverage, validity=validity)
+        try:
+            if db.k_eff < 0:   # k > 64: no contigs (reference src/fracture.rs:212-215)
+                ng = len(group_offsets) - 1
+                z = np.zeros
+                return ContigBatch(k_eff=-1, unitig_offsets=z(ng + 1, np.int64), seq_offsets=z(1, np.int64), seq=z(0, np.uint8),
+                                   counts=z(0, np.uint16), exts=z(0, np.uint8), cyclic=z(0, np.uint8),
+                                   largest=np.full(ng, -1, np.int64), largest_flags=z(ng, np.uint8))
+            return self.compress_unitigs(db, min_length)
+        finally:
+            db.free()
 
     # ---- Arrow-native entry (SURVEY 8f-4): one call per frame ----------------------------------------------------------------------
     def count_prune_arrow(self, reads, k: int, min_coverage: int, flags: int = 0) -> GraphBatch:

@@ -449,3 +449,54 @@ def test_many_tiny_groups(engine, oracle):
     goff = np.concatenate([[0], np.cumsum(reads_per)]).astype(np.int64)
     for k, mc in ((17, 1), (31, 1), (12, 2)):
         _both(engine, oracle, data, offs, goff, k, mc, csr=False, ctx=f"tiny groups k={k}")
+
+
+def _check_unitigs(engine, oracle, data, offs, goff, k, mc, min_length, validity=None, ctx=""):
+    ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity)
+    got = engine.assemble(data, offs, goff, k, mc, min_length=min_length, validity=validity)
+    assert got.n_groups == len(goff) - 1
+    for g in range(got.n_groups):
+        nodes = oracle.batch_group_as_tuples(ref, g)
+        want = oracle.compress_unitigs_full(nodes, ref.k_eff)
+        have = got.group(g)
+        assert {s: (c, e, cy) for s, c, e, cy in have} == want, f"{ctx} group {g}"
+        assert len(have) == len(want)
+        heads = [s[:ref.k_eff] for s, _, _, _ in have]
+        assert heads == sorted(heads), f"{ctx} group {g}: unitigs not listed by ascending first k-mer"
+        # the plugin's answer: longest contig of at least min_length bases (reference src/fracture.rs:258-277)
+        cand = [s for s in want if len(s) >= min_length]
+        seq, fl = got.assembled(g)
+        if not cand:
+            assert seq == "" and fl == 0
+        else:
+            top = max(len(s) for s in cand)
+            assert len(seq) == top and seq in want
+            assert (fl & 1) == (1 if sum(1 for s in cand if len(s) == top) > 1 else 0)
+            assert bool(fl & 2) == want[seq][2]
+    return got
+
+
+def test_unitig_compaction_and_plugin_contig(engine, oracle):
+    """unitigs (set, counts, exts) against the oracle's restatement of compress_graph, and the contig
+    assemble_sequences_expr(method="compression") returns.  The reference's own expectation for its 2-read fixture
+    (44-bp contig, comment at src/fracture.rs:611) is reproduced on the device."""
+    e = load_golden()["reference_test_expectations"]["test_full_assembly_with_path_finding"]
+    data, offs, validity = oracle.strings_to_arrow(e["reads"])
+    got = _check_unitigs(engine, oracle, data, offs, np.array([0, len(e["reads"])]), e["k"], e["min_coverage"], 0, ctx="B1")
+    assert got.assembled(0) == (e["expected_contig"], 0)
+    rng = np.random.default_rng(99)
+    for k, mc, ml in ((5, 1, 0), (9, 1, 12), (13, 2, 0), (17, 1, 40), (31, 2, 0), (33, 1, 0), (64, 1, 70)):
+        groups = random_groups(rng, 40, max_reads=14, max_len=140, tmpl_len=160)
+        groups.append(["ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"] * 3)   # pure cycles
+        groups.append(["A" * 90])                                                                          # self-loop k-mer
+        groups.append([])
+        data, offs, validity, goff = groups_to_arrow(groups)
+        _check_unitigs(engine, oracle, data, offs, goff, k, mc, ml, validity=validity, ctx=f"unitigs k={k} mc={mc}")
+    # the headline shape: the consensus path, cut where an error k-mer seen twice branches off (1..19 unitigs per UMI)
+    from rogtk_b200 import synth
+    data, offs, goff = synth.synth_reads(synth.config_seed(2), 0, 40, 50, 300, 1000)
+    got = _check_unitigs(engine, oracle, data, offs, goff, 31, 2, 200, ctx="cfg2 unitigs")
+    assert all(len(got.assembled(g)[0]) >= 200 for g in range(40)) and len(got.assembled(1)[0]) == 969
+    # k > 64: no contigs
+    got = engine.assemble(data, offs, goff, 65, 2)
+    assert got.k_eff == -1 and list(got.largest) == [-1] * 40

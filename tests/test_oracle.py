@@ -62,6 +62,27 @@ def test_reference_unit_test_expectations(oracle):
     assert oracle.shortest_path_contig(oracle.batch_group_as_tuples(b, 0), b.k_eff, e["start_anchor"], e["end_anchor"]) is None
 
 
+def test_unitig_restatements_agree(oracle):
+    """compress_unitigs (walks from the smallest unused k-mer in both directions) and compress_unitigs_full (heads first, then
+    cycles) give the same contig set; the full form also folds counts and exts (reference src/fracture.rs:351-383)."""
+    rng = np.random.default_rng(77)
+    for k, mc in ((5, 1), (9, 1), (13, 2), (17, 1), (33, 1)):
+        groups = random_groups(rng, 30, max_reads=14, max_len=100, tmpl_len=90)
+        groups.append(["ACGTACGTACGTACGTACGTACGT"] * 3)                  # pure cycle
+        groups.append(["AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"])     # self-loop k-mer
+        data, offs, validity, goff = groups_to_arrow(groups)
+        b = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity)
+        for g in range(len(groups)):
+            nodes = oracle.batch_group_as_tuples(b, g)
+            full = oracle.compress_unitigs_full(nodes, b.k_eff)
+            assert set(full) == oracle.compress_unitigs(nodes, b.k_eff), (k, mc, g)
+            assert sum(len(c) - b.k_eff + 1 for c in full) == len(nodes)   # every node is in exactly one unitig
+    e = load_golden()["reference_test_expectations"]["test_full_assembly_with_path_finding"]
+    b = _run(oracle, e["reads"], e["k"], e["min_coverage"])
+    full = oracle.compress_unitigs_full(oracle.batch_group_as_tuples(b, 0), b.k_eff)
+    assert list(full) == [e["expected_contig"]] and full[e["expected_contig"]][1] == 0   # one chain, no dangling exts
+
+
 @pytest.mark.parametrize("k,exact", [(3, False), (4, False), (7, False), (13, False), (17, False), (31, False), (33, False),
                                      (64, False), (5, True), (21, True), (47, True), (1, True)])
 def test_two_oracles_agree(oracle, k, exact):
