@@ -373,11 +373,17 @@ class Engine:
         return self._to_numpy(out)
 
     # ---- unitig compaction + contig selection ------------------------------------------------------------------------
-    def compress_unitigs(self, batch: DeviceBatch, min_length: int = 0) -> ContigBatch:
+    def compress_unitigs(self, batch: DeviceBatch, min_length: int = 0, sizes_only: bool = False):
         """Unitigs (maximal non-branching paths, saturating-summed counts) of a device-resident batch and, per group, the
-        contig assemble_sequences_expr(method="compression") returns (longest with at least min_length bases)."""
+        contig assemble_sequences_expr(method="compression") returns (longest with at least min_length bases).
+        sizes_only=True leaves the result in HBM, frees it and returns (n_unitigs, n_bases, device ms): timing without D2H."""
         out = _ffi.ContigBatchC()
-        self._check(self._lib.rogtk_gpu_compress_unitigs(self._ctx, ctypes.byref(batch._c), int(min_length), 0, ctypes.byref(out)))
+        self._check(self._lib.rogtk_gpu_compress_unitigs(self._ctx, ctypes.byref(batch._c), int(min_length),
+                                                         _ffi.OUTPUT_ON_DEVICE if sizes_only else 0, ctypes.byref(out)))
+        if sizes_only:
+            r = (int(out.n_unitigs), int(out.n_bases), float(out.ms_total))
+            self._lib.rogtk_gpu_free_contigs(self._ctx, ctypes.byref(out))
+            return r
 
         def arr(ptr, n, dt):
             if n == 0 or not ptr:
