@@ -250,6 +250,49 @@ def test_device_resident_path_and_invariants_at_scale(engine, oracle):
         engine.device_free(p)
 
 
+def test_full_size_headline_config(engine, oracle):
+    """BASELINE configs[1] at its full size (1M UMIs x 50 x 300 bp, k=31, min_cov=2), device-resident in and out as in
+    bench.py: size-independent properties on the whole result, the first half of the batch re-counted on its own, and 96
+    UMIs sampled across the batch compared bit for bit with the oracle (the generator is counter-based, so any UMI's reads
+    can be regenerated on the host)."""
+    from rogtk_b200 import synth
+    seed = synth.config_seed(2)
+    n, R, L, T = 1_000_000, 50, 300, 1000
+    d_data, d_off, d_goff, nbytes = engine.synth_reads_device(seed, 0, n, R, L, T, 655)
+    try:
+        db = engine.count_prune_device(d_data, nbytes, d_off, n * R, d_goff, n, 31, 2)
+        assert db.n_observations == n * R * (L - 31) and db.n_spilled_groups == 0 and db.n_multipass_groups == 0 and db.k_eff == 32
+        off = engine.d2h(db._c.kmer_offsets, (n + 1) * 8, np.int64)
+        per = np.diff(off)
+        assert off[0] == 0 and off[-1] == db.n_kmers and per.min() > 0
+        # every consensus 32-mer is covered ~13x: at least the 969 - (a few masked by errors) survive; error k-mers seen twice add a few
+        assert 900 <= per.mean() <= 1100 and per.max() < 8192
+        # the first half of the batch on its own: same offsets (groups are independent)
+        half = n // 2
+        db2 = engine.count_prune_device(d_data, half * R * L, d_off, half * R, d_goff, half, 31, 2)
+        off2 = engine.d2h(db2._c.kmer_offsets, (half + 1) * 8, np.int64)
+        assert np.array_equal(off2, off[:half + 1])
+        # sampled groups: counts, exts, k-mers bit for bit (and identical between the two runs)
+        rng = np.random.default_rng(5)
+        picks = sorted(set([0, 1, half - 1, half, n - 1] + [int(x) for x in rng.integers(0, n, 91)]))
+        for g in picks:
+            a, b = int(off[g]), int(off[g + 1])
+            lo = engine.d2h(db._c.kmers_lo + a * 8, (b - a) * 8, np.uint64)
+            ex = engine.d2h(db._c.exts + a, b - a, np.uint8)
+            ct = engine.d2h(db._c.counts + a * 2, (b - a) * 2, np.uint16)
+            data, offs, goff = synth.synth_reads(seed, g, 1, R, L, T)
+            ref = oracle.count_prune_batch(data, offs, goff, 31, 2)
+            assert np.array_equal(lo, ref.kmers_lo) and np.array_equal(ex, ref.exts) and np.array_equal(ct, ref.counts), g
+            assert np.all(lo[1:] > lo[:-1]) and ct.min() >= 2
+            if g < half:
+                assert np.array_equal(engine.d2h(db2._c.kmers_lo + a * 8, (b - a) * 8, np.uint64), lo)
+        db2.free()
+        db.free()
+    finally:
+        for p in (d_data, d_off, d_goff):
+            engine.device_free(p)
+
+
 def test_chunked_overlapped_host_path(oracle, monkeypatch):
     """Large host batches are cut into chunks whose H2D / compute / D2H overlap (rogtk_gpu.cu run_chunked).  Force tiny chunks
     and compare every output array, including CSR and statistics whose indices must be re-based across chunks."""
