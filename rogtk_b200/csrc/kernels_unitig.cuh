@@ -44,7 +44,11 @@ __device__ __forceinline__ int64_t group_of(const int64_t *offsets, int64_t n_gr
     return a;
 }
 
-// fix_exts + the unique successor (if the fixed right nibble has exactly one bit)
+// fix_exts + the unique successor (if the fixed right nibble has exactly one bit).  Only right neighbours are searched: a left
+// ext bit c of node j stems from an observation "c then j", which is also an observation "i = c+j[:-1] then last base of j",
+// so j's surviving left bits are exactly {first base of i : i is a node and one of its surviving right exts names j}; they
+// are OR-ed into j's byte from i's side (k_unitig_fixleft intersects with j's own left nibble for batches of foreign origin).
+// fx is addressed as 32-bit words (four nodes per word) for the atomics and must be zero on entry.
 __global__ void k_unitig_links(UnitigArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,30 +58,35 @@ __global__ void k_unitig_links(UnitigArgs a)
     const int kbits = 2 * a.K;
     const uint64_t xl = a.lo[i], xh = a.hi ? a.hi[i] : 0ull;
     const uint32_t e = a.exts[i];
+    const int top = kbits - 2;   // bit position of the first base
+    const uint32_t first = (uint32_t)((top >= 64 ? xh >> (top - 64) : xl >> top) & 3ull);
+    uint32_t *fxw = reinterpret_cast<uint32_t *>(a.fx);
     uint32_t f = 0;
     int64_t succ = -1;
     for (uint32_t b = 0; b < 4; b++) {
-        if ((e >> (4 + b)) & 1u) {   // right neighbour: drop the first base, append b
-            uint64_t yl = (xl << 2) | b, yh = (xh << 2) | (xl >> 62);
-            if (kbits < 64) { yl &= (1ull << kbits) - 1ull; yh = 0; }
-            else if (kbits == 64) yh = 0;
-            else if (kbits < 128) yh &= (1ull << (kbits - 64)) - 1ull;
-            const int64_t j = find_in_group(a.lo + o, a.hi ? a.hi + o : nullptr, n, yh, yl);
-            if (j >= 0) {
-                f |= 16u << b;
-                succ = j;
-            }
-        }
-        if ((e >> b) & 1u) {         // left neighbour: prepend b, drop the last base
-            uint64_t yl = (xl >> 2) | (xh << 62), yh = xh >> 2;
-            const int top = kbits - 2;   // bit position of the first base
-            if (top >= 64) yh |= (uint64_t)b << (top - 64); else yl |= (uint64_t)b << top;
-            const int64_t j = find_in_group(a.lo + o, a.hi ? a.hi + o : nullptr, n, yh, yl);
-            if (j >= 0) f |= 1u << b;
+        if (!((e >> (4 + b)) & 1u)) continue;   // right neighbour: drop the first base, append b
+        uint64_t yl = (xl << 2) | b, yh = (xh << 2) | (xl >> 62);
+        if (kbits < 64) { yl &= (1ull << kbits) - 1ull; yh = 0; }
+        else if (kbits == 64) yh = 0;
+        else if (kbits < 128) yh &= (1ull << (kbits - 64)) - 1ull;
+        const int64_t j = find_in_group(a.lo + o, a.hi ? a.hi + o : nullptr, n, yh, yl);
+        if (j >= 0) {
+            f |= 16u << b;
+            succ = j;
+            const int64_t jj = o + j;
+            atomicOr(fxw + (jj >> 2), (1u << first) << (8 * (int)(jj & 3)));
         }
     }
-    a.fx[i] = (uint8_t)f;
+    if (f) atomicOr(fxw + (i >> 2), f << (8 * (int)(i & 3)));
     a.nxt[i] = __popc(f >> 4) == 1 ? (int32_t)succ : -1;
+}
+
+__global__ void k_unitig_fixleft(UnitigArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint32_t f = a.fx[i];
+    a.fx[i] = (uint8_t)((f & 0xf0u) | (f & a.exts[i] & 15u));
 }
 
 // keep the link only if the successor has exactly one (fixed) left ext and is not the node itself; mark linked-to nodes

@@ -1236,9 +1236,10 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
         const int64_t n = in->n_kmers, ng = in->n_groups;
         const int K = in->k_eff;
         const size_t nn = (size_t)std::max<int64_t>(n, 1);
-        DevBuf fx(nn, st), nxt(nn * 4, st), fl(nn, st), hlen(nn * 4, st), hcnt(nn * 2, st), hext(nn, st), is_head(nn * 4, st),
+        DevBuf fx(nn + 4, st), nxt(nn * 4, st), fl(nn, st), hlen(nn * 4, st), hcnt(nn * 2, st), hext(nn, st), is_head(nn * 4, st),
             upos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st), uoff((size_t)(ng + 1) * 8, st);
         CK(cudaMemsetAsync(fl.p, 0, nn, st));
+        CK(cudaMemsetAsync(fx.p, 0, nn + 4, st));
         UnitigArgs a{};
         a.n = n; a.n_groups = ng; a.offsets = in->kmer_offsets;
         a.lo = in->kmers_lo; a.hi = K > 32 ? in->kmers_hi : nullptr; a.exts = in->exts; a.counts = in->counts; a.K = K;
@@ -1247,11 +1248,12 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
         if (n > 0) {
             const unsigned gb = blocks_for(n, 256);
             k_unitig_links<<<gb, 256, 0, st>>>(a);
+            k_unitig_fixleft<<<gb, 256, 0, st>>>(a);
             k_unitig_next<<<gb, 256, 0, st>>>(a);
             k_unitig_heads<<<gb, 256, 0, st>>>(a);
             k_unitig_cycles<<<gb, 256, 0, st>>>(a);
             k_unitig_headflags<<<gb, 256, 0, st>>>(a.flags, n, is_head.as<int32_t>());
-            ctx->launches += 5;
+            ctx->launches += 6;
         }
         exclusive_scan<int32_t>(is_head.as<int32_t>(), n, upos.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
         k_thr_offsets<<<blocks_for(ng + 1, 256), 256, 0, st>>>(in->kmer_offsets, ng, upos.as<int64_t>(), uoff.as<int64_t>());
