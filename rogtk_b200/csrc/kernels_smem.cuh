@@ -868,22 +868,27 @@ struct SortArgs {
     const int32_t *seg_list;
 };
 
-// SEG = false: work items are groups.  SEG = true: segments of multi-pass groups (item i = pass i % SM_PMAX of list entry
-// i / SM_PMAX); the k-mers of a segment lie in 1/P of the k-mer space, so the buckets subdivide that range.
-template <int W, bool SEG>
-__global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_items)
+// Counting sort of one work item per CTA pass.  SEG = false: work items are groups.  SEG = true: segments of multi-pass
+// groups (item i = pass i % SM_PMAX of list entry i / SM_PMAX); the k-mers of a segment lie in 1/P of the k-mer space, so the
+// buckets subdivide that range.  LIST = true: the items are those named in in_list (what a smaller instantiation passed on).
+// Two instantiations: CAP = sort_small_max() with 128 threads (36 KB, 6 CTAs/SM: the headline shape, ~1000 survivors per
+// group) and CAP = 6144 with 512 threads (two CTAs/SM: min_coverage <= 1 keeps ~4500 k-mers per group; the bitonic kernel that
+// used to take those groups was 10x slower).  Items that do not fit, or have a crowded bucket, go to the output list.
+template <int W, bool SEG, int CAP, int NT, bool LIST>
+__global__ void __launch_bounds__(NT) k_sort_small(SortArgs a, int64_t n_items, const int32_t *in_list)
 {
-    constexpr int SORT_SMALL_MAX = sort_small_max<W>();
-    __shared__ uint64_t s_lo[SORT_SMALL_MAX];
-    __shared__ uint64_t s_hi[W == 2 ? SORT_SMALL_MAX : 1];
-    __shared__ uint32_t s_val[SORT_SMALL_MAX];      // exts | count << 8
-    __shared__ uint32_t s_hist[SM_SORT_BUCKETS];
-    __shared__ uint16_t s_order[SORT_SMALL_MAX];
-    __shared__ uint16_t s_fin[SORT_SMALL_MAX];
-    __shared__ uint32_t s_ws[8];
+    extern __shared__ __align__(16) uint8_t sort_raw[];
+    uint64_t *s_lo = reinterpret_cast<uint64_t *>(sort_raw);
+    uint64_t *s_hi = s_lo + CAP;                                             // only touched when W == 2
+    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_lo + (W == 2 ? 2 : 1) * CAP);   // exts | count << 8
+    uint32_t *s_hist = s_val + CAP;
+    uint32_t *s_ws = s_hist + SM_SORT_BUCKETS;
+    uint16_t *s_order = reinterpret_cast<uint16_t *>(s_ws + 32);
+    uint16_t *s_fin = s_order + CAP;
     __shared__ int s_flag;
     const int tid = threadIdx.x;
-    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int64_t it = LIST ? (int64_t)in_list[w] : w;
         int64_t ps, o;
         int n;
         const int kb = a.kbits;
@@ -905,14 +910,14 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
             n = (int)(a.kmer_offsets[it + 1] - o);
         }
         if (n == 0) continue;
-        if (n > SORT_SMALL_MAX) {
+        if (n > CAP) {
             if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)it;
             continue;
         }
-        __syncthreads();   // previous group's shared data no longer in use
+        __syncthreads();   // previous item's shared data no longer in use
         if (tid == 0) s_flag = 0;
-        for (int j = tid; j < SM_SORT_BUCKETS; j += SORT_NT) s_hist[j] = 0;
-        for (int j = tid; j < n; j += SORT_NT) {
+        for (int j = tid; j < SM_SORT_BUCKETS; j += NT) s_hist[j] = 0;
+        for (int j = tid; j < n; j += NT) {
             s_lo[j] = a.p_lo[ps + j];
             if (W == 2) s_hi[j] = a.p_hi[ps + j];
             s_val[j] = (uint32_t)a.p_exts[ps + j] | ((uint32_t)a.p_counts[ps + j] << 8);
@@ -927,19 +932,19 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
             if (W == 2) return sort_bucket<2>(Key<2>{s_lo[j], s_hi[j]}, kb);
             return sort_bucket<1>(Key<1>{s_lo[j]}, kb);
         };
-        for (int j = tid; j < n; j += SORT_NT) atomicAdd(&s_hist[bucket_of(j)], 1u);
+        for (int j = tid; j < n; j += NT) atomicAdd(&s_hist[bucket_of(j)], 1u);
         __syncthreads();
-        {   // exclusive scan of the bucket sizes (8 per thread)
-            constexpr int PER = SM_SORT_BUCKETS / SORT_NT;
-            uint32_t loc[PER], s = 0, mx = 0;
+        {   // exclusive scan of the bucket sizes (PER per thread)
+            constexpr int PER = SM_SORT_BUCKETS / NT;
+            uint32_t loc[PER], sum = 0, mx = 0;
 #pragma unroll
             for (int t = 0; t < PER; t++) {
                 loc[t] = s_hist[tid * PER + t];
-                s += loc[t];
+                sum += loc[t];
                 mx = loc[t] > mx ? loc[t] : mx;
             }
             if (mx > (uint32_t)SM_MAX_BUCKET) s_flag = 1;
-            uint32_t x = s;
+            uint32_t x = sum;
             const unsigned lane = tid & 31u, warp = tid >> 5;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -949,8 +954,8 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
             if (lane == 31) s_ws[warp] = x;
             __syncthreads();
             uint32_t base = 0;
-            for (unsigned w = 0; w < warp; w++) base += s_ws[w];
-            uint32_t e0 = base + x - s;
+            for (unsigned ww = 0; ww < warp; ww++) base += s_ws[ww];
+            uint32_t e0 = base + x - sum;
 #pragma unroll
             for (int t = 0; t < PER; t++) {
                 s_hist[tid * PER + t] = e0;
@@ -962,17 +967,17 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
             if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)it;
             continue;
         }
-        for (int j = tid; j < n; j += SORT_NT) s_order[atomicAdd(&s_hist[bucket_of(j)], 1u)] = (uint16_t)j;
+        for (int j = tid; j < n; j += NT) s_order[atomicAdd(&s_hist[bucket_of(j)], 1u)] = (uint16_t)j;
         __syncthreads();
         // s_hist[b] is now the END of bucket b.  Every survivor ranks itself inside its (tiny) bucket: final position =
         // bucket start + number of bucket members with a smaller k-mer (k-mers are distinct).
-        for (int j = tid; j < n; j += SORT_NT) {
+        for (int j = tid; j < n; j += NT) {
             const uint32_t b = bucket_of(j);
-            const uint32_t s = b ? s_hist[b - 1] : 0u, e = s_hist[b];
-            uint32_t r = s;
-            if (e - s > 1u) {
+            const uint32_t st = b ? s_hist[b - 1] : 0u, en = s_hist[b];
+            uint32_t r = st;
+            if (en - st > 1u) {
                 const uint64_t lj = s_lo[j], hj = (W == 2) ? s_hi[j] : 0ull;
-                for (uint32_t i = s; i < e; i++) {
+                for (uint32_t i = st; i < en; i++) {
                     const uint16_t oi = s_order[i];
                     const uint64_t li = s_lo[oi], hi_i = (W == 2) ? s_hi[oi] : 0ull;
                     r += (hi_i < hj || (hi_i == hj && li < lj)) ? 1u : 0u;
@@ -981,7 +986,7 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
             s_fin[r] = (uint16_t)j;
         }
         __syncthreads();
-        for (int j = tid; j < n; j += SORT_NT) {
+        for (int j = tid; j < n; j += NT) {
             const int idx = s_fin[j];
             a.o_lo[o + j] = s_lo[idx];
             if (W == 2) a.o_hi[o + j] = s_hi[idx];
@@ -991,6 +996,10 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_small(SortArgs a, int64_t n_it
         }
     }
 }
+template <int W, int CAP>
+constexpr size_t sort_count_smem() { return (size_t)CAP * (8 * W + 4 + 2 + 2) + SM_SORT_BUCKETS * 4 + 32 * 4; }
+constexpr int SORT_MID_NT = 512;
+constexpr int SORT_MID_CAP = 6144;   // 102 KB of shared memory for 8-byte keys: two CTAs per SM
 
 // SEG = false: one work item per group listed in big_ids.  SEG = true: big_ids lists segments of multi-pass groups; the
 // segments of a group hold ascending k-mer ranges, so ordering each one in place orders the group.
@@ -1062,58 +1071,84 @@ __global__ void __launch_bounds__(SORT_BIG_NT) k_sort_big(SortArgs a, int64_t n_
 template <int W>
 constexpr size_t sort_big_smem() { return (size_t)SORT_BIG_MAX * (8 * W + 4); }
 
-// host launcher: pool (unsorted, completion order) -> dense, group-ordered, k-mer-ascending arrays
+// host launcher: pool (unsorted, completion order) -> dense, group-ordered, k-mer-ascending arrays.  Three tiers per kind of
+// work item (groups; segments of multi-pass groups): small counting sort -> mid counting sort -> bitonic sort.
+template <int W>
+inline void run_sort_gather_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, SortArgs a, int64_t n_groups, int64_t n_seg_groups,
+                              int64_t *launches)
+{
+    constexpr int SMALL = sort_small_max<W>();
+    const int64_t n_seg_items = n_seg_groups * SM_PMAX;
+    // lists: [0] groups small->mid, [1] segments small->mid, [2] groups mid->bitonic, [3] segments mid->bitonic
+    DevBuf ctr(32, st), l0((size_t)n_groups * 4 + 16, st), l1((size_t)n_seg_items * 4 + 16, st);
+    CK(cudaMemsetAsync(ctr.p, 0, 32, st));
+    unsigned long long *d_n = ctr.as<unsigned long long>();
+    SortArgs g = a, s = a;
+    g.big_ids = l0.as<int32_t>(); g.n_big = d_n;
+    s.big_ids = l1.as<int32_t>(); s.n_big = d_n + 1;
+    {
+        const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 16);
+        k_sort_small<W, false, SMALL, SORT_NT, false><<<grid, SORT_NT, sort_count_smem<W, SMALL>(), st>>>(g, n_groups, nullptr);
+        if (launches) *launches += 1;
+    }
+    if (n_seg_items > 0) {
+        const unsigned grid = (unsigned)std::min<int64_t>(n_seg_items, (int64_t)sm_count * 16);
+        k_sort_small<W, true, SMALL, SORT_NT, false><<<grid, SORT_NT, sort_count_smem<W, SMALL>(), st>>>(s, n_seg_items, nullptr);
+        if (launches) *launches += 1;
+    }
+    unsigned long long n_mid[2] = {0, 0};
+    Peek pk(peek_slot, st, launches);
+    pk.add(d_n, 16, n_mid);
+    pk.sync();
+    if (!n_mid[0] && !n_mid[1]) return;
+    DevBuf l2((size_t)n_mid[0] * 4 + 16, st), l3((size_t)n_mid[1] * 4 + 16, st);
+    SortArgs g2 = g, s2 = s;
+    g2.big_ids = l2.as<int32_t>(); g2.n_big = d_n + 2;
+    s2.big_ids = l3.as<int32_t>(); s2.n_big = d_n + 3;
+    if (n_mid[0]) {
+        const unsigned grid = (unsigned)std::min<int64_t>((int64_t)n_mid[0], (int64_t)sm_count);
+        k_sort_small<W, false, SORT_MID_CAP, SORT_MID_NT, true>
+            <<<grid, SORT_MID_NT, sort_count_smem<W, SORT_MID_CAP>(), st>>>(g2, (int64_t)n_mid[0], g.big_ids);
+        if (launches) *launches += 1;
+    }
+    if (n_mid[1]) {
+        const unsigned grid = (unsigned)std::min<int64_t>((int64_t)n_mid[1], (int64_t)sm_count);
+        k_sort_small<W, true, SORT_MID_CAP, SORT_MID_NT, true>
+            <<<grid, SORT_MID_NT, sort_count_smem<W, SORT_MID_CAP>(), st>>>(s2, (int64_t)n_mid[1], s.big_ids);
+        if (launches) *launches += 1;
+    }
+    unsigned long long n_big[2] = {0, 0};
+    pk.add(d_n + 2, 16, n_big);
+    pk.sync();
+    if (n_big[0]) {
+        const unsigned grid = (unsigned)std::min<int64_t>((int64_t)n_big[0], (int64_t)sm_count * 2);
+        k_sort_big<W, false><<<grid, SORT_BIG_NT, sort_big_smem<W>(), st>>>(g2, (int64_t)n_big[0]);
+        if (launches) *launches += 1;
+    }
+    if (n_big[1]) {
+        const unsigned grid = (unsigned)std::min<int64_t>((int64_t)n_big[1], (int64_t)sm_count * 2);
+        k_sort_big<W, true><<<grid, SORT_BIG_NT, sort_big_smem<W>(), st>>>(s2, (int64_t)n_big[1]);
+        if (launches) *launches += 1;
+    }
+}
+
 inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, int K, int64_t n_groups, const int64_t *pool_start, const int64_t *kmer_offsets,
                             const uint64_t *p_lo, const uint64_t *p_hi, const uint8_t *p_exts, const uint16_t *p_counts, uint64_t *o_lo,
                             uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts, int64_t *launches, const SegRec *segs = nullptr,
                             const int32_t *seg_count = nullptr, const int32_t *seg_list = nullptr, int64_t n_seg_groups = 0)
 {
-    DevBuf big((size_t)n_groups * 4 + 16, st), ctr(16, st);
-    CK(cudaMemsetAsync(ctr.p, 0, 16, st));
     SortArgs a{};
     a.n_groups = n_groups;
     a.pool_start = pool_start;
     a.kmer_offsets = kmer_offsets;
     a.p_lo = p_lo; a.p_hi = p_hi; a.p_exts = p_exts; a.p_counts = p_counts;
     a.o_lo = o_lo; a.o_hi = o_hi; a.o_exts = o_exts; a.o_counts = o_counts;
-    a.big_ids = big.as<int32_t>();
-    a.n_big = ctr.as<unsigned long long>();
     a.kbits = 2 * K;
-    const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 16);
-    if (K > 32) k_sort_small<2, false><<<grid, SORT_NT, 0, st>>>(a, n_groups);
-    else k_sort_small<1, false><<<grid, SORT_NT, 0, st>>>(a, n_groups);
-    if (launches) *launches += 1;
-    // segments of the multi-pass groups: same counting sort, items = (list entry, pass)
-    const int64_t n_seg_items = n_seg_groups * SM_PMAX;
-    DevBuf big_seg((size_t)n_seg_items * 4 + 16, st);
-    SortArgs b = a;
-    if (n_seg_groups > 0) {
-        b.segs = segs;
-        b.seg_count = seg_count;
-        b.seg_list = seg_list;
-        b.big_ids = big_seg.as<int32_t>();
-        b.n_big = ctr.as<unsigned long long>() + 1;
-        const unsigned g3 = (unsigned)std::min<int64_t>(n_seg_items, (int64_t)sm_count * 16);
-        if (K > 32) k_sort_small<2, true><<<g3, SORT_NT, 0, st>>>(b, n_seg_items);
-        else k_sort_small<1, true><<<g3, SORT_NT, 0, st>>>(b, n_seg_items);
-        if (launches) *launches += 1;
-    }
-    unsigned long long n_big[2] = {0, 0};
-    Peek pk(peek_slot, st, launches);
-    pk.add(ctr.p, 16, n_big);
-    pk.sync();
-    if (n_big[0]) {
-        const unsigned g2 = (unsigned)std::min<int64_t>((int64_t)n_big[0], (int64_t)sm_count * 2);
-        if (K > 32) k_sort_big<2, false><<<g2, SORT_BIG_NT, sort_big_smem<2>(), st>>>(a, (int64_t)n_big[0]);
-        else k_sort_big<1, false><<<g2, SORT_BIG_NT, sort_big_smem<1>(), st>>>(a, (int64_t)n_big[0]);
-        if (launches) *launches += 1;
-    }
-    if (n_big[1]) {
-        const unsigned g2 = (unsigned)std::min<int64_t>((int64_t)n_big[1], (int64_t)sm_count * 2);
-        if (K > 32) k_sort_big<2, true><<<g2, SORT_BIG_NT, sort_big_smem<2>(), st>>>(b, (int64_t)n_big[1]);
-        else k_sort_big<1, true><<<g2, SORT_BIG_NT, sort_big_smem<1>(), st>>>(b, (int64_t)n_big[1]);
-        if (launches) *launches += 1;
-    }
+    a.segs = segs;
+    a.seg_count = seg_count;
+    a.seg_list = seg_list;
+    if (K > 32) run_sort_gather_w<2>(st, peek_slot, sm_count, a, n_groups, n_seg_groups, launches);
+    else run_sort_gather_w<1>(st, peek_slot, sm_count, a, n_groups, n_seg_groups, launches);
 }
 
 // -----------------------------------------------------------------------------------------------------------------------------
@@ -1148,6 +1183,14 @@ inline void smem_path_configure()
     cfg(k_smem_count<1, true, true>, smem_bytes<1>());
     cfg(k_smem_count<1, false, true>, smem_bytes<1>());
     cfg(k_smem_count<2, false, true>, smem_bytes<2>());
+    CK(cudaFuncSetAttribute(k_sort_small<1, false, SORT_MID_CAP, SORT_MID_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sort_count_smem<1, SORT_MID_CAP>()));
+    CK(cudaFuncSetAttribute(k_sort_small<1, true, SORT_MID_CAP, SORT_MID_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sort_count_smem<1, SORT_MID_CAP>()));
+    CK(cudaFuncSetAttribute(k_sort_small<2, false, SORT_MID_CAP, SORT_MID_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sort_count_smem<2, SORT_MID_CAP>()));
+    CK(cudaFuncSetAttribute(k_sort_small<2, true, SORT_MID_CAP, SORT_MID_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sort_count_smem<2, SORT_MID_CAP>()));
     CK(cudaFuncSetAttribute(k_sort_big<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<1>()));
     CK(cudaFuncSetAttribute(k_sort_big<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<2>()));
     CK(cudaFuncSetAttribute(k_sort_big<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_big_smem<1>()));
