@@ -291,6 +291,19 @@ def main():
                 "kernel": "k_smem_count<1>", "kernel_ms": ms_hot_avg, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                 "pipeline_frac": alg / (ms_dev_max * 1e-3) / 1e9 / peak}
 
+    # ---- next row f-2 (outside the timed region): unitig compaction + the plugin's contig on the same device-resident batch ------
+    next_rows = None
+    if rank == 0 and args.gpus == 1:
+        try:
+            db = eng.count_prune_device(d_data, n_bytes, d_off, n_reads, d_goff, n_umis, cfg["k"], cfg["min_cov"])
+            nu, nb, ms_u = eng.compress_unitigs(db, 200, sizes_only=True)
+            nu, nb, ms_u = eng.compress_unitigs(db, 200, sizes_only=True)
+            db.free()
+            next_rows = {"unitig_compaction": {"ms": ms_u, "unitigs": nu, "contig_bases": nb, "min_length": 200,
+                                               "api": "rogtk_gpu_compress_unitigs, device-resident in and out"}}
+        except Exception as exc:   # reported, never fatal for the headline line
+            next_rows = {"unitig_compaction": {"error": str(exc)[:200]}}
+
     # ---- e2e: host (pinned) Arrow buffers -> C ABI -> host arrays; H2D + D2H inside the timed region -------------------
     e2e = None
     cpu = None
@@ -365,7 +378,8 @@ def main():
                        "l2": "inputs (15 GB/GPU) far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the library stream around the whole device pipeline, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "survivors_per_step": int(n_kmers), "spilled_groups": int(n_spill), "observations_per_step": int(obs_all)})
+            "survivors_per_step": int(n_kmers), "spilled_groups": int(n_spill), "observations_per_step": int(obs_all),
+            "next_rows": next_rows})
         print(json.dumps(line))
     for p in (d_data, d_off, d_goff):
         eng.device_free(p)
