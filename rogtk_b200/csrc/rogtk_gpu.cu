@@ -289,6 +289,8 @@ extern "C" int rogtk_gpu_device_count(void)
     return n;
 }
 
+extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx);
+
 extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, int *err)
 {
     auto fail = [&](int code) -> rogtk_gpu_ctx * {
@@ -308,7 +310,7 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) {
-            delete ctx;
+            rogtk_gpu_destroy(ctx);
             return fail(ROGTK_ERR_UNSUPPORTED);   // sm_100a only
         }
         ctx->sm_count = prop.multiProcessorCount;
@@ -329,7 +331,8 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         smem_path_configure();
     } catch (const CudaFail &f) {
         fprintf(stderr, "rogtk_gpu_create: %s: %s\n", f.what, cudaGetErrorString(f.e));
-        delete ctx;
+        cudaGetLastError();
+        rogtk_gpu_destroy(ctx);   // releases whatever was created so far
         return fail(ROGTK_ERR_CUDA);
     }
     if (err) *err = ROGTK_OK;
@@ -340,7 +343,7 @@ extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->pinned_size) cudaFreeHost(kv.first);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->peek_slot) cudaFreeHost(ctx->peek_slot);
