@@ -494,6 +494,51 @@ def test_many_tiny_groups(engine, oracle):
         _both(engine, oracle, data, offs, goff, k, mc, csr=False, ctx=f"tiny groups k={k}")
 
 
+@pytest.mark.parametrize("k,exact", [(31, False), (15, False), (64, False), (27, True), (45, True)])
+def test_three_counting_paths_agree_on_skewed_batches(engine, k, exact):
+    """One shared-memory table, several shared-memory passes, HBM tables: bit-identical batches on randomized skewed inputs
+    (group sizes 0..900 reads, read lengths 0..400, per-group error rates 0..10 %, a few unrelated-read groups), larger than
+    what the oracle-checked tests cover."""
+    rng = np.random.default_rng(1234 + k)
+    chunks, lens, rows_per_group = [], [], []
+    for g in range(160):
+        u = rng.random()
+        n_reads = int(rng.integers(0, 12)) if u < 0.3 else int(np.exp(rng.uniform(0, np.log(900))))
+        T = int(rng.integers(40, 1500))
+        tmpl = rng.integers(0, 4, size=T, dtype=np.uint8)
+        err = rng.uniform(0, 0.1)
+        unrelated = rng.random() < 0.05
+        for _ in range(n_reads):
+            L = int(rng.integers(0, min(400, T) + 1))
+            if unrelated:
+                b = rng.integers(0, 4, size=L, dtype=np.uint8)
+            else:
+                s0 = int(rng.integers(0, T - L + 1))
+                b = tmpl[s0:s0 + L].copy()
+                flip = rng.random(L) < err
+                b[flip] = rng.integers(0, 4, size=int(flip.sum()), dtype=np.uint8)
+            a = np.frombuffer(b"ACGT", dtype=np.uint8)[b]
+            if L and rng.random() < 0.02:
+                a = a.copy()
+                a[int(rng.integers(0, L))] = ord("N")
+            chunks.append(a)
+            lens.append(L)
+        rows_per_group.append(n_reads)
+    data = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    goff = np.concatenate([[0], np.cumsum(rows_per_group)]).astype(np.int64)
+    base = EMIT_STATS | EMIT_CSR | (EXACT_K if exact else 0)
+    for mc in (1, 2, 5):
+        a = engine.count_prune(data, offs, goff, k, mc, flags=base)
+        b = engine.count_prune(data, offs, goff, k, mc, flags=base | NO_MULTIPASS)
+        c = engine.count_prune(data, offs, goff, k, mc, flags=base | FORCE_SPILL)
+        assert a.n_multipass_groups > 0 and b.n_multipass_groups == 0 and b.n_spilled_groups >= a.n_multipass_groups
+        assert c.n_spilled_groups == 160
+        for other, name in ((b, "no multipass"), (c, "hbm tables only")):
+            assert_batches_equal(other, a, check_csr=True, ctx=f"paths k={k} mc={mc}: {name}")
+        check_invariants(a, mc)
+
+
 def _check_unitigs(engine, oracle, data, offs, goff, k, mc, min_length, validity=None, ctx=""):
     ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity)
     got = engine.assemble(data, offs, goff, k, mc, min_length=min_length, validity=validity)
