@@ -52,6 +52,7 @@ extern "C" {
 #define ROGTK_OUTPUT_ON_DEVICE (1u << 4) /* leave the result arrays in device memory */
 #define ROGTK_FORCE_SPILL (1u << 5)      /* testing: bypass the shared-memory tables, use the HBM tables only */
 #define ROGTK_NO_MULTIPASS (1u << 6)     /* testing: groups beyond one shared-memory table go straight to the HBM tables */
+#define ROGTK_UNITIG_NODE_PARALLEL (1u << 7) /* testing: rogtk_gpu_compress_unitigs uses the node-parallel kernels for every batch */
 
 typedef struct rogtk_gpu_ctx rogtk_gpu_ctx;
 

@@ -27,6 +27,7 @@ INPUT_ON_DEVICE = 1 << 3
 OUTPUT_ON_DEVICE = 1 << 4
 FORCE_SPILL = 1 << 5
 NO_MULTIPASS = 1 << 6
+UNITIG_NODE_PARALLEL = 1 << 7
 
 # every symbol include/rogtk_gpu.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [

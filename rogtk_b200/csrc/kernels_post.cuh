@@ -121,8 +121,8 @@ __global__ void k_csr(int64_t n_kmers, int64_t n_groups, const int64_t *kmer_off
     const uint32_t e = exts[i] >> 4;
     int deg = 0;
     int64_t w = cols ? row_ptr[i] : 0;
-    for (uint32_t bb = 0; bb < 4; bb++) {
-        if (!((e >> bb) & 1u)) continue;
+    for (uint32_t m = e; m; m &= m - 1u) {   // ascending set bits; t-th bit per iteration keeps a warp's lanes together
+        const uint32_t bb = (uint32_t)__ffs((int)m) - 1u;
         uint64_t yl = (xl << 2) | bb, yh = (xh << 2) | (xl >> 62);
         if (kbits < 64) { yl &= (1ull << kbits) - 1ull; yh = 0; }
         else if (kbits == 64) yh = 0;

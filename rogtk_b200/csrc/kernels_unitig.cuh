@@ -63,8 +63,8 @@ __global__ void k_unitig_links(UnitigArgs a)
     uint32_t *fxw = reinterpret_cast<uint32_t *>(a.fx);
     uint32_t f = 0;
     int64_t succ = -1;
-    for (uint32_t b = 0; b < 4; b++) {
-        if (!((e >> (4 + b)) & 1u)) continue;   // right neighbour: drop the first base, append b
+    for (uint32_t m = e >> 4; m; m &= m - 1u) {   // right neighbours (t-th set bit per iteration, so a warp's lanes search together)
+        const uint32_t b = (uint32_t)__ffs((int)m) - 1u;   // drop the first base, append b
         uint64_t yl = (xl << 2) | b, yh = (xh << 2) | (xl >> 62);
         if (kbits < 64) { yl &= (1ull << kbits) - 1ull; yh = 0; }
         else if (kbits == 64) yh = 0;
@@ -252,6 +252,298 @@ __global__ void k_unitig_largest(int64_t n_groups, const int64_t *uoff, const in
     }
     largest[g] = best;
     lflags[g] = best < 0 ? 0 : (uint8_t)(tie | (ucyc[best] ? 2 : 0));
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Fused per-group variant: one CTA holds a whole group (<= NMAX nodes) in shared memory -- neighbour searches, link building,
+// list ranking by pointer jumping (ceil(log2 n) rounds instead of serial chain walks), per-unitig sums, and the ASCII
+// sequences staged in shared memory and written out as aligned words.  Two passes of the same body: EMIT = false counts the
+// unitigs and contig bases of every group (-> two scans give every group its slice of the outputs), EMIT = true writes them.
+// Used when every group of the batch fits (the per-UMI workloads); otherwise the node-parallel kernels above run.
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct UnitigGroupArgs {
+    int64_t n_groups;
+    const int64_t *offsets;
+    const uint64_t *lo, *hi;
+    const uint8_t *exts;
+    const uint16_t *counts;
+    int K;
+    int n_min;              // this launch takes the groups with n_min < nodes <= NMAX (and the empty ones when n_min == 0)
+    // EMIT = false
+    int32_t *g_nu;          // [n_groups] unitigs of the group
+    int64_t *g_nb;          // [n_groups] contig bases of the group
+    // EMIT = true
+    const int64_t *uoff;    // [n_groups+1] exclusive scan of g_nu
+    const int64_t *sbase;   // [n_groups+1] exclusive scan of g_nb
+    int64_t *seq_offsets;   // [n_unitigs]
+    uint8_t *seq;
+    int32_t *ulen;
+    uint16_t *ucnt;
+    uint8_t *uext, *ucyc;
+};
+
+template <int W, int NMAX>
+constexpr size_t unitig_group_smem()
+{
+    return (size_t)NMAX * (8 * W + 4 + 4 + 4 + 1 + 2 + 2 + 2 + 1 + 2) + 64 * 4;
+}
+
+__global__ void k_max_group(const int64_t *offsets, int64_t n_groups, unsigned long long *out)
+{
+    unsigned long long m = 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long d = (unsigned long long)(offsets[g + 1] - offsets[g]);
+        m = d > m ? d : m;
+    }
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// exclusive block scan of two values per thread (NT threads); ws: 2 * 32 words
+template <int NT>
+__device__ __forceinline__ void block_scan_pair(uint32_t a, uint32_t b, uint32_t &ea, uint32_t &eb, uint32_t &ta, uint32_t &tb, uint32_t *ws)
+{
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t xa = a, xb = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, d), yb = __shfl_up_sync(0xffffffffu, xb, d);
+        if (lane >= (unsigned)d) { xa += ya; xb += yb; }
+    }
+    __syncthreads();   // ws may still be read from a previous call
+    if (lane == 31) { ws[warp] = xa; ws[32 + warp] = xb; }
+    __syncthreads();
+    uint32_t ba = 0, bb = 0;
+    ta = 0; tb = 0;
+    for (int w = 0; w < NT / 32; w++) {
+        const uint32_t sa = ws[w], sb = ws[32 + w];
+        if (w < (int)warp) { ba += sa; bb += sb; }
+        ta += sa; tb += sb;
+    }
+    ea = ba + xa - a;
+    eb = bb + xb - b;
+}
+
+template <int W, int NMAX, int NT, bool EMIT>
+__global__ void __launch_bounds__(NT) k_unitig_group(UnitigGroupArgs a)
+{
+    extern __shared__ __align__(16) uint8_t ug_raw[];
+    uint64_t *s_lo = reinterpret_cast<uint64_t *>(ug_raw);
+    uint64_t *s_hi = s_lo + NMAX;                                                   // only touched when W == 2
+    uint32_t *s_pr0 = reinterpret_cast<uint32_t *>(s_lo + (W == 2 ? 2 : 1) * NMAX);   // (head candidate | distance << 16), double buffered
+    uint32_t *s_pr1 = s_pr0 + NMAX;
+    uint32_t *s_sum = s_pr1 + NMAX;                                                 // per head: count sum, later its start in the staging
+    uint32_t *s_fxw = s_sum + NMAX;                                                 // fixed exts, one byte per node (NMAX / 4 words)
+    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_fxw + NMAX / 4);
+    int16_t *s_nxt = reinterpret_cast<int16_t *>(s_cnt + NMAX);
+    int16_t *s_pred = s_nxt + NMAX;                                                 // linking predecessor; later: nodes of the unitig (heads)
+    uint8_t *s_ex = reinterpret_cast<uint8_t *>(s_pred + NMAX);                     // exts; later flags: 1 head, 2 cyclic
+    uint8_t *s_stage = s_ex + NMAX;                                                 // 2 * NMAX bytes of contig text
+    uint32_t *s_ws = reinterpret_cast<uint32_t *>(s_stage + 2 * NMAX);
+    uint8_t *s_fx = reinterpret_cast<uint8_t *>(s_fxw);
+    const int tid = threadIdx.x;
+    const int K = a.K, kbits = 2 * a.K;
+
+    auto find = [&](int n, uint64_t khi, uint64_t klo) -> int {
+        int lo_ = 0, hi_ = n;
+        while (lo_ < hi_) {
+            const int m = (lo_ + hi_) >> 1;
+            const uint64_t mh = W == 2 ? s_hi[m] : 0ull, ml = s_lo[m];
+            if (mh == khi && ml == klo) return m;
+            if (mh < khi || (mh == khi && ml < klo)) lo_ = m + 1; else hi_ = m;
+        }
+        return -1;
+    };
+
+    for (int64_t g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+        const int64_t o = a.offsets[g];
+        const int n = (int)(a.offsets[g + 1] - o);
+        if (n > NMAX || n <= a.n_min) {   // another launch's group (the host excludes batches with n > the largest NMAX)
+            if (n == 0 && a.n_min == 0 && !EMIT && tid == 0) {
+                a.g_nu[g] = 0;
+                a.g_nb[g] = 0;
+            }
+            continue;
+        }
+        __syncthreads();   // shared arrays of the previous group are no longer read
+        // ---- 1. stage the group ---------------------------------------------------------------------------------------
+        for (int i = tid; i < n; i += NT) {
+            s_lo[i] = a.lo[o + i];
+            if (W == 2) s_hi[i] = a.hi[o + i];
+            s_ex[i] = a.exts[o + i];
+            s_cnt[i] = a.counts[o + i];
+            s_pred[i] = -1;
+            s_sum[i] = 0;
+        }
+        for (int i = tid; i < (n + 3) / 4; i += NT) s_fxw[i] = 0;
+        __syncthreads();
+        // ---- 2. fix_exts (right side searched, left side OR-ed in from the linking node) + unique successor ---------------------
+        for (int i = tid; i < n; i += NT) {
+            const uint64_t xl = s_lo[i], xh = W == 2 ? s_hi[i] : 0ull;
+            const uint32_t e = s_ex[i];
+            const int top = kbits - 2;
+            const uint32_t first = (uint32_t)((top >= 64 ? xh >> (top - 64) : xl >> top) & 3ull);
+            uint32_t f = 0;
+            int succ = -1;
+            for (uint32_t m = e >> 4; m; m &= m - 1u) {   // t-th set bit per iteration: the lanes of a warp search together
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                uint64_t yl = (xl << 2) | b, yh = (xh << 2) | (xl >> 62);
+                if (kbits < 64) { yl &= (1ull << kbits) - 1ull; yh = 0; }
+                else if (kbits == 64) yh = 0;
+                else if (kbits < 128) yh &= (1ull << (kbits - 64)) - 1ull;
+                const int j = find(n, yh, yl);
+                if (j >= 0) {
+                    f |= 16u << b;
+                    succ = j;
+                    atomicOr(&s_fxw[j >> 2], (1u << first) << (8 * (j & 3)));
+                }
+            }
+            if (f) atomicOr(&s_fxw[i >> 2], f << (8 * (i & 3)));
+            s_nxt[i] = __popc(f >> 4) == 1 ? (int16_t)succ : (int16_t)-1;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const uint32_t f = s_fx[i];
+            s_fx[i] = (uint8_t)((f & 0xf0u) | (f & s_ex[i] & 15u));
+        }
+        __syncthreads();
+        // ---- 3. links: the successor must have exactly one left ext and differ from the node ------------------------------------------
+        for (int i = tid; i < n; i += NT) {
+            const int j = s_nxt[i];
+            if (j < 0) continue;
+            if (j == i || __popc(s_fx[j] & 15u) != 1) s_nxt[i] = -1;
+            else s_pred[j] = (int16_t)i;   // one writer: j's only left neighbour
+        }
+        __syncthreads();
+        // ---- 4. list ranking by pointer jumping: (node reached, distance to it); heads are fixed points -----------------------------
+        for (int i = tid; i < n; i += NT) {
+            const int p = s_pred[i];
+            s_pr0[i] = p >= 0 ? ((uint32_t)p | (1u << 16)) : (uint32_t)i;
+            s_ex[i] = p >= 0 ? 0 : 1;   // flags from here on: bit 0 head, bit 1 cyclic
+        }
+        __syncthreads();
+        uint32_t *pin = s_pr0, *pout = s_pr1;
+        for (int span = 1; span < n; span <<= 1) {
+            for (int i = tid; i < n; i += NT) {
+                const uint32_t v = pin[i], w = pin[v & 0xffffu];
+                pout[i] = (w & 0xffffu) | ((((v >> 16) + (w >> 16)) & 0xffffu) << 16);
+            }
+            __syncthreads();
+            uint32_t *t = pin; pin = pout; pout = t;
+        }
+        // ---- 5. what does not end at a head is a pure cycle: its smallest member becomes the head and ranks the others ----------------
+        for (int i = tid; i < n; i += NT) {
+            if (s_ex[pin[i] & 0xffffu] & 1u) continue;   // chain node (or head)
+            s_ex[i] |= 4u;                               // cycle member (own byte; bit 0 of other bytes is stable here)
+            int cur = i, len = 0;
+            bool smallest = true;
+            do {
+                if (cur < i) { smallest = false; break; }
+                len++;
+                cur = s_nxt[cur];
+            } while (cur != i && len <= n);
+            if (!smallest) continue;
+            cur = i;
+            for (int r = 0; r < len; r++) {   // (only this thread writes the members' entries; nobody reads them before the barrier)
+                pout[cur] = (uint32_t)i | ((uint32_t)r << 16);
+                cur = s_nxt[cur];
+            }
+            pout[i] |= 0x80000000u;   // marks the cycle head for the merge below
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            if (!(s_ex[i] & 4u)) continue;
+            const uint32_t v = pout[i];
+            pin[i] = v & 0x7fffffffu;
+            if (v & 0x80000000u) s_ex[i] = 7;   // head of a cycle
+        }
+        __syncthreads();
+        // ---- 6. per unitig: nodes, saturating count sum, exts of the tail ------------------------------------------------------------------
+        for (int i = tid; i < n; i += NT) pout[i] = 0;   // per head: number of nodes
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const uint32_t v = pin[i];
+            const int h = (int)(v & 0xffffu), r = (int)(v >> 16);
+            atomicAdd(&s_sum[h], (uint32_t)s_cnt[i]);
+            atomicMax(&pout[h], (uint32_t)r + 1u);
+            const int nx = s_nxt[i];
+            if (nx < 0 || nx == h) s_pred[h] = (int16_t)(s_fx[i] & 0xf0u);   // the tail (one per unitig) leaves its right nibble
+        }
+        __syncthreads();
+        // ---- 7. order of the unitigs = order of their heads; every thread owns a contiguous range of nodes -------------------------------
+        const int per = (n + NT - 1) / NT;
+        const int c0 = tid * per < n ? tid * per : n, c1 = c0 + per < n ? c0 + per : n;
+        uint32_t my_heads = 0, my_bases = 0;
+        for (int i = c0; i < c1; i++)
+            if (s_ex[i] & 1u) {
+                my_heads++;
+                my_bases += (uint32_t)K + pout[i] - 1u;
+            }
+        uint32_t eh, eb, th, tb;
+        block_scan_pair<NT>(my_heads, my_bases, eh, eb, th, tb, s_ws);
+        if (!EMIT) {
+            if (tid == 0) {
+                a.g_nu[g] = (int32_t)th;
+                a.g_nb[g] = (int64_t)tb;
+            }
+            continue;
+        }
+        const int64_t u0 = a.uoff[g], sb = a.sbase[g];
+        const bool staged = tb <= 2u * (uint32_t)NMAX;
+        {
+            uint32_t hb = eh, bb = eb;
+            for (int i = c0; i < c1; i++) {
+                if (!(s_ex[i] & 1u)) continue;
+                const uint32_t len = (uint32_t)K + pout[i] - 1u;
+                const int64_t u = u0 + hb;
+                a.seq_offsets[u] = sb + bb;
+                a.ulen[u] = (int32_t)len;
+                a.ucnt[u] = (uint16_t)(s_sum[i] > 65535u ? 65535u : s_sum[i]);
+                a.uext[u] = (uint8_t)((s_fx[i] & 15u) | ((uint32_t)s_pred[i] & 0xf0u));
+                a.ucyc[u] = (s_ex[i] & 2u) ? 1 : 0;
+                s_sum[i] = bb;   // start of the unitig's text inside the group's slice
+                hb++;
+                bb += len;
+            }
+        }
+        __syncthreads();
+        // ---- 8. text: the head writes its k-mer, every other node its last base; staged, then stored as aligned words -------------------
+        uint8_t *text = staged ? s_stage : a.seq + sb;
+        for (int i = tid; i < n; i += NT) {
+            const uint32_t v = pin[i];
+            const int h = (int)(v & 0xffffu), r = (int)(v >> 16);
+            const uint32_t start = s_sum[h];
+            if (r == 0) {
+                const uint64_t xl = s_lo[i], xh = W == 2 ? s_hi[i] : 0ull;
+                for (int p = 0; p < K; p++) {
+                    const int sh = 2 * (K - 1 - p);
+                    const uint32_t code = (uint32_t)((sh >= 64 ? xh >> (sh - 64) : xl >> sh) & 3ull);
+                    text[start + p] = (uint8_t)((0x54474341u >> (8u * code)) & 0xffu);
+                }
+            } else {
+                text[start + K - 1 + r] = (uint8_t)((0x54474341u >> (8u * (uint32_t)(s_lo[i] & 3ull))) & 0xffu);
+            }
+        }
+        if (staged) {
+            __syncthreads();
+            uint8_t *dst = a.seq + sb;
+            const uint32_t head = (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);   // bytes before the first aligned word
+            const uint32_t hb = head < tb ? head : tb;
+            if ((uint32_t)tid < hb) dst[tid] = s_stage[tid];
+            const uint32_t nw = (tb - hb) / 4;
+            uint32_t *dw = reinterpret_cast<uint32_t *>(dst + hb);
+            for (uint32_t w = tid; w < nw; w += NT) {
+                const uint8_t *s = s_stage + hb + 4 * w;
+                dw[w] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+            }
+            const uint32_t done = hb + 4 * nw;
+            if ((uint32_t)tid < tb - done) dst[done + tid] = s_stage[done + tid];
+        }
+    }
 }
 
 }  // namespace rogtk

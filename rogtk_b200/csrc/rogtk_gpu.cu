@@ -1218,6 +1218,95 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
 // -----------------------------------------------------------------------------------------------------------------
 // unitig compaction + contig selection
 // -----------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int UG_SMALL_NMAX = 1536, UG_SMALL_NT = 256;   // 46 KB (8-byte keys): 4 CTAs per SM
+constexpr int UG_BIG_NMAX = 6144, UG_BIG_NT = 1024;      // 184 KB: 1 CTA per SM
+
+template <int W, int NMAX, int NT>
+void unitig_fused_launch(rogtk_gpu_ctx *ctx, UnitigGroupArgs &a, bool emit, int64_t ng)
+{
+    const size_t smem = unitig_group_smem<W, NMAX>();
+    // (per device, cheap: set on every call rather than tracked per context)
+    CK(cudaFuncSetAttribute(k_unitig_group<W, NMAX, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_unitig_group<W, NMAX, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = std::max<int>(1, std::min<int>(2048 / NT, (int)((ctx->smem_optin + 1024) / (smem + 1024))));
+    const unsigned grid = (unsigned)std::min<int64_t>(ng, (int64_t)ctx->sm_count * per_sm);
+    if (emit) k_unitig_group<W, NMAX, NT, true><<<grid, NT, smem, ctx->stream>>>(a);
+    else k_unitig_group<W, NMAX, NT, false><<<grid, NT, smem, ctx->stream>>>(a);
+    ctx->launches++;
+}
+
+void unitig_fused(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_length, bool all_small, bool out_dev, BatchOwner *own,
+                  rogtk_contig_batch *out)
+{
+    cudaStream_t st = ctx->stream;
+    const int64_t ng = in->n_groups;
+    const int K = in->k_eff;
+    DevBuf g_nu((size_t)ng * 4, st), g_nb((size_t)ng * 8, st), uoff((size_t)(ng + 1) * 8, st), sbase((size_t)(ng + 1) * 8, st),
+        scr(scan_scratch_bytes(ng), st);
+    UnitigGroupArgs a{};
+    a.n_groups = ng; a.offsets = in->kmer_offsets; a.lo = in->kmers_lo; a.hi = K > 32 ? in->kmers_hi : nullptr;
+    a.exts = in->exts; a.counts = in->counts; a.K = K;
+    a.g_nu = g_nu.as<int32_t>(); a.g_nb = g_nb.as<int64_t>();
+    // groups of up to UG_SMALL_NMAX nodes (and the empty ones) in the small instantiation, the others in the large one
+    auto launch = [&](bool emit) {
+        a.n_min = 0;
+        if (K > 32) unitig_fused_launch<2, UG_SMALL_NMAX, UG_SMALL_NT>(ctx, a, emit, ng);
+        else unitig_fused_launch<1, UG_SMALL_NMAX, UG_SMALL_NT>(ctx, a, emit, ng);
+        if (all_small) return;
+        a.n_min = UG_SMALL_NMAX;
+        if (K > 32) unitig_fused_launch<2, UG_BIG_NMAX, UG_BIG_NT>(ctx, a, emit, ng);
+        else unitig_fused_launch<1, UG_BIG_NMAX, UG_BIG_NT>(ctx, a, emit, ng);
+    };
+    launch(false);
+    exclusive_scan<int32_t>(g_nu.as<int32_t>(), ng, uoff.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+    exclusive_scan<int64_t>(g_nb.as<int64_t>(), ng, sbase.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+    int64_t nu = 0, nb = 0;
+    Peek pk(ctx->peek_slot, st, &ctx->launches);
+    pk.add(uoff.as<int64_t>() + ng, 8, &nu);
+    pk.add(sbase.as<int64_t>() + ng, 8, &nb);
+    pk.sync();
+    const size_t nun = (size_t)std::max<int64_t>(nu, 1);
+    DevBuf soff((nun + 1) * 8, st), seq((size_t)std::max<int64_t>(nb, 1) + 8, st), ulen(nun * 4, st), ucnt(nun * 2, st), uext(nun, st),
+        ucyc(nun, st), largest((size_t)std::max<int64_t>(ng, 1) * 8, st), lflags((size_t)std::max<int64_t>(ng, 1), st);
+    a.uoff = uoff.as<int64_t>(); a.sbase = sbase.as<int64_t>();
+    a.seq_offsets = soff.as<int64_t>(); a.seq = seq.as<uint8_t>(); a.ulen = ulen.as<int32_t>(); a.ucnt = ucnt.as<uint16_t>();
+    a.uext = uext.as<uint8_t>(); a.ucyc = ucyc.as<uint8_t>();
+    launch(true);
+    CK(cudaMemcpyAsync(soff.as<int64_t>() + nu, sbase.as<int64_t>() + ng, 8, cudaMemcpyDeviceToDevice, st));
+    k_unitig_largest<<<blocks_for(ng, 256), 256, 0, st>>>(ng, uoff.as<int64_t>(), ulen.as<int32_t>(), ucyc.as<uint8_t>(), min_length,
+                                                          largest.as<int64_t>(), lflags.as<uint8_t>());
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[3], st));
+    out->n_groups = ng;
+    out->n_unitigs = nu;
+    out->n_bases = nb;
+    out->k_eff = K;
+    out->on_device = out_dev ? 1 : 0;
+    auto give = [&](DevBuf &b, size_t bytes) -> void * {
+        if (out_dev) {
+            void *p = b.detach();
+            own->ptrs.push_back(p);
+            return p;
+        }
+        void *h = pinned_get(ctx, bytes);
+        own->ptrs.push_back(h);
+        if (bytes) CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, st));
+        return h;
+    };
+    out->unitig_offsets = (int64_t *)give(uoff, (size_t)(ng + 1) * 8);
+    out->seq_offsets = (int64_t *)give(soff, (size_t)(nu + 1) * 8);
+    out->seq = (uint8_t *)give(seq, (size_t)nb);
+    out->counts = (uint16_t *)give(ucnt, (size_t)nu * 2);
+    out->exts = (uint8_t *)give(uext, (size_t)nu);
+    out->cyclic = (uint8_t *)give(ucyc, (size_t)nu);
+    out->largest = (int64_t *)give(largest, (size_t)ng * 8);
+    out->largest_flags = (uint8_t *)give(lflags, (size_t)ng);
+}
+
+}  // namespace
+
 extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_length, uint32_t flags,
                                           rogtk_contig_batch *out)
 {
@@ -1239,6 +1328,21 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
         const int64_t n = in->n_kmers, ng = in->n_groups;
         const int K = in->k_eff;
         const size_t nn = (size_t)std::max<int64_t>(n, 1);
+        // every group small enough for one CTA's shared memory: fused per-group kernels (two passes), else node-parallel kernels
+        unsigned long long max_n = 0;
+        if (n > 0 && ng > 0 && !(flags & ROGTK_UNITIG_NODE_PARALLEL)) {
+            DevBuf mx(8, st);
+            CK(cudaMemsetAsync(mx.p, 0, 8, st));
+            k_max_group<<<ctx->sm_count * 4, 256, 0, st>>>(in->kmer_offsets, ng, mx.as<unsigned long long>());
+            Peek pk0(ctx->peek_slot, st, &ctx->launches);
+            pk0.add(mx.p, 8, &max_n);
+            pk0.sync();
+            ctx->launches++;
+        }
+        const bool fused = max_n > 0 && max_n <= (unsigned long long)UG_BIG_NMAX;
+        if (fused) {
+            unitig_fused(ctx, in, min_length, max_n <= (unsigned long long)UG_SMALL_NMAX, out_dev, own, out);
+        } else {
         DevBuf fx(nn + 4, st), nxt(nn * 4, st), fl(nn, st), hlen(nn * 4, st), hcnt(nn * 2, st), hext(nn, st), is_head(nn * 4, st),
             upos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st), uoff((size_t)(ng + 1) * 8, st);
         CK(cudaMemsetAsync(fl.p, 0, nn, st));
@@ -1307,6 +1411,7 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
         out->cyclic = (uint8_t *)give(ucyc, (size_t)nu);
         out->largest = (int64_t *)give(largest, (size_t)ng * 8);
         out->largest_flags = (uint8_t *)give(lflags, (size_t)ng);
+        }
         CK(cudaStreamSynchronize(st));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));

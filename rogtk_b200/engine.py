@@ -373,13 +373,14 @@ class Engine:
         return self._to_numpy(out)
 
     # ---- unitig compaction + contig selection ------------------------------------------------------------------------
-    def compress_unitigs(self, batch: DeviceBatch, min_length: int = 0, sizes_only: bool = False):
+    def compress_unitigs(self, batch: DeviceBatch, min_length: int = 0, sizes_only: bool = False, node_parallel: bool = False):
         """Unitigs (maximal non-branching paths, saturating-summed counts) of a device-resident batch and, per group, the
         contig assemble_sequences_expr(method="compression") returns (longest with at least min_length bases).
-        sizes_only=True leaves the result in HBM, frees it and returns (n_unitigs, n_bases, device ms): timing without D2H."""
+        sizes_only=True leaves the result in HBM, frees it and returns (n_unitigs, n_bases, device ms): timing without D2H.
+        node_parallel=True forces the node-parallel kernels (used when a group exceeds one CTA's shared memory) for testing."""
         out = _ffi.ContigBatchC()
-        self._check(self._lib.rogtk_gpu_compress_unitigs(self._ctx, ctypes.byref(batch._c), int(min_length),
-                                                         _ffi.OUTPUT_ON_DEVICE if sizes_only else 0, ctypes.byref(out)))
+        f = (_ffi.OUTPUT_ON_DEVICE if sizes_only else 0) | (_ffi.UNITIG_NODE_PARALLEL if node_parallel else 0)
+        self._check(self._lib.rogtk_gpu_compress_unitigs(self._ctx, ctypes.byref(batch._c), int(min_length), f, ctypes.byref(out)))
         if sizes_only:
             r = (int(out.n_unitigs), int(out.n_bases), float(out.ms_total))
             self._lib.rogtk_gpu_free_contigs(self._ctx, ctypes.byref(out))
@@ -401,7 +402,7 @@ class Engine:
         return res
 
     def assemble(self, data: np.ndarray, offsets: np.ndarray, group_offsets: np.ndarray, k: int, min_coverage: int,
-                 min_length: int = 0, validity: np.ndarray | None = None) -> ContigBatch:
+                 min_length: int = 0, validity: np.ndarray | None = None, node_parallel: bool = False) -> ContigBatch:
         """reads -> pruned de Bruijn nodes -> unitigs -> the plugin's contig per group, all on the device
         (assemble_sequences_expr with method="compression", reference src/expressions.rs:695-762)."""
         db = self.count_prune_to_device(data, offsets, group_offsets, k, min_coverage, validity=validity)
@@ -412,7 +413,7 @@ class Engine:
                 return ContigBatch(k_eff=-1, unitig_offsets=z(ng + 1, np.int64), seq_offsets=z(1, np.int64), seq=z(0, np.uint8),
                                    counts=z(0, np.uint16), exts=z(0, np.uint8), cyclic=z(0, np.uint8),
                                    largest=np.full(ng, -1, np.int64), largest_flags=z(ng, np.uint8))
-            return self.compress_unitigs(db, min_length)
+            return self.compress_unitigs(db, min_length, node_parallel=node_parallel)
         finally:
             db.free()
 

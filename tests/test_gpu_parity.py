@@ -542,6 +542,10 @@ def test_three_counting_paths_agree_on_skewed_batches(engine, k, exact):
 def _check_unitigs(engine, oracle, data, offs, goff, k, mc, min_length, validity=None, ctx=""):
     ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity)
     got = engine.assemble(data, offs, goff, k, mc, min_length=min_length, validity=validity)
+    # the two implementations (one CTA per group in shared memory / node-parallel kernels) must give identical batches
+    alt = engine.assemble(data, offs, goff, k, mc, min_length=min_length, validity=validity, node_parallel=True)
+    for f in ("unitig_offsets", "seq_offsets", "seq", "counts", "exts", "cyclic", "largest", "largest_flags"):
+        assert np.array_equal(getattr(got, f), getattr(alt, f)), f"{ctx}: fused vs node-parallel differ in {f}"
     assert got.n_groups == len(goff) - 1
     for g in range(got.n_groups):
         nodes = oracle.batch_group_as_tuples(ref, g)
@@ -585,6 +589,14 @@ def test_unitig_compaction_and_plugin_contig(engine, oracle):
     data, offs, goff = synth.synth_reads(synth.config_seed(2), 0, 40, 50, 300, 1000)
     got = _check_unitigs(engine, oracle, data, offs, goff, 31, 2, 200, ctx="cfg2 unitigs")
     assert all(len(got.assembled(g)[0]) >= 200 for g in range(40)) and len(got.assembled(1)[0]) == 969
+    # min_coverage 1 keeps ~4500 nodes per UMI: the large instantiation of the per-group kernel; a 300-read group of unrelated
+    # reads (> 6144 nodes) sends the whole batch to the node-parallel kernels
+    data1, offs1, goff1 = synth.synth_reads(synth.config_seed(2), 100, 6, 50, 300, 1000)
+    _check_unitigs(engine, oracle, data1, offs1, goff1, 31, 1, 100, ctx="cfg2 unitigs mc=1")
+    rngu = np.random.default_rng(3)
+    big = [["".join("ACGT"[x] for x in rngu.integers(0, 4, 120)) for _ in range(300)], ["ACGTTGCAAGGCTTAACCGGTTAACCGGATATCGCGATTA" * 3] * 4]
+    d4, o4, v4, g4 = groups_to_arrow(big)
+    _check_unitigs(engine, oracle, d4, o4, g4, 31, 1, 0, validity=v4, ctx="one group beyond a CTA")
     # k > 64: no contigs
     got = engine.assemble(data, offs, goff, 65, 2)
     assert got.k_eff == -1 and list(got.largest) == [-1] * 40
