@@ -868,23 +868,24 @@ struct SortArgs {
     const int32_t *seg_list;
 };
 
-// Counting sort of one work item per CTA pass.  SEG = false: work items are groups.  SEG = true: segments of multi-pass
+// Counting sort of one work item per CTA pass: survivors are read once into registers, counted per bucket (top 10 k-mer bits),
+// scattered from the registers into shared memory in bucket order, and every survivor then ranks itself inside its tiny bucket
+// and is written straight to its final position (4 block barriers, no index indirection).  SEG = false: work items are groups.  SEG = true: segments of multi-pass
 // groups (item i = pass i % SM_PMAX of list entry i / SM_PMAX); the k-mers of a segment lie in 1/P of the k-mer space, so the
 // buckets subdivide that range.  LIST = true: the items are those named in in_list (what a smaller instantiation passed on).
 // Two instantiations: CAP = sort_small_max() with 128 threads (36 KB, 6 CTAs/SM: the headline shape, ~1000 survivors per
-// group) and CAP = 6144 with 512 threads (two CTAs/SM: min_coverage <= 1 keeps ~4500 k-mers per group; the bitonic kernel that
+// group) and CAP = 8192 with 512 threads (two CTAs/SM: min_coverage <= 1 keeps ~4500 k-mers per group; the bitonic kernel that
 // used to take those groups was 10x slower).  Items that do not fit, or have a crowded bucket, go to the output list.
 template <int W, bool SEG, int CAP, int NT, bool LIST>
 __global__ void __launch_bounds__(NT) k_sort_small(SortArgs a, int64_t n_items, const int32_t *in_list)
 {
+    constexpr int EPT = (CAP + NT - 1) / NT;   // survivors a thread keeps in registers between the passes
     extern __shared__ __align__(16) uint8_t sort_raw[];
-    uint64_t *s_lo = reinterpret_cast<uint64_t *>(sort_raw);
+    uint64_t *s_lo = reinterpret_cast<uint64_t *>(sort_raw);                 // bucket-ordered keys
     uint64_t *s_hi = s_lo + CAP;                                             // only touched when W == 2
-    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_lo + (W == 2 ? 2 : 1) * CAP);   // exts | count << 8
+    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_lo + (W == 2 ? 2 : 1) * CAP);   // exts | count << 8, bucket-ordered
     uint32_t *s_hist = s_val + CAP;
     uint32_t *s_ws = s_hist + SM_SORT_BUCKETS;
-    uint16_t *s_order = reinterpret_cast<uint16_t *>(s_ws + 32);
-    uint16_t *s_fin = s_order + CAP;
     __shared__ int s_flag;
     const int tid = threadIdx.x;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
@@ -914,25 +915,34 @@ __global__ void __launch_bounds__(NT) k_sort_small(SortArgs a, int64_t n_items, 
             if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)it;
             continue;
         }
-        __syncthreads();   // previous item's shared data no longer in use
-        if (tid == 0) s_flag = 0;
-        for (int j = tid; j < SM_SORT_BUCKETS; j += NT) s_hist[j] = 0;
-        for (int j = tid; j < n; j += NT) {
-            s_lo[j] = a.p_lo[ps + j];
-            if (W == 2) s_hi[j] = a.p_hi[ps + j];
-            s_val[j] = (uint32_t)a.p_exts[ps + j] | ((uint32_t)a.p_counts[ps + j] << 8);
-        }
-        __syncthreads();
-        auto bucket_of = [&](int j) -> uint32_t {
+        auto bucket_of = [&](uint64_t lo, uint64_t hi) -> uint32_t {
             if (SEG) {   // position inside the segment's k-mer range, scaled to the bucket count (monotone in the k-mer)
-                const uint32_t t = W == 2 ? key_top32(Key<2>{s_lo[j], s_hi[j]}, kb) : key_top32(Key<1>{s_lo[j]}, kb);
+                const uint32_t t = W == 2 ? key_top32(Key<2>{lo, hi}, kb) : key_top32(Key<1>{lo}, kb);
                 const uint64_t b = ((uint64_t)(t - seg_first) * seg_np) >> (32 - SM_SORT_BITS);
                 return b < (uint64_t)SM_SORT_BUCKETS ? (uint32_t)b : (uint32_t)(SM_SORT_BUCKETS - 1);
             }
-            if (W == 2) return sort_bucket<2>(Key<2>{s_lo[j], s_hi[j]}, kb);
-            return sort_bucket<1>(Key<1>{s_lo[j]}, kb);
+            if (W == 2) return sort_bucket<2>(Key<2>{lo, hi}, kb);
+            return sort_bucket<1>(Key<1>{lo}, kb);
         };
-        for (int j = tid; j < n; j += NT) atomicAdd(&s_hist[bucket_of(j)], 1u);
+        // ---- survivors of the item -> registers; bucket histogram ---------------------------------------------------------------
+        uint64_t klo[EPT], khi[W == 2 ? EPT : 1];
+        uint32_t kv[EPT];
+        __syncthreads();   // previous item's shared data no longer in use
+        if (tid == 0) s_flag = 0;
+        for (int j = tid; j < SM_SORT_BUCKETS; j += NT) s_hist[j] = 0;
+#pragma unroll
+        for (int t = 0; t < EPT; t++) {
+            const int j = tid + t * NT;
+            if (j < n) {
+                klo[t] = a.p_lo[ps + j];
+                if (W == 2) khi[t] = a.p_hi[ps + j];
+                kv[t] = (uint32_t)a.p_exts[ps + j] | ((uint32_t)a.p_counts[ps + j] << 8);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < EPT; t++)
+            if (tid + t * NT < n) atomicAdd(&s_hist[bucket_of(klo[t], W == 2 ? khi[t] : 0ull)], 1u);
         __syncthreads();
         {   // exclusive scan of the bucket sizes (PER per thread)
             constexpr int PER = SM_SORT_BUCKETS / NT;
@@ -967,39 +977,42 @@ __global__ void __launch_bounds__(NT) k_sort_small(SortArgs a, int64_t n_items, 
             if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)it;
             continue;
         }
-        for (int j = tid; j < n; j += NT) s_order[atomicAdd(&s_hist[bucket_of(j)], 1u)] = (uint16_t)j;
+        // ---- registers -> shared memory in bucket order (arrival order inside a bucket) ----------------------------------------------
+#pragma unroll
+        for (int t = 0; t < EPT; t++) {
+            if (tid + t * NT < n) {
+                const uint32_t pos = atomicAdd(&s_hist[bucket_of(klo[t], W == 2 ? khi[t] : 0ull)], 1u);
+                s_lo[pos] = klo[t];
+                if (W == 2) s_hi[pos] = khi[t];
+                s_val[pos] = kv[t];
+            }
+        }
         __syncthreads();
-        // s_hist[b] is now the END of bucket b.  Every survivor ranks itself inside its (tiny) bucket: final position =
-        // bucket start + number of bucket members with a smaller k-mer (k-mers are distinct).
+        // s_hist[b] is now the END of bucket b.  Every survivor ranks itself inside its (tiny) bucket -- final position = bucket
+        // start + number of bucket members with a smaller k-mer (k-mers are distinct) -- and goes straight to the dense output.
         for (int j = tid; j < n; j += NT) {
-            const uint32_t b = bucket_of(j);
+            const uint64_t lj = s_lo[j], hj = (W == 2) ? s_hi[j] : 0ull;
+            const uint32_t b = bucket_of(lj, hj);
             const uint32_t st = b ? s_hist[b - 1] : 0u, en = s_hist[b];
             uint32_t r = st;
             if (en - st > 1u) {
-                const uint64_t lj = s_lo[j], hj = (W == 2) ? s_hi[j] : 0ull;
                 for (uint32_t i = st; i < en; i++) {
-                    const uint16_t oi = s_order[i];
-                    const uint64_t li = s_lo[oi], hi_i = (W == 2) ? s_hi[oi] : 0ull;
+                    const uint64_t li = s_lo[i], hi_i = (W == 2) ? s_hi[i] : 0ull;
                     r += (hi_i < hj || (hi_i == hj && li < lj)) ? 1u : 0u;
                 }
             }
-            s_fin[r] = (uint16_t)j;
-        }
-        __syncthreads();
-        for (int j = tid; j < n; j += NT) {
-            const int idx = s_fin[j];
-            a.o_lo[o + j] = s_lo[idx];
-            if (W == 2) a.o_hi[o + j] = s_hi[idx];
-            const uint32_t v = s_val[idx];
-            a.o_exts[o + j] = (uint8_t)v;
-            a.o_counts[o + j] = (uint16_t)(v >> 8);
+            a.o_lo[o + r] = lj;
+            if (W == 2) a.o_hi[o + r] = hj;
+            const uint32_t v = s_val[j];
+            a.o_exts[o + r] = (uint8_t)v;
+            a.o_counts[o + r] = (uint16_t)(v >> 8);
         }
     }
 }
 template <int W, int CAP>
-constexpr size_t sort_count_smem() { return (size_t)CAP * (8 * W + 4 + 2 + 2) + SM_SORT_BUCKETS * 4 + 32 * 4; }
+constexpr size_t sort_count_smem() { return (size_t)CAP * (8 * W + 4) + SM_SORT_BUCKETS * 4 + 32 * 4; }
 constexpr int SORT_MID_NT = 512;
-constexpr int SORT_MID_CAP = 6144;   // 102 KB of shared memory for 8-byte keys: two CTAs per SM
+constexpr int SORT_MID_CAP = SM_TSIZE;   // every single-table group fits; 100 KB of shared memory for 8-byte keys: two CTAs per SM
 
 // SEG = false: one work item per group listed in big_ids.  SEG = true: big_ids lists segments of multi-pass groups; the
 // segments of a group hold ascending k-mer ranges, so ordering each one in place orders the group.

@@ -1,5 +1,7 @@
+#!/bin/bash
+# launch list of a min_coverage=1 step (mid-size counting sort tier) on 50 k UMIs
 mkdir -p gpurun_out
-CMD2="python bench.py --umis 20000 --steps 1 --warmup 1 --no-e2e --no-cpu"
-timeout 300 $CMD2 > gpurun_out/plain2.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sort_small -s 1 -c 1 -o gpurun_out/prof_sort $CMD2 > gpurun_out/ncu.log 2>&1
-tail -2 gpurun_out/ncu.log
+CMD="python tools/unitig_probe.py 50000"
+timeout 300 $CMD > gpurun_out/sort_plain.log 2>&1 || { tail -5 gpurun_out/sort_plain.log; exit 1; }
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_sortmid.csv $CMD > gpurun_out/ncu_sortmid.log 2>&1
+tail -3 gpurun_out/sort_plain.log

@@ -14,7 +14,8 @@ for mc in (2, 1):
     for it in range(3):
         nu, nb, ms = eng.compress_unitigs(db, 200, sizes_only=True)
         best = ms if best is None else min(best, ms)
-    print(f"min_cov={mc}: {n} UMIs, {db.n_kmers} nodes ({db.n_kmers / n:.0f}/UMI): count+prune {db.ms_total:.2f} ms; unitigs {best:.2f} ms "
+    print(f"min_cov={mc}: {n} UMIs, {db.n_kmers} nodes ({db.n_kmers / n:.0f}/UMI): count+prune {db.ms_total:.2f} ms "
+          f"(multi-pass groups {db.n_multipass_groups}, HBM-table groups {db.n_spilled_groups}); unitigs {best:.2f} ms "
           f"({db.n_kmers / best / 1e6:.2f} G nodes/s), {nu / n:.1f} unitigs/UMI, {nb / n:.0f} contig bases/UMI", flush=True)
     db.free()
 # flags on a host-visible subset
