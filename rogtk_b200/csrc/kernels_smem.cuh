@@ -845,7 +845,7 @@ __global__ void k_obs_upper_bound(ColView col, int K, unsigned long long *out)
 // -----------------------------------------------------------------------------------------------------------------------------
 constexpr int SORT_NT = 128;
 template <int W>
-constexpr int sort_small_max() { return W == 2 ? 1408 : 2048; }   // static shared memory stays under 48 KB
+constexpr int sort_small_max() { return W == 2 ? 1408 : 1536; }   // 12 (W=1) / 11 (W=2) survivors per thread in registers
 constexpr int SORT_BIG_NT = 256;
 constexpr int SORT_BIG_MAX = SM_TSIZE;   // a shared-memory table never yields more survivors than it has slots
 
@@ -873,11 +873,11 @@ struct SortArgs {
 // and is written straight to its final position (4 block barriers, no index indirection).  SEG = false: work items are groups.  SEG = true: segments of multi-pass
 // groups (item i = pass i % SM_PMAX of list entry i / SM_PMAX); the k-mers of a segment lie in 1/P of the k-mer space, so the
 // buckets subdivide that range.  LIST = true: the items are those named in in_list (what a smaller instantiation passed on).
-// Two instantiations: CAP = sort_small_max() with 128 threads (36 KB, 6 CTAs/SM: the headline shape, ~1000 survivors per
+// Two instantiations: CAP = sort_small_max() with 128 threads (23 KB and 64 registers, 8 CTAs/SM: the headline shape, ~1000 survivors per
 // group) and CAP = 8192 with 512 threads (two CTAs/SM: min_coverage <= 1 keeps ~4500 k-mers per group; the bitonic kernel that
 // used to take those groups was 10x slower).  Items that do not fit, or have a crowded bucket, go to the output list.
 template <int W, bool SEG, int CAP, int NT, bool LIST>
-__global__ void __launch_bounds__(NT) k_sort_small(SortArgs a, int64_t n_items, const int32_t *in_list)
+__global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_small(SortArgs a, int64_t n_items, const int32_t *in_list)
 {
     constexpr int EPT = (CAP + NT - 1) / NT;   // survivors a thread keeps in registers between the passes
     extern __shared__ __align__(16) uint8_t sort_raw[];
