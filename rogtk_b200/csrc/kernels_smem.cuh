@@ -32,7 +32,7 @@ constexpr int SM_TBITS = 13;          // 8192 slots
 constexpr int SM_TSIZE = 1 << SM_TBITS;
 constexpr int SM_SORT_BITS = 10;
 constexpr int SM_SORT_BUCKETS = 1 << SM_SORT_BITS;
-constexpr int SM_POOL_CHUNK = 32768;   // survivors a CTA reserves from the pool at a time
+constexpr int SM_POOL_CHUNK = 65536;   // survivors a CTA reserves from the pool at a time (a group needs room for SM_TSIZE + 1)
 constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this -> bitonic kernel
 // Multi-pass variant for groups that do not fit one table / one staged span (MULTI = true): the k-mer space is cut into
 // P equal ranges (range of a k-mer = floor(top 32 bits * P / 2^32)); pass p re-reads the group's reads in slabs of
@@ -698,6 +698,16 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             if (tid == 0 && pf_stage == 1) pf_advance();   // next group's byte range
             if (lane == 0) ws[40 + warp] = wq.n;   // leftovers (< 32 per warp) are finished by the whole CTA below
         }
+        if (tid == 0) {
+            // pool space for whatever this table can yield (<= SM_TSIZE + 1 survivors): one global atomic per SM_POOL_CHUNK, not per group
+            if (cta_pool_pos + (int64_t)(SM_TSIZE + 1) > cta_pool_end) {
+                cta_pool_pos = (int64_t)atomicAdd(a.pool_cursor, (unsigned long long)SM_POOL_CHUNK);
+                cta_pool_end = cta_pool_pos + (int64_t)SM_POOL_CHUNK;
+            }
+            misc[4] = (uint32_t)cta_pool_pos;
+            misc[5] = (uint32_t)((uint64_t)cta_pool_pos >> 32);
+            misc[6] = 0;   // survivors written so far
+        }
         __syncthreads();
         if (total != 0 && !misc[3]) {
             // every thread takes at most one leftover observation and probes until it lands
@@ -743,43 +753,15 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         }
 
         PHASE_MARK(3);
-        // ---- min-coverage prune: survivors go to the pool unsorted; k_sort_small / k_sort_big order them while building the
-        //      dense output, at far higher occupancy than this kernel's 2 CTAs/SM -----------------------------------------------
-        const uint4 *tval4 = reinterpret_cast<const uint4 *>(tval);
-        uint32_t cnt = 0;
-        for (uint32_t j = tid; j < tsize / 4; j += SM_NT) {
-            const uint4 vv = tval4[j];
-            cnt += ((vv.x >> 8) >= thr) + ((vv.y >> 8) >= thr) + ((vv.z >> 8) >= thr) + ((vv.w >> 8) >= thr);
-        }
-        const uint32_t sv = misc[2];
-        const bool special_survives = (sv >> 8) >= thr;
-        uint32_t nS;
-        uint32_t rank = block_scan_u32(cnt, &nS, ws);   // this thread's first position among the survivors
-        const uint32_t n_out = nS + (special_survives ? 1u : 0u);
-        if (tid == 0 && n_out) {
-            if (cta_pool_pos + (int64_t)n_out > cta_pool_end) {   // one global atomic per ~SM_POOL_CHUNK survivors, not per group
-                const unsigned long long chunk = n_out > (uint32_t)SM_POOL_CHUNK ? n_out : (uint32_t)SM_POOL_CHUNK;
-                cta_pool_pos = (int64_t)atomicAdd(a.pool_cursor, chunk);
-                cta_pool_end = cta_pool_pos + (int64_t)chunk;
-            }
-            const unsigned long long pb0 = (unsigned long long)cta_pool_pos;
-            cta_pool_pos += n_out;
-            misc[4] = (uint32_t)pb0;
-            misc[5] = (uint32_t)(pb0 >> 32);
-        }
-        __syncthreads();
-        if (!MULTI && n_out == 0) {
-            cta_obs += total;
-            continue;
-        }
+        // ---- min-coverage prune + compaction in one pass: survivors go to the pool unsorted (k_sort_small / k_sort_big order them
+        //      while building the dense output, at far higher occupancy than this kernel's 2 CTAs/SM).  A thread keeps its slots'
+        //      value words in registers, a warp reserves its range of the group's pool slice with one shared atomic. ----------------
         const int64_t pb = (int64_t)(((unsigned long long)misc[5] << 32) | misc[4]);
-        if (n_out != 0 && (pb + (int64_t)n_out > a.pool_cap || n_out > (uint32_t)SM_TSIZE)) {
-            // survivor pool exhausted (or a segment the ordering kernel cannot hold): the HBM path (own pool) takes the group
+        if (pb + (int64_t)(SM_TSIZE + 1) > a.pool_cap) {   // survivor pool exhausted: the HBM path (own pool) takes the group
             defer(g);
             in_group = false;
             continue;
         }
-        PHASE_MARK(4);
         auto emit = [&](int64_t pos, KT kq, uint32_t v) {
             const Key<W> k = S::unpack(kq);
             a.pool_lo[pos] = k.lo;
@@ -787,18 +769,60 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             a.pool_exts[pos] = (uint8_t)v;
             a.pool_counts[pos] = (uint16_t)((v >> 8) > 65535u ? 65535u : (v >> 8));
         };
-        if (n_out != 0) {
-            for (uint32_t j = tid; j < tsize / 4; j += SM_NT) {
-                const uint4 vv = tval4[j];
-                const uint32_t c[4] = {vv.x, vv.y, vv.z, vv.w};
-                if (((c[0] >> 8) >= thr) | ((c[1] >> 8) >= thr) | ((c[2] >> 8) >= thr) | ((c[3] >> 8) >= thr)) {
+        {
+            constexpr int CIT = (SM_TSIZE / 4 + SM_NT - 1) / SM_NT;
+            const uint4 *tval4 = reinterpret_cast<const uint4 *>(tval);
+            uint4 vv[CIT];
+            uint32_t cnt = 0;
 #pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if ((c[t] >> 8) >= thr) emit(pb + (int64_t)(rank++), tkey[4 * j + t], c[t]);
+            for (int it = 0; it < CIT; it++) {
+                const uint32_t j = (uint32_t)tid + (uint32_t)it * SM_NT;
+                vv[it] = make_uint4(0u, 0u, 0u, 0u);
+                if (j < tsize / 4) {
+                    vv[it] = tval4[j];
+                    cnt += ((vv[it].x >> 8) >= thr) + ((vv[it].y >> 8) >= thr) + ((vv[it].z >> 8) >= thr) + ((vv[it].w >> 8) >= thr);
                 }
             }
-            if (special_survives && tid == 0) emit(pb + (int64_t)nS, S::empty(), sv);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += y;
+            }
+            uint32_t wbase = 0;
+            if (lane == 31u && incl) wbase = atomicAdd(const_cast<uint32_t *>(&misc[6]), incl);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            int64_t pos = pb + (int64_t)(wbase + incl - cnt);
+            if (cnt) {
+#pragma unroll
+                for (int it = 0; it < CIT; it++) {
+                    const uint32_t j = (uint32_t)tid + (uint32_t)it * SM_NT;
+                    const uint32_t c[4] = {vv[it].x, vv[it].y, vv[it].z, vv[it].w};
+                    if (((c[0] >> 8) >= thr) | ((c[1] >> 8) >= thr) | ((c[2] >> 8) >= thr) | ((c[3] >> 8) >= thr)) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++)
+                            if ((c[t] >> 8) >= thr) emit(pos++, tkey[4 * j + t], c[t]);
+                    }
+                }
+            }
+            if (tid == 0) {
+                const uint32_t sv = misc[2];
+                if ((sv >> 8) >= thr) emit(pb + (int64_t)atomicAdd(const_cast<uint32_t *>(&misc[6]), 1u), S::empty(), sv);
+            }
         }
+        __syncthreads();
+        const uint32_t n_out = misc[6];
+        if (tid == 0) cta_pool_pos += n_out;
+        if (!MULTI && n_out == 0) {
+            cta_obs += total;
+            continue;
+        }
+        if (n_out > (uint32_t)SM_TSIZE) {   // (a full table plus the side word) more than the ordering kernels hold: HBM path
+            defer(g);
+            in_group = false;
+            continue;
+        }
+        PHASE_MARK(4);
         if (!MULTI) {
             if (tid == 0) {
                 a.nsurv[g] = (int64_t)n_out;
