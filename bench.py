@@ -284,21 +284,21 @@ def main():
     alg = algorithmic_bytes(n_umis, n_reads, n_bytes, n_kmers)
     achieved = alg / (ms_hot_avg * 1e-3) / 1e9 if ms_hot_avg > 0 else 0.0
     # DRAM traffic of k_smem_count from the committed ncu --set full capture (profiles/r01_ncu_k_smem_count_full.txt:
-    # dram__bytes_read.sum 308.67 MB + dram__bytes_write.sum 156.22 MB for a 20 000-UMI launch of this workload shape),
+    # dram__bytes_read.sum 308.63 MB + dram__bytes_write.sum 154.84 MB for a 20 000-UMI launch of this workload shape),
     # scaled to this launch's UMI count; only quoted for the shape it was measured on.
-    traffic = (308.670464e6 + 156.22144e6) / 20000.0 * n_umis if cfg["name"] == "cfg2" else None
+    traffic = (308.627712e6 + 154.83776e6) / 20000.0 * n_umis if cfg["name"] == "cfg2" else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k_smem_count<1>", "kernel_ms": ms_hot_avg, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                 "pipeline_frac": alg / (ms_dev_max * 1e-3) / 1e9 / peak}
     if cfg["name"] == "cfg2" and ms_hot_avg > 0:
-        # What actually limits the kernel: warp instructions issued.  69 646 per UMI group is smsp__inst_executed.sum of
-        # the committed ncu capture (profiles/r01_ncu_k_smem_count_full.txt: 1 392 922 974 for 20 000 UMIs of this shape); the peak is
+        # What actually limits the kernel: warp instructions issued.  68 781 per UMI group is smsp__inst_executed.sum of
+        # the committed ncu capture (profiles/r01_ncu_k_smem_count_full.txt: 1 375 618 895 for 20 000 UMIs of this shape); the peak is
         # one warp instruction per scheduler per clock: SMs x 4 x the SM clock sampled during the timed region.
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        inst_rate = 1392922974.0 / 20000.0 * n_umis / (ms_hot_avg * 1e-3)
+        inst_rate = 1375618895.0 / 20000.0 * n_umis / (ms_hot_avg * 1e-3)
         inst_peak = 148 * 4 * sm_mhz * 1e6
         roofline["issue"] = {"achieved_warp_inst_per_s": inst_rate, "peak_warp_inst_per_s": inst_peak, "frac": inst_rate / inst_peak,
-                             "warp_inst_per_umi": 1392922974.0 / 20000.0}
+                             "warp_inst_per_umi": 1375618895.0 / 20000.0}
 
     # ---- next row f-2 (outside the timed region): unitig compaction + the plugin's contig on the same device-resident batch ------
     next_rows = None
