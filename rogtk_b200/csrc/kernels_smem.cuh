@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             wq.n = 0;
             wq.budget = 64 + (int)(total >> 1);   // drain steps allowed per warp: far above any non-full table's need
             uint32_t *special = const_cast<uint32_t *>(&misc[2]);
+            const uint32_t unit_ctr_addr = (uint32_t)__cvta_generic_to_shared(const_cast<uint32_t *>(&misc[7]));
             // first probe + claim of one observation; returns true when it must queue for further probing
             auto first_probe = [&](KT kp, uint32_t h, uint32_t ex, KT cur) -> bool {
                 if (kp == S::empty()) {   // the all-ones k-mer is the EMPTY marker: counted in a side word
@@ -545,7 +546,10 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             };
             while (true) {
                 uint32_t unit = 0;
-                if (lane == 0) unit = atomicAdd(const_cast<uint32_t *>(&misc[7]), 1u);
+                // (inline PTX: for a warp-uniform address the compiler wraps atomicAdd in a vote/popc/shuffle aggregation
+                //  sequence -- 17 instructions per unit for an add that only lane 0 performs)
+                if (lane == 0)
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(unit) : "r"(unit_ctr_addr) : "memory");
                 unit = __shfl_sync(0xffffffffu, unit, 0);
                 if (unit >= nunits || misc[3] || wq.budget <= 0) break;
                 const int lo = unit_read[unit];   // read of this unit
