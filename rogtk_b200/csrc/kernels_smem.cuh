@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                 // (inline PTX: for a warp-uniform address the compiler wraps atomicAdd in a vote/popc/shuffle aggregation
                 //  sequence -- 17 instructions per unit for an add that only lane 0 performs)
                 if (lane == 0)
-                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(unit) : "r"(unit_ctr_addr) : "memory");
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(unit) : "r"(unit_ctr_addr));
                 unit = __shfl_sync(0xffffffffu, unit, 0);
                 if (unit >= nunits || misc[3] || wq.budget <= 0) break;
                 const int lo = unit_read[unit];   // read of this unit
