@@ -220,6 +220,19 @@ def test_baseline_config_subsets(engine, oracle, cfg):
     _both(engine, oracle, data, offs, goff, k, 1, csr=True, ctx=cfg + " mc=1")
 
 
+@pytest.mark.parametrize("k", [11, 16, 17, 31, 33, 63])
+def test_baseline_config3_subset(engine, oracle, k):
+    """BASELINE configs[2]: skewed reads per UMI (log-uniform 1..5000; the first 40 UMIs hold groups of 3028, 2120 and 3962
+    reads), L=150, T=500, min_cov=2, k sweep over K = 16 / 32 / 64 -- all three counting paths in one batch."""
+    from rogtk_b200 import synth
+    seed = synth.config_seed(3)
+    rp = synth.skewed_reads_per_umi(seed, 40)
+    data, offs, goff = synth.synth_reads(seed, 0, len(rp), rp, 150, 500)
+    got, ref = _both(engine, oracle, data, offs, goff, k, 2, csr=(k == 31), ctx=f"cfg3 k={k}")
+    assert got.n_spilled_groups >= 3 and got.n_multipass_groups >= 5
+    check_invariants(got, 2)
+
+
 def test_device_resident_path_and_invariants_at_scale(engine, oracle):
     """Inputs generated in HBM, outputs left in HBM (the `value` path of bench.py) at 20k UMIs of the cfg2 shape:
     size-independent properties + a sampled comparison against the oracle."""
