@@ -1257,7 +1257,8 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     const size_t entry = (W == 2 ? 19 : 11);
     int64_t pool_cap = (int64_t)(ub / (min_cov > 1 ? min_cov : 1)) + 1;
     pool_cap = std::min<int64_t>(pool_cap, (int64_t)(workspace_bytes / 2 / entry));
-    pool_cap += pool_cap / 4 + (int64_t)sm_count * 2 * SM_POOL_CHUNK;   // per-CTA chunking leaves unused tails
+    // per-CTA chunking leaves unused tails: one open chunk per running CTA, up to SM_TSIZE + 1 entries at every chunk switch
+    pool_cap += pool_cap / 4 + std::min<int64_t>(n_groups, (int64_t)sm_count * 2) * 2 * SM_POOL_CHUNK;
     pool_cap = std::max<int64_t>(pool_cap, 1024);
     res.keep.emplace_back((size_t)pool_cap * 8, st);
     uint64_t *p_lo = res.keep.back().as<uint64_t>();
