@@ -10,6 +10,10 @@
 // profiles/r01_microbench_smem.txt): random-address shared atomicAdd sustains 16 ops/ns/SM, more than a plain
 // LDS+STS read-modify-write, so no barrier-synchronised election scheme is needed; warps run the whole counting
 // phase without a single __syncthreads.
+//
+// The same kernel body, instantiated with MULTI = true, takes the groups that exceed one table or one staged span: the k-mer
+// space is cut into P ranges and the group's reads are re-staged slab by slab once per range.  A count of
+// (count << 8) cannot overflow there either: a multi-pass group has at most SM_PMAX * SM_PASS_OBS = 131 072 bases.
 #pragma once
 #include <cstdlib>
 #include <vector>
