@@ -321,7 +321,7 @@ class Engine:
 
 
     def count_prune_to_device(self, data: np.ndarray, offsets: np.ndarray, group_offsets: np.ndarray, k: int, min_coverage: int,
-                              validity: np.ndarray | None = None, flags: int = 0) -> DeviceBatch:
+                              validity: np.ndarray | None = None, flags: int = 0, validity_bit_offset: int = 0) -> DeviceBatch:
         """Host Arrow buffers in, result left in HBM (used by the global-spectrum mode before the all-to-all)."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -331,7 +331,8 @@ class Engine:
         dptr = (ctypes.c_void_p * 1)(data.ctypes.data if data.size else None)
         dlen = (ctypes.c_int64 * 1)(data.size)
         col = _ffi.StrCol(layout=_ffi.UTF8_I64, n_buffers=1, n_rows=len(offsets) - 1,
-                          validity=validity.ctypes.data if validity is not None else None, validity_bit_offset=0,
+                          validity=validity.ctypes.data if validity is not None else None,
+                          validity_bit_offset=int(validity_bit_offset),
                           offsets_or_views=offsets.ctypes.data, data=dptr, data_len=dlen)
         c = self._call(col, group_offsets.ctypes.data, len(group_offsets) - 1, k, min_coverage,
                        (flags | _ffi.OUTPUT_ON_DEVICE) & ~_ffi.INPUT_ON_DEVICE)
@@ -418,11 +419,41 @@ class Engine:
             db.free()
 
     # ---- Arrow-native entry: one call per frame ----------------------------------------------------------------------
-    def count_prune_arrow(self, reads, k: int, min_coverage: int, flags: int = 0) -> GraphBatch:
-        """`reads` is a pyarrow List/LargeList of String/LargeString/StringView (one row per UMI group: what
-        `df.group_by("umi").agg(pl.col("seq"))` hands to a batched plugin call), or a ChunkedArray of those.  The list
-        offsets are the group offsets; the child string buffers go to the C ABI without re-encoding.  Null lists are empty
-        groups, null strings are dropped (reference src/expressions.rs:737-740)."""
+    def assemble_arrow(self, reads, k: int, min_coverage: int, min_length: int = 0):
+        """The batched form of assemble_sequences_expr(method="compression") (reference src/expressions.rs:695-762): `reads` is a
+        pyarrow List(String) array with one row per group; returns (pyarrow LargeStringArray with the contig of every group, ""
+        where the reference returns no contig; uint8 flags per group: bit 0 tie in length, bit 1 cyclic -- recompute those groups
+        with the reference if its tie-break matters).  Reads -> nodes -> unitigs -> choice all happen on the device."""
+        import pyarrow as pa
+        goff, child = self._arrow_groups(reads)
+        ct = child.type
+        if not (pa.types.is_large_string(ct) or pa.types.is_large_binary(ct)):
+            child = child.cast(pa.large_string())   # one host copy for Utf8 / Utf8View children (this entry only)
+        bufs = child.buffers()
+        validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None
+        offs = np.frombuffer(bufs[1], dtype=np.int64)[child.offset:child.offset + len(child) + 1]
+        data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None else np.zeros(0, np.uint8)
+        db = self.count_prune_to_device(data, offs, goff, k, min_coverage, validity=validity, validity_bit_offset=child.offset)
+        try:
+            ng = len(goff) - 1
+            if db.k_eff < 0:
+                return pa.array([""] * ng, type=pa.large_string()), np.zeros(ng, np.uint8)
+            cb = self.compress_unitigs(db, min_length)
+        finally:
+            db.free()
+        u = cb.largest
+        has = u >= 0
+        starts = np.where(has, cb.seq_offsets[np.maximum(u, 0)], 0)
+        lens = np.where(has, cb.seq_offsets[np.maximum(u, 0) + 1] - starts, 0)
+        out_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out = np.empty(int(out_off[-1]), dtype=np.uint8)
+        for g in np.nonzero(has)[0]:   # (a gather; groups are few compared with bases)
+            out[out_off[g]:out_off[g + 1]] = cb.seq[starts[g]:starts[g] + lens[g]]
+        arr = pa.LargeStringArray.from_buffers(ng, pa.py_buffer(out_off), pa.py_buffer(out))
+        return arr, cb.largest_flags
+
+    def _arrow_groups(self, reads):
+        """(group_offsets int64, child string array) of a List(String) array; null lists become empty groups."""
         import pyarrow as pa
         if isinstance(reads, pa.ChunkedArray):
             reads = reads.combine_chunks() if reads.num_chunks != 1 else reads.chunk(0)
@@ -435,12 +466,23 @@ class Engine:
         if reads.null_count:   # a null list is an empty group
             valid = np.unpackbits(np.frombuffer(lbufs[0], dtype=np.uint8), bitorder="little")[reads.offset:reads.offset + n_groups]
             lens = np.diff(goff) * valid
-            # rows of null lists are skipped by collapsing their range; keep absolute row indices monotone
             keep_rows = np.repeat(valid.astype(bool), np.diff(goff))
-            child = reads.values.slice(int(goff[0]), int(goff[-1] - goff[0])).filter(pa.array(keep_rows))
+            vals = reads.values.slice(int(goff[0]), int(goff[-1] - goff[0]))
+            if hasattr(pa.types, "is_string_view") and (pa.types.is_string_view(vals.type) or pa.types.is_binary_view(vals.type)):
+                vals = vals.cast(pa.large_string())   # pyarrow has no filter kernel for view arrays
+            child = vals.filter(pa.array(keep_rows))
             goff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         else:
             child = reads.values
+        return goff, child
+
+    def count_prune_arrow(self, reads, k: int, min_coverage: int, flags: int = 0) -> GraphBatch:
+        """`reads` is a pyarrow List/LargeList of String/LargeString/StringView (one row per UMI group: what
+        `df.group_by("umi").agg(pl.col("seq"))` hands to a batched plugin call), or a ChunkedArray of those.  The list
+        offsets are the group offsets; the child string buffers go to the C ABI without re-encoding.  Null lists are empty
+        groups, null strings are dropped (reference src/expressions.rs:737-740)."""
+        import pyarrow as pa
+        goff, child = self._arrow_groups(reads)
         ct = child.type
         bufs = child.buffers()
         validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None

@@ -613,3 +613,27 @@ def test_unitig_compaction_and_plugin_contig(engine, oracle):
     # k > 64: no contigs
     got = engine.assemble(data, offs, goff, 65, 2)
     assert got.k_eff == -1 and list(got.largest) == [-1] * 40
+
+
+def test_assemble_arrow_batched_expression(engine, oracle):
+    """The batched form of assemble_sequences_expr(method="compression"): List(String) in, one contig string per group out
+    (reference src/expressions.rs:695-762 returns one String per group; "" when there is no contig)."""
+    import pyarrow as pa
+    rng = np.random.default_rng(21)
+    groups = random_groups(rng, 30, max_reads=16, max_len=150, tmpl_len=180, p_null=0.05)
+    groups[3] = None            # null list: empty group
+    groups[7] = []
+    for typ in (pa.list_(pa.string()), pa.large_list(pa.large_string()), pa.list_(pa.string_view())):
+        arr = pa.array(groups, type=typ)
+        contigs, flags = engine.assemble_arrow(arr, 17, 1, min_length=40)
+        assert len(contigs) == 30 and contigs.type == pa.large_string()
+        for g, reads in enumerate(groups):
+            nodes = oracle.count_prune_group_py([r for r in (reads or []) if r is not None], 17, 1)
+            want = [s for s in oracle.compress_unitigs(nodes, 32) if len(s) >= 40]
+            got = contigs[g].as_py()
+            if not want:
+                assert got == "" and flags[g] == 0
+            else:
+                top = max(len(s) for s in want)
+                assert len(got) == top and got in want
+                assert (flags[g] & 1) == (1 if sum(1 for s in want if len(s) == top) > 1 else 0)
