@@ -19,6 +19,8 @@
 #include <chrono>
 #include <vector>
 
+#include <unistd.h>
+
 #include "common.cuh"
 #include "host_util.cuh"
 #include "kernels_post.cuh"
@@ -53,6 +55,8 @@ struct rogtk_gpu_ctx {
     // cache of pinned host blocks (size -> pointers) so steady-state calls do not pay cudaHostAlloc
     std::multimap<size_t, void *> pinned_free;
     std::map<void *, size_t> pinned_size;
+    size_t pinned_cached = 0;        // bytes sitting in pinned_free
+    size_t pinned_cache_cap = 0;     // above this, returned blocks are released (smallest first); set in rogtk_gpu_create
 };
 
 namespace {
@@ -73,6 +77,7 @@ void *pinned_get(rogtk_gpu_ctx *ctx, size_t bytes)
     auto it = ctx->pinned_free.lower_bound(bytes);
     if (it != ctx->pinned_free.end() && it->first <= bytes + bytes / 4 + 4096) {
         void *p = it->second;
+        ctx->pinned_cached -= it->first;
         ctx->pinned_free.erase(it);
         return p;
     }
@@ -87,6 +92,16 @@ void pinned_put(rogtk_gpu_ctx *ctx, void *p)
     auto it = ctx->pinned_size.find(p);
     if (it == ctx->pinned_size.end()) return;
     ctx->pinned_free.emplace(it->second, p);
+    ctx->pinned_cached += it->second;
+    // a long-lived context fed with many batch sizes must not pile up pinned memory: keep the large blocks (expensive to
+    // page-lock again), release the small ones first
+    while (ctx->pinned_cached > ctx->pinned_cache_cap && !ctx->pinned_free.empty()) {
+        auto sm = ctx->pinned_free.begin();
+        ctx->pinned_cached -= sm->first;
+        ctx->pinned_size.erase(sm->second);
+        cudaFreeHost(sm->second);
+        ctx->pinned_free.erase(sm);
+    }
 }
 
 struct BatchOwner {
@@ -319,6 +334,11 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
         if (const char *e = getenv("ROGTK_CHUNK_BYTES")) ctx->chunk_bytes = (size_t)std::max(4096ll, atoll(e));
+        {   // cache of page-locked result blocks: a quarter of the host's memory unless ROGTK_PINNED_CACHE_BYTES says otherwise
+            const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+            ctx->pinned_cache_cap = pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz / 4 : (size_t)16 << 30;
+            if (const char *e = getenv("ROGTK_PINNED_CACHE_BYTES")) ctx->pinned_cache_cap = (size_t)std::max(0ll, atoll(e));
+        }
         for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
         CK(cudaHostAlloc((void **)&ctx->peek_slot, Peek::SLOT_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
         size_t free_b = 0, total_b = 0;

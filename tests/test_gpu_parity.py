@@ -637,3 +637,15 @@ def test_assemble_arrow_batched_expression(engine, oracle):
                 top = max(len(s) for s in want)
                 assert len(got) == top and got in want
                 assert (flags[g] & 1) == (1 if sum(1 for s in want if len(s) == top) > 1 else 0)
+
+
+def test_pinned_cache_cap(oracle, monkeypatch):
+    """ROGTK_PINNED_CACHE_BYTES bounds the page-locked blocks a context keeps between calls (0: every block is released)."""
+    import rogtk_b200
+    monkeypatch.setenv("ROGTK_PINNED_CACHE_BYTES", "0")
+    rng = np.random.default_rng(8)
+    with rogtk_b200.Engine(device=0) as eng:
+        for n in (5, 40, 12):
+            data, offs, validity, goff = groups_to_arrow(random_groups(rng, n))
+            got = eng.count_prune(data, offs, goff, 21, 1, validity=validity, flags=EMIT_STATS)
+            assert_batches_equal(got, oracle.count_prune_batch(data, offs, goff, 21, 1, validity=validity), ctx=f"cache cap n={n}")
