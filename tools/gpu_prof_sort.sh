@@ -1,7 +1,7 @@
 #!/bin/bash
-# launch list of a min_coverage=1 step (mid-size counting sort tier) on 50 k UMIs
+# ncu --set full of k_sort_small (the second kernel of the step) on 20 k UMIs of the headline shape
 mkdir -p gpurun_out
-CMD="python tools/unitig_probe.py 50000"
-timeout 300 $CMD > gpurun_out/sort_plain.log 2>&1 || { tail -5 gpurun_out/sort_plain.log; exit 1; }
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_sortmid.csv $CMD > gpurun_out/ncu_sortmid.log 2>&1
-tail -3 gpurun_out/sort_plain.log
+CMD="python bench.py --umis 20000 --steps 1 --warmup 1 --no-e2e --no-cpu"
+timeout 300 $CMD > gpurun_out/plain_sort.log 2>&1 || { tail -5 gpurun_out/plain_sort.log; exit 1; }
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sort_small -s 1 -c 1 -o gpurun_out/prof_sort_r01k $CMD > gpurun_out/ncu_sort.log 2>&1
+tail -1 gpurun_out/ncu_sort.log
