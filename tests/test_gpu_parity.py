@@ -649,3 +649,17 @@ def test_pinned_cache_cap(oracle, monkeypatch):
             data, offs, validity, goff = groups_to_arrow(random_groups(rng, n))
             got = eng.count_prune(data, offs, goff, 21, 1, validity=validity, flags=EMIT_STATS)
             assert_batches_equal(got, oracle.count_prune_batch(data, offs, goff, 21, 1, validity=validity), ctx=f"cache cap n={n}")
+
+
+def test_small_workspace_many_spill_waves(oracle):
+    """A context created with a 1 MB workspace: the HBM-table path has to process its groups in many waves (and one group
+    larger than a wave on its own); results must not change."""
+    import rogtk_b200
+    from rogtk_b200 import synth
+    rp = np.array([30, 700, 45, 12, 260, 90, 1500, 3, 64, 410])
+    data, offs, goff = synth.synth_reads(synth.config_seed(3), 11, len(rp), rp, 150, 500)
+    with rogtk_b200.Engine(device=0, workspace_bytes=1 << 20) as eng:
+        for k, flags in ((31, FORCE_SPILL), (47, FORCE_SPILL), (31, 0), (16, NO_MULTIPASS)):
+            got = eng.count_prune(data, offs, goff, k, 2, flags=flags | EMIT_STATS | EMIT_CSR)
+            ref = oracle.count_prune_batch(data, offs, goff, k, 2, emit_csr=True)
+            assert_batches_equal(got, ref, check_csr=True, ctx=f"small workspace k={k} flags={flags}")
