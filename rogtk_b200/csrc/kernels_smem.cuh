@@ -1264,6 +1264,7 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     // per-CTA chunking leaves unused tails: one open chunk per running CTA, up to SM_TSIZE + 1 entries at every chunk switch
     pool_cap += pool_cap / 4 + std::min<int64_t>(n_groups, (int64_t)sm_count * 2) * 2 * SM_POOL_CHUNK;
     pool_cap = std::max<int64_t>(pool_cap, 1024);
+    if (const char *e = getenv("ROGTK_DEBUG_POOL_CAP")) pool_cap = std::max<int64_t>(1024, atoll(e));   // tests: exhaust the pool
     res.keep.emplace_back((size_t)pool_cap * 8, st);
     uint64_t *p_lo = res.keep.back().as<uint64_t>();
     uint64_t *p_hi = nullptr;

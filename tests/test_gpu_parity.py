@@ -663,3 +663,19 @@ def test_small_workspace_many_spill_waves(oracle):
             got = eng.count_prune(data, offs, goff, k, 2, flags=flags | EMIT_STATS | EMIT_CSR)
             ref = oracle.count_prune_batch(data, offs, goff, k, 2, emit_csr=True)
             assert_batches_equal(got, ref, check_csr=True, ctx=f"small workspace k={k} flags={flags}")
+
+
+def test_survivor_pool_exhaustion_falls_back(engine, oracle, monkeypatch):
+    """ROGTK_DEBUG_POOL_CAP shrinks the survivor pool of the shared-memory paths: groups that find no room are handed to the
+    HBM-table path (which sizes its own storage); the batch is unchanged."""
+    from rogtk_b200 import synth
+    data, offs, goff = synth.synth_reads(synth.config_seed(2), 500, 400, 50, 300, 1000)
+    ref = oracle.count_prune_batch(data, offs, goff, 31, 2)
+    for cap in (1024, 20000, 150000):
+        monkeypatch.setenv("ROGTK_DEBUG_POOL_CAP", str(cap))
+        got = engine.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)
+        assert_batches_equal(got, ref, ctx=f"pool cap {cap}")
+        assert got.n_spilled_groups > 0
+    monkeypatch.delenv("ROGTK_DEBUG_POOL_CAP")
+    got = engine.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)
+    assert got.n_spilled_groups == 0
