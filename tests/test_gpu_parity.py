@@ -679,3 +679,29 @@ def test_survivor_pool_exhaustion_falls_back(engine, oracle, monkeypatch):
     monkeypatch.delenv("ROGTK_DEBUG_POOL_CAP")
     got = engine.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)
     assert got.n_spilled_groups == 0
+
+
+def test_two_word_kmers_at_scale(engine, oracle):
+    """K = 64 (k = 47 and k = 63; 128-bit keys, one CTA per SM) on 5000 UMIs of the headline shape, device-resident: invariants
+    on the whole batch and the first / last 100 UMIs against the oracle."""
+    from rogtk_b200 import synth
+    seed = synth.config_seed(2)
+    n, R, L, T = 5000, 50, 300, 1000
+    d_data, d_off, d_goff, nbytes = engine.synth_reads_device(seed, 0, n, R, L, T, 655)
+    try:
+        for k in (47, 63):
+            db = engine.count_prune_device(d_data, nbytes, d_off, n * R, d_goff, n, k, 2, flags=EMIT_STATS)
+            assert db.k_eff == 64 and db.n_observations == n * R * (L - 63) and db.n_spilled_groups == 0
+            got = db.to_host()
+            db.free()
+            check_invariants(got, 2)
+            for base in (0, n - 100):
+                data, offs, goff = synth.synth_reads(seed, base, 100, R, L, T)
+                ref = oracle.count_prune_batch(data, offs, goff, k, 2)
+                a, b = int(got.kmer_offsets[base]), int(got.kmer_offsets[base + 100])
+                assert np.array_equal(got.kmer_offsets[base:base + 101] - a, ref.kmer_offsets)
+                assert np.array_equal(got.kmers_lo[a:b], ref.kmers_lo) and np.array_equal(got.kmers_hi[a:b], ref.kmers_hi)
+                assert np.array_equal(got.exts[a:b], ref.exts) and np.array_equal(got.counts[a:b], ref.counts)
+    finally:
+        for p in (d_data, d_off, d_goff):
+            engine.device_free(p)
