@@ -24,9 +24,15 @@
 
 namespace rogtk {
 
-constexpr int SM_NT = 384;            // threads per CTA
+constexpr int SM_NT = 384;            // threads per CTA, one-word keys (2 CTAs per SM)
+constexpr int SM_NT2 = 640;           // two-word keys: the 160 KB table leaves one CTA per SM, so it gets more warps
+template <int W>
+constexpr int sm_nt() { return W == 2 ? SM_NT2 : SM_NT; }
+template <int W>
+constexpr int sm_nwarp() { return sm_nt<W>() / 32; }
+// words of the 64-word scratch `ws`: block-scan partials, misc, group id (MULTI), per-warp queue leftovers
+constexpr int WS_SCAN = 0, WS_MISC = 24, WS_GID = 40, WS_LEFT = 42;
 constexpr int SM_MAXR = 256;          // max rows per group on this path
-constexpr int SM_NWARP = SM_NT / 32;
 constexpr int SM_MAX_BASES = 16384;   // bases staged per group (including <=15 bytes of alignment slack)
 constexpr int SM_PK_WORDS = SM_MAX_BASES / 16 + 8;   // 1 word of front pad, tail pad for window over-reads
 constexpr int SM_UNIT = 128;          // windows per work unit (one warp, 4 consecutive windows per lane)
@@ -53,7 +59,7 @@ struct SegRec {          // survivors of one pass of a multi-pass group
 template <int W>
 constexpr int scratch_bytes()   // pk + per-warp queues; reused by the sort (histogram + order)
 {
-    return SM_PK_WORDS * 4 + SM_NWARP * SM_QCAP * (int)(sizeof(typename KeySlot<W>::T) + 4);
+    return SM_PK_WORDS * 4 + sm_nwarp<W>() * SM_QCAP * (int)(sizeof(typename KeySlot<W>::T) + 4);
 }
 
 template <int W>
@@ -162,7 +168,8 @@ __device__ __forceinline__ uint32_t sort_bucket<2>(const Key<2> &k, int kbits)
     return sh >= 64 ? (uint32_t)(k.hi >> (sh - 64)) : (uint32_t)((k.hi << (64 - sh)) | (k.lo >> sh));
 }
 
-// block-wide exclusive scan of one u32 per thread (SM_NT threads); ws = 9 words of shared scratch
+// block-wide exclusive scan of one u32 per thread (NW warps); ws = NW words of shared scratch
+template <int NW>
 __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *total, uint32_t *ws)
 {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -176,7 +183,7 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *total, 
     __syncthreads();
     uint32_t base = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < SM_NWARP; w++) {
+    for (int w = 0; w < NW; w++) {
         uint32_t s = ws[w];
         if (w < (int)warp) base += s;
         tot += s;
@@ -299,8 +306,9 @@ __device__ __forceinline__ void queue_push(WarpQueue<W> &q, bool pend, typename 
     } while (0)
 
 template <int W, bool K32, bool MULTI>
-__global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs a)
+__global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(SmemArgs a)
 {
+    constexpr int NT = sm_nt<W>(), NW = sm_nwarp<W>();
     using S = KeySlot<W>;
     using KT = typename S::T;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -311,10 +319,10 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     uint8_t *qbytes = reinterpret_cast<uint8_t *>(scratch + SM_PK_WORDS);        // per-warp queues (W=1: 8 B keys)
     uint32_t *rstart = scratch + scratch_bytes<W>() / 4;
     uint32_t *ucum = rstart + SM_MAXR + 1;               // work units before read r
-    uint32_t *ws = ucum + SM_MAXR + 1;                     // 64 words: [0..11] scan, [16..31] misc, [32..33] group id (MULTI), [40..51] queue leftovers
+    uint32_t *ws = ucum + SM_MAXR + 1;                     // 64 words, see WS_*
     uint8_t *bad = reinterpret_cast<uint8_t *>(ws + 64);
     uint16_t *unit_read = reinterpret_cast<uint16_t *>(bad + SM_MAXR);   // read index of every work unit
-    volatile uint32_t *misc = ws + 16;   // [0],[1] ticket [2] all-ones k-mer value [3] abort [4],[5] pool base [6] big bucket [7] unit counter [8..15] r0,r1,b0,b1
+    volatile uint32_t *misc = ws + WS_MISC;   // [0],[1] ticket [2] all-ones k-mer value [3] abort [4],[5] pool base [6] big bucket [7] unit counter [8..15] r0,r1,b0,b1
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
     const int K = a.K;
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
     long long t_phase = clock64();
     WarpQueue<W> wq;
     wq.key = reinterpret_cast<KT *>(qbytes) + warp * SM_QCAP;
-    wq.hx = reinterpret_cast<uint32_t *>(reinterpret_cast<KT *>(qbytes) + SM_NWARP * SM_QCAP) + warp * SM_QCAP;
+    wq.hx = reinterpret_cast<uint32_t *>(reinterpret_cast<KT *>(qbytes) + NW * SM_QCAP) + warp * SM_QCAP;
     wq.n = 0;
     wq.budget = 0;
 
@@ -379,14 +387,14 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                 misc[12] = (uint32_t)pf_b0; misc[13] = (uint32_t)((uint64_t)pf_b0 >> 32);
                 misc[14] = (uint32_t)pf_b1; misc[15] = (uint32_t)((uint64_t)pf_b1 >> 32);
                 if (MULTI) {
-                    ws[32] = (uint32_t)pf_gid;
-                    ws[33] = (uint32_t)((uint64_t)pf_gid >> 32);
+                    ws[WS_GID] = (uint32_t)pf_gid;
+                    ws[WS_GID + 1] = (uint32_t)((uint64_t)pf_gid >> 32);
                 }
             }
             __syncthreads();
             item = (int64_t)(((unsigned long long)misc[1] << 32) | misc[0]);
             if (item >= n_items) break;
-            g = MULTI ? (int64_t)(((uint64_t)ws[33] << 32) | ws[32]) : item;
+            g = MULTI ? (int64_t)(((uint64_t)ws[WS_GID + 1] << 32) | ws[WS_GID]) : item;
             r0 = (int64_t)(((uint64_t)misc[9] << 32) | misc[8]);
             r1 = (int64_t)(((uint64_t)misc[11] << 32) | misc[10]);
             b0 = (int64_t)(((uint64_t)misc[13] << 32) | misc[12]);
@@ -438,9 +446,9 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             }
             if (s0 == r0) {   // a pass starts: empty table of full size
                 uint4 *kq = reinterpret_cast<uint4 *>(tkey);
-                for (int j = tid; j < (int)(SM_TSIZE * sizeof(KT) / 16); j += SM_NT) kq[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                for (int j = tid; j < (int)(SM_TSIZE * sizeof(KT) / 16); j += NT) kq[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
                 uint4 *vq = reinterpret_cast<uint4 *>(tval);
-                for (int j = tid; j < SM_TSIZE / 4; j += SM_NT) vq[j] = make_uint4(0u, 0u, 0u, 0u);
+                for (int j = tid; j < SM_TSIZE / 4; j += NT) vq[j] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
         const int64_t nrows = s1 - s0;
@@ -455,7 +463,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         const int nr = (int)nrows;
 
         // ---- per-read base offsets inside the staged span, null rows ----------------------------------------------
-        for (int r = tid; r <= nr; r += SM_NT) rstart[r] = (uint32_t)(col_off(a.col, s0 + r) - sb0) + slack;
+        for (int r = tid; r <= nr; r += NT) rstart[r] = (uint32_t)(col_off(a.col, s0 + r) - sb0) + slack;
         if (tid < nr) bad[tid] = col_valid(a.col, s0 + tid) ? 0 : 1;
         __syncthreads();
 
@@ -467,7 +475,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             uint4 v[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int c = tid + i * SM_NT;
+                const int c = tid + i * NT;
                 v[i] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
                 if (c < nchunks) {
                     const uint8_t *p = a0 + 16 * c;
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int c = tid + i * SM_NT;
+                const int c = tid + i * NT;
                 if (c < nchunks) {
                     pk[c] = (pack4(v[i].x) << 24) | (pack4(v[i].y) << 16) | (pack4(v[i].z) << 8) | pack4(v[i].w);
                     const bool ok = valid4(v[i].x) & valid4(v[i].y) & valid4(v[i].z) & valid4(v[i].w);
@@ -501,8 +509,8 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
                 const uint32_t len = rstart[tid + 1] - rstart[tid];
                 if (!bad[tid] && len >= (uint32_t)K) nk = len - K + 1;
             }
-            block_scan_u32(nk, &total, ws);
-            const uint32_t ex = block_scan_u32((nk + SM_UNIT - 1) / SM_UNIT, &nunits, ws);
+            block_scan_u32<NW>(nk, &total, ws);
+            const uint32_t ex = block_scan_u32<NW>((nk + SM_UNIT - 1) / SM_UNIT, &nunits, ws);
             if (tid < SM_MAXR) ucum[tid] = ex;
             if (tid == 0) ucum[SM_MAXR] = nunits;
             for (uint32_t j = 0; j < (nk + SM_UNIT - 1) / SM_UNIT; j++) unit_read[ex + j] = (uint16_t)tid;
@@ -519,10 +527,10 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             // keys = EMPTY (all ones), vals = 0
             uint4 *kq = reinterpret_cast<uint4 *>(tkey);
             const int nkq = (int)(tsize * sizeof(KT) / 16);
-            for (int j = tid; j < nkq; j += SM_NT) kq[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+            for (int j = tid; j < nkq; j += NT) kq[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
             uint4 *vq = reinterpret_cast<uint4 *>(tval);
             const int nvq = (int)(tsize / 4);
-            for (int j = tid; j < nvq; j += SM_NT) vq[j] = make_uint4(0u, 0u, 0u, 0u);
+            for (int j = tid; j < nvq; j += NT) vq[j] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
 
@@ -704,7 +712,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             }
             if (wq.budget <= 0) misc[3] = 1;   // never spin on a full table: the HBM path takes the group
             if (tid == 0 && pf_stage == 1) pf_advance();   // next group's byte range
-            if (lane == 0) ws[40 + warp] = wq.n;   // leftovers (< 32 per warp) are finished by the whole CTA below
+            if (lane == 0) ws[WS_LEFT + warp] = wq.n;   // leftovers (< 32 per warp) are finished by the whole CTA below
         }
         if (tid == 0) {
             // pool space for whatever this table can yield (<= SM_TSIZE + 1 survivors): one global atomic per SM_POOL_CHUNK, not per group
@@ -720,9 +728,9 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
         if (total != 0 && !misc[3]) {
             // every thread takes at most one leftover observation and probes until it lands
             const uint32_t wsrc = (uint32_t)tid >> 5, isrc = (uint32_t)tid & 31u;   // thread t <- entry isrc of warp wsrc
-            if (wsrc < (uint32_t)SM_NWARP && isrc < ws[40 + wsrc]) {
+            if (wsrc < (uint32_t)NW && isrc < ws[WS_LEFT + wsrc]) {
                 const KT kp = (reinterpret_cast<KT *>(qbytes) + wsrc * SM_QCAP)[isrc];
-                const uint32_t hx = (reinterpret_cast<uint32_t *>(reinterpret_cast<KT *>(qbytes) + SM_NWARP * SM_QCAP) + wsrc * SM_QCAP)[isrc];
+                const uint32_t hx = (reinterpret_cast<uint32_t *>(reinterpret_cast<KT *>(qbytes) + NW * SM_QCAP) + wsrc * SM_QCAP)[isrc];
                 uint32_t h = hx & 0xffffu;
                 uint32_t guard = 0;
                 while (true) {
@@ -778,13 +786,13 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             a.pool_counts[pos] = (uint16_t)((v >> 8) > 65535u ? 65535u : (v >> 8));
         };
         {
-            constexpr int CIT = (SM_TSIZE / 4 + SM_NT - 1) / SM_NT;
+            constexpr int CIT = (SM_TSIZE / 4 + NT - 1) / NT;
             const uint4 *tval4 = reinterpret_cast<const uint4 *>(tval);
             uint4 vv[CIT];
             uint32_t cnt = 0;
 #pragma unroll
             for (int it = 0; it < CIT; it++) {
-                const uint32_t j = (uint32_t)tid + (uint32_t)it * SM_NT;
+                const uint32_t j = (uint32_t)tid + (uint32_t)it * NT;
                 vv[it] = make_uint4(0u, 0u, 0u, 0u);
                 if (j < tsize / 4) {
                     vv[it] = tval4[j];
@@ -804,7 +812,7 @@ __global__ void __launch_bounds__(SM_NT, (W == 1 ? 2 : 1)) k_smem_count(SmemArgs
             if (cnt) {
 #pragma unroll
                 for (int it = 0; it < CIT; it++) {
-                    const uint32_t j = (uint32_t)tid + (uint32_t)it * SM_NT;
+                    const uint32_t j = (uint32_t)tid + (uint32_t)it * NT;
                     const uint32_t c[4] = {vv[it].x, vv[it].y, vv[it].z, vv[it].w};
                     if (((c[0] >> 8) >= thr) | ((c[1] >> 8) >= thr) | ((c[2] >> 8) >= thr) | ((c[3] >> 8) >= thr)) {
 #pragma unroll
@@ -1306,11 +1314,11 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     CK(cudaEventRecord(ev_a, st));
     if (W == 1) {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 2);
-        if (K == 32) k_smem_count<1, true, false><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
-        else k_smem_count<1, false, false><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
+        if (K == 32) k_smem_count<1, true, false><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
+        else k_smem_count<1, false, false><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count);
-        k_smem_count<2, false, false><<<grid, SM_NT, smem_bytes<2>(), st>>>(a);
+        k_smem_count<2, false, false><<<grid, sm_nt<2>(), smem_bytes<2>(), st>>>(a);
     }
     CK(cudaEventRecord(ev_b, st));
     if (launches) *launches += 2;
@@ -1342,11 +1350,11 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
         a.phase_cycles = nullptr;
         if (W == 1) {
             const unsigned grid = (unsigned)std::min<int64_t>(n_a, (int64_t)sm_count * 2);
-            if (K == 32) k_smem_count<1, true, true><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
-            else k_smem_count<1, false, true><<<grid, SM_NT, smem_bytes<1>(), st>>>(a);
+            if (K == 32) k_smem_count<1, true, true><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
+            else k_smem_count<1, false, true><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
         } else {
             const unsigned grid = (unsigned)std::min<int64_t>(n_a, (int64_t)sm_count);
-            k_smem_count<2, false, true><<<grid, SM_NT, smem_bytes<2>(), st>>>(a);
+            k_smem_count<2, false, true><<<grid, sm_nt<2>(), smem_bytes<2>(), st>>>(a);
         }
         if (launches) *launches += 1;
         unsigned long long n_b = 0;
