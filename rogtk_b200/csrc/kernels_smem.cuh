@@ -40,6 +40,25 @@ constexpr int SM_QCAP = 64;           // per-warp queue of collided observations
 constexpr int SM_MAX_UNITS = SM_MAX_BASES / SM_UNIT + SM_MAXR;   // work units of one group
 constexpr int SM_TBITS = 13;          // 8192 slots
 constexpr int SM_TSIZE = 1 << SM_TBITS;
+// slots of the table a CTA can hold.  One-word keys: 8192 (12 B per slot, two CTAs per SM).  Two-word keys have the SM to
+// themselves, and K = 64 makes every read error spoil 64 windows, so the table takes what fits: 9728 slots of 20 B (not a power
+// of two: home slot = umulhi(hash, slots), wrap-around by comparison).
+template <int W>
+constexpr int table_slots() { return W == 2 ? 9728 : SM_TSIZE; }
+template <int W>
+__device__ __forceinline__ uint32_t home_slot(uint32_t hash, uint32_t tsize, int tshift) { return W == 2 ? __umulhi(hash, tsize) : hash >> tshift; }
+template <int W>
+__device__ __forceinline__ uint32_t next_slot(uint32_t h, uint32_t tsize)
+{
+    if (W == 2) return h + 1u == tsize ? 0u : h + 1u;
+    return (h + 1u) & (tsize - 1u);
+}
+template <int W>
+__device__ __forceinline__ uint32_t prev_slot(uint32_t h, uint32_t tsize)
+{
+    if (W == 2) return h == 0u ? tsize - 1u : h - 1u;
+    return (h - 1u) & (tsize - 1u);
+}
 constexpr int SM_SORT_BITS = 10;
 constexpr int SM_SORT_BUCKETS = 1 << SM_SORT_BITS;
 constexpr int SM_POOL_CHUNK = 65536;   // survivors a CTA reserves from the pool at a time (a group needs room for SM_TSIZE + 1)
@@ -65,7 +84,7 @@ constexpr int scratch_bytes()   // pk + per-warp queues; reused by the sort (his
 template <int W>
 constexpr size_t smem_bytes()
 {
-    return (size_t)SM_TSIZE * sizeof(typename KeySlot<W>::T) + (size_t)SM_TSIZE * 4 + (size_t)scratch_bytes<W>() +
+    return (size_t)table_slots<W>() * sizeof(typename KeySlot<W>::T) + (size_t)table_slots<W>() * 4 + (size_t)scratch_bytes<W>() +
            (size_t)(SM_MAXR + 1) * 4 * 2 + 64 * 4 + SM_MAXR + SM_MAX_UNITS * 2 + 64;
 }
 
@@ -241,7 +260,7 @@ struct WarpQueue {   // collided observations of one warp, waiting for their nex
 // One probe step for up to 32 queued observations (one per lane, full width).  Resolved ones are applied, the others are
 // pushed back.  Returns false when the probe bound is exceeded (table hopelessly full).
 template <int W>
-__device__ __forceinline__ void queue_drain_step(WarpQueue<W> &q, typename KeySlot<W>::T *tkey, uint32_t *tval, uint32_t tmask,
+__device__ __forceinline__ void queue_drain_step(WarpQueue<W> &q, typename KeySlot<W>::T *tkey, uint32_t *tval, uint32_t tsize,
                                                  uint32_t lane)
 {
     using S = KeySlot<W>;
@@ -254,7 +273,7 @@ __device__ __forceinline__ void queue_drain_step(WarpQueue<W> &q, typename KeySl
     if (lane < take) {
         kp = q.key[base + lane];
         hx = q.hx[base + lane];
-        uint32_t h = ((hx & 0xffffu) + 1u) & tmask;
+        uint32_t h = next_slot<W>(hx & 0xffffu, tsize);
         KT cur = tkey[h];
         if (cur == S::empty()) cur = atomicCAS(&tkey[h], S::empty(), kp);
         if (cur == kp || cur == S::empty()) {
@@ -277,7 +296,7 @@ __device__ __forceinline__ void queue_drain_step(WarpQueue<W> &q, typename KeySl
 
 template <int W>
 __device__ __forceinline__ void queue_push(WarpQueue<W> &q, bool pend, typename KeySlot<W>::T kp, uint32_t h, uint32_t ex,
-                                           typename KeySlot<W>::T *tkey, uint32_t *tval, uint32_t tmask, uint32_t lane)
+                                           typename KeySlot<W>::T *tkey, uint32_t *tval, uint32_t tsize, uint32_t lane)
 {
     const uint32_t m = __ballot_sync(0xffffffffu, pend);
     if (m == 0) return;
@@ -290,7 +309,7 @@ __device__ __forceinline__ void queue_push(WarpQueue<W> &q, bool pend, typename 
     __syncwarp();
     // keep fewer than 32 entries queued, so that the next push (<= 32 entries) always fits in SM_QCAP
     while (q.n >= 32u && q.budget > 0) {
-        queue_drain_step<W>(q, tkey, tval, tmask, lane);
+        queue_drain_step<W>(q, tkey, tval, tsize, lane);
         q.budget--;
     }
     if (q.n >= 32u) q.n = 0;   // budget exhausted: the caller sees budget <= 0 and gives the group up
@@ -305,16 +324,19 @@ __device__ __forceinline__ void queue_push(WarpQueue<W> &q, bool pend, typename 
         }                                                                \
     } while (0)
 
-template <int W, bool K32, bool MULTI>
+// KF: the K the wide window path is specialised for (32 with one-word keys, 64 with two-word keys), 0 = generic path only
+template <int W, int KF, bool MULTI>
 __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(SmemArgs a)
 {
     constexpr int NT = sm_nt<W>(), NW = sm_nwarp<W>();
+    constexpr bool K32 = KF == 32, K64 = KF == 64;
+    static_assert(KF == 0 || (KF == 32 && W == 1) || (KF == 64 && W == 2), "wide path: K = 32 or K = 64");
     using S = KeySlot<W>;
     using KT = typename S::T;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     KT *tkey = reinterpret_cast<KT *>(smem_raw);
-    uint32_t *tval = reinterpret_cast<uint32_t *>(tkey + SM_TSIZE);
-    uint32_t *scratch = tval + SM_TSIZE;
+    uint32_t *tval = reinterpret_cast<uint32_t *>(tkey + table_slots<W>());
+    uint32_t *scratch = tval + table_slots<W>();
     uint32_t *pk = scratch + 1;                                                  // pk[-1] is a readable pad word
     uint8_t *qbytes = reinterpret_cast<uint8_t *>(scratch + SM_PK_WORDS);        // per-warp queues (W=1: 8 B keys)
     uint32_t *rstart = scratch + scratch_bytes<W>() / 4;
@@ -446,9 +468,9 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
             }
             if (s0 == r0) {   // a pass starts: empty table of full size
                 uint4 *kq = reinterpret_cast<uint4 *>(tkey);
-                for (int j = tid; j < (int)(SM_TSIZE * sizeof(KT) / 16); j += NT) kq[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                for (int j = tid; j < (int)(table_slots<W>() * sizeof(KT) / 16); j += NT) kq[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
                 uint4 *vq = reinterpret_cast<uint4 *>(tval);
-                for (int j = tid; j < SM_TSIZE / 4; j += NT) vq[j] = make_uint4(0u, 0u, 0u, 0u);
+                for (int j = tid; j < table_slots<W>() / 4; j += NT) vq[j] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
         const int64_t nrows = s1 - s0;
@@ -521,7 +543,8 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
         int tbits = MULTI ? SM_TBITS : 8;
         if (!MULTI)
             while (tbits < SM_TBITS && (1u << tbits) < 2u * total) tbits++;
-        const uint32_t tsize = 1u << tbits, tmask = tsize - 1u;
+        // (two-word keys: the largest table is not a power of two, see table_slots)
+        const uint32_t tsize = (MULTI || (W == 2 && 2u * total > (uint32_t)SM_TSIZE)) ? (uint32_t)table_slots<W>() : 1u << tbits;
         const int tshift = 32 - tbits;
         if (!MULTI) {
             // keys = EMPTY (all ones), vals = 0
@@ -596,7 +619,7 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
                         act[u] = (uint32_t)u < R && j0 + (uint32_t)u < ulen;
                         if (MULTI) act[u] = act[u] && pass_of(kh[u], (uint32_t)P) == (uint32_t)pass;
                         ex[u] = (has_l ? (1u << lb) : 0u) | (has_r ? (16u << nb) : 0u);
-                        h[u] = hash32(kl[u], kh[u]) >> tshift;
+                        h[u] = home_slot<W>(hash32(kl[u], kh[u]), tsize, tshift);
                         if (u < 3) {
                             kh[u + 1] = __funnelshift_l(kl[u], kh[u], 2);
                             kl[u + 1] = (kl[u] << 2) | nb;
@@ -640,7 +663,7 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             pm |= act[u] ? (1u << u) : 0u;
-                            h[u] = (h[u] - 1u) & tmask;
+                            h[u] = prev_slot<W>(h[u], tsize);
                         }
                     }
                     __syncwarp();
@@ -669,7 +692,7 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
                         wq.n += tot;
                         __syncwarp();
                         while (wq.n >= 32u && wq.budget > 0) {
-                            queue_drain_step<W>(wq, tkey, tval, tmask, lane);
+                            queue_drain_step<W>(wq, tkey, tval, tsize, lane);
                             wq.budget--;
                         }
                         if (wq.n >= 32u) wq.n = 0;   // budget exhausted (checked by the caller)
@@ -677,9 +700,70 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             const KT kp = S::pack(Key<W>{((uint64_t)kh[u] << 32) | kl[u]});
-                            queue_push<W>(wq, pend[u], kp, h[u], ex[u], tkey, tval, tmask, lane);
+                            queue_push<W>(wq, pend[u], kp, h[u], ex[u], tkey, tval, tsize, lane);
                         }
                     }
+                } else if (K64 && ulen > 48u) {
+                    // ---- K == 64: the same scheme with four-word k-mers; seven packed words hold the bases of a lane's windows -------
+                    const uint32_t R = (ulen + 31u) >> 5;
+                    const uint32_t j0 = R * lane;
+                    const uint32_t p = p0 + (j0 < ulen ? j0 : 0u);
+                    const uint32_t q = rs + p;
+                    const int32_t w = (int32_t)(q >> 4);
+                    const uint32_t s = 2u * (q & 15u);
+                    const uint32_t xm = pk[w - 1], x0 = pk[w], x1 = pk[w + 1], x2 = pk[w + 2], x3 = pk[w + 3], x4 = pk[w + 4], x5 = pk[w + 5];
+                    uint32_t k3 = __funnelshift_l(x1, x0, s), k2 = __funnelshift_l(x2, x1, s), k1 = __funnelshift_l(x3, x2, s),
+                             k0 = __funnelshift_l(x4, x3, s);                // bases q .. q+63, first base in the top bits of k3
+                    const uint32_t tail = __funnelshift_l(x5, x4, s);        // bases q+64 .. q+79
+                    uint32_t lb = __funnelshift_l(x0, xm, s) & 3u;           // base q-1
+                    KT kp[4];
+                    uint32_t ex[4], h[4];
+                    bool act[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t nb = (tail >> (30 - 2 * u)) & 3u;     // right neighbour of window u
+                        const bool has_l = u ? true : (p != 0u);
+                        const bool has_r = (p + u + 1u) < nk;
+                        act[u] = (uint32_t)u < R && j0 + (uint32_t)u < ulen;
+                        if (MULTI) act[u] = act[u] && pass_of(k3, (uint32_t)P) == (uint32_t)pass;
+                        ex[u] = (has_l ? (1u << lb) : 0u) | (has_r ? (16u << nb) : 0u);
+                        const Key<2> key{((uint64_t)k1 << 32) | k0, ((uint64_t)k3 << 32) | k2};
+                        h[u] = home_slot<W>(hash32(key), tsize, tshift);
+                        kp[u] = KeySlot<2>::pack(key);
+                        if ((k3 & k2 & k1 & k0) == 0xffffffffu && act[u]) {   // the all-ones k-mer is the EMPTY marker: side word
+                            val_add(special, ex[u]);
+                            act[u] = false;
+                        }
+                        lb = k3 >> 30;                                       // left neighbour of the next window
+                        k3 = __funnelshift_l(k2, k3, 2);
+                        k2 = __funnelshift_l(k1, k2, 2);
+                        k1 = __funnelshift_l(k0, k1, 2);
+                        k0 = (k0 << 2) | nb;
+                    }
+                    const bool sparse = MULTI && P > 1;
+                    uint32_t pm = 0;   // bit u: window u must queue (it collided, or the pass is sparse)
+                    if (!sparse) {
+                        KT cur[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) cur[u] = act[u] ? tkey[h[u]] : S::empty();
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            KT c = cur[u];
+                            if (act[u] && c == S::empty()) c = atomicCAS(&tkey[h[u]], S::empty(), kp[u]);
+                            const bool ok = (c == kp[u]) | (c == S::empty());
+                            if (act[u] && ok) val_add(&tval[h[u]], ex[u]);
+                            pm |= (act[u] && !ok) ? (1u << u) : 0u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            pm |= act[u] ? (1u << u) : 0u;
+                            h[u] = prev_slot<W>(h[u], tsize);
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 4; u++) queue_push<W>(wq, (pm >> u) & 1u, kp[u], h[u], ex[u], tkey, tval, tsize, lane);
                 } else {
                     // ---- generic: 32 windows per pass, one per lane ------------------------------------------------------------------
                     for (uint32_t pb = 0; pb < ulen; pb += 32u) {
@@ -695,18 +779,18 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
                                 const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
                                 // Exts of iter_kmer_exts with seq_exts = Exts::empty()
                                 ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
-                                h = hash32(key) >> tshift;
+                                h = home_slot<W>(hash32(key), tsize, tshift);
                                 kp = S::pack(key);
                                 if (MULTI && P > 1 && !(kp == S::empty())) {   // sparse pass: queue, drain 32 wide
                                     pend = true;
-                                    h = (h - 1u) & tmask;
+                                    h = prev_slot<W>(h, tsize);
                                 } else {
                                     pend = first_probe(kp, h, ex, tkey[h]);
                                 }
                             }
                         }
                         __syncwarp();
-                        queue_push<W>(wq, pend, kp, h, ex, tkey, tval, tmask, lane);
+                        queue_push<W>(wq, pend, kp, h, ex, tkey, tval, tsize, lane);
                     }
                 }
             }
@@ -716,7 +800,7 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
         }
         if (tid == 0) {
             // pool space for whatever this table can yield (<= SM_TSIZE + 1 survivors): one global atomic per SM_POOL_CHUNK, not per group
-            if (cta_pool_pos + (int64_t)(SM_TSIZE + 1) > cta_pool_end) {
+            if (cta_pool_pos + (int64_t)(table_slots<W>() + 1) > cta_pool_end) {
                 cta_pool_pos = (int64_t)atomicAdd(a.pool_cursor, (unsigned long long)SM_POOL_CHUNK);
                 cta_pool_end = cta_pool_pos + (int64_t)SM_POOL_CHUNK;
             }
@@ -734,7 +818,7 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
                 uint32_t h = hx & 0xffffu;
                 uint32_t guard = 0;
                 while (true) {
-                    h = (h + 1) & tmask;
+                    h = next_slot<W>(h, tsize);
                     KT cur = tkey[h];
                     if (cur == S::empty()) cur = atomicCAS(&tkey[h], S::empty(), kp);
                     if (cur == kp || cur == S::empty()) {
@@ -773,7 +857,7 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
         //      while building the dense output, at far higher occupancy than this kernel's 2 CTAs/SM).  A thread keeps its slots'
         //      value words in registers, a warp reserves its range of the group's pool slice with one shared atomic. ----------------
         const int64_t pb = (int64_t)(((unsigned long long)misc[5] << 32) | misc[4]);
-        if (pb + (int64_t)(SM_TSIZE + 1) > a.pool_cap) {   // survivor pool exhausted: the HBM path (own pool) takes the group
+        if (pb + (int64_t)(table_slots<W>() + 1) > a.pool_cap) {   // survivor pool exhausted: the HBM path (own pool) takes the group
             defer(g);
             in_group = false;
             continue;
@@ -786,7 +870,7 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
             a.pool_counts[pos] = (uint16_t)((v >> 8) > 65535u ? 65535u : (v >> 8));
         };
         {
-            constexpr int CIT = (SM_TSIZE / 4 + NT - 1) / NT;
+            constexpr int CIT = (table_slots<W>() / 4 + NT - 1) / NT;
             const uint4 *tval4 = reinterpret_cast<const uint4 *>(tval);
             uint4 vv[CIT];
             uint32_t cnt = 0;
@@ -1230,12 +1314,14 @@ inline void smem_path_configure()
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     };
-    cfg(k_smem_count<1, true, false>, smem_bytes<1>());
-    cfg(k_smem_count<1, false, false>, smem_bytes<1>());
-    cfg(k_smem_count<2, false, false>, smem_bytes<2>());
-    cfg(k_smem_count<1, true, true>, smem_bytes<1>());
-    cfg(k_smem_count<1, false, true>, smem_bytes<1>());
-    cfg(k_smem_count<2, false, true>, smem_bytes<2>());
+    cfg(k_smem_count<1, 32, false>, smem_bytes<1>());
+    cfg(k_smem_count<1, 0, false>, smem_bytes<1>());
+    cfg(k_smem_count<2, 0, false>, smem_bytes<2>());
+    cfg(k_smem_count<2, 64, false>, smem_bytes<2>());
+    cfg(k_smem_count<1, 32, true>, smem_bytes<1>());
+    cfg(k_smem_count<1, 0, true>, smem_bytes<1>());
+    cfg(k_smem_count<2, 0, true>, smem_bytes<2>());
+    cfg(k_smem_count<2, 64, true>, smem_bytes<2>());
     CK(cudaFuncSetAttribute(k_sort_small<1, false, SORT_MID_CAP, SORT_MID_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sort_count_smem<1, SORT_MID_CAP>()));
     CK(cudaFuncSetAttribute(k_sort_small<1, true, SORT_MID_CAP, SORT_MID_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1314,11 +1400,12 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     CK(cudaEventRecord(ev_a, st));
     if (W == 1) {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 2);
-        if (K == 32) k_smem_count<1, true, false><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
-        else k_smem_count<1, false, false><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
+        if (K == 32) k_smem_count<1, 32, false><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
+        else k_smem_count<1, 0, false><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count);
-        k_smem_count<2, false, false><<<grid, sm_nt<2>(), smem_bytes<2>(), st>>>(a);
+        if (K == 64) k_smem_count<2, 64, false><<<grid, sm_nt<2>(), smem_bytes<2>(), st>>>(a);
+        else k_smem_count<2, 0, false><<<grid, sm_nt<2>(), smem_bytes<2>(), st>>>(a);
     }
     CK(cudaEventRecord(ev_b, st));
     if (launches) *launches += 2;
@@ -1350,11 +1437,12 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
         a.phase_cycles = nullptr;
         if (W == 1) {
             const unsigned grid = (unsigned)std::min<int64_t>(n_a, (int64_t)sm_count * 2);
-            if (K == 32) k_smem_count<1, true, true><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
-            else k_smem_count<1, false, true><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
+            if (K == 32) k_smem_count<1, 32, true><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
+            else k_smem_count<1, 0, true><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
         } else {
             const unsigned grid = (unsigned)std::min<int64_t>(n_a, (int64_t)sm_count);
-            k_smem_count<2, false, true><<<grid, sm_nt<2>(), smem_bytes<2>(), st>>>(a);
+            if (K == 64) k_smem_count<2, 64, true><<<grid, sm_nt<2>(), smem_bytes<2>(), st>>>(a);
+            else k_smem_count<2, 0, true><<<grid, sm_nt<2>(), smem_bytes<2>(), st>>>(a);
         }
         if (launches) *launches += 1;
         unsigned long long n_b = 0;
