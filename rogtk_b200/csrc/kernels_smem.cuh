@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
 {
     constexpr int NT = sm_nt<W>(), NW = sm_nwarp<W>();
     constexpr bool K32 = KF == 32, K64 = KF == 64;
+    static_assert(NW <= WS_MISC && WS_LEFT + NW <= 64, "scratch words: scan partials and queue leftovers are per warp");
     static_assert(KF == 0 || (KF == 32 && W == 1) || (KF == 64 && W == 2), "wide path: K = 32 or K = 64");
     using S = KeySlot<W>;
     using KT = typename S::T;
