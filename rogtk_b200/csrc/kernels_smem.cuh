@@ -430,12 +430,15 @@ __global__ void __launch_bounds__(sm_nt<W>(), (W == 1 ? 2 : 1)) k_smem_count(Sme
             if (b1 <= b0) continue;
             if (MULTI) {
                 const int64_t ub = b1 - b0;   // every observation starts at its own base
+                const int64_t pass_obs = K > 32 ? SM_PASS_OBS / 2 : SM_PASS_OBS;
                 if (ub > SM_PASS_OBS * SM_PMAX) {   // too much work for one CTA: HBM-table path
                     defer(g);
                     continue;
                 }
                 P = 1;
-                if (2 * K > 12) P = (int)((ub + SM_PASS_OBS - 1) / SM_PASS_OBS);   // <= 4^K <= 4096 distinct k-mers otherwise
+                // (<= 4^K <= 4096 distinct k-mers when K <= 6; long k-mers: every read error spoils K windows, plan half the bases per pass)
+                if (2 * K > 12) P = (int)((ub + pass_obs - 1) / pass_obs);
+                if (P > SM_PMAX) P = SM_PMAX;
                 in_group = true;
                 pass = 0;
                 srow = r0;
