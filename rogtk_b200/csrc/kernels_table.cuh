@@ -95,7 +95,9 @@ __global__ void k_spill_plan_caps(const int64_t *group_offsets, const int32_t *i
     const int64_t g = ids ? ids[list_base + i] : list_base + i;
     const int64_t u = (int64_t)ub[i];
     const int64_t want = u + (u >> 1) + 8;
-    int64_t cap = 16;
+    // at least 32 slots: every table then starts at a multiple of 32, so the 32 slots a warp extracts per step belong to one
+    // group and the survivor records come out grouped by listed group (what the segmented sort relies on)
+    int64_t cap = 32;
     while (cap < want) cap <<= 1;
     rows[i] = group_offsets[g + 1] - group_offsets[g];
     caps[i] = cap;
@@ -248,13 +250,14 @@ __global__ void __launch_bounds__(SPILL_EXTRACT_NT) k_spill_extract(SpillArgs a)
             int64_t i = i0;
             while (i + 1 < a.n_list && a.slot_off[i + 1] <= slot) i++;
             g = a.ids ? a.ids[a.list_base + i] : a.list_base + i;
-            const typename S::T kp = reinterpret_cast<const typename S::T *>(a.keys)[slot];
-            if (kp != S::empty()) {
-                const uint32_t v = a.vals[slot];
+            // a claimed slot always carries a count >= 1 (the claimer adds right after its CAS), an empty one has val == 0:
+            // the counting pass needs the value words only, the key is read for survivors
+            const uint32_t v = a.vals[slot];
+            {
                 uint32_t c = v & TV_COUNT_MASK;
                 if (c > 65535u) c = 65535u;
                 if (c >= a.min_cov && c > 0) {
-                    const Key<W> k = S::unpack(kp);
+                    const Key<W> k = a.count_only ? Key<W>::zero() : S::unpack(reinterpret_cast<const typename S::T *>(a.keys)[slot]);
                     rec.hi = k.hi_word();
                     rec.lo = k.lo;
                     rec.grank = (uint32_t)(a.list_base + i);
@@ -310,6 +313,26 @@ __global__ void k_gather_i64(const int64_t *src, const int32_t *ids, int64_t lis
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[ids ? ids[list_base + i] : list_base + i];
+}
+
+// survivor records -> key columns + identity permutation (for the segmented sort), and the gather that applies a permutation
+__global__ void k_rec_split(const SpillRec *recs, int64_t n, uint64_t *lo, uint64_t *hi, uint32_t *idx)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lo[i] = recs[i].lo;
+    if (hi) hi[i] = recs[i].hi;
+    idx[i] = (uint32_t)i;
+}
+__global__ void k_gather_u64(const uint64_t *src, const uint32_t *idx, int64_t n, uint64_t *dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_rec_gather(const SpillRec *src, const uint32_t *idx, int64_t n, SpillRec *dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
 }
 
 __global__ void k_spill_scatter(const SpillRec *recs, int64_t n_recs, const int32_t *ids, int64_t list_base, const int64_t *list_rec_off,

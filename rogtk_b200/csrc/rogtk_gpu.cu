@@ -6,6 +6,7 @@
 
 #include <cub/device/device_merge_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 #include <cuda/std/tuple>
 
 #include <algorithm>
@@ -125,16 +126,38 @@ struct SpecKey2 {
     __host__ __device__ ::cuda::std::tuple<uint64_t &, uint64_t &> operator()(SpecRec &r) const { return {r.hi, r.lo}; }
 };
 // orders n records by (group rank, k-mer); the result is in `recs` (which may be replaced by a new buffer).  One listed group
-// (a giant UMI group, the global-spectrum local count): LSD radix sort over the k-mer's 2K bits.  Several groups: the key
-// would be 74..160 bits of a 24-byte record, where the comparison merge sort measured faster (600 groups x 7.6 k records).
+// (a giant UMI group, the global-spectrum local count): LSD radix sort over the k-mer's 2K bits.  Several groups: the
+// extraction leaves the records grouped by listed group already (slot order), so only the k-mers inside every group need
+// ordering: cub::DeviceSegmentedSort on the key columns with the record index as value (segments = seg_off[0..n_seg]), two
+// stable passes for two-word keys, then one gather of the records (library calls off the hot path).
 template <int W>
-void sort_spill_records(cudaStream_t st, DevBuf &recs, int64_t n, int K, int64_t n_ranks)
+void sort_spill_records(cudaStream_t st, DevBuf &recs, int64_t n, int K, int64_t n_seg, const int64_t *seg_off)
 {
     size_t tmp_bytes = 0;
-    if (n_ranks > 1) {
-        CK(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, recs.as<SpillRec>(), n, SpillRecLess(), st));
+    if (n > (int64_t)0xffffffffll) throw ArgFail{ROGTK_ERR_UNSUPPORTED, "more than 2^32 survivor records in one wave"};
+    if (n_seg > 1) {
+        DevBuf lo((size_t)n * 8, st), lo2((size_t)n * 8, st), hi(W == 2 ? (size_t)n * 8 : 0, st), idx((size_t)n * 4, st), idx2((size_t)n * 4, st);
+        const unsigned gb = blocks_for(n, 256);
+        k_rec_split<<<gb, 256, 0, st>>>(recs.as<SpillRec>(), n, lo.as<uint64_t>(), W == 2 ? hi.as<uint64_t>() : nullptr, idx.as<uint32_t>());
+        CK(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp_bytes, lo.as<uint64_t>(), lo2.as<uint64_t>(), idx.as<uint32_t>(),
+                                                     idx2.as<uint32_t>(), n, n_seg, seg_off, seg_off + 1, st));
         DevBuf tmp(tmp_bytes, st);
-        CK(cub::DeviceMergeSort::SortKeys(tmp.p, tmp_bytes, recs.as<SpillRec>(), n, SpillRecLess(), st));
+        CK(cub::DeviceSegmentedSort::StableSortPairs(tmp.p, tmp_bytes, lo.as<uint64_t>(), lo2.as<uint64_t>(), idx.as<uint32_t>(),
+                                                     idx2.as<uint32_t>(), n, n_seg, seg_off, seg_off + 1, st));
+        const uint32_t *order = idx2.as<uint32_t>();
+        if (W == 2) {   // second (more significant) key word, stable
+            k_gather_u64<<<gb, 256, 0, st>>>(hi.as<uint64_t>(), idx2.as<uint32_t>(), n, lo.as<uint64_t>());
+            size_t tb2 = 0;
+            CK(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tb2, lo.as<uint64_t>(), lo2.as<uint64_t>(), idx2.as<uint32_t>(),
+                                                         idx.as<uint32_t>(), n, n_seg, seg_off, seg_off + 1, st));
+            DevBuf tmp2(tb2, st);
+            CK(cub::DeviceSegmentedSort::StableSortPairs(tmp2.p, tb2, lo.as<uint64_t>(), lo2.as<uint64_t>(), idx2.as<uint32_t>(),
+                                                         idx.as<uint32_t>(), n, n_seg, seg_off, seg_off + 1, st));
+            order = idx.as<uint32_t>();
+        }
+        DevBuf sorted((size_t)n * sizeof(SpillRec), st);
+        k_rec_gather<<<gb, 256, 0, st>>>(recs.as<SpillRec>(), order, n, sorted.as<SpillRec>());
+        recs = std::move(sorted);
         return;
     }
     DevBuf sorted((size_t)n * sizeof(SpillRec), st);
@@ -272,16 +295,16 @@ void run_spill(rogtk_gpu_ctx *ctx, const ColView &col, const int64_t *d_group_of
         a.count_only = 0;
         k_spill_extract<W><<<x_grid, SPILL_EXTRACT_NT, 0, st>>>(a);
         ctx->launches += 2;
-        if (wv.n_recs > 1) {
-            sort_spill_records<W>(st, wv.recs, wv.n_recs, K, n_list_total);
-            ctx->launches += 3;
-        }
-        // survivors per listed group -> record offsets of the wave
+        // survivors per listed group -> record offsets of the wave (the records are in slot order, i.e. grouped by listed group)
         DevBuf ns((size_t)nl * 8, st);
         k_gather_i64<<<blocks_for(nl, 256), 256, 0, st>>>(d_nsurv, d_ids, i0, nl, ns.as<int64_t>());
         ctx->launches++;
         wv.rec_off.alloc((size_t)(nl + 1) * 8, st);
         exclusive_scan<int64_t>(ns.as<int64_t>(), nl, wv.rec_off.as<int64_t>(), scratch.as<int64_t>(), st, &ctx->launches);
+        if (wv.n_recs > 1) {
+            sort_spill_records<W>(st, wv.recs, wv.n_recs, K, nl, wv.rec_off.as<int64_t>());
+            ctx->launches += 4;
+        }
         waves.push_back(std::move(wv));
         i0 = i1;
     }

@@ -705,3 +705,22 @@ def test_two_word_kmers_at_scale(engine, oracle):
     finally:
         for p in (d_data, d_off, d_goff):
             engine.device_free(p)
+
+
+def test_many_tiny_groups_with_sentinel_kmer_through_hbm_tables(engine, oracle):
+    """The all-T k-mer lives outside the HBM tables and is emitted with its group's first slots; with hundreds of tiny tables
+    the survivor records must still come out grouped by group (the per-group segmented sort depends on it)."""
+    rng = np.random.default_rng(17)
+    groups = []
+    for g in range(300):
+        reads = []
+        if g % 3 != 1:
+            reads.append("T" * int(rng.integers(33, 70)))
+        if g % 2:
+            reads.append("".join("ACGT"[x] for x in rng.integers(0, 4, int(rng.integers(20, 60)))))
+        if g % 5 == 0:
+            reads.append("T" * 40 + "A" + "T" * 35)
+        groups.append(reads)
+    data, offs, validity, goff = groups_to_arrow(groups)
+    for k in (16, 32, 64):
+        _both(engine, oracle, data, offs, goff, k, 1, validity=validity, spill=True, ctx=f"tiny sentinel groups k={k}")
