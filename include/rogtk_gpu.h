@@ -196,8 +196,10 @@ int rogtk_gpu_memcpy_d2h(rogtk_gpu_ctx *ctx, void *dst, const void *src, size_t 
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx);
 /* diagnostics: enable per-phase clock64 accounting inside k_smem_count and read the cycles of the last batch
- * (0 meta, 1 ingest, 2 prefix+clear, 3 count, 4 prune+reserve, 5 compact), summed over CTAs */
-int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint64_t *out8);
+ * (0 meta, 1 ingest, 2 prefix+clear, 3 count, 4 prune+reserve, 5 compact), summed over CTAs; with the link-walk kernel
+ * also event counts: 8 walked windows, 9 densely inserted windows, 10 range heads, 11 probe steps, 12 dense warp steps,
+ * 13 walk warp steps, 14 k-mer compares through a reference, 15 ranges whose walk broke.  out16: 16 words */
+int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint64_t *out16);
 /* write a >L2 scratch buffer (L2 flush between timed iterations) */
 int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx);
 

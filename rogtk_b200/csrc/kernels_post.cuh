@@ -35,7 +35,10 @@ struct View16 {
     uint32_t len, a, b, c;
 };
 
-__global__ void k_view_len(const View16 *views, int64_t n_rows, const uint8_t *validity, int64_t vbo, int64_t *lens)
+// lengths of the valid rows; an out-of-line view that names a buffer the column does not have, or bytes beyond that buffer's
+// length, sets *err (the call returns ROGTK_ERR_INVALID_ARG before anything is gathered)
+__global__ void k_view_len(const View16 *views, int64_t n_rows, const uint8_t *validity, int64_t vbo, int n_buffers,
+                           const int64_t *buf_len, int64_t *lens, int *err)
 {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
@@ -44,22 +47,83 @@ __global__ void k_view_len(const View16 *views, int64_t n_rows, const uint8_t *v
         int64_t b = r + vbo;
         ok = (validity[b >> 3] >> (b & 7)) & 1;
     }
-    lens[r] = ok ? (int64_t)views[r].len : 0;
+    const View16 v = views[r];
+    if (ok && v.len > 12u) {
+        // (lengths are int32 in Arrow: a negative one shows up here as >= 2^31)
+        if (v.len >= 0x80000000u || v.b >= (uint32_t)n_buffers || (int64_t)v.c + (int64_t)v.len > buf_len[v.b]) {
+            atomicOr(err, 8);
+            ok = false;
+        }
+    }
+    lens[r] = ok ? (int64_t)v.len : 0;
 }
 
-// one warp per row
-__global__ void k_view_gather(const View16 *views, int64_t n_rows, const uint8_t *const *bufs, const int64_t *offsets,
-                              uint8_t *out)
+// One warp per row.  Out-of-line rows are copied with 16-byte loads: the source is read in aligned 16-byte chunks (the two
+// chunks that straddle a destination chunk are funnel-shifted together byte-wise), the destination is written in aligned
+// 16-byte chunks wherever a whole chunk belongs to the row; the ragged head and tail bytes go one by one.
+__device__ __forceinline__ uint4 shift_bytes(uint4 a, uint4 b, unsigned s)   // bytes s .. s+15 of the 32 bytes a:b (s < 16)
+{
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const unsigned ws = s >> 2, bs = (s & 3u) * 8u;
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {   // select w[ws + i], w[ws + i + 1] without dynamic register indexing
+            if ((int)ws == j) {
+                lo = w[j + i];
+                hi = w[j + i + 1 < 8 ? j + i + 1 : 7];
+            }
+        }
+        o[i] = bs ? __funnelshift_r(lo, hi, bs) : lo;
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+__global__ void k_view_gather(const View16 *views, int64_t n_rows, const uint8_t *const *bufs, const int64_t *buf_len,
+                              const int64_t *offsets, uint8_t *out)
 {
     int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_rows) return;
     const unsigned lane = lane_id();
-    int64_t o = offsets[r];
-    int64_t len = offsets[r + 1] - o;   // 0 for null rows
+    const int64_t o = offsets[r];
+    const int64_t len = offsets[r + 1] - o;   // 0 for null rows
     if (len == 0) return;
     const View16 v = views[r];
-    const uint8_t *src = (v.len <= 12) ? reinterpret_cast<const uint8_t *>(&views[r]) + 4 : bufs[v.b] + v.c;
-    for (int64_t j = lane; j < len; j += 32) out[o + j] = src[j];
+    if (v.len <= 12) {
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(&views[r]) + 4;
+        if (lane < len) out[o + lane] = src[lane];
+        return;
+    }
+    const uint8_t *base = bufs[v.b];
+    const uint8_t *src = base + v.c;
+    const int64_t blen = buf_len[v.b];
+    uint8_t *dst = out + o;
+    // destination chunks [d0, d1): 16-byte aligned, entirely inside the row
+    const int64_t head = (int64_t)((16u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+    const int64_t h = head < len ? head : len;
+    const int64_t nchunk = (len - h) >> 4;
+    for (int64_t j = lane; j < h; j += 32) dst[j] = src[j];
+    if (nchunk > 0) {
+        const uint8_t *s0 = src + h;                                   // source byte of the first aligned destination chunk
+        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(s0) & 15u);
+        const uint4 *sa = reinterpret_cast<const uint4 *>(s0 - sh);    // aligned (buffers come from cudaMalloc / the staged copy: base 256-aligned)
+        const bool base_aligned = (reinterpret_cast<uintptr_t>(base) & 15u) == 0;
+        for (int64_t c = lane; c < nchunk; c += 32) {
+            uint4 val;
+            const int64_t sb = (int64_t)(reinterpret_cast<const uint8_t *>(sa + c) - base);   // offset of the first load in the buffer
+            if (base_aligned && sb >= 0 && sb + (sh ? 32 : 16) <= blen) {   // every loaded byte lies inside the buffer
+                const uint4 a = sa[c];
+                val = sh ? shift_bytes(a, sa[c + 1], sh) : a;
+            } else {   // edge of the buffer / unaligned buffer: byte loads
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int t = 0; t < 16; t++) w[t >> 2] |= (uint32_t)s0[c * 16 + t] << (8 * (t & 3));
+                val = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4 *>(dst + h + c * 16) = val;
+        }
+    }
+    for (int64_t j = h + nchunk * 16 + lane; j < len; j += 32) dst[j] = src[j];
 }
 
 // ---------------------------------------------------------------------------------------------------------------

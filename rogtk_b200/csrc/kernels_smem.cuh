@@ -107,7 +107,7 @@ struct SmemArgs {
     uint16_t *pool_counts;
     int32_t *deferred_ids;           // groups handed to the HBM-table path
     unsigned long long *n_deferred;
-    unsigned long long *phase_cycles;   // optional [8] per-phase SM cycles summed over CTAs (diagnostics)
+    unsigned long long *phase_cycles;   // optional [16]: [0..7] per-phase SM cycles summed over CTAs, [8..15] event counts of k_walk_count (diagnostics)
     // MULTI only: the groups to process (tickets index this list), one SegRec per (list entry, pass), passes used per entry
     const int32_t *group_list;
     int64_t n_list;
@@ -1292,9 +1292,20 @@ inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, i
     else run_sort_gather_w<1>(st, peek_slot, sm_count, a, n_groups, n_seg_groups, launches);
 }
 
+}  // namespace rogtk
+#include "kernels_walk.cuh"
+namespace rogtk {
+
 // -----------------------------------------------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------------------------------------------
+// knobs read once per context (rogtk_gpu_create), never per call
+struct SmemTuning {
+    int walk_rl_bits = 0;          // 0 (default): k_smem_count counts the first tier.  3..6: the experimental link-walk kernel
+                                   // k_walk_count with ranges of 1 << bits windows per lane (measured slower)
+    int64_t debug_pool_cap = 0;    // tests: force a tiny survivor pool
+};
+
 struct SmemResult {
     const int32_t *deferred_ids = nullptr;
     int64_t n_deferred = 0;
@@ -1326,6 +1337,10 @@ inline void smem_path_configure()
     cfg(k_smem_count<1, 0, true>, smem_bytes<1>());
     cfg(k_smem_count<2, 0, true>, smem_bytes<2>());
     cfg(k_smem_count<2, 64, true>, smem_bytes<2>());
+    cfg(k_walk_count<1, false>, walk_smem_bytes<1>());
+    cfg(k_walk_count<2, false>, walk_smem_bytes<2>());
+    cfg(k_walk_count<1, true>, walk_smem_bytes<1>());
+    cfg(k_walk_count<2, true>, walk_smem_bytes<2>());
     CK(cudaFuncSetAttribute(k_sort_small<1, false, SORT_MID_CAP, SORT_MID_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sort_count_smem<1, SORT_MID_CAP>()));
     CK(cudaFuncSetAttribute(k_sort_small<1, true, SORT_MID_CAP, SORT_MID_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1344,11 +1359,14 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
                           const uint8_t *data_end,
                           const int64_t *d_group_offsets, int64_t n_groups, int K, uint32_t min_cov, unsigned long long *d_nobs,
                           int64_t *d_nsurv, SmemResult &res, int64_t *launches, cudaEvent_t ev_a, cudaEvent_t ev_b,
-                          unsigned long long *phase_out /* host [8] or nullptr */, bool multipass = true)
+                          unsigned long long *phase_out /* host [16] or nullptr */, bool multipass = true, const SmemTuning &tune = SmemTuning())
 {
     const int W = K > 32 ? 2 : 1;
-    DevBuf ctr(128, st);
-    CK(cudaMemsetAsync(ctr.p, 0, 128, st));
+    const bool walk = tune.walk_rl_bits >= WK_MIN_RL_BITS;
+    // CTAs the first-tier kernel runs at once (each keeps one chunk of the survivor pool open)
+    const int64_t first_ctas = (int64_t)sm_count * (walk ? walk_min_blocks_rt(W) : (W == 1 ? 2 : 1));
+    DevBuf ctr(256, st);
+    CK(cudaMemsetAsync(ctr.p, 0, 256, st));
     unsigned long long *d_ctr = ctr.as<unsigned long long>();   // [0] ticket [1] pool cursor [2] n_deferred [3] obs upper bound
     k_obs_upper_bound<<<sm_count * 4, 256, 0, st>>>(col, K, d_ctr + 3);
     unsigned long long ub = 0;
@@ -1360,9 +1378,9 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     int64_t pool_cap = (int64_t)(ub / (min_cov > 1 ? min_cov : 1)) + 1;
     pool_cap = std::min<int64_t>(pool_cap, (int64_t)(workspace_bytes / 2 / entry));
     // per-CTA chunking leaves unused tails: one open chunk per running CTA, up to SM_TSIZE + 1 entries at every chunk switch
-    pool_cap += pool_cap / 4 + std::min<int64_t>(n_groups, (int64_t)sm_count * 2) * 2 * SM_POOL_CHUNK;
+    pool_cap += pool_cap / 4 + std::min<int64_t>(n_groups, first_ctas) * 2 * SM_POOL_CHUNK;
     pool_cap = std::max<int64_t>(pool_cap, 1024);
-    if (const char *e = getenv("ROGTK_DEBUG_POOL_CAP")) pool_cap = std::max<int64_t>(1024, atoll(e));   // tests: exhaust the pool
+    if (tune.debug_pool_cap) pool_cap = std::max<int64_t>(1024, tune.debug_pool_cap);   // tests: exhaust the pool
     res.keep.emplace_back((size_t)pool_cap * 8, st);
     uint64_t *p_lo = res.keep.back().as<uint64_t>();
     uint64_t *p_hi = nullptr;
@@ -1402,7 +1420,16 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     a.n_deferred = d_ctr + 2;
     a.phase_cycles = phase_out ? d_ctr + 8 : nullptr;
     CK(cudaEventRecord(ev_a, st));
-    if (W == 1) {
+    if (walk) {
+        const unsigned grid = (unsigned)std::min<int64_t>(n_groups, first_ctas);
+        if (phase_out) {   // diagnostics build of the same kernel: phase cycles + event counts
+            if (W == 1) k_walk_count<1, true><<<grid, WK_NT, walk_smem_bytes<1>(), st>>>(a, tune.walk_rl_bits);
+            else k_walk_count<2, true><<<grid, WK_NT, walk_smem_bytes<2>(), st>>>(a, tune.walk_rl_bits);
+        } else {
+            if (W == 1) k_walk_count<1, false><<<grid, WK_NT, walk_smem_bytes<1>(), st>>>(a, tune.walk_rl_bits);
+            else k_walk_count<2, false><<<grid, WK_NT, walk_smem_bytes<2>(), st>>>(a, tune.walk_rl_bits);
+        }
+    } else if (W == 1) {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 2);
         if (K == 32) k_smem_count<1, 32, false><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
         else k_smem_count<1, 0, false><<<grid, sm_nt<1>(), smem_bytes<1>(), st>>>(a);
@@ -1415,7 +1442,7 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     if (launches) *launches += 2;
     unsigned long long h_ctr[3];
     pk.add(d_ctr, 24, h_ctr);
-    if (phase_out) pk.add(d_ctr + 8, 64, phase_out);
+    if (phase_out) pk.add(d_ctr + 8, 128, phase_out);
     pk.sync();
     CK(cudaEventElapsedTime(&res.ms_kernel, ev_a, ev_b));
     res.n_deferred = (int64_t)h_ctr[2];

@@ -51,7 +51,8 @@ struct rogtk_gpu_ctx {
     size_t smem_optin = 0;
     void *flush_buf = nullptr;
     bool phase_enabled = false;
-    unsigned long long phase_cycles[8] = {};
+    SmemTuning tune;                // environment knobs, read once in rogtk_gpu_create
+    unsigned long long phase_cycles[16] = {};
     size_t flush_bytes = 0;
     // cache of pinned host blocks (size -> pointers) so steady-state calls do not pay cudaHostAlloc
     std::multimap<size_t, void *> pinned_free;
@@ -70,6 +71,27 @@ void set_error(rogtk_gpu_ctx *ctx, const char *fmt, ...)
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     if (ctx) ctx->last_error = buf;
+}
+
+// maps the exception in flight to an error code + last_error text; call inside catch (...)
+int fail_code(rogtk_gpu_ctx *ctx)
+{
+    try {
+        throw;
+    } catch (const ArgFail &a) {
+        set_error(ctx, "%s", a.msg.c_str());
+        return a.code < 0 ? a.code : ROGTK_ERR_INTERNAL;
+    } catch (const CudaFail &f) {
+        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
+        cudaGetLastError();
+        return f.e == cudaErrorMemoryAllocation ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
+    } catch (const std::bad_alloc &) {
+        set_error(ctx, "host out of memory");
+        return ROGTK_ERR_OOM;
+    } catch (...) {
+        set_error(ctx, "unexpected internal error");
+        return ROGTK_ERR_INTERNAL;
+    }
 }
 
 void *pinned_get(rogtk_gpu_ctx *ctx, size_t bytes)
@@ -347,7 +369,7 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         CK(cudaSetDevice(device));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
-        if (prop.major < 10) {
+        if (prop.major != 10) {   // the library holds sm_100a code only
             rogtk_gpu_destroy(ctx);
             return fail(ROGTK_ERR_UNSUPPORTED);   // sm_100a only
         }
@@ -357,6 +379,11 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
         if (const char *e = getenv("ROGTK_CHUNK_BYTES")) ctx->chunk_bytes = (size_t)std::max(4096ll, atoll(e));
+        if (const char *e = getenv("ROGTK_DEBUG_POOL_CAP")) ctx->tune.debug_pool_cap = atoll(e);   // tests: exhaust the survivor pool
+        if (const char *e = getenv("ROGTK_WALK_RL")) {   // experiments: 0 = round-1 counting kernel, 3..6 = log2(windows per lane range)
+            const int v = atoi(e);
+            ctx->tune.walk_rl_bits = v <= 0 ? 0 : std::min(std::max(v, WK_MIN_RL_BITS), 6);
+        }
         {   // cache of page-locked result blocks: a quarter of the host's memory unless ROGTK_PINNED_CACHE_BYTES says otherwise
             const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
             ctx->pinned_cache_cap = pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz / 4 : (size_t)16 << 30;
@@ -476,22 +503,36 @@ void stage_input(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     if (c->layout != ROGTK_UTF8_VIEW) throw ArgFail{ROGTK_ERR_INVALID_ARG, "unknown string layout"};
     // Utf8View: gather on the device into a contiguous LargeUtf8-like column
     const View16 *views = (const View16 *)to_device(ctx, s, c->offsets_or_views, (size_t)n * 16, on_device);
-    std::vector<const uint8_t *> h_bufs((size_t)std::max(1, c->n_buffers), nullptr);
-    for (int b = 0; b < c->n_buffers; b++) h_bufs[b] = (const uint8_t *)to_device(ctx, s, c->data[b], (size_t)c->data_len[b], on_device);
-    s.keep.emplace_back(h_bufs.size() * sizeof(void *), st);
+    if (c->n_buffers < 0 || (c->n_buffers > 0 && (!c->data || !c->data_len))) throw ArgFail{ROGTK_ERR_INVALID_ARG, "view layout: null buffer table"};
+    const size_t nb = (size_t)std::max(1, c->n_buffers);
+    // buffer table for the device: nb pointers, then nb lengths (a null / empty variadic buffer keeps its index, with length 0)
+    std::vector<uint64_t> h_tab(2 * nb, 0);
+    for (int b = 0; b < c->n_buffers; b++) {
+        const int64_t len = c->data[b] ? c->data_len[b] : 0;
+        if (len < 0) throw ArgFail{ROGTK_ERR_INVALID_ARG, "view layout: negative buffer length"};
+        h_tab[b] = (uint64_t) reinterpret_cast<uintptr_t>(to_device(ctx, s, c->data[b], (size_t)len, on_device));
+        h_tab[nb + b] = (uint64_t)len;
+    }
+    s.keep.emplace_back(h_tab.size() * 8, st);
     const uint8_t *const *d_bufs = s.keep.back().as<const uint8_t *>();
-    CK(cudaMemcpyAsync(s.keep.back().p, h_bufs.data(), h_bufs.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
-    DevBuf lens((size_t)std::max<int64_t>(1, n) * 8, st), scratch(scan_scratch_bytes(n), st);
+    const int64_t *d_buf_len = s.keep.back().as<int64_t>() + nb;
+    CK(cudaMemcpyAsync(s.keep.back().p, h_tab.data(), h_tab.size() * 8, cudaMemcpyHostToDevice, st));
+    DevBuf lens((size_t)std::max<int64_t>(1, n) * 8, st), scratch(scan_scratch_bytes(n), st), verr(16, st);
+    CK(cudaMemsetAsync(verr.p, 0, 16, st));
     s.keep.emplace_back((size_t)(n + 1) * 8, st);
     int64_t *offs = s.keep.back().as<int64_t>();
-    k_view_len<<<blocks_for(n, 256), 256, 0, st>>>(views, n, s.col.validity, s.col.validity_bit_offset, lens.as<int64_t>());
+    k_view_len<<<blocks_for(n, 256), 256, 0, st>>>(views, n, s.col.validity, s.col.validity_bit_offset, c->n_buffers, d_buf_len,
+                                                   lens.as<int64_t>(), verr.as<int>());
     exclusive_scan<int64_t>(lens.as<int64_t>(), n, offs, scratch.as<int64_t>(), st, &ctx->launches);
     int64_t total = 0;
+    int h_verr = 0;
     CK(cudaMemcpyAsync(&total, offs + n, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));   // also keeps h_bufs alive long enough
+    CK(cudaMemcpyAsync(&h_verr, verr.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // also keeps h_tab alive long enough
+    if (h_verr) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: a string view names a missing data buffer or bytes beyond its end;"};
     s.keep.emplace_back((size_t)total, st);
     uint8_t *data = s.keep.back().as<uint8_t>();
-    k_view_gather<<<blocks_for(n * 32, 256), 256, 0, st>>>(views, n, d_bufs, offs, data);
+    k_view_gather<<<blocks_for(n * 32, 256), 256, 0, st>>>(views, n, d_bufs, d_buf_len, offs, data);
     ctx->launches += 2;
     s.col.off64 = 1;
     s.col.offsets = offs;
@@ -569,7 +610,7 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     if (!(flags & ROGTK_FORCE_SPILL) && n_groups > 0) {
         run_smem_path(ctx->stream, ctx->peek_slot, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_begin, in.data_end, in.group_offsets,
                       n_groups, K, min_coverage, d_nobs, nsurv.as<int64_t>(), sm, &ctx->launches, ctx->ev[4], ctx->ev[5],
-                      ctx->phase_enabled ? ctx->phase_cycles : nullptr, !(flags & ROGTK_NO_MULTIPASS));
+                      ctx->phase_enabled ? ctx->phase_cycles : nullptr, !(flags & ROGTK_NO_MULTIPASS), ctx->tune);
         d_spill_ids = sm.deferred_ids;
         n_spill = sm.n_deferred;
     }
@@ -678,11 +719,19 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         return o64 ? ((const int64_t *)c->offsets_or_views)[row] : (int64_t)((const int32_t *)c->offsets_or_views)[row];
     };
     // chunk boundaries (whole groups)
+    // The host itself indexes with the string offsets at the group boundaries (chunk cuts, copy ranges): those are checked
+    // here; everything between two boundaries is checked on the device (k_validate) against the copied slice.
     std::vector<int64_t> cut{0};
     {
         int64_t start_byte = off_at(group_offsets[0]);
+        int64_t prev_end = start_byte;
+        if (start_byte < 0 || start_byte > c->data_len[0])
+            throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: string offsets exceed the data buffer;"};
         for (int64_t g = 0; g < n_groups; g++) {
             const int64_t end_byte = off_at(group_offsets[g + 1]);
+            if (end_byte < prev_end) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: string offsets not monotone;"};
+            if (end_byte > c->data_len[0]) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: string offsets exceed the data buffer;"};
+            prev_end = end_byte;
             if (end_byte - start_byte >= (int64_t)ctx->chunk_bytes && g + 1 < n_groups) {
                 cut.push_back(g + 1);
                 start_byte = end_byte;
@@ -765,6 +814,19 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     };
 
     HostArr h_off, h_lo, h_hi, h_exts, h_counts, h_stats, h_rowptr, h_cols;
+    struct HostGuard {   // an error on the way out hands the page-locked blocks back to the context's cache
+        rogtk_gpu_ctx *ctx;
+        HostArr *arr[8];
+        cudaStream_t drain;
+        bool armed = true;
+        ~HostGuard()
+        {
+            if (!armed) return;
+            cudaStreamSynchronize(drain);   // no copy may still be writing into a block that goes back to the cache
+            for (HostArr *h : arr)
+                if (h->p) pinned_put(ctx, h->p);
+        }
+    } host_guard{ctx, {&h_off, &h_lo, &h_hi, &h_exts, &h_counts, &h_stats, &h_rowptr, &h_cols}, s_out};
     host_reserve(ctx, h_off, (size_t)(n_groups + 1) * 8, 0, s_out);
     if (flags & ROGTK_EMIT_STATS) host_reserve(ctx, h_stats, (size_t)n_groups * 12 + 16, 0, s_out);
     int64_t base_k = 0, base_e = 0, n_obs = 0, n_spill = 0, n_multi = 0;
@@ -878,6 +940,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     out->ms_total = ms_total;
     out->ms_count = ms_count;
     out->ms_hot_kernel = ms_hot;
+    host_guard.armed = false;   // the blocks now belong to the batch
     CK(cudaGetLastError());
 }
 
@@ -997,19 +1060,8 @@ extern "C" int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strco
     int rc = ROGTK_ERR_INTERNAL;
     try {
         rc = count_prune_impl(ctx, reads, group_offsets, n_groups, k, min_coverage, flags, out);
-    } catch (const ArgFail &a) {
-        set_error(ctx, "%s", a.msg.c_str());
-        rc = a.code;
-    } catch (const CudaFail &f) {
-        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
-        rc = (f.e == cudaErrorMemoryAllocation) ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
-        cudaGetLastError();
-    } catch (const std::bad_alloc &) {
-        set_error(ctx, "host out of memory");
-        rc = ROGTK_ERR_OOM;
     } catch (...) {
-        set_error(ctx, "unexpected internal error");
-        rc = ROGTK_ERR_INTERNAL;
+        rc = fail_code(ctx);
     }
     if (rc != ROGTK_OK && out && out->_owner) {
         BatchOwner *own = reinterpret_cast<BatchOwner *>(out->_owner);
@@ -1115,13 +1167,8 @@ extern "C" int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
         out->ms_total = ms;
         CK(cudaGetLastError());
-    } catch (const CudaFail &f) {
-        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
-        rc = (f.e == cudaErrorMemoryAllocation) ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
-        cudaGetLastError();
     } catch (...) {
-        set_error(ctx, "unexpected internal error");
-        rc = ROGTK_ERR_INTERNAL;
+        rc = fail_code(ctx);
     }
     if (rc != ROGTK_OK) {
         for (void *p : own->ptrs) {
@@ -1157,10 +1204,8 @@ extern "C" int rogtk_gpu_spectrum_split(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
         ctx->launches++;
         CK(cudaMemcpyAsync(h_bounds, b.p, (size_t)(n_ranks + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-    } catch (const CudaFail &f) {
-        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
-        cudaGetLastError();
-        return ROGTK_ERR_CUDA;
+    } catch (...) {
+        return fail_code(ctx);
     }
     return ROGTK_OK;
 }
@@ -1239,13 +1284,8 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
         out->ms_total = ms;
         CK(cudaGetLastError());
-    } catch (const CudaFail &f) {
-        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
-        rc = (f.e == cudaErrorMemoryAllocation) ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
-        cudaGetLastError();
     } catch (...) {
-        set_error(ctx, "unexpected internal error");
-        rc = ROGTK_ERR_INTERNAL;
+        rc = fail_code(ctx);
     }
     if (rc != ROGTK_OK) {
         for (void *p : own->ptrs) {
@@ -1460,16 +1500,8 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
         out->ms_total = ms;
         CK(cudaGetLastError());
-    } catch (const CudaFail &f) {
-        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
-        rc = (f.e == cudaErrorMemoryAllocation) ? ROGTK_ERR_OOM : ROGTK_ERR_CUDA;
-        cudaGetLastError();
-    } catch (const ArgFail &f) {
-        set_error(ctx, "%s", f.msg.c_str());
-        rc = f.code > 0 ? f.code : ROGTK_ERR_INTERNAL;
     } catch (...) {
-        set_error(ctx, "unexpected internal error");
-        rc = ROGTK_ERR_INTERNAL;
+        rc = fail_code(ctx);
     }
     if (rc != ROGTK_OK) {
         for (void *p : own->ptrs) {
@@ -1514,9 +1546,8 @@ extern "C" int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t 
         ctx->launches++;
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
-    } catch (const CudaFail &f) {
-        set_error(ctx, "CUDA error in %s: %s", f.what, cudaGetErrorString(f.e));
-        return ROGTK_ERR_CUDA;
+    } catch (...) {
+        return fail_code(ctx);
     }
     return ROGTK_OK;
 }
@@ -1581,12 +1612,12 @@ extern "C" int rogtk_gpu_memcpy_d2h(rogtk_gpu_ctx *ctx, void *dst, const void *s
 }
 extern "C" int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint64_t *out8)
+extern "C" int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint64_t *out16)
 {
     if (!ctx) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->phase_enabled = enable != 0;
-    if (out8) memcpy(out8, ctx->phase_cycles, sizeof(ctx->phase_cycles));
+    if (out16) memcpy(out16, ctx->phase_cycles, sizeof(ctx->phase_cycles));
     return ROGTK_OK;
 }
 

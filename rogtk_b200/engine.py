@@ -185,7 +185,7 @@ class Engine:
 
     def phase_cycles(self, enable: bool = True) -> np.ndarray:
         """diagnostics: per-phase SM cycles of the last batch inside k_smem_count (summed over CTAs)"""
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(16, dtype=np.uint64)
         self._check(self._lib.rogtk_gpu_debug_phase_cycles(self._ctx, int(enable), out.ctypes.data))
         return out
 
@@ -498,6 +498,7 @@ class Engine:
                 bufs = child.buffers()
                 validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None
             views = np.frombuffer(bufs[1], dtype=np.uint8)[:len(child) * 16].reshape(-1, 16)
-            data_bufs = [np.frombuffer(b, dtype=np.uint8) for b in bufs[2:] if b is not None]
+            # (a null variadic buffer keeps its place: the views name buffers by index)
+            data_bufs = [np.frombuffer(b, dtype=np.uint8) if b is not None else np.zeros(0, np.uint8) for b in bufs[2:]]
             return self.count_prune_views(views, data_bufs, goff, k, min_coverage, validity=validity, flags=flags)
         raise TypeError(f"unsupported child type {ct}")

@@ -435,6 +435,66 @@ def test_malformed_input_is_rejected_not_faulted(engine):
     assert got.n_observations == 26
 
 
+def test_malformed_input_on_the_chunked_path(oracle, monkeypatch):
+    """The overlapped host path cuts the batch with the caller's offsets before any kernel sees them: bad offsets at a group
+    boundary are rejected on the host, bad offsets inside a chunk on the device, and the context stays usable (its page-locked
+    blocks go back to the cache)."""
+    import rogtk_b200
+    from rogtk_b200 import synth
+    monkeypatch.setenv("ROGTK_CHUNK_BYTES", "8192")
+    data, offs, goff = synth.synth_reads(synth.config_seed(2), 3, 40, 20, 150, 500)
+    with rogtk_b200.Engine(device=0) as eng:
+        ref = oracle.count_prune_batch(data, offs, goff, 31, 2)
+        assert_batches_equal(eng.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS), ref, ctx="chunked, clean")
+        bad = []
+        o = offs.copy(); o[goff[20]] = o[goff[20]] - 7000; bad.append(o)          # decreases at a group boundary
+        o = offs.copy(); o[goff[30]:] += 1 << 40; bad.append(o)                    # beyond the data buffer from a boundary on
+        o = offs.copy(); o[goff[10] + 3] = o[goff[10] + 2] - 1; bad.append(o)      # decreases inside a chunk
+        o = offs.copy(); o[-1] = len(data) + 5; bad.append(o)                      # last offset beyond the buffer
+        for o in bad:
+            with pytest.raises(rogtk_b200.RogtkGpuError) as ei:
+                eng.count_prune(data, o, goff, 31, 2)
+            assert ei.value.code == -1
+        assert_batches_equal(eng.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS), ref, ctx="chunked, after errors")
+
+
+def test_malformed_views_are_rejected(engine, oracle):
+    """Utf8View rows that name a data buffer the column does not have, or bytes beyond a buffer's end, come back as
+    ROGTK_ERR_INVALID_ARG (no device fault); a null variadic buffer keeps its index."""
+    import rogtk_b200
+    reads = [b"ACGTACGTACGTACGTACGTAC", b"ACGT", b"TTGACCAGTACCAGTTTGACCA", b"GGGGGGGGGGGGGTTTTTTTTTTTAAAC"]
+    buf0 = np.frombuffer(reads[0] + reads[2], dtype=np.uint8)
+    buf2 = np.frombuffer(reads[3], dtype=np.uint8)
+
+    def view(r, b=0, off=0):
+        v = np.zeros(16, np.uint8)
+        v[:4] = np.frombuffer(np.uint32(len(r)).tobytes(), np.uint8)
+        if len(r) <= 12:
+            v[4:4 + len(r)] = np.frombuffer(r, np.uint8)
+        else:
+            v[4:8] = np.frombuffer(r[:4], np.uint8)
+            v[8:12] = np.frombuffer(np.uint32(b).tobytes(), np.uint8)
+            v[12:16] = np.frombuffer(np.uint32(off).tobytes(), np.uint8)
+        return v
+
+    good = np.stack([view(reads[0], 0, 0), view(reads[1]), view(reads[2], 0, len(reads[0])), view(reads[3], 2, 0)])
+    goff = np.array([0, 2, 4])
+    data = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    ref = oracle.count_prune_batch(data, offs, goff, 8, 1)
+    # buffer 1 is an empty (null) variadic buffer that keeps its place
+    got = engine.count_prune_views(good, [buf0, np.zeros(0, np.uint8), buf2], goff, 8, 1, flags=EMIT_STATS)
+    assert_batches_equal(got, ref, ctx="views with an empty buffer in the middle")
+    for bad_view in (view(reads[3], 3, 0), view(reads[3], 2, 5), view(reads[3], 1, 0), view(reads[0], 0, 1 << 31)):
+        bad = good.copy()
+        bad[3] = bad_view
+        with pytest.raises(rogtk_b200.RogtkGpuError) as ei:
+            engine.count_prune_views(bad, [buf0, np.zeros(0, np.uint8), buf2], goff, 8, 1)
+        assert ei.value.code == -1
+    got = engine.count_prune_views(good, [buf0, np.zeros(0, np.uint8), buf2], goff, 8, 1, flags=EMIT_STATS)
+    assert_batches_equal(got, ref, ctx="views after errors")
+
+
 def test_arrow_list_of_strings_entry(engine, oracle):
     """a List(String) column (one row per UMI) goes through in one call; list offsets are the group offsets.
     Covers String, LargeString and StringView children, null strings, null lists and a sliced array."""
@@ -666,19 +726,42 @@ def test_small_workspace_many_spill_waves(oracle):
 
 
 def test_survivor_pool_exhaustion_falls_back(engine, oracle, monkeypatch):
-    """ROGTK_DEBUG_POOL_CAP shrinks the survivor pool of the shared-memory paths: groups that find no room are handed to the
-    HBM-table path (which sizes its own storage); the batch is unchanged."""
+    """ROGTK_DEBUG_POOL_CAP (read when a context is created) shrinks the survivor pool of the shared-memory paths: groups that
+    find no room are handed to the HBM-table path (which sizes its own storage); the batch is unchanged."""
+    import rogtk_b200
     from rogtk_b200 import synth
     data, offs, goff = synth.synth_reads(synth.config_seed(2), 500, 400, 50, 300, 1000)
     ref = oracle.count_prune_batch(data, offs, goff, 31, 2)
     for cap in (1024, 20000, 150000):
         monkeypatch.setenv("ROGTK_DEBUG_POOL_CAP", str(cap))
-        got = engine.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)
-        assert_batches_equal(got, ref, ctx=f"pool cap {cap}")
-        assert got.n_spilled_groups > 0
+        with rogtk_b200.Engine(device=0) as eng:
+            got = eng.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)
+            assert_batches_equal(got, ref, ctx=f"pool cap {cap}")
+            assert got.n_spilled_groups > 0
     monkeypatch.delenv("ROGTK_DEBUG_POOL_CAP")
     got = engine.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)
     assert got.n_spilled_groups == 0
+
+
+@pytest.mark.parametrize("rl", [3, 5])
+def test_link_walk_kernel_matches_oracle(oracle, monkeypatch, rl):
+    """The experimental first-tier kernel k_walk_count (ROGTK_WALK_RL, read when a context is created): 8-byte
+    reference slots + successor links.  Same batches as the default kernel: golden shape, skewed groups, K = 4 .. 64, nulls."""
+    import rogtk_b200
+    from rogtk_b200 import synth
+    monkeypatch.setenv("ROGTK_WALK_RL", str(rl))
+    with rogtk_b200.Engine(device=0) as eng:
+        data, offs, goff = synth.synth_reads(synth.config_seed(2), 77, 300, 50, 300, 1000)
+        for k, mc in ((31, 2), (47, 2), (13, 1), (4, 1), (63, 3), (8, 0)):
+            got = eng.count_prune(data, offs, goff, k, mc, flags=EMIT_STATS | EMIT_CSR)
+            ref = oracle.count_prune_batch(data, offs, goff, k, mc, emit_csr=True)
+            assert_batches_equal(got, ref, check_csr=True, ctx=f"walk rl={rl} k={k} min_cov={mc}")
+        rp = np.array([1, 2, 700, 45, 12, 260, 90, 3, 64, 5, 110])
+        data, offs, goff = synth.synth_reads(synth.config_seed(3), 5, len(rp), rp, 150, 500)
+        for k in (17, 33):
+            got = eng.count_prune(data, offs, goff, k, 2, flags=EMIT_STATS)
+            ref = oracle.count_prune_batch(data, offs, goff, k, 2)
+            assert_batches_equal(got, ref, ctx=f"walk rl={rl} skewed k={k}")
 
 
 def test_two_word_kmers_at_scale(engine, oracle):
