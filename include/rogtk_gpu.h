@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ROGTK_GPU_ABI_VERSION 1
+#define ROGTK_GPU_ABI_VERSION 2
 
 /* error codes (0 = success; never throws, never aborts) */
 #define ROGTK_OK 0
@@ -161,6 +161,112 @@ typedef struct rogtk_contig_batch {
 int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_length, uint32_t flags,
                                rogtk_contig_batch *out);
 void rogtk_gpu_free_contigs(rogtk_gpu_ctx *ctx, rogtk_contig_batch *batch);
+
+/* ---- whole-expression entries -------------------------------------------------------
+ * One call per frame for what the reference does with one plugin call per group.  They compose the device primitives above
+ * (count once per K_eff, rogtk_gpu_rethreshold per min_coverage, unitigs on the device) with the host restatement of the
+ * path-finding methods (rogtk_b200/csrc/pathfind_host.h follows src/djfind.rs line by line; its f64 weights use the host's libm
+ * log, as Rust's f64::ln does).  Results come back as Arrow LargeUtf8 buffers (int64 offsets + bytes), one row per group. */
+#define ROGTK_METHOD_COMPRESSION 0          /* AssemblyMethod::Compression        (src/djfind.rs:19-28) */
+#define ROGTK_METHOD_SHORTEST_PATH 1        /* AssemblyMethod::ShortestPath{..}: both anchors required */
+#define ROGTK_METHOD_SHORTEST_PATH_AUTO 2   /* AssemblyMethod::ShortestPathAuto */
+
+/* AssemblyKwargs (src/expressions.rs:669-687) without the fields the reference ignores (export_graphs, prefix and the three
+ * optimisation leftovers).  Anchors are NUL-terminated; with per-group anchors (assemble_sequences_with_anchors_expr,
+ * src/expressions.rs:770-849: first row of inputs[1] / inputs[2]) pass anchor_offsets/_data arrays instead (LargeUtf8 layout, one
+ * row per group) and leave the scalars NULL. */
+typedef struct rogtk_assembly_params {
+    int64_t k;
+    uint32_t min_coverage;
+    int32_t method;                     /* ROGTK_METHOD_* */
+    const char *start_anchor;           /* NULL = None */
+    const char *end_anchor;
+    int64_t min_length;                 /* 0 = None */
+    int32_t only_largest;               /* both expressions hard-wire Some(true) (src/expressions.rs:748); fracture_sequences passes its own */
+    int32_t auto_k;                     /* k = estimate_k(group) per group (src/fracture.rs:203-209); host-resident input only */
+    const int64_t *start_anchor_offsets;/* [n_groups+1] or NULL */
+    const uint8_t *start_anchor_data;
+    const int64_t *end_anchor_offsets;
+    const uint8_t *end_anchor_data;
+    const int32_t *node_rank;           /* optional, shortest-path methods: node_rank[i] = the reference's graph node id (boomphf
+                                           slot order) of survivor i inside its group; NULL = ascending k-mer order.  Needs the
+                                           survivor layout of a previous call with the same arguments; ties only. */
+    int32_t host_threads;               /* worker threads of the host path search; 0 = all cores */
+    int32_t _pad;
+} rogtk_assembly_params;
+
+/* one string per row (Arrow LargeUtf8); flags per row: bit 0 = several longest contigs of equal length, bit 1 = the contig is a
+ * pure cycle (both: the reference's choice depends on boomphf order, see rogtk_contig_batch), bit 2 = the group used a k of its
+ * own (auto_k) */
+typedef struct rogtk_string_batch {
+    int64_t n_rows;
+    int64_t n_bytes;
+    int64_t *offsets;        /* [n_rows+1] */
+    uint8_t *data;           /* [n_bytes] */
+    uint8_t *flags;          /* [n_rows] */
+    float ms_device;         /* device time (CUDA events) */
+    float ms_host;           /* host time of the path search / drivers */
+    int64_t n_count_passes;  /* counting passes over the reads this call made (the reference makes one per probe) */
+    void *_owner;            /* internal */
+} rogtk_string_batch;
+void rogtk_gpu_free_strings(rogtk_gpu_ctx *ctx, rogtk_string_batch *b);
+
+/* assemble_sequences_expr / assemble_sequences_with_anchors_expr / fracture_sequences for n_groups groups at once: per group the
+ * contigs joined with '\n' ("" when there is none: k > 64, no valid reads, anchors or path missing, nothing >= min_length).
+ * Errors the reference raises for bad method / anchor combinations (src/expressions.rs:700-731) come back as
+ * ROGTK_ERR_INVALID_ARG with the reference's message in rogtk_gpu_last_error.  Compression copies only the contigs back
+ * (about 1.2 KB per UMI of the headline shape instead of the 10.5 KB of node arrays). */
+int rogtk_gpu_assemble_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets, int64_t n_groups,
+                             const rogtk_assembly_params *params, uint32_t flags, rogtk_string_batch *out);
+
+/* sweep_assembly_params_expr (src/expressions.rs:880-955): Struct{k, min_coverage, contig_length} rows, cells in the reference's
+ * order (k outer, min_coverage inner), group-major: row g * n_cells + c.  The reads are counted once per distinct K_eff of the k
+ * range; every min_coverage comes from rogtk_gpu_rethreshold. */
+typedef struct rogtk_sweep_params {
+    int64_t k_start, k_end, k_step, cov_start, cov_end, cov_step;
+    int32_t method;
+    int32_t host_threads;
+    const char *start_anchor, *end_anchor;
+} rogtk_sweep_params;
+typedef struct rogtk_sweep_result {
+    int64_t n_groups, n_cells;
+    int64_t *k, *min_coverage, *contig_length;   /* [n_groups * n_cells] */
+    float ms_device, ms_host;
+    int64_t n_count_passes;
+    void *_owner;
+} rogtk_sweep_result;
+int rogtk_gpu_sweep_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets, int64_t n_groups,
+                          const rogtk_sweep_params *params, uint32_t flags, rogtk_sweep_result *out);
+void rogtk_gpu_free_sweep(rogtk_gpu_ctx *ctx, rogtk_sweep_result *r);
+
+/* optimize_assembly_expr (src/fracture_opt.rs:120-367): the (k, min_coverage) hill-climb per group, Struct{contig, k, min_coverage,
+ * length, input_sequences}; a group without a result gets the reference's zero-filled row (src/fracture_opt.rs:342-354).  All groups
+ * advance one iteration at a time; every (K_eff, min_coverage) cell any group asks for is evaluated once for the whole batch. */
+typedef struct rogtk_optimize_params {
+    int64_t start_k, start_min_coverage;
+    int64_t max_iterations;             /* <= 0 = the reference's default 50 */
+    int32_t explore_k, prioritize_length;
+    int32_t method;
+    int32_t host_threads;
+    const char *start_anchor, *end_anchor;   /* both required (src/fracture_opt.rs:298-302) */
+} rogtk_optimize_params;
+typedef struct rogtk_optimize_result {
+    rogtk_string_batch contig;          /* one row per group */
+    uint32_t *k, *min_coverage, *length, *input_sequences;   /* [n_groups] */
+    int64_t n_cells_evaluated;          /* distinct (K_eff, min_coverage) cells computed */
+    int64_t n_probes;                   /* assemble_and_check calls the reference would have made (each a full recount there) */
+    void *_owner;
+} rogtk_optimize_result;
+int rogtk_gpu_optimize_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets, int64_t n_groups,
+                             const rogtk_optimize_params *params, uint32_t flags, rogtk_optimize_result *out);
+void rogtk_gpu_free_optimize(rogtk_gpu_ctx *ctx, rogtk_optimize_result *r);
+
+/* host-only: the shortest-path methods on node arrays the caller already holds (one group; CSR as rogtk_graph_batch emits it with
+ * csr_row_ptr rebased to the group).  Returns the number of bytes written to `out` (at most cap; the contig is n_nodes + K - 1
+ * bases), 0 when there is no contig, -needed when cap is too small.  start/end NULL = shortest_path_auto. */
+int64_t rogtk_host_shortest_path(int k_eff, int32_t n_nodes, const uint64_t *kmers_lo, const uint64_t *kmers_hi, const uint16_t *counts,
+                                 const int64_t *csr_row_ptr, const int32_t *csr_col, const int32_t *node_rank, const char *start_anchor,
+                                 const char *end_anchor, uint8_t *out, int64_t cap);
 
 /* ---- global k-mer spectrum: one group spanning the reads of every rank (BASELINE configs[4]) -----------------------
  * The reference has no multi-process analogue: it is the un-grouped call of the same expression (one filter_kmers over all

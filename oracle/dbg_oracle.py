@@ -402,3 +402,324 @@ def shortest_path_contig(nodes, K: int, start_anchor: str, end_anchor: str):
                 path.reverse()
                 return path[0] + "".join(p[K - 1:] for p in path[1:])
     return None
+
+
+# ----------------------------------------------------------------------------------------------------
+# Whole-expression restatements (TEST INFRASTRUCTURE): the reference's drivers, literally -- one full recount per probe,
+# exactly as src/fracture.rs:188-280, src/djfind.rs, src/expressions.rs:880-955 and src/fracture_opt.rs:120-282 do it.
+# The product (rogtk_b200/csrc/assemble_host.cuh, pathfind_host.h) counts once per K_eff and re-thresholds; these do not.
+# ----------------------------------------------------------------------------------------------------
+class _RustMinHeap:
+    """std::collections::BinaryHeap<MinScored<f64, NodeIndex>> (Rust std + petgraph 0.7.1 scored.rs, restated from the published
+    algorithms): push = sift_up; pop = swap the last element into the root, sift_down_to_bottom, sift_up.  Items
+    are (score, node); MinScored compares the score only, reversed (smallest score = greatest element)."""
+
+    def __init__(self):
+        self.d = []
+
+    @staticmethod
+    def _le(a, b):   # a <= b under MinScored's order  <=>  not (a.score < b.score)
+        return not (a[0] < b[0])
+
+    def _sift_up(self, start, pos):
+        el = self.d[pos]
+        while pos > start:
+            parent = (pos - 1) // 2
+            if self._le(el, self.d[parent]):
+                break
+            self.d[pos] = self.d[parent]
+            pos = parent
+        self.d[pos] = el
+
+    def push(self, item):
+        self.d.append(item)
+        self._sift_up(0, len(self.d) - 1)
+
+    def pop(self):
+        if not self.d:
+            return None
+        item = self.d.pop()
+        if self.d:
+            item, self.d[0] = self.d[0], item
+            end = len(self.d)
+            pos, el = 0, self.d[0]
+            child = 1
+            while child <= max(end - 2, 0) and end >= 2:
+                if self._le(self.d[child], self.d[child + 1]):
+                    child += 1
+                self.d[pos] = self.d[child]
+                pos = child
+                child = 2 * pos + 1
+            if child == end - 1:
+                self.d[pos] = self.d[child]
+                pos = child
+            self.d[pos] = el
+            self._sift_up(0, pos)
+        return item
+
+
+class _PetGraph:
+    """petgraph::Graph as src/djfind.rs:78-121 fills it: nodes in graph-node order (`order` = list of k-mer strings in the
+    reference's node-id order; ascending when the caller has nothing better), edges per node over the right neighbours in base
+    order, weight -ln(mean coverage).  Adjacency lists are newest-first, like petgraph's."""
+
+    def __init__(self, nodes, order=None):
+        self.seq = list(order) if order is not None else [km for km, _, _ in nodes]
+        cov = {km: c for km, _, c in nodes}
+        ext = {km: e for km, e, _ in nodes}
+        idx = {km: i for i, km in enumerate(self.seq)}
+        n = len(self.seq)
+        self.out = [[] for _ in range(n)]   # (to, weight), newest first
+        self.inc = [[] for _ in range(n)]   # (from, weight), newest first
+        for i, km in enumerate(self.seq):
+            for b in range(4):
+                if ext[km] & (16 << b):
+                    nxt = km[1:] + "ACGT"[b]
+                    if nxt in idx:   # (a neighbour bit whose k-mer was pruned resolves to nothing)
+                        w = -math.log((float(cov[km]) + float(cov[nxt])) / 2.0)
+                        self.out[i].insert(0, (idx[nxt], w))
+                        self.inc[idx[nxt]].insert(0, (i, w))
+
+    def dijkstra(self, start):
+        scores, visited = {start: 0.0}, set()
+        heap = _RustMinHeap()
+        heap.push((0.0, start))
+        while True:
+            it = heap.pop()
+            if it is None:
+                break
+            score, node = it
+            if node in visited:
+                continue
+            for nxt, w in self.out[node]:
+                if nxt in visited:
+                    continue
+                ns = score + w
+                if nxt in scores:
+                    if ns < scores[nxt]:
+                        scores[nxt] = ns
+                        heap.push((ns, nxt))
+                else:
+                    scores[nxt] = ns
+                    heap.push((ns, nxt))
+            visited.add(node)
+        return scores
+
+    def find_shortest_path(self, starts, ends):
+        """src/djfind.rs:157-247"""
+        best, min_w = None, math.inf
+        for s in starts:
+            dist = self.dijkstra(s)
+            for e in ends:
+                if e not in dist:
+                    continue
+                tw = dist[e]
+                if not tw < min_w:
+                    continue
+                path, cur, valid, it = [e], e, False, 0
+                while cur != s:
+                    it += 1
+                    if it > 1000:
+                        break
+                    best_prev, best_dist, cd = None, math.inf, dist[cur]
+                    for nb, _w in self.inc[cur]:
+                        if nb not in dist:
+                            continue
+                        ew = next(w for t, w in self.out[nb] if t == cur)   # graph.find_edge(neighbor, current)
+                        if abs(dist[nb] + ew - cd) < 1e-9 and dist[nb] < best_dist:
+                            best_dist, best_prev = dist[nb], nb
+                    if best_prev is None:
+                        break
+                    path.append(best_prev)
+                    cur = best_prev
+                    if cur == s:
+                        valid = True
+                if valid:
+                    best, min_w = (path[::-1], tw), tw
+        return best
+
+    def concat(self, path, K):
+        return self.seq[path[0]] + "".join(self.seq[p][K - 1:] for p in path[1:])
+
+
+def path_finding_contig(nodes, K, start_anchor, end_anchor, order=None):
+    """AssemblyMethod::ShortestPath (src/djfind.rs:257-304): contig or None."""
+    if not nodes:
+        return None
+    pg = _PetGraph(nodes, order)
+    starts = [i for i, s in enumerate(pg.seq) if s.startswith(start_anchor)]
+    ends = [i for i, s in enumerate(pg.seq) if s.endswith(end_anchor)]
+    if not starts or not ends:
+        return None
+    r = pg.find_shortest_path(starts, ends)
+    return pg.concat(r[0], K) if r else None
+
+
+def auto_path_finding_contig(nodes, K, order=None):
+    """AssemblyMethod::ShortestPathAuto (src/djfind.rs:309-492): contig or None."""
+    if not nodes:
+        return None
+    pg = _PetGraph(nodes, order)
+    cov = {km: c for km, _, c in nodes}
+    avg = sum(float(cov[s]) for s in pg.seq) / len(pg.seq)
+    thr = min(65535, int(max(avg * 0.1, 1.0)))
+    sc, ec = [], []
+    for i, s in enumerate(pg.seq):
+        if cov[s] < thr:
+            continue
+        ind, outd = len(pg.inc[i]), len(pg.out[i])
+        if ind == 0 and outd > 0:
+            sc.append(i)
+        if outd == 0 and ind > 0:
+            ec.append(i)
+    if not sc or not ec:
+        return None
+    if len(sc) == 1 and len(ec) == 1:
+        return path_finding_contig(nodes, K, pg.seq[sc[0]], pg.seq[ec[0]], order)
+    best, evaluated = None, 0
+    for s in sc:
+        for e in ec:
+            if evaluated >= 100:
+                break
+            evaluated += 1
+            r = pg.find_shortest_path([s], [e])
+            if not r:
+                continue
+            path, tw = r
+            plen = float(sum(len(pg.seq[p]) for p in path))
+            with np.errstate(divide="ignore", invalid="ignore"):   # IEEE semantics like Rust's f64: 1.0 / 0.0 = inf
+                mean_cov = float(np.float64(1.0) / (np.float64(tw) / np.float64(len(path))))
+            score = 0.6 * min(plen / 5000.0, 1.0) + 0.4 * min(mean_cov / 100.0, 1.0)
+            if best is None or score > best[1]:
+                best = (pg.concat(path, K), score)
+    return best[0] if best else None
+
+
+def estimate_k_py(reads) -> int:
+    """src/fracture.rs:24-54 (reads: the group's non-null strings)"""
+    lens = [len(r) for r in reads if len(r) > 0]
+    if not lens:
+        return 31
+    k = int(math.floor(sum(lens) / len(lens) / 3.0 + 0.5))   # f64::round: half away from zero (positive here)
+    if k % 2 == 0:
+        k -= 1
+    if k < 0:
+        return 63   # usize wrap
+    return min(max(k, 11), 63)
+
+
+def assemble_sequences_py(reads, k, min_coverage, method="compression", start_anchor=None, end_anchor=None, min_length=None,
+                          only_largest=False, auto_k=False):
+    """src/fracture.rs:188-280 for one group (reads: list[str|bytes|None]; None rows are dropped first like the plugin's
+    .flatten()).  Returns (contigs, info): contigs is the reference's Vec<String> with the Compression contigs listed by ascending
+    first k-mer (the reference lists them in boomphf order); info = {"tie": several longest, "cyclic": chosen contig is a cycle}."""
+    seqs = [r.decode() if isinstance(r, bytes) else r for r in reads if r is not None]
+    if auto_k:
+        k = estimate_k_py(seqs)
+    info = {"tie": False, "cyclic": False, "k": k}
+    if k > 64:
+        return [], info
+    K = k_eff_py(k)
+    nodes = count_prune_group_py(seqs, k, min_coverage)
+    if not [s for s in seqs if all(ch in "ACGT" for ch in s.upper())]:
+        return [], info
+    if method == "compression":
+        full = compress_unitigs_full(nodes, K)
+        firsts = {}
+        for c in full:
+            firsts[c] = c[:K]
+        contigs = sorted(full, key=lambda c: firsts[c])
+    elif method == "shortest_path":
+        c = path_finding_contig(nodes, K, start_anchor, end_anchor)
+        contigs, full = ([c] if c is not None else []), {}
+    elif method == "shortest_path_auto":
+        c = auto_path_finding_contig(nodes, K)
+        contigs, full = ([c] if c is not None else []), {}
+    else:
+        raise ValueError("Invalid assembly method")
+    ml = min_length or 0
+    contigs = [c for c in contigs if len(c) >= ml]
+    if not contigs:
+        return [], info
+    if only_largest:
+        mx = max(len(c) for c in contigs)
+        cands = [c for c in contigs if len(c) == mx]
+        info["tie"] = len(cands) > 1
+        best = cands[0]
+        info["cyclic"] = bool(full.get(best, (0, 0, False))[2])
+        return [best], info
+    return contigs, info
+
+
+def sweep_py(reads, k_start, k_end, k_step, cov_start, cov_end, cov_step, method="compression", start_anchor=None, end_anchor=None):
+    """src/expressions.rs:880-955: rows (k, min_coverage, contig_length), one full recount per cell."""
+    rows = []
+    for k in range(k_start, k_end + 1, k_step):
+        for cov in range(cov_start, cov_end + 1, cov_step):
+            contigs, _ = assemble_sequences_py(reads, k, cov, method, start_anchor, end_anchor, None, True, False)
+            rows.append((k, cov, len(contigs[0]) if contigs else 0))
+    return rows
+
+
+def optimize_py(reads, start_k, start_min_coverage, start_anchor, end_anchor, method="shortest_path", max_iterations=50, explore_k=False,
+                prioritize_length=False):
+    """src/fracture_opt.rs:120-356: (contig, k, min_coverage, length, input_sequences) and the number of assemble_and_check calls."""
+    seqs = [r for r in reads if r is not None]
+    n_probes = [0]
+
+    def check(k, cov):
+        n_probes[0] += 1
+        contigs, _ = assemble_sequences_py(seqs, k, cov, method, start_anchor, end_anchor, None, True, False)
+        c = contigs[0] if contigs else ""
+        return {"contig": c, "k": k, "cov": cov, "length": len(c), "has": (start_anchor in c) and (end_anchor in c)}
+
+    tested = {(start_k, start_min_coverage)}
+    best_anch, best_len = None, None
+    cur = check(start_k, start_min_coverage)
+    if cur["has"]:
+        best_anch = cur
+    if best_len is None or cur["length"] > best_len["length"]:
+        best_len = cur
+    paths = [{"k": cur["k"], "cov": cur["cov"], "length": cur["length"], "steps": 0}]
+
+    def apply(d, k, cov):
+        if d == "W":
+            return (k, cov - 1) if cov > 1 else None
+        if d == "E":
+            return (k, cov + 1)
+        if d == "N":
+            return (k - 1, cov) if k > 4 else None
+        return (k + 1, cov) if k < 64 else None
+
+    dirs = ["W", "E", "N", "S"] if explore_k else ["W", "E"]
+    result = "unset"
+    for _ in range(max_iterations):
+        new_paths = []
+        for p in paths:
+            for d in dirs:
+                np_ = apply(d, p["k"], p["cov"])
+                if np_ is None or np_ in tested:
+                    continue
+                tested.add(np_)
+                r = check(*np_)
+                if r["has"] and (best_anch is None or r["length"] > best_anch["length"]):
+                    best_anch = r
+                if best_len is None or r["length"] > best_len["length"]:
+                    best_len = r
+                if r["has"] and not prioritize_length:
+                    result = r
+                    break
+                if r["contig"]:
+                    new_paths.append({"k": np_[0], "cov": np_[1], "length": r["length"],
+                                      "steps": 0 if r["length"] > p["length"] else p["steps"] + 1})
+            if result != "unset":
+                break
+        if result != "unset" or not new_paths:
+            break
+        new_paths.sort(key=lambda q: (-q["length"], q["steps"]))   # stable, like slice::sort_by
+        paths = new_paths[:4]
+    if result == "unset":
+        result = best_len if prioritize_length else best_anch
+    if result is None:
+        return ("", 0, 0, 0, len(seqs)), n_probes[0]
+    return (result["contig"], result["k"], result["cov"], result["length"], len(seqs)), n_probes[0]

@@ -37,7 +37,10 @@ SYMBOLS = [
     "rogtk_gpu_pinned_free", "rogtk_gpu_memcpy_h2d", "rogtk_gpu_memcpy_d2h", "rogtk_gpu_launch_count", "rogtk_gpu_flush_l2", "rogtk_gpu_debug_phase_cycles",
     "rogtk_gpu_spectrum_owner", "rogtk_gpu_spectrum_split", "rogtk_gpu_spectrum_merge", "rogtk_gpu_rethreshold",
     "rogtk_gpu_compress_unitigs", "rogtk_gpu_free_contigs",
+    "rogtk_gpu_assemble_batch", "rogtk_gpu_free_strings", "rogtk_gpu_sweep_batch", "rogtk_gpu_free_sweep",
+    "rogtk_gpu_optimize_batch", "rogtk_gpu_free_optimize", "rogtk_host_shortest_path",
 ]
+METHODS = {"compression": 0, "shortest_path": 1, "shortest_path_auto": 2}
 
 
 class StrCol(ctypes.Structure):
@@ -95,6 +98,80 @@ class ContigBatchC(ctypes.Structure):
         ("largest_flags", ctypes.c_void_p),
         ("ms_total", ctypes.c_float),
         ("_pad0", ctypes.c_float),
+        ("_owner", ctypes.c_void_p),
+    ]
+
+
+class AssemblyParamsC(ctypes.Structure):
+    _fields_ = [
+        ("k", ctypes.c_int64),
+        ("min_coverage", ctypes.c_uint32),
+        ("method", ctypes.c_int32),
+        ("start_anchor", ctypes.c_char_p),
+        ("end_anchor", ctypes.c_char_p),
+        ("min_length", ctypes.c_int64),
+        ("only_largest", ctypes.c_int32),
+        ("auto_k", ctypes.c_int32),
+        ("start_anchor_offsets", ctypes.c_void_p),
+        ("start_anchor_data", ctypes.c_void_p),
+        ("end_anchor_offsets", ctypes.c_void_p),
+        ("end_anchor_data", ctypes.c_void_p),
+        ("node_rank", ctypes.c_void_p),
+        ("host_threads", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
+    ]
+
+
+class StringBatchC(ctypes.Structure):
+    _fields_ = [
+        ("n_rows", ctypes.c_int64),
+        ("n_bytes", ctypes.c_int64),
+        ("offsets", ctypes.c_void_p),
+        ("data", ctypes.c_void_p),
+        ("flags", ctypes.c_void_p),
+        ("ms_device", ctypes.c_float),
+        ("ms_host", ctypes.c_float),
+        ("n_count_passes", ctypes.c_int64),
+        ("_owner", ctypes.c_void_p),
+    ]
+
+
+class SweepParamsC(ctypes.Structure):
+    _fields_ = [
+        ("k_start", ctypes.c_int64), ("k_end", ctypes.c_int64), ("k_step", ctypes.c_int64),
+        ("cov_start", ctypes.c_int64), ("cov_end", ctypes.c_int64), ("cov_step", ctypes.c_int64),
+        ("method", ctypes.c_int32),
+        ("host_threads", ctypes.c_int32),
+        ("start_anchor", ctypes.c_char_p),
+        ("end_anchor", ctypes.c_char_p),
+    ]
+
+
+class SweepResultC(ctypes.Structure):
+    _fields_ = [
+        ("n_groups", ctypes.c_int64), ("n_cells", ctypes.c_int64),
+        ("k", ctypes.c_void_p), ("min_coverage", ctypes.c_void_p), ("contig_length", ctypes.c_void_p),
+        ("ms_device", ctypes.c_float), ("ms_host", ctypes.c_float),
+        ("n_count_passes", ctypes.c_int64),
+        ("_owner", ctypes.c_void_p),
+    ]
+
+
+class OptimizeParamsC(ctypes.Structure):
+    _fields_ = [
+        ("start_k", ctypes.c_int64), ("start_min_coverage", ctypes.c_int64), ("max_iterations", ctypes.c_int64),
+        ("explore_k", ctypes.c_int32), ("prioritize_length", ctypes.c_int32),
+        ("method", ctypes.c_int32), ("host_threads", ctypes.c_int32),
+        ("start_anchor", ctypes.c_char_p), ("end_anchor", ctypes.c_char_p),
+    ]
+
+
+class OptimizeResultC(ctypes.Structure):
+    _fields_ = [
+        ("contig", StringBatchC),
+        ("k", ctypes.c_void_p), ("min_coverage", ctypes.c_void_p), ("length", ctypes.c_void_p), ("input_sequences", ctypes.c_void_p),
+        ("n_cells_evaluated", ctypes.c_int64),
+        ("n_probes", ctypes.c_int64),
         ("_owner", ctypes.c_void_p),
     ]
 
@@ -158,6 +235,19 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_compress_unitigs.argtypes = [vp, ctypes.POINTER(GraphBatchC), i64, u32, ctypes.POINTER(ContigBatchC)]
     lib.rogtk_gpu_compress_unitigs.restype = ctypes.c_int
     lib.rogtk_gpu_free_contigs.argtypes = [vp, ctypes.POINTER(ContigBatchC)]
+    lib.rogtk_gpu_assemble_batch.argtypes = [vp, ctypes.POINTER(StrCol), vp, i64, ctypes.POINTER(AssemblyParamsC), u32,
+                                             ctypes.POINTER(StringBatchC)]
+    lib.rogtk_gpu_assemble_batch.restype = ctypes.c_int
+    lib.rogtk_gpu_free_strings.argtypes = [vp, ctypes.POINTER(StringBatchC)]
+    lib.rogtk_gpu_sweep_batch.argtypes = [vp, ctypes.POINTER(StrCol), vp, i64, ctypes.POINTER(SweepParamsC), u32, ctypes.POINTER(SweepResultC)]
+    lib.rogtk_gpu_sweep_batch.restype = ctypes.c_int
+    lib.rogtk_gpu_free_sweep.argtypes = [vp, ctypes.POINTER(SweepResultC)]
+    lib.rogtk_gpu_optimize_batch.argtypes = [vp, ctypes.POINTER(StrCol), vp, i64, ctypes.POINTER(OptimizeParamsC), u32,
+                                             ctypes.POINTER(OptimizeResultC)]
+    lib.rogtk_gpu_optimize_batch.restype = ctypes.c_int
+    lib.rogtk_gpu_free_optimize.argtypes = [vp, ctypes.POINTER(OptimizeResultC)]
+    lib.rogtk_host_shortest_path.argtypes = [ctypes.c_int, i32, vp, vp, vp, vp, vp, vp, ctypes.c_char_p, ctypes.c_char_p, vp, i64]
+    lib.rogtk_host_shortest_path.restype = i64
     lib.rogtk_gpu_flush_l2.argtypes = [vp]
     lib.rogtk_gpu_flush_l2.restype = ctypes.c_int
     _lib = lib

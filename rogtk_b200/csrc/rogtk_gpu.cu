@@ -1637,3 +1637,5 @@ extern "C" int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx)
     cudaMemsetAsync(ctx->flush_buf, ++tick & 0xff, ctx->flush_bytes, ctx->stream);
     return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? ROGTK_OK : ROGTK_ERR_CUDA;
 }
+
+#include "assemble_host.cuh"

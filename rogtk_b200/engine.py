@@ -147,6 +147,26 @@ def shard_of(umi_id: int, n_shards: int) -> int:
     return int(_ffi.load().rogtk_gpu_shard_of(int(umi_id) & 0xFFFFFFFFFFFFFFFF, int(n_shards)))
 
 
+@dataclass
+class StringBatch:
+    """One string per group (Arrow LargeUtf8 buffers).  flags: bit 0 several longest contigs, bit 1 cyclic contig, bit 2 the group
+    used its own k (auto_k), bit 3 several contigs listed (ascending first k-mer; the reference lists them in boomphf order)."""
+    offsets: np.ndarray
+    data: np.ndarray
+    flags: np.ndarray
+    ms_device: float = 0.0
+    ms_host: float = 0.0
+    n_count_passes: int = 0
+
+    def strings(self) -> list[str]:
+        b = self.data.tobytes()
+        return [b[int(self.offsets[i]):int(self.offsets[i + 1])].decode() for i in range(len(self.offsets) - 1)]
+
+    def to_arrow(self):
+        import pyarrow as pa
+        return pa.LargeStringArray.from_buffers(len(self.offsets) - 1, pa.py_buffer(self.offsets), pa.py_buffer(self.data))
+
+
 class Engine:
     """One context == one GPU + one stream.  Not a fallback-capable object: construction fails without a B200."""
 
@@ -417,6 +437,131 @@ class Engine:
             return self.compress_unitigs(db, min_length, node_parallel=node_parallel)
         finally:
             db.free()
+
+    # ---- whole-expression entries: the reference's Python API (rogtk/__init__.py:104-324), one call per frame -----------------------------
+    def _host_col(self, data, offsets, validity=None, validity_bit_offset=0):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets)
+        if offsets.dtype == np.int32:
+            layout = _ffi.UTF8_I32
+        else:
+            offsets = offsets.astype(np.int64, copy=False)
+            layout = _ffi.UTF8_I64
+        if validity is not None:
+            validity = np.ascontiguousarray(validity, dtype=np.uint8)
+        dptr = (ctypes.c_void_p * 1)(data.ctypes.data if data.size else None)
+        dlen = (ctypes.c_int64 * 1)(data.size)
+        col = _ffi.StrCol(layout=layout, n_buffers=1, n_rows=len(offsets) - 1,
+                          validity=validity.ctypes.data if validity is not None else None,
+                          validity_bit_offset=int(validity_bit_offset), offsets_or_views=offsets.ctypes.data, data=dptr, data_len=dlen)
+        return col, (data, offsets, validity, dptr, dlen)
+
+    @staticmethod
+    def _strings_out(c: "_ffi.StringBatchC") -> "StringBatch":
+        n, nb = int(c.n_rows), int(c.n_bytes)
+
+        def arr(ptr, cnt, dt):
+            if not ptr or cnt == 0:
+                return np.zeros(0, dtype=dt)
+            ct = np.ctypeslib.as_ctypes_type(np.dtype(dt))
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(cnt,)).copy()
+
+        off = arr(c.offsets, n + 1, np.int64) if n else np.zeros(1, np.int64)
+        return StringBatch(offsets=off, data=arr(c.data, nb, np.uint8), flags=arr(c.flags, n, np.uint8), ms_device=float(c.ms_device),
+                           ms_host=float(c.ms_host), n_count_passes=int(c.n_count_passes))
+
+    def assemble_sequences(self, data, offsets, group_offsets, k: int = 10, min_coverage: int = 5, method: str = "shortest_path",
+                           start_anchor: str | None = None, end_anchor: str | None = None, min_length: int | None = None,
+                           only_largest: bool = True, auto_k: bool = False, validity=None, validity_bit_offset: int = 0,
+                           anchors_per_group=None, node_rank=None, host_threads: int = 0, flags: int = 0) -> "StringBatch":
+        """rogtk.assemble_sequences / assemble_sequences_with_anchors (reference rogtk/__init__.py:104-234 -> src/expressions.rs:695-849)
+        for every group of a frame: one row per group with the contig ("" where the reference returns none).  The expression
+        hard-wires only_largest=True (src/expressions.rs:748); pass only_largest=False for fracture_sequences' listing
+        (src/fracture.rs:506-564).  anchors_per_group = (start list, end list) gives every group its own anchors."""
+        col, keep = self._host_col(data, offsets, validity, validity_bit_offset)
+        goff = np.ascontiguousarray(group_offsets, dtype=np.int64)
+        if method not in _ffi.METHODS:
+            raise RogtkGpuError(-1, "Invalid assembly method. Must be 'compression', 'shortest_path', or 'shortest_path_auto'")
+        p = _ffi.AssemblyParamsC(k=int(k), min_coverage=int(min_coverage), method=_ffi.METHODS[method],
+                                 start_anchor=start_anchor.encode() if start_anchor is not None else None,
+                                 end_anchor=end_anchor.encode() if end_anchor is not None else None,
+                                 min_length=int(min_length or 0), only_largest=int(bool(only_largest)), auto_k=int(bool(auto_k)),
+                                 host_threads=int(host_threads))
+        if anchors_per_group is not None:
+            sl, el = anchors_per_group
+            so = np.concatenate([[0], np.cumsum([len(x) for x in sl])]).astype(np.int64)
+            eo = np.concatenate([[0], np.cumsum([len(x) for x in el])]).astype(np.int64)
+            sd = np.frombuffer("".join(sl).encode() or b"\0", dtype=np.uint8).copy()
+            ed = np.frombuffer("".join(el).encode() or b"\0", dtype=np.uint8).copy()
+            p.start_anchor_offsets, p.start_anchor_data = so.ctypes.data, sd.ctypes.data
+            p.end_anchor_offsets, p.end_anchor_data = eo.ctypes.data, ed.ctypes.data
+            keep = keep + (so, eo, sd, ed)
+        if node_rank is not None:
+            node_rank = np.ascontiguousarray(node_rank, dtype=np.int32)
+            p.node_rank = node_rank.ctypes.data
+        out = _ffi.StringBatchC()
+        self._check(self._lib.rogtk_gpu_assemble_batch(self._ctx, ctypes.byref(col), goff.ctypes.data, len(goff) - 1, ctypes.byref(p),
+                                                       int(flags) & ~(_ffi.INPUT_ON_DEVICE | _ffi.OUTPUT_ON_DEVICE), ctypes.byref(out)))
+        res = self._strings_out(out)
+        self._lib.rogtk_gpu_free_strings(self._ctx, ctypes.byref(out))
+        return res
+
+    def sweep_assembly_params(self, data, offsets, group_offsets, k_start: int = 5, k_end: int = 64, k_step: int = 1, cov_start: int = 1,
+                              cov_end: int = 150, cov_step: int = 1, method: str = "shortest_path", start_anchor: str | None = None,
+                              end_anchor: str | None = None, validity=None, validity_bit_offset: int = 0, host_threads: int = 0):
+        """rogtk.sweep_assembly_params (reference rogtk/__init__.py:236-287 -> src/expressions.rs:880-955) for every group: returns
+        dict(k, min_coverage, contig_length: int64 [n_groups, n_cells], n_count_passes, ms_device, ms_host)."""
+        col, keep = self._host_col(data, offsets, validity, validity_bit_offset)
+        goff = np.ascontiguousarray(group_offsets, dtype=np.int64)
+        if method not in _ffi.METHODS:
+            raise RogtkGpuError(-1, f"Invalid assembly method: Unknown assembly method: {method}")
+        p = _ffi.SweepParamsC(k_start=k_start, k_end=k_end, k_step=k_step, cov_start=cov_start, cov_end=cov_end, cov_step=cov_step,
+                              method=_ffi.METHODS[method], host_threads=int(host_threads),
+                              start_anchor=start_anchor.encode() if start_anchor is not None else None,
+                              end_anchor=end_anchor.encode() if end_anchor is not None else None)
+        out = _ffi.SweepResultC()
+        self._check(self._lib.rogtk_gpu_sweep_batch(self._ctx, ctypes.byref(col), goff.ctypes.data, len(goff) - 1, ctypes.byref(p), 0,
+                                                    ctypes.byref(out)))
+        ng, nc = int(out.n_groups), int(out.n_cells)
+
+        def arr(ptr):
+            if ng * nc == 0:
+                return np.zeros((ng, nc), np.int64)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_int64)), shape=(ng * nc,)).copy().reshape(ng, nc)
+
+        res = dict(k=arr(out.k), min_coverage=arr(out.min_coverage), contig_length=arr(out.contig_length),
+                   n_count_passes=int(out.n_count_passes), ms_device=float(out.ms_device), ms_host=float(out.ms_host))
+        self._lib.rogtk_gpu_free_sweep(self._ctx, ctypes.byref(out))
+        return res
+
+    def optimize_assembly(self, data, offsets, group_offsets, start_anchor: str, end_anchor: str, method: str = "shortest_path",
+                          start_k: int = 31, start_min_coverage: int = 1, max_iterations: int | None = None, explore_k: bool = False,
+                          prioritize_length: bool = False, validity=None, validity_bit_offset: int = 0, host_threads: int = 0):
+        """rogtk.optimize_assembly (reference rogtk/__init__.py:289-324 -> src/fracture_opt.rs:120-367) for every group: returns
+        dict(contig: StringBatch, k, min_coverage, length, input_sequences: uint32 [n_groups], n_cells_evaluated, n_probes)."""
+        col, keep = self._host_col(data, offsets, validity, validity_bit_offset)
+        goff = np.ascontiguousarray(group_offsets, dtype=np.int64)
+        if method not in _ffi.METHODS:
+            raise RogtkGpuError(-1, f"Unknown assembly method: {method}")
+        p = _ffi.OptimizeParamsC(start_k=start_k, start_min_coverage=start_min_coverage, max_iterations=int(max_iterations or 0),
+                                 explore_k=int(bool(explore_k)), prioritize_length=int(bool(prioritize_length)), method=_ffi.METHODS[method],
+                                 host_threads=int(host_threads),
+                                 start_anchor=start_anchor.encode() if start_anchor is not None else None,
+                                 end_anchor=end_anchor.encode() if end_anchor is not None else None)
+        out = _ffi.OptimizeResultC()
+        self._check(self._lib.rogtk_gpu_optimize_batch(self._ctx, ctypes.byref(col), goff.ctypes.data, len(goff) - 1, ctypes.byref(p), 0,
+                                                       ctypes.byref(out)))
+        ng = len(goff) - 1
+
+        def arr(ptr):
+            if ng == 0:
+                return np.zeros(0, np.uint32)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(ng,)).copy()
+
+        res = dict(contig=self._strings_out(out.contig), k=arr(out.k), min_coverage=arr(out.min_coverage), length=arr(out.length),
+                   input_sequences=arr(out.input_sequences), n_cells_evaluated=int(out.n_cells_evaluated), n_probes=int(out.n_probes))
+        self._lib.rogtk_gpu_free_optimize(self._ctx, ctypes.byref(out))
+        return res
 
     # ---- Arrow-native entry (SURVEY 8f-4): one call per frame ----------------------------------------------------------------------
     def assemble_arrow(self, reads, k: int, min_coverage: int, min_length: int = 0):

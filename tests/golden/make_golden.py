@@ -55,6 +55,9 @@ def main():
         out["cases"].append({
             "name": name, "reads": reads, "k": k, "min_coverage": mc, "k_eff": b.k_eff,
             "n_observations": b.n_observations, "sha256": dig, "pinned_by_survey": (name, k, mc) in SURVEY_DIGESTS,
+            # no output of the real crates exists for any case (no Rust toolchain here): tools/dump_filter_kmers + check_dump.py
+            # flip this to true the day somebody runs them
+            "pinned_by_reference": False,
             "stats": [int(x) for x in b.stats[0]],
             "kmers": [r[0] for r in rows], "exts": [r[1] for r in rows], "counts": [r[2] for r in rows],
             "csr_row_ptr": [int(x) for x in b.csr_row_ptr], "csr_col": [int(x) for x in b.csr_col],

@@ -27,7 +27,7 @@ def test_header_symbols_exported():
     assert sorted(_ffi.SYMBOLS) == declared
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert lib.rogtk_gpu_abi_version() == 1
+    assert lib.rogtk_gpu_abi_version() == 2
 
 
 def test_host_helpers_match_oracle(oracle):
