@@ -101,6 +101,29 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
+def kernel_build_id() -> str:
+    """sha1 over the CUDA sources: ncu-derived counters are only quoted for the build they were captured on"""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "rogtk_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_counters():
+    """profiles/ncu_counters.json (written by tools/ncu_counters.py from an ncu --set full capture): per kernel the DRAM bytes and
+    warp instructions of ONE launch over `umis` UMI groups of the bench shape, and the build id of the sources it ran on."""
+    p = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    if not os.path.exists(p):
+        return {}, None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get("kernels", {}), d.get("build_id")
+
+
 def algorithmic_bytes(n_groups, n_reads, n_bytes, n_kmers, key_bytes=8):
     """read every input byte + offsets once, write every survivor once.
     B_in = ASCII bytes + 8*(reads+1) per group ; B_out = S*(W+1+2) + 8 per group."""
@@ -147,6 +170,15 @@ def cpu_baseline(cfg, host=None, target_seconds=15.0, threads=0):
                       f"algorithm (oracle/dbg_oracle.c), OpenMP dynamic schedule over groups",
             "umis_per_s": n / t,
             "single_thread": {"value": obs1 / t1, "unit": "obs/s", "sample": f"first {n1} UMIs ({t1:.2f} s)"}}
+
+
+def eng_walk_bits() -> int:
+    """the first-tier counting kernel the library will launch (ROGTK_WALK_RL, read by rogtk_gpu_create)"""
+    try:
+        v = int(os.environ.get("ROGTK_WALK_RL", "0"))
+    except ValueError:
+        v = 0
+    return 0 if v <= 0 else min(max(v, 3), 6)
 
 
 def main():
@@ -256,9 +288,15 @@ def main():
     # each rank owns a disjoint range of UMI indices (its hash shard, materialised as a contiguous range)
     d_data, d_off, d_goff, n_bytes = eng.synth_reads_device(seed, rank * n_umis, n_umis, R, L, cfg["template"], cfg["err64k"])
 
-    def step():
-        db = eng.count_prune_device(d_data, n_bytes, d_off, n_reads, d_goff, n_umis, cfg["k"], cfg["min_cov"])
+    stage_acc = {}
+
+    def step(flags=0, acc=None):
+        db = eng.count_prune_device(d_data, n_bytes, d_off, n_reads, d_goff, n_umis, cfg["k"], cfg["min_cov"], flags=flags)
         r = (db.ms_total, db.ms_hot_kernel, db.n_observations, db.n_kmers, db.n_spilled_groups)
+        if acc is not None:
+            for k_, v_ in db.stage_ms.items():
+                acc[k_] = acc.get(k_, 0.0) + v_
+            acc["n_edges"] = db.n_edges
         db.free()
         return r
 
@@ -273,7 +311,7 @@ def main():
     t0 = time.perf_counter()
     ms_dev, ms_hot = 0.0, 0.0
     for _ in range(args.steps):
-        ms_total, ms_k, n_obs, n_kmers, n_spill = step()
+        ms_total, ms_k, n_obs, n_kmers, n_spill = step(acc=stage_acc)
         ms_dev += ms_total
         ms_hot += ms_k
     wall = time.perf_counter() - t0
@@ -290,22 +328,69 @@ def main():
     peak, peak_src = load_peaks()
     alg = algorithmic_bytes(n_umis, n_reads, n_bytes, n_kmers)
     achieved = alg / (ms_hot_avg * 1e-3) / 1e9 if ms_hot_avg > 0 else 0.0
-    # DRAM traffic of k_smem_count from the committed ncu --set full capture (profiles/r01_ncu_k_smem_count_full.txt:
-    # dram__bytes_read.sum 308.63 MB + dram__bytes_write.sum 154.84 MB for a 20 000-UMI launch of this workload shape),
-    # scaled to this launch's UMI count; only quoted for the shape it was measured on.
-    traffic = (308.627712e6 + 154.83776e6) / 20000.0 * n_umis if cfg["name"] == "cfg2" else None
+    # ncu-derived counters (DRAM bytes, warp instructions) come from profiles/ncu_counters.json and are quoted only when that capture
+    # ran on the sources this library was built from; otherwise they are null (stale) rather than silently wrong.
+    counters, cap_build = ncu_counters()
+    build_id = kernel_build_id()
+    fresh = cap_build == build_id
+
+    def per_launch(kernel, field):
+        c = counters.get(kernel)
+        if not (fresh and c and cfg["name"] == "cfg2"):
+            return None
+        return c[field] / c["umis"] * n_umis
+
+    hot_name = "k_smem_count<1,32,false>" if eng_walk_bits() == 0 else "k_walk_count<1>"
+    traffic = per_launch(hot_name, "dram_bytes")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_smem_count<1>", "kernel_ms": ms_hot_avg, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                "pipeline_frac": alg / (ms_dev_max * 1e-3) / 1e9 / peak}
-    if cfg["name"] == "cfg2" and ms_hot_avg > 0:
-        # What actually limits the kernel: warp instructions issued.  68 781 per UMI group is smsp__inst_executed.sum of
-        # the committed ncu capture (profiles/r01_ncu_k_smem_count_full.txt: 1 375 618 895 for 20 000 UMIs of this shape); the peak is
-        # one warp instruction per scheduler per clock: SMs x 4 x the SM clock sampled during the timed region.
+                "kernel": hot_name, "kernel_ms": ms_hot_avg, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                "pipeline_frac": alg / (ms_dev_max * 1e-3) / 1e9 / peak,
+                "counters": {"source": "profiles/ncu_counters.json", "capture_build": cap_build, "this_build": build_id,
+                             "fresh": fresh}}
+    wi = per_launch(hot_name, "warp_inst")
+    if wi is not None and ms_hot_avg > 0:
+        # What actually limits the kernel: warp instructions issued, against one per scheduler per clock
+        # (SMs x 4 x the SM clock sampled during the timed region).
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        inst_rate = 1375618895.0 / 20000.0 * n_umis / (ms_hot_avg * 1e-3)
+        inst_rate = wi / (ms_hot_avg * 1e-3)
         inst_peak = 148 * 4 * sm_mhz * 1e6
         roofline["issue"] = {"achieved_warp_inst_per_s": inst_rate, "peak_warp_inst_per_s": inst_peak, "frac": inst_rate / inst_peak,
-                             "warp_inst_per_umi": 1375618895.0 / 20000.0}
+                             "warp_inst_per_umi": wi / n_umis}
+    # every kernel group of the step, timed live with CUDA events on the library's stream (averages over the timed steps)
+    st_ms = {k_: v_ / args.steps for k_, v_ in stage_acc.items() if k_ != "n_edges"}
+    sort_bytes = n_kmers * 22 + 16 * n_umis          # pool read + dense write per survivor, offsets per group
+    kernels = [{"kernel": hot_name, "bound": "hbm", "ms": ms_hot_avg, "algorithmic_bytes": alg,
+                "achieved": achieved, "peak": peak, "frac": achieved / peak, "traffic": traffic},
+               {"kernel": "k_sort_small (+mid/big tiers)", "bound": "hbm", "ms": st_ms.get("sort"), "algorithmic_bytes": sort_bytes,
+                "achieved": sort_bytes / (st_ms["sort"] * 1e-3) / 1e9 if st_ms.get("sort") else None, "peak": peak,
+                "frac": sort_bytes / (st_ms["sort"] * 1e-3) / 1e9 / peak if st_ms.get("sort") else None,
+                "traffic": per_launch("k_sort_small", "dram_bytes")}]
+    roofline["kernels"] = kernels
+
+    # ---- the same step with the successor CSR and the node statistics switched on (north_star: "CSR adjacency emit") ------------
+    value_with_csr = None
+    if rank == 0 or world > 1:
+        from rogtk_b200 import _ffi as _f
+        csr_acc = {}
+        step(flags=_f.EMIT_CSR | _f.EMIT_STATS)
+        ms_csr_total = 0.0
+        n_csr_steps = max(1, min(args.steps, 3))
+        for _ in range(n_csr_steps):
+            ms_csr_total += step(flags=_f.EMIT_CSR | _f.EMIT_STATS, acc=csr_acc)[0]
+        ms_csr_step = max_over_ranks(ms_csr_total / n_csr_steps)
+        n_edges = csr_acc.get("n_edges", 0)
+        csr_ms = csr_acc.get("csr", 0.0) / n_csr_steps
+        stats_ms = csr_acc.get("stats", 0.0) / n_csr_steps
+        csr_bytes = n_kmers * (8 + 1) * 2 + n_kmers * 8 + n_edges * 4      # keys + exts read in both passes, row_ptr + col written
+        stats_bytes = n_kmers + 12 * n_umis
+        value_with_csr = {"value": obs_all / (ms_csr_step * 1e-3), "unit": "obs/s", "ms_per_step": ms_csr_step, "steps": n_csr_steps,
+                          "flags": "ROGTK_EMIT_CSR | ROGTK_EMIT_STATS", "edges_per_step": int(n_edges)}
+        kernels.append({"kernel": "k_csr (degree pass + scan + fill)", "bound": "hbm", "ms": csr_ms, "algorithmic_bytes": csr_bytes,
+                        "achieved": csr_bytes / (csr_ms * 1e-3) / 1e9 if csr_ms else None, "peak": peak,
+                        "frac": csr_bytes / (csr_ms * 1e-3) / 1e9 / peak if csr_ms else None, "traffic": None})
+        kernels.append({"kernel": "k_stats", "bound": "hbm", "ms": stats_ms, "algorithmic_bytes": stats_bytes,
+                        "achieved": stats_bytes / (stats_ms * 1e-3) / 1e9 if stats_ms else None, "peak": peak,
+                        "frac": stats_bytes / (stats_ms * 1e-3) / 1e9 / peak if stats_ms else None, "traffic": None})
 
     # ---- next row f-2 (outside the timed region): unitig compaction + the plugin's contig on the same device-resident batch ------
     next_rows = None
@@ -372,11 +457,74 @@ def main():
         e2e = {"value": e2e_obs / dt, "unit": "obs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "umis_per_rank": n_umis,
                "api": "rogtk_gpu_count_prune_batch (C ABI via ctypes), pinned host Arrow buffers in, pinned host arrays out"}
+
+        def view(ptr, n, dt_):
+            ct = np.ctypeslib.as_ctypes_type(np.dtype(dt_))
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,))
+
+        # ---- the same call on what a Polars / pyarrow caller really holds: PAGEABLE buffers, and the Utf8View layout -----------------
+        variants = [{"name": "pinned LargeUtf8", "ms_per_step": dt * 1e3, "value": e2e_obs / dt}]
+        if world == 1:
+            pv = (view(h_data, n_bytes, np.uint8), view(h_off, n_reads + 1, np.int64), view(h_goff, n_umis + 1, np.int64))
+            p_data, p_off, p_goff = (np.array(x, copy=True) for x in pv)     # ordinary (pageable) allocations
+
+            def timed(fn, reps=1):
+                fn()
+                t0_ = time.perf_counter()
+                for _ in range(reps):
+                    fn()
+                return (time.perf_counter() - t0_) / reps
+
+            dptr2 = (ctypes.c_void_p * 1)(p_data.ctypes.data)
+            col2 = _ffi.StrCol(layout=_ffi.UTF8_I64, n_buffers=1, n_rows=n_reads, validity=None, validity_bit_offset=0,
+                               offsets_or_views=p_off.ctypes.data, data=dptr2, data_len=dlen)
+
+            def pageable_step():
+                out = _ffi.GraphBatchC()
+                eng._check(lib.rogtk_gpu_count_prune_batch(ctx, ctypes.byref(col2), ctypes.c_void_p(p_goff.ctypes.data), n_umis, cfg["k"],
+                                                           cfg["min_cov"], 0, ctypes.byref(out)))
+                lib.rogtk_gpu_free_batch(ctx, ctypes.byref(out))
+
+            dt_p = timed(pageable_step, args.e2e_steps)
+            variants.append({"name": "pageable LargeUtf8", "ms_per_step": dt_p * 1e3, "value": e2e_obs / dt_p})
+            # Utf8View: 16-byte views + data buffers of < 2 GiB (Arrow's variadic buffers), every read out of line (300 B > 12)
+            chunk = (1 << 31) // L * L
+            o = p_off[:-1]
+            views = np.zeros((n_reads, 4), dtype=np.uint32)
+            views[:, 0] = L
+            views[:, 1] = p_data[:4].view(np.uint32)[0] if n_bytes >= 4 else 0        # prefix bytes (not read by the library)
+            views[:, 2] = (o // chunk).astype(np.uint32)
+            views[:, 3] = (o % chunk).astype(np.uint32)
+            nb_ = int((n_bytes + chunk - 1) // chunk)
+            bufs = [p_data[i * chunk:min(n_bytes, (i + 1) * chunk)] for i in range(nb_)]
+            bptr = (ctypes.c_void_p * nb_)(*[b_.ctypes.data for b_ in bufs])
+            blen = (ctypes.c_int64 * nb_)(*[b_.size for b_ in bufs])
+            col3 = _ffi.StrCol(layout=_ffi.UTF8_VIEW, n_buffers=nb_, n_rows=n_reads, validity=None, validity_bit_offset=0,
+                               offsets_or_views=views.ctypes.data, data=bptr, data_len=blen)
+
+            def view_step():
+                out = _ffi.GraphBatchC()
+                eng._check(lib.rogtk_gpu_count_prune_batch(ctx, ctypes.byref(col3), ctypes.c_void_p(p_goff.ctypes.data), n_umis, cfg["k"],
+                                                           cfg["min_cov"], 0, ctypes.byref(out)))
+                assert int(out.n_kmers) == nk
+                lib.rogtk_gpu_free_batch(ctx, ctypes.byref(out))
+
+            dt_v = timed(view_step, 1)
+            variants.append({"name": "pageable Utf8View", "ms_per_step": dt_v * 1e3, "value": e2e_obs / dt_v, "data_buffers": nb_})
+            # the plugin-level call: reads in, contigs out (Compression; about 1.2 KB per UMI come back instead of 10.5 KB of nodes)
+            def asm_step():
+                r_ = eng.assemble_sequences(pv[0], pv[1], pv[2], k=cfg["k"], min_coverage=cfg["min_cov"], method="compression", min_length=200)
+                return r_
+
+            t0_ = time.perf_counter()
+            r_ = asm_step()
+            dt_a = time.perf_counter() - t0_
+            variants.append({"name": "assemble_sequences(compression) pinned in, contigs out", "ms_per_step": dt_a * 1e3, "value": e2e_obs / dt_a,
+                             "d2h_bytes": int(r_.data.size + r_.offsets.size * 8), "ms_device": r_.ms_device})
+            del p_data, p_off, p_goff, views, bufs
+        e2e["variants"] = variants
         host_views = None
         if rank == 0 and args.gpus == 1 and not args.no_cpu:
-            def view(ptr, n, dt):
-                ct = np.ctypeslib.as_ctypes_type(np.dtype(dt))
-                return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,))
             host_views = (view(h_data, n_bytes, np.uint8), view(h_off, n_reads + 1, np.int64), view(h_goff, n_umis + 1, np.int64))
             cpu = cpu_baseline(cfg, host=host_views)
         for p in (h_data, h_off, h_goff):
@@ -393,7 +541,8 @@ def main():
             "config": {"workload": workload, "parallelism": f"umi-sharded x{world}, no collective",
                        "l2": "inputs (15 GB/GPU) far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the library stream around the whole device pipeline, max over ranks"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "value_with_csr": value_with_csr, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
             "survivors_per_step": int(n_kmers), "spilled_groups": int(n_spill), "observations_per_step": int(obs_all),
             "next_rows": next_rows})
         print(json.dumps(line))

@@ -90,6 +90,10 @@ typedef struct rogtk_graph_batch {
     float ms_hot_kernel;     /* device time of the k_smem_count launch alone (the dominant kernel; roofline numerator) */
     int32_t n_multipass_groups; /* groups counted in several shared-memory passes (more distinct k-mers / bases than one table holds) */
     int64_t n_spilled_groups;/* groups that went through the HBM-table path */
+    float ms_sort;           /* device time of the ordering kernels (pool -> dense, ascending output) */
+    float ms_csr;            /* device time of the successor CSR (0 unless ROGTK_EMIT_CSR) */
+    float ms_stats;          /* device time of the node statistics (0 unless ROGTK_EMIT_STATS) */
+    float _pad1;
     void *_owner;            /* internal */
 } rogtk_graph_batch;
 

@@ -77,6 +77,10 @@ class GraphBatchC(ctypes.Structure):
         ("ms_hot_kernel", ctypes.c_float),
         ("n_multipass_groups", ctypes.c_int32),
         ("n_spilled_groups", ctypes.c_int64),
+        ("ms_sort", ctypes.c_float),
+        ("ms_csr", ctypes.c_float),
+        ("ms_stats", ctypes.c_float),
+        ("_pad1", ctypes.c_float),
         ("_owner", ctypes.c_void_p),
     ]
 

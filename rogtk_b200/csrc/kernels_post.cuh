@@ -200,6 +200,138 @@ __global__ void k_csr(int64_t n_kmers, int64_t n_groups, const int64_t *kmer_off
     if (!cols) degree[i] = deg;
 }
 
+
+// Per-group variant: one CTA takes one group at a time and stages its ascending k-mers in shared memory together with a table of
+// bucket starts (bucket = top 11 k-mer bits; the group's k-mers are sorted, so a bucket is a run of about one entry): the
+// successor of a node is found by one table load and a scan of its bucket instead of a 20-step binary search for the group and a
+// 10-step one for the k-mer in global memory (k_csr: ~250 instructions per lookup, issue-bound).  Groups of more than CSR_CAP
+// nodes (not the per-UMI workloads) search in global memory with the same kernel.  FILL = false: edges per group (-> exclusive
+// scan = every group's first CSR entry).  FILL = true: tiles of NT nodes, a block scan of the degrees gives every node its row;
+// row_ptr and the successor indices are written tile by tile.
+constexpr int CSR_NT = 256;
+constexpr int CSR_CAP = 2048;
+constexpr int CSR_BBITS = 11;
+template <int W>
+__device__ __forceinline__ uint32_t csr_bucket(uint64_t klo, uint64_t khi, int kbits)
+{
+    if (kbits <= CSR_BBITS) return (uint32_t)klo;
+    const int sh = kbits - CSR_BBITS;
+    if (W == 1) return (uint32_t)(klo >> sh);
+    return sh >= 64 ? (uint32_t)(khi >> (sh - 64)) : (uint32_t)((khi << (64 - sh)) | (klo >> sh));
+}
+template <int W, bool FILL>
+__global__ void __launch_bounds__(CSR_NT) k_csr_group(int64_t n_groups, const int64_t *kmer_offsets, const uint64_t *lo, const uint64_t *hi,
+                                                     const uint8_t *exts, int K, int64_t *group_edges, const int64_t *group_base,
+                                                     int64_t *row_ptr, int32_t *cols)
+{
+    __shared__ uint64_t s_lo[CSR_CAP];
+    __shared__ uint64_t s_hi[W == 2 ? CSR_CAP : 1];
+    __shared__ uint16_t s_start[1 << CSR_BBITS];
+    __shared__ uint32_t s_ws[CSR_NT / 32 + 1];
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    const int kbits = 2 * K;
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int64_t o = kmer_offsets[g];
+        const int n = (int)(kmer_offsets[g + 1] - o);
+        if (n == 0) {
+            if (!FILL && tid == 0) group_edges[g] = 0;
+            continue;
+        }
+        const bool staged = n <= CSR_CAP;
+        __syncthreads();   // the previous group's shared data is no longer read
+        if (staged) {
+            for (int j = tid; j < (1 << CSR_BBITS); j += CSR_NT) s_start[j] = 0xffffu;
+            for (int j = tid; j < n; j += CSR_NT) {
+                s_lo[j] = lo[o + j];
+                if (W == 2) s_hi[j] = hi[o + j];
+            }
+            __syncthreads();
+            for (int j = tid; j < n; j += CSR_NT) {   // the first node of every bucket
+                const uint32_t bk = csr_bucket<W>(s_lo[j], W == 2 ? s_hi[j] : 0ull, kbits);
+                if (j == 0 || csr_bucket<W>(s_lo[j - 1], W == 2 ? s_hi[j - 1] : 0ull, kbits) != bk) s_start[bk] = (uint16_t)j;
+            }
+            __syncthreads();
+        }
+        auto find = [&](uint64_t yh, uint64_t yl) -> int {
+            if (!staged) return (int)find_in_group(lo + o, W == 2 ? hi + o : nullptr, n, yh, yl);
+            const uint32_t bk = csr_bucket<W>(yl, yh, kbits);
+            uint32_t j = s_start[bk];
+            if (j == 0xffffu) return -1;
+            for (; j < (uint32_t)n; j++) {   // ascending inside the bucket
+                const uint64_t ml = s_lo[j], mh = W == 2 ? s_hi[j] : 0ull;
+                if (mh == yh && ml == yl) return (int)j;
+                if (mh > yh || (mh == yh && ml > yl)) return -1;
+            }
+            return -1;
+        };
+        int64_t run = FILL ? group_base[g] : 0;   // CSR entries before the current tile
+        uint32_t total = 0;
+        for (int t0 = 0; t0 < n; t0 += CSR_NT) {
+            const int i = t0 + tid;
+            int s0 = -1, s1 = -1, s2 = -1, s3 = -1;   // successors in base order (registers: no indexed array)
+            int deg = 0;
+            if (i < n) {
+                const uint64_t xl = staged ? s_lo[i] : lo[o + i], xh = W == 2 ? (staged ? s_hi[i] : hi[o + i]) : 0ull;
+                const uint32_t e = exts[o + i] >> 4;
+#pragma unroll
+                for (uint32_t bb = 0; bb < 4; bb++) {
+                    if (!(e & (1u << bb))) continue;
+                    uint64_t yl = (xl << 2) | bb, yh = (xh << 2) | (xl >> 62);
+                    if (kbits < 64) { yl &= (1ull << kbits) - 1ull; yh = 0; }
+                    else if (kbits == 64) yh = 0;
+                    else if (kbits < 128) yh &= (1ull << (kbits - 64)) - 1ull;
+                    const int j = find(yh, yl);
+                    if (j >= 0) {
+                        if (bb == 0) s0 = j; else if (bb == 1) s1 = j; else if (bb == 2) s2 = j; else s3 = j;
+                        deg++;
+                    }
+                }
+            }
+            if (!FILL) {
+                total += (uint32_t)deg;
+                continue;
+            }
+            // exclusive block scan of the degrees
+            uint32_t x = (uint32_t)deg;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (unsigned)d) x += y;
+            }
+            if (lane == 31) s_ws[warp] = x;
+            __syncthreads();
+            uint32_t base = 0, tile = 0;
+#pragma unroll
+            for (int w = 0; w < CSR_NT / 32; w++) {
+                const uint32_t sw = s_ws[w];
+                if (w < (int)warp) base += sw;
+                tile += sw;
+            }
+            __syncthreads();
+            if (i < n) {
+                int64_t w0 = run + (int64_t)(base + x - (uint32_t)deg);
+                row_ptr[o + i] = w0;
+                if (s0 >= 0) cols[w0++] = s0;
+                if (s1 >= 0) cols[w0++] = s1;
+                if (s2 >= 0) cols[w0++] = s2;
+                if (s3 >= 0) cols[w0++] = s3;
+            }
+            run += tile;
+        }
+        if (!FILL) {
+            for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+            if (lane == 0) s_ws[warp] = total;
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t t = 0;
+                for (int w = 0; w < CSR_NT / 32; w++) t += s_ws[w];
+                group_edges[g] = (int64_t)t;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // threshold re-use: the reference re-counts all reads for every (k, min_coverage) cell of
 // sweep_assembly_params_expr (src/expressions.rs:901-941) and every probe of optimize_assembly (src/fracture_opt.rs:243-263),

@@ -41,7 +41,7 @@ struct rogtk_gpu_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t out_stream = nullptr;
     size_t chunk_bytes = (size_t)256 << 20;   // read bytes per chunk of the overlapped host->host path
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[12] = {};   // 0 start, 1/2 counting, 3 end, 4/5 hot kernel, 6/7 ordering, 8/9 stats, 10/11 CSR
     size_t workspace_bytes = 0;
     std::mutex mu;
     std::string last_error;
@@ -566,10 +566,62 @@ void fill_empty_batch(rogtk_gpu_ctx *ctx, int64_t n_groups, bool out_dev, uint32
     }
 }
 
+// Successor CSR of a dense batch: row_ptr[n_kmers + 1], cols[n_edges].  Per-UMI batches (every group fits a CTA-sized search) use
+// the per-group shared-memory kernel; a batch with a very large group (global spectrum, giant UMIs) keeps the node-parallel one.
+void emit_csr(rogtk_gpu_ctx *ctx, int64_t n_groups, int64_t n_kmers, const int64_t *off, const uint64_t *lo, const uint64_t *hi,
+              const uint8_t *exts, int K, DevBuf &rowptr, DevBuf &cols, int64_t &n_edges)
+{
+    cudaStream_t st = ctx->stream;
+    rowptr.alloc((size_t)(n_kmers + 1) * 8, st);
+    n_edges = 0;
+    if (n_kmers == 0 || n_groups == 0) {
+        CK(cudaMemsetAsync(rowptr.p, 0, 8, st));
+        cols.alloc(16, st);
+        return;
+    }
+    unsigned long long max_n = 0;
+    {
+        DevBuf mx(8, st);
+        CK(cudaMemsetAsync(mx.p, 0, 8, st));
+        k_max_group<<<ctx->sm_count * 4, 256, 0, st>>>(off, n_groups, mx.as<unsigned long long>());
+        Peek pk(ctx->peek_slot, st, &ctx->launches);
+        pk.add(mx.p, 8, &max_n);
+        pk.sync();
+        ctx->launches++;
+    }
+    Peek pk(ctx->peek_slot, st, &ctx->launches);
+    if (max_n <= 16ull * CSR_CAP) {
+        DevBuf ge((size_t)n_groups * 8, st), gb((size_t)(n_groups + 1) * 8, st), scr(scan_scratch_bytes(n_groups), st);
+        const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)ctx->sm_count * 8);
+        if (K > 32) k_csr_group<2, false><<<grid, CSR_NT, 0, st>>>(n_groups, off, lo, hi, exts, K, ge.as<int64_t>(), nullptr, nullptr, nullptr);
+        else k_csr_group<1, false><<<grid, CSR_NT, 0, st>>>(n_groups, off, lo, hi, exts, K, ge.as<int64_t>(), nullptr, nullptr, nullptr);
+        exclusive_scan<int64_t>(ge.as<int64_t>(), n_groups, gb.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+        pk.add(gb.as<int64_t>() + n_groups, 8, &n_edges);
+        pk.sync();
+        cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
+        if (K > 32)
+            k_csr_group<2, true><<<grid, CSR_NT, 0, st>>>(n_groups, off, lo, hi, exts, K, nullptr, gb.as<int64_t>(), rowptr.as<int64_t>(), cols.as<int32_t>());
+        else
+            k_csr_group<1, true><<<grid, CSR_NT, 0, st>>>(n_groups, off, lo, hi, exts, K, nullptr, gb.as<int64_t>(), rowptr.as<int64_t>(), cols.as<int32_t>());
+        CK(cudaMemcpyAsync(rowptr.as<int64_t>() + n_kmers, gb.as<int64_t>() + n_groups, 8, cudaMemcpyDeviceToDevice, st));
+        ctx->launches += 2;
+        return;
+    }
+    DevBuf deg((size_t)n_kmers * 4, st), scr(scan_scratch_bytes(n_kmers), st);
+    k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, off, lo, hi, exts, K, deg.as<int32_t>(), nullptr, nullptr);
+    exclusive_scan<int32_t>(deg.as<int32_t>(), n_kmers, rowptr.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+    pk.add(rowptr.as<int64_t>() + n_kmers, 8, &n_edges);
+    pk.sync();
+    cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
+    k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, off, lo, hi, exts, K, nullptr, rowptr.as<int64_t>(), cols.as<int32_t>());
+    ctx->launches += 2;
+}
+
 struct DeviceResult {   // dense, group-ordered result of one pipeline run, still in HBM
     DevBuf off, lo, hi, exts, counts, stats, rowptr, cols;
     int64_t n_kmers = 0, n_edges = 0, n_obs = 0, n_spill = 0, n_multi = 0;
     float ms_hot = 0.f;
+    bool has_stats = false, has_csr = false;   // ev[8..11] were recorded
 };
 
 // The device pipeline on ctx->stream: count (shared-memory path, then HBM-table path for deferred groups), scan, gather,
@@ -638,6 +690,7 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     r.exts.alloc(nk, st);
     r.counts.alloc(nk * 2, st);
     uint64_t *p_hi = K > 32 ? r.hi.as<uint64_t>() : nullptr;
+    CK(cudaEventRecord(ctx->ev[6], st));
     if (sm.n_pool_groups > 0)
         run_sort_gather(st, ctx->peek_slot, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
                         sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches,
@@ -651,33 +704,24 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
         ctx->launches++;
     }
 
+    CK(cudaEventRecord(ctx->ev[7], st));
     // ---- optional node statistics and successor CSR ---------------------------------------------------------------------
     int64_t n_edges = 0;
     if (flags & ROGTK_EMIT_STATS) {
+        CK(cudaEventRecord(ctx->ev[8], st));
+        r.has_stats = true;
         r.stats.alloc((size_t)n_groups * 12 + 16, st);
         if (n_groups > 0) {
             k_stats<<<ctx->sm_count * 8, 256, 0, st>>>(n_groups, r.off.as<int64_t>(), r.exts.as<uint8_t>(), r.stats.as<uint32_t>());
             ctx->launches++;
         }
+        CK(cudaEventRecord(ctx->ev[9], st));
     }
     if (flags & ROGTK_EMIT_CSR) {
-        DevBuf deg(nk * 4, st), scr(scan_scratch_bytes(n_kmers), st);
-        r.rowptr.alloc((size_t)(n_kmers + 1) * 8, st);
-        if (n_kmers > 0) {
-            k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, r.off.as<int64_t>(), r.lo.as<uint64_t>(), p_hi,
-                                                            r.exts.as<uint8_t>(), K, deg.as<int32_t>(), nullptr, nullptr);
-            ctx->launches++;
-        }
-        exclusive_scan<int32_t>(deg.as<int32_t>(), n_kmers, r.rowptr.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
-        pk.add(r.rowptr.as<int64_t>() + n_kmers, 8, &n_edges);
-        pk.sync();
-        r.cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
-        if (n_kmers > 0) {
-            k_csr<<<blocks_for(n_kmers, 256), 256, 0, st>>>(n_kmers, n_groups, r.off.as<int64_t>(), r.lo.as<uint64_t>(), p_hi,
-                                                            r.exts.as<uint8_t>(), K, nullptr, r.rowptr.as<int64_t>(),
-                                                            r.cols.as<int32_t>());
-            ctx->launches++;
-        }
+        CK(cudaEventRecord(ctx->ev[10], st));
+        r.has_csr = true;
+        emit_csr(ctx, n_groups, n_kmers, r.off.as<int64_t>(), r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), K, r.rowptr, r.cols, n_edges);
+        CK(cudaEventRecord(ctx->ev[11], st));
     }
     CK(cudaEventRecord(ctx->ev[3], st));
     r.n_kmers = n_kmers;
@@ -830,7 +874,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     host_reserve(ctx, h_off, (size_t)(n_groups + 1) * 8, 0, s_out);
     if (flags & ROGTK_EMIT_STATS) host_reserve(ctx, h_stats, (size_t)n_groups * 12 + 16, 0, s_out);
     int64_t base_k = 0, base_e = 0, n_obs = 0, n_spill = 0, n_multi = 0;
-    float ms_total = 0, ms_count = 0, ms_hot = 0;
+    float ms_total = 0, ms_count = 0, ms_hot = 0, ms_sort = 0, ms_csr = 0, ms_stats = 0;
     const int64_t total_bytes = std::max<int64_t>(1, off_at(group_offsets[n_groups]) - off_at(group_offsets[0]));
     std::vector<DeviceResult> inflight(2);
 
@@ -895,6 +939,16 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
         ms_count += ms;
         ms_hot += r.ms_hot;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+        ms_sort += ms;
+        if (r.has_stats) {
+            CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
+            ms_stats += ms;
+        }
+        if (r.has_csr) {
+            CK(cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]));
+            ms_csr += ms;
+        }
         base_k += r.n_kmers;
         base_e += r.n_edges;
         n_obs += r.n_obs;
@@ -940,6 +994,9 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     out->ms_total = ms_total;
     out->ms_count = ms_count;
     out->ms_hot_kernel = ms_hot;
+    out->ms_sort = ms_sort;
+    out->ms_csr = ms_csr;
+    out->ms_stats = ms_stats;
     host_guard.armed = false;   // the blocks now belong to the batch
     CK(cudaGetLastError());
 }
@@ -1031,6 +1088,16 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
     CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
     out->ms_count = ms;
     out->ms_hot_kernel = r.ms_hot;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+    out->ms_sort = ms;
+    if (r.has_stats) {
+        CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
+        out->ms_stats = ms;
+    }
+    if (r.has_csr) {
+        CK(cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]));
+        out->ms_csr = ms;
+    }
     CK(cudaGetLastError());
     return ROGTK_OK;
 }
@@ -1120,18 +1187,7 @@ extern "C" int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch
             if (ng > 0) k_stats<<<ctx->sm_count * 8, 256, 0, st>>>(ng, n_off.as<int64_t>(), o_exts.as<uint8_t>(), d_stats.as<uint32_t>());
         }
         if (flags & ROGTK_EMIT_CSR) {
-            DevBuf deg(no * 4, st), scr2(scan_scratch_bytes(n_out), st);
-            d_rowptr.alloc((size_t)(n_out + 1) * 8, st);
-            if (n_out > 0)
-                k_csr<<<blocks_for(n_out, 256), 256, 0, st>>>(n_out, ng, n_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi, o_exts.as<uint8_t>(), K,
-                                                              deg.as<int32_t>(), nullptr, nullptr);
-            exclusive_scan<int32_t>(deg.as<int32_t>(), n_out, d_rowptr.as<int64_t>(), scr2.as<int64_t>(), st, &ctx->launches);
-            CK(cudaMemcpyAsync(&n_edges, d_rowptr.as<int64_t>() + n_out, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            d_cols.alloc((size_t)std::max<int64_t>(n_edges, 1) * 4, st);
-            if (n_out > 0)
-                k_csr<<<blocks_for(n_out, 256), 256, 0, st>>>(n_out, ng, n_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi, o_exts.as<uint8_t>(), K,
-                                                              nullptr, d_rowptr.as<int64_t>(), d_cols.as<int32_t>());
+            emit_csr(ctx, ng, n_out, n_off.as<int64_t>(), o_lo.as<uint64_t>(), p_hi, o_exts.as<uint8_t>(), K, d_rowptr, d_cols, n_edges);
         }
         CK(cudaEventRecord(ctx->ev[3], st));
         out->n_groups = ng;

@@ -75,6 +75,13 @@ class DeviceBatch:
             self._engine._lib.rogtk_gpu_free_batch(self._engine._ctx, ctypes.byref(self._c))
             self._c = None
 
+    @property
+    def stage_ms(self) -> dict:
+        """device time per stage of the pipeline that produced this batch (CUDA events on the library's stream)"""
+        c = self._c
+        return {"hot_kernel": float(c.ms_hot_kernel), "count": float(c.ms_count), "sort": float(c.ms_sort), "csr": float(c.ms_csr),
+                "stats": float(c.ms_stats), "total": float(c.ms_total)}
+
     def to_host(self) -> GraphBatch:
         e, c = self._engine, self._c
 
