@@ -22,7 +22,7 @@ def test_header_symbols_exported():
     from rogtk_b200 import _ffi
     lib = _ffi.load()
     hdr = open(os.path.join(ROOT, "include", "rogtk_gpu.h")).read()
-    declared = sorted(set(re.findall(r"\b(rogtk_gpu_[a-z0-9_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(rogtk_(?:gpu|host)_[a-z0-9_]+)\s*\(", hdr)))
     assert declared, "no declarations found"
     assert sorted(_ffi.SYMBOLS) == declared
     for name in declared:
