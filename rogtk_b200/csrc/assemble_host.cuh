@@ -19,59 +19,6 @@
 
 namespace {
 
-// ---- device side: one string per group out of a device-resident contig batch ---------------------------------------------------
-// only_largest: the unitig `largest[g]` (already filtered by min_length); otherwise every unitig of at least min_length bases,
-// joined with '\n' in listing order
-__global__ void k_contig_row_len(int64_t ng, const int64_t *uoff, const int64_t *soff, const int64_t *largest, int64_t min_length,
-                                 int only_largest, int64_t *row_len, uint8_t *row_many)
-{
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ng) return;
-    int64_t len = 0, cnt = 0;
-    if (only_largest) {
-        const int64_t u = largest[g];
-        if (u >= 0) len = soff[u + 1] - soff[u];
-    } else {
-        for (int64_t u = uoff[g]; u < uoff[g + 1]; u++) {
-            const int64_t l = soff[u + 1] - soff[u];
-            if (l >= min_length) {
-                len += l + (cnt ? 1 : 0);
-                cnt++;
-            }
-        }
-    }
-    row_len[g] = len;
-    if (row_many) row_many[g] = cnt > 1 ? 8 : 0;
-}
-// one warp per group
-__global__ void k_contig_row_fill(int64_t ng, const int64_t *uoff, const int64_t *soff, const uint8_t *seq, const int64_t *largest,
-                                  int64_t min_length, int only_largest, const int64_t *row_off, uint8_t *out)
-{
-    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= ng) return;
-    const unsigned lane = threadIdx.x & 31u;
-    int64_t o = row_off[g];
-    if (only_largest) {
-        const int64_t u = largest[g];
-        if (u < 0) return;
-        const int64_t s = soff[u], l = soff[u + 1] - s;
-        for (int64_t j = lane; j < l; j += 32) out[o + j] = seq[s + j];
-        return;
-    }
-    bool first = true;
-    for (int64_t u = uoff[g]; u < uoff[g + 1]; u++) {
-        const int64_t s = soff[u], l = soff[u + 1] - s;
-        if (l < min_length) continue;
-        if (!first) {
-            if (lane == 0) out[o] = (uint8_t)'\n';
-            o++;
-        }
-        first = false;
-        for (int64_t j = lane; j < l; j += 32) out[o + j] = seq[s + j];
-        o += l;
-    }
-}
-
 struct HostStrings {   // one string per group, LargeUtf8 layout, plain host memory
     std::vector<int64_t> off;
     std::vector<uint8_t> data, flags;
@@ -440,6 +387,38 @@ extern "C" int rogtk_gpu_assemble_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
             classes.assign(ks.begin(), ks.end());
         } else {
             classes.push_back(p->k);
+        }
+        if (p->method == ROGTK_METHOD_COMPRESSION && !p->auto_k) {
+            // large host-resident input: the overlapped path (H2D of the next chunk and D2H of the previous one under the compute),
+            // unitigs on the device per chunk, only the contigs come back -- straight into the page-locked blocks handed to the caller
+            ChunkPost post;
+            post.min_length = min_length;
+            post.only_largest = p->only_largest != 0;
+            rogtk_graph_batch info;
+            bool ran = false;
+            {
+                std::lock_guard<std::mutex> lk(ctx->mu);
+                ran = assemble_compression_chunked(ctx, reads, group_offsets, n_groups, p->k, p->min_coverage, flags, post, &info);
+                if (ran) {
+                    for (HostArr *h : {&post.h_soff, &post.h_sdata, &post.h_sflags})
+                        if (h->p) own->ptrs.push_back(h->p);
+                }
+            }
+            if (ran) {
+                out->n_rows = n_groups;
+                out->n_bytes = post.n_bytes;
+                out->offsets = (int64_t *)post.h_soff.p;
+                out->data = post.h_sdata.p;
+                out->flags = post.h_sflags.p;
+                out->ms_device = info.ms_total + post.ms_unitig;
+                out->n_count_passes = 1;
+                if (!out->data) {   // no contig at all: still a valid (empty) data buffer
+                    std::lock_guard<std::mutex> lk(ctx->mu);
+                    out->data = (uint8_t *)pinned_get(ctx, 16);
+                    own->ptrs.push_back(out->data);
+                }
+                return ROGTK_OK;
+            }
         }
         HostStrings result;
         result.off.assign((size_t)n_groups + 1, 0);

@@ -546,4 +546,58 @@ __global__ void __launch_bounds__(NT) k_unitig_group(UnitigGroupArgs a)
     }
 }
 
+// ---- device side: one string per group out of a device-resident contig batch ---------------------------------------------------
+// only_largest: the unitig `largest[g]` (already filtered by min_length); otherwise every unitig of at least min_length bases,
+// joined with '\n' in listing order
+__global__ void k_contig_row_len(int64_t ng, const int64_t *uoff, const int64_t *soff, const int64_t *largest, int64_t min_length,
+                                 int only_largest, int64_t *row_len, uint8_t *row_many)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ng) return;
+    int64_t len = 0, cnt = 0;
+    if (only_largest) {
+        const int64_t u = largest[g];
+        if (u >= 0) len = soff[u + 1] - soff[u];
+    } else {
+        for (int64_t u = uoff[g]; u < uoff[g + 1]; u++) {
+            const int64_t l = soff[u + 1] - soff[u];
+            if (l >= min_length) {
+                len += l + (cnt ? 1 : 0);
+                cnt++;
+            }
+        }
+    }
+    row_len[g] = len;
+    if (row_many) row_many[g] = cnt > 1 ? 8 : 0;
+}
+// one warp per group
+__global__ void k_contig_row_fill(int64_t ng, const int64_t *uoff, const int64_t *soff, const uint8_t *seq, const int64_t *largest,
+                                  int64_t min_length, int only_largest, const int64_t *row_off, uint8_t *out)
+{
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= ng) return;
+    const unsigned lane = threadIdx.x & 31u;
+    int64_t o = row_off[g];
+    if (only_largest) {
+        const int64_t u = largest[g];
+        if (u < 0) return;
+        const int64_t s = soff[u], l = soff[u + 1] - s;
+        for (int64_t j = lane; j < l; j += 32) out[o + j] = seq[s + j];
+        return;
+    }
+    bool first = true;
+    for (int64_t u = uoff[g]; u < uoff[g + 1]; u++) {
+        const int64_t s = soff[u], l = soff[u + 1] - s;
+        if (l < min_length) continue;
+        if (!first) {
+            if (lane == 0) out[o] = (uint8_t)'\n';
+            o++;
+        }
+        first = false;
+        for (int64_t j = lane; j < l; j += 32) out[o + j] = seq[s + j];
+        o += l;
+    }
+}
+
+
 }  // namespace rogtk

@@ -15,7 +15,11 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <atomic>
+#include <condition_variable>
+#include <exception>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <chrono>
 #include <vector>
@@ -41,7 +45,7 @@ struct rogtk_gpu_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t out_stream = nullptr;
     size_t chunk_bytes = (size_t)256 << 20;   // read bytes per chunk of the overlapped host->host path
-    cudaEvent_t ev[12] = {};   // 0 start, 1/2 counting, 3 end, 4/5 hot kernel, 6/7 ordering, 8/9 stats, 10/11 CSR
+    cudaEvent_t ev[14] = {};   // 0 start, 1/2 counting, 3 end, 4/5 hot kernel, 6/7 ordering, 8/9 stats, 10/11 CSR, 12/13 unitigs
     size_t workspace_bytes = 0;
     std::mutex mu;
     std::string last_error;
@@ -52,6 +56,8 @@ struct rogtk_gpu_ctx {
     void *flush_buf = nullptr;
     bool phase_enabled = false;
     SmemTuning tune;                // environment knobs, read once in rogtk_gpu_create
+    int stage_threads = 8;          // host threads that copy pageable / view input into the pinned bounce buffers (ROGTK_STAGE_THREADS)
+    std::mutex pin_mu;              // the pinned cache is also used by the staging thread of the chunked path
     unsigned long long phase_cycles[16] = {};
     size_t flush_bytes = 0;
     // cache of pinned host blocks (size -> pointers) so steady-state calls do not pay cudaHostAlloc
@@ -96,6 +102,7 @@ int fail_code(rogtk_gpu_ctx *ctx)
 
 void *pinned_get(rogtk_gpu_ctx *ctx, size_t bytes)
 {
+    std::lock_guard<std::mutex> plk(ctx->pin_mu);
     if (bytes == 0) bytes = 16;
     auto it = ctx->pinned_free.lower_bound(bytes);
     if (it != ctx->pinned_free.end() && it->first <= bytes + bytes / 4 + 4096) {
@@ -112,6 +119,7 @@ void *pinned_get(rogtk_gpu_ctx *ctx, size_t bytes)
 void pinned_put(rogtk_gpu_ctx *ctx, void *p)
 {
     if (!p) return;
+    std::lock_guard<std::mutex> plk(ctx->pin_mu);
     auto it = ctx->pinned_size.find(p);
     if (it == ctx->pinned_size.end()) return;
     ctx->pinned_free.emplace(it->second, p);
@@ -379,6 +387,11 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
         if (const char *e = getenv("ROGTK_CHUNK_BYTES")) ctx->chunk_bytes = (size_t)std::max(4096ll, atoll(e));
+        {
+            const unsigned hw = std::thread::hardware_concurrency();
+            ctx->stage_threads = (int)std::min(16u, std::max(1u, hw / 2));
+            if (const char *e = getenv("ROGTK_STAGE_THREADS")) ctx->stage_threads = std::max(1, atoi(e));
+        }
         if (const char *e = getenv("ROGTK_DEBUG_POOL_CAP")) ctx->tune.debug_pool_cap = atoll(e);   // tests: exhaust the survivor pool
         if (const char *e = getenv("ROGTK_WALK_RL")) {   // experiments: 0 = round-1 counting kernel, 3..6 = log2(windows per lane range)
             const int v = atoi(e);
@@ -742,7 +755,10 @@ void host_reserve(rogtk_gpu_ctx *ctx, HostArr &a, size_t need, size_t used, cuda
     if (need <= a.cap) return;
     size_t ncap = std::max(need + need / 4 + 4096, a.cap + a.cap / 2);
     uint8_t *np_ = (uint8_t *)pinned_get(ctx, ncap);
-    ncap = ctx->pinned_size[np_];
+    {
+        std::lock_guard<std::mutex> plk(ctx->pin_mu);
+        ncap = ctx->pinned_size[np_];
+    }
     if (a.p) {
         CK(cudaStreamSynchronize(drain));   // copies into the old block must have landed
         if (used) memcpy(np_, a.p, used);
@@ -752,29 +768,148 @@ void host_reserve(rogtk_gpu_ctx *ctx, HostArr &a, size_t need, size_t used, cuda
     a.cap = ncap;
 }
 
+void compress_unitigs_impl(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_length, uint32_t flags, rogtk_contig_batch *out,
+                           BatchOwner *own);
+
+// What the chunked path does with a chunk's device-resident node arrays instead of copying them to the host: the Compression
+// method (unitigs + the expression's contig choice) on the device, and only the resulting strings travel back.
+struct ChunkPost {
+    int64_t min_length = 0;
+    bool only_largest = true;
+    HostArr h_soff, h_sdata, h_sflags;   // [n_groups+1] int64 | bytes | [n_groups] flags (page-locked, handed to the caller)
+    int64_t n_bytes = 0;
+    float ms_unitig = 0.f;
+};
+
+// one string per group out of a device-resident contig batch (roff: [ng+1] chunk-local offsets)
+void contig_rows_device(rogtk_gpu_ctx *ctx, const rogtk_contig_batch &cb, int64_t min_length, bool only_largest, DevBuf &roff, DevBuf &rows,
+                        DevBuf &rflags, int64_t &nbytes)
+{
+    cudaStream_t st = ctx->stream;
+    const int64_t ng = cb.n_groups;
+    const size_t ngn = (size_t)std::max<int64_t>(ng, 1);
+    DevBuf rlen(ngn * 8, st), scr(scan_scratch_bytes(ng), st);
+    roff.alloc((ngn + 1) * 8, st);
+    rflags.alloc(ngn, st);
+    if (ng > 0)
+        k_contig_row_len<<<blocks_for(ng, 256), 256, 0, st>>>(ng, cb.unitig_offsets, cb.seq_offsets, cb.largest, min_length, only_largest ? 1 : 0,
+                                                              rlen.as<int64_t>(), only_largest ? nullptr : rflags.as<uint8_t>());
+    if (only_largest && ng > 0) CK(cudaMemcpyAsync(rflags.p, cb.largest_flags, (size_t)ng, cudaMemcpyDeviceToDevice, st));
+    exclusive_scan<int64_t>(rlen.as<int64_t>(), ng, roff.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+    nbytes = 0;
+    Peek pk(ctx->peek_slot, st, &ctx->launches);
+    pk.add(roff.as<int64_t>() + ng, 8, &nbytes);
+    pk.sync();
+    rows.alloc((size_t)std::max<int64_t>(nbytes, 1), st);
+    if (ng > 0)
+        k_contig_row_fill<<<blocks_for(ng * 32, 256), 256, 0, st>>>(ng, cb.unitig_offsets, cb.seq_offsets, cb.seq, cb.largest, min_length,
+                                                                   only_largest ? 1 : 0, roff.as<int64_t>(), rows.as<uint8_t>());
+    ctx->launches += 2;
+}
+
+// ---- host staging of the chunked path ------------------------------------------------------------------------------------------
+bool host_ptr_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+// fn(begin, end) over [0, n) on up to nt threads (the calling thread takes the first slice)
+template <typename F>
+void host_parallel(int64_t n, int nt, int64_t min_per_thread, F &&fn)
+{
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, n / std::max<int64_t>(1, min_per_thread)));
+    if (nt <= 1) {
+        fn((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::exception_ptr err;
+    std::mutex em;
+    for (int t = 1; t < nt; t++)
+        th.emplace_back([&, t]() {
+            try {
+                fn(n * t / nt, n * (t + 1) / nt);
+            } catch (...) {
+                std::lock_guard<std::mutex> l(em);
+                err = std::current_exception();
+            }
+        });
+    try {
+        fn((int64_t)0, n / nt);
+    } catch (...) {
+        std::lock_guard<std::mutex> l(em);
+        err = std::current_exception();
+    }
+    for (auto &t : th) t.join();
+    if (err) std::rethrow_exception(err);
+}
+
 // Host Arrow buffers in, host arrays out, for batches much larger than ctx->chunk_bytes: the groups are cut into chunks of
 // ~chunk_bytes of read data; H2D of chunk c+1 and D2H of chunk c-1 run on their own streams while chunk c is being counted.
+// Page-locked offset-layout input is copied straight from the caller's buffers.  Anything else -- PAGEABLE buffers (what Polars and
+// pyarrow hand over: a cudaMemcpyAsync from pageable memory is staged synchronously by the driver and stalls the pipeline) and the
+// Utf8View layout (rows scattered over several data buffers) -- goes through two page-locked bounce buffers that a staging thread
+// fills one chunk ahead with ctx->stage_threads copy threads; views are gathered into the contiguous offsets layout on the way, so the
+// device sees the same column either way.
 void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group_offsets, int64_t n_groups, int K,
-                 uint32_t min_coverage, uint32_t flags, rogtk_graph_batch *out, BatchOwner *own)
+                 uint32_t min_coverage, uint32_t flags, rogtk_graph_batch *out, BatchOwner *own, ChunkPost *post = nullptr)
 {
-    const bool o64 = c->layout == ROGTK_UTF8_I64;
+    const bool is_view = c->layout == ROGTK_UTF8_VIEW;
+    const bool o64 = is_view || c->layout == ROGTK_UTF8_I64;   // (gathered views get int64 offsets)
     const int osz = o64 ? 8 : 4;
+    const int nt = ctx->stage_threads;
+    const View16 *views = is_view ? (const View16 *)c->offsets_or_views : nullptr;
     auto off_at = [&](int64_t row) -> int64_t {
-        return o64 ? ((const int64_t *)c->offsets_or_views)[row] : (int64_t)((const int32_t *)c->offsets_or_views)[row];
+        return c->layout == ROGTK_UTF8_I64 ? ((const int64_t *)c->offsets_or_views)[row] : (int64_t)((const int32_t *)c->offsets_or_views)[row];
     };
-    // chunk boundaries (whole groups)
-    // The host itself indexes with the string offsets at the group boundaries (chunk cuts, copy ranges): those are checked
-    // here; everything between two boundaries is checked on the device (k_validate) against the copied slice.
+    auto row_valid = [&](int64_t r) -> bool {
+        if (!c->validity) return true;
+        const int64_t b = r + c->validity_bit_offset;
+        return (c->validity[b >> 3] >> (b & 7)) & 1;
+    };
+    const bool direct = !is_view && host_ptr_pinned(c->data[0]) && host_ptr_pinned(c->offsets_or_views);
+    // byte position of every group boundary in the (virtual) contiguous column.  Offsets layout: the caller's offsets, checked here
+    // because the host itself indexes with them (chunk cuts, copy ranges); everything between two boundaries is checked on the
+    // device (k_validate) against the copied slice.  Views: the running sum of the valid rows' lengths, every view checked.
+    std::vector<int64_t> gpos;
+    if (is_view) {
+        if (c->n_buffers < 0 || (c->n_buffers > 0 && (!c->data || !c->data_len))) throw ArgFail{ROGTK_ERR_INVALID_ARG, "view layout: null buffer table"};
+        gpos.assign((size_t)n_groups + 1, 0);
+        std::atomic<int> bad{0};
+        host_parallel(n_groups, nt, 4096, [&](int64_t g0, int64_t g1) {
+            for (int64_t g = g0; g < g1; g++) {
+                int64_t sum = 0;
+                for (int64_t r = group_offsets[g]; r < group_offsets[g + 1]; r++) {
+                    if (!row_valid(r)) continue;
+                    const View16 v = views[r];
+                    if (v.len > 12u && (v.len >= 0x80000000u || v.b >= (uint32_t)c->n_buffers || !c->data[v.b] ||
+                                        (int64_t)v.c + (int64_t)v.len > c->data_len[v.b]))
+                        bad = 1;
+                    else
+                        sum += (int64_t)v.len;
+                }
+                gpos[(size_t)g + 1] = sum;
+            }
+        });
+        if (bad) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: a string view names a missing data buffer or bytes beyond its end;"};
+        for (int64_t g = 0; g < n_groups; g++) gpos[(size_t)g + 1] += gpos[(size_t)g];
+    }
+    auto gbyte = [&](int64_t g) -> int64_t { return is_view ? gpos[(size_t)g] : off_at(group_offsets[g]); };
     std::vector<int64_t> cut{0};
     {
-        int64_t start_byte = off_at(group_offsets[0]);
+        int64_t start_byte = gbyte(0);
         int64_t prev_end = start_byte;
-        if (start_byte < 0 || start_byte > c->data_len[0])
+        const int64_t limit = is_view ? gpos[(size_t)n_groups] : c->data_len[0];
+        if (start_byte < 0 || start_byte > limit)
             throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: string offsets exceed the data buffer;"};
         for (int64_t g = 0; g < n_groups; g++) {
-            const int64_t end_byte = off_at(group_offsets[g + 1]);
+            const int64_t end_byte = gbyte(g + 1);
             if (end_byte < prev_end) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: string offsets not monotone;"};
-            if (end_byte > c->data_len[0]) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: string offsets exceed the data buffer;"};
+            if (end_byte > limit) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: string offsets exceed the data buffer;"};
             prev_end = end_byte;
             if (end_byte - start_byte >= (int64_t)ctx->chunk_bytes && g + 1 < n_groups) {
                 cut.push_back(g + 1);
@@ -817,11 +952,152 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         if (trace) host_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
     };
 
+    // ---- bounce buffers + staging thread (pageable / view input) -------------------------------------------------------------------
+    struct Bounce {
+        uint8_t *data = nullptr, *offs = nullptr, *goff = nullptr, *valid = nullptr;
+        size_t data_cap = 0, offs_cap = 0, goff_cap = 0, valid_cap = 0;
+        cudaEvent_t h2d_done = nullptr;
+    } bounce[2];
+    struct StageSync {
+        std::mutex m;
+        std::condition_variable cv;
+        std::vector<char> filled, issued;
+        bool abort = false;
+        std::exception_ptr err;
+    } ss;
+    ss.filled.assign((size_t)n_chunks, 0);
+    ss.issued.assign((size_t)n_chunks, 0);
+    auto bounce_fit = [&](uint8_t *&p, size_t &cap, size_t need) {
+        if (need <= cap) return;
+        if (p) pinned_put(ctx, p);
+        p = (uint8_t *)pinned_get(ctx, need + need / 8 + 4096);
+        cap = need + need / 8 + 4096;
+    };
+    auto fill_chunk = [&](int ci) {   // staging thread: chunk ci -> bounce[ci & 1]
+        Bounce &bb = bounce[ci & 1];
+        const int64_t g0 = cut[ci], g1 = cut[ci + 1];
+        const int64_t r0 = group_offsets[g0], r1 = group_offsets[g1];
+        const int64_t b0 = gbyte(g0), b1 = gbyte(g1);
+        bounce_fit(bb.data, bb.data_cap, (size_t)(b1 - b0) + 32);
+        bounce_fit(bb.offs, bb.offs_cap, (size_t)(r1 - r0 + 1) * osz);
+        bounce_fit(bb.goff, bb.goff_cap, (size_t)(g1 - g0 + 1) * 8);
+        memcpy(bb.goff, group_offsets + g0, (size_t)(g1 - g0 + 1) * 8);
+        if (c->validity) {
+            const int64_t by0 = (r0 + c->validity_bit_offset) >> 3, by1 = (r1 + c->validity_bit_offset + 7) >> 3;
+            bounce_fit(bb.valid, bb.valid_cap, (size_t)(by1 - by0) + 8);
+            memcpy(bb.valid, c->validity + by0, (size_t)(by1 - by0));
+        }
+        if (!is_view) {
+            memcpy(bb.offs, (const uint8_t *)c->offsets_or_views + (size_t)r0 * osz, (size_t)(r1 - r0 + 1) * osz);
+            host_parallel(b1 - b0, nt, 4 << 20, [&](int64_t x0, int64_t x1) { memcpy(bb.data + x0, c->data[0] + b0 + x0, (size_t)(x1 - x0)); });
+            return;
+        }
+        // views: offsets of the rows (absolute positions in the virtual column), then the bytes
+        int64_t *offs = (int64_t *)bb.offs;
+        const int64_t nr = r1 - r0;
+        const int slices = (int)std::max<int64_t>(1, std::min<int64_t>(nt, nr / 8192));
+        std::vector<int64_t> sbase((size_t)slices + 1, 0);
+        auto vlen = [&](int64_t r) -> int64_t { return row_valid(r) ? (int64_t)views[r].len : 0; };
+        host_parallel(slices, slices, 1, [&](int64_t s0, int64_t s1) {
+            for (int64_t sl = s0; sl < s1; sl++) {
+                int64_t sum = 0;
+                for (int64_t r = r0 + nr * sl / slices; r < r0 + nr * (sl + 1) / slices; r++) sum += vlen(r);
+                sbase[(size_t)sl + 1] = sum;
+            }
+        });
+        for (int sl = 0; sl < slices; sl++) sbase[(size_t)sl + 1] += sbase[(size_t)sl];
+        host_parallel(slices, slices, 1, [&](int64_t s0, int64_t s1) {
+            for (int64_t sl = s0; sl < s1; sl++) {
+                int64_t pos = sbase[(size_t)sl];
+                for (int64_t r = r0 + nr * sl / slices; r < r0 + nr * (sl + 1) / slices; r++) {
+                    offs[r - r0] = b0 + pos;
+                    const int64_t len = vlen(r);
+                    if (len) {
+                        const View16 &v = views[r];
+                        const uint8_t *src = v.len <= 12u ? reinterpret_cast<const uint8_t *>(&v) + 4 : c->data[v.b] + v.c;
+                        memcpy(bb.data + pos, src, (size_t)len);
+                        pos += len;
+                    }
+                }
+            }
+        });
+        offs[nr] = b1;
+    };
+    std::thread stager;
+    struct StagerGuard {   // an exception on the main thread must not unwind locals the staging thread still uses
+        StageSync &ss;
+        std::thread &t;
+        rogtk_gpu_ctx *ctx;
+        Bounce *b;
+        ~StagerGuard()
+        {
+            {
+                std::lock_guard<std::mutex> l(ss.m);
+                ss.abort = true;
+            }
+            ss.cv.notify_all();
+            if (t.joinable()) t.join();
+            for (int i = 0; i < 2; i++) {
+                if (b[i].h2d_done) {
+                    cudaEventSynchronize(b[i].h2d_done);
+                    cudaEventDestroy(b[i].h2d_done);
+                }
+                for (uint8_t *p : {b[i].data, b[i].offs, b[i].goff, b[i].valid})
+                    if (p) pinned_put(ctx, p);
+            }
+        }
+    } stager_guard{ss, stager, ctx, bounce};
+    if (!direct) {
+        for (auto &bb : bounce) CK(cudaEventCreateWithFlags(&bb.h2d_done, cudaEventDisableTiming));
+        const int dev = ctx->device;
+        stager = std::thread([&, dev]() {
+            try {
+                cudaSetDevice(dev);
+                for (int ci = 0; ci < n_chunks; ci++) {
+                    if (ci >= 2) {   // bounce[ci & 1] still feeds the copy of chunk ci - 2
+                        std::unique_lock<std::mutex> l(ss.m);
+                        ss.cv.wait(l, [&] { return ss.abort || ss.issued[(size_t)ci - 2]; });
+                        if (ss.abort) return;
+                        l.unlock();
+                        if (cudaEventSynchronize(bounce[ci & 1].h2d_done) != cudaSuccess) throw CudaFail{cudaGetLastError(), "staging: cudaEventSynchronize"};
+                    }
+                    {
+                        std::lock_guard<std::mutex> l(ss.m);
+                        if (ss.abort) return;
+                    }
+                    fill_chunk(ci);
+                    {
+                        std::lock_guard<std::mutex> l(ss.m);
+                        ss.filled[(size_t)ci] = 1;
+                    }
+                    ss.cv.notify_all();
+                }
+            } catch (...) {
+                std::lock_guard<std::mutex> l(ss.m);
+                ss.err = std::current_exception();
+                ss.cv.notify_all();
+            }
+        });
+    }
+
     auto stage_chunk = [&](int ci) {
         InSet &x = sets[ci & 1];
         const int64_t g0 = cut[ci], g1 = cut[ci + 1];
         const int64_t r0 = group_offsets[g0], r1 = group_offsets[g1];
-        const int64_t b0 = off_at(r0), b1 = off_at(r1);
+        const int64_t b0 = gbyte(g0), b1 = gbyte(g1);
+        const uint8_t *src_data = nullptr, *src_offs = nullptr, *src_goff = nullptr, *src_valid = nullptr;
+        if (direct) {
+            src_data = c->data[0] + b0;
+            src_offs = (const uint8_t *)c->offsets_or_views + (size_t)r0 * osz;
+            src_goff = (const uint8_t *)(group_offsets + g0);
+        } else {
+            std::unique_lock<std::mutex> l(ss.m);
+            ss.cv.wait(l, [&] { return ss.err || ss.filled[(size_t)ci]; });
+            if (ss.err) std::rethrow_exception(ss.err);
+            l.unlock();
+            Bounce &bb = bounce[ci & 1];
+            src_data = bb.data; src_offs = bb.offs; src_goff = bb.goff; src_valid = bb.valid;
+        }
         CK(cudaStreamWaitEvent(s_in, x.consumed, 0));   // the compute that last read this set has finished
         const size_t pad = (size_t)(b0 & 15);           // keep the 16-byte phase of the bytes so that aligned chunks stay inside
         x.data.alloc(pad + (size_t)(b1 - b0) + 32, s_in);
@@ -829,10 +1105,9 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         x.goff.alloc((size_t)(g1 - g0 + 1) * 8, s_in);
         hmark();
         tmark(s_in);
-        if (b1 > b0) CK(cudaMemcpyAsync(x.data.as<uint8_t>() + pad, c->data[0] + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s_in));
-        CK(cudaMemcpyAsync(x.offs.p, (const uint8_t *)c->offsets_or_views + (size_t)r0 * osz, (size_t)(r1 - r0 + 1) * osz,
-                           cudaMemcpyHostToDevice, s_in));
-        CK(cudaMemcpyAsync(x.goff.p, group_offsets + g0, (size_t)(g1 - g0 + 1) * 8, cudaMemcpyHostToDevice, s_in));
+        if (b1 > b0) CK(cudaMemcpyAsync(x.data.as<uint8_t>() + pad, src_data, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s_in));
+        CK(cudaMemcpyAsync(x.offs.p, src_offs, (size_t)(r1 - r0 + 1) * osz, cudaMemcpyHostToDevice, s_in));
+        CK(cudaMemcpyAsync(x.goff.p, src_goff, (size_t)(g1 - g0 + 1) * 8, cudaMemcpyHostToDevice, s_in));
         Staged &s = x.st;
         s = Staged();
         s.col.n_rows = r1 - r0;
@@ -850,10 +1125,18 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
             const int64_t bit0 = r0 + c->validity_bit_offset, bit1 = r1 + c->validity_bit_offset;
             const int64_t by0 = bit0 >> 3, by1 = (bit1 + 7) >> 3;
             x.valid.alloc((size_t)(by1 - by0) + 8, s_in);
-            if (by1 > by0) CK(cudaMemcpyAsync(x.valid.p, c->validity + by0, (size_t)(by1 - by0), cudaMemcpyHostToDevice, s_in));
+            if (by1 > by0) CK(cudaMemcpyAsync(x.valid.p, direct ? c->validity + by0 : src_valid, (size_t)(by1 - by0), cudaMemcpyHostToDevice, s_in));
             s.col.validity = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(x.valid.p) - (uintptr_t)by0);
         }
         CK(cudaEventRecord(x.ready, s_in));
+        if (!direct) {
+            CK(cudaEventRecord(bounce[ci & 1].h2d_done, s_in));
+            {
+                std::lock_guard<std::mutex> l(ss.m);
+                ss.issued[(size_t)ci] = 1;
+            }
+            ss.cv.notify_all();
+        }
         tmark(s_in);
     };
 
@@ -871,11 +1154,32 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
                 if (h->p) pinned_put(ctx, h->p);
         }
     } host_guard{ctx, {&h_off, &h_lo, &h_hi, &h_exts, &h_counts, &h_stats, &h_rowptr, &h_cols}, s_out};
+    struct PostGuard {
+        rogtk_gpu_ctx *ctx;
+        ChunkPost *post;
+        cudaStream_t drain;
+        bool armed = true;
+        ~PostGuard()
+        {
+            if (!armed || !post) return;
+            cudaStreamSynchronize(drain);
+            for (HostArr *h : {&post->h_soff, &post->h_sdata, &post->h_sflags})
+                if (h->p) {
+                    pinned_put(ctx, h->p);
+                    h->p = nullptr;
+                }
+        }
+    } post_guard{ctx, post, s_out};
+    if (post) {
+        host_reserve(ctx, post->h_soff, (size_t)(n_groups + 1) * 8, 0, s_out);
+        host_reserve(ctx, post->h_sflags, (size_t)n_groups + 16, 0, s_out);
+        post->n_bytes = 0;
+    }
     host_reserve(ctx, h_off, (size_t)(n_groups + 1) * 8, 0, s_out);
     if (flags & ROGTK_EMIT_STATS) host_reserve(ctx, h_stats, (size_t)n_groups * 12 + 16, 0, s_out);
     int64_t base_k = 0, base_e = 0, n_obs = 0, n_spill = 0, n_multi = 0;
     float ms_total = 0, ms_count = 0, ms_hot = 0, ms_sort = 0, ms_csr = 0, ms_stats = 0;
-    const int64_t total_bytes = std::max<int64_t>(1, off_at(group_offsets[n_groups]) - off_at(group_offsets[0]));
+    const int64_t total_bytes = std::max<int64_t>(1, gbyte(n_groups) - gbyte(0));
     std::vector<DeviceResult> inflight(2);
 
     stage_chunk(0);
@@ -893,12 +1197,55 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         if (base_k) k_add_i64<<<blocks_for(ng + 1, 256), 256, 0, s_comp>>>(r.off.as<int64_t>(), ng + 1, base_k);
         if ((flags & ROGTK_EMIT_CSR) && base_e)
             k_add_i64<<<blocks_for(r.n_kmers + 1, 256), 256, 0, s_comp>>>(r.rowptr.as<int64_t>(), r.n_kmers + 1, base_e);
+        const int64_t done_bytes = std::max<int64_t>(1, gbyte(g1) - gbyte(0));
+        const double scale = (double)total_bytes / (double)done_bytes;
+        if (post) {
+            // Compression on the chunk's device-resident nodes; only the strings go back
+            rogtk_graph_batch view{};
+            view.n_groups = ng; view.n_kmers = r.n_kmers; view.k_eff = K; view.on_device = 1;
+            view.kmer_offsets = r.off.as<int64_t>(); view.kmers_lo = r.lo.as<uint64_t>(); view.kmers_hi = K > 32 ? r.hi.as<uint64_t>() : nullptr;
+            view.exts = r.exts.as<uint8_t>(); view.counts = r.counts.as<uint16_t>();
+            if (base_k) k_add_i64<<<blocks_for(ng + 1, 256), 256, 0, s_comp>>>(r.off.as<int64_t>(), ng + 1, -base_k);   // chunk-local again
+            rogtk_contig_batch cb{};
+            BatchOwner cown;
+            cown.on_device = true;
+            DevBuf roff, rows, rflags;
+            int64_t nb = 0;
+            try {
+                compress_unitigs_impl(ctx, &view, post->min_length, ROGTK_OUTPUT_ON_DEVICE, &cb, &cown);
+                contig_rows_device(ctx, cb, post->min_length, post->only_largest, roff, rows, rflags, nb);
+            } catch (...) {
+                for (void *p : cown.ptrs) cudaFreeAsync(p, s_comp);
+                throw;
+            }
+            for (void *p : cown.ptrs) cudaFreeAsync(p, s_comp);
+            if (post->n_bytes) k_add_i64<<<blocks_for(ng + 1, 256), 256, 0, s_comp>>>(roff.as<int64_t>(), ng + 1, post->n_bytes);
+            CK(cudaEventRecord(comp_done, s_comp));
+            CK(cudaEventRecord(x.consumed, s_comp));
+            tmark(s_comp);
+            const size_t need_b = (size_t)(post->n_bytes + nb);
+            const size_t est_b = (size_t)((double)need_b * scale * 1.05) + 4096;
+            host_reserve(ctx, post->h_sdata, std::max(need_b, ci == 0 ? est_b : need_b) + 16, (size_t)post->n_bytes, s_out);
+            CK(cudaStreamWaitEvent(s_out, comp_done, 0));
+            tmark(s_out);
+            CK(cudaMemcpyAsync(post->h_soff.p + (size_t)g0 * 8, roff.p, (size_t)(ng + 1) * 8, cudaMemcpyDeviceToHost, s_out));
+            if (nb) CK(cudaMemcpyAsync(post->h_sdata.p + (size_t)post->n_bytes, rows.p, (size_t)nb, cudaMemcpyDeviceToHost, s_out));
+            if (ng) CK(cudaMemcpyAsync(post->h_sflags.p + (size_t)g0, rflags.p, (size_t)ng, cudaMemcpyDeviceToHost, s_out));
+            roff.st = rows.st = rflags.st = s_out;
+            roff.release(); rows.release(); rflags.release();
+            tmark(s_out);
+            r.off.release(); r.lo.release(); r.hi.release(); r.exts.release(); r.counts.release();
+            r.stats.release(); r.rowptr.release(); r.cols.release();
+            CK(cudaEventSynchronize(ctx->ev[13]));
+            float msu = 0;
+            CK(cudaEventElapsedTime(&msu, ctx->ev[12], ctx->ev[13]));
+            post->ms_unitig += msu;
+            post->n_bytes += nb;
+        } else {
         CK(cudaEventRecord(comp_done, s_comp));
         CK(cudaEventRecord(x.consumed, s_comp));
         tmark(s_comp);
         // capacity of the final host arrays: after the first chunk extrapolate from bytes processed
-        const int64_t done_bytes = std::max<int64_t>(1, off_at(group_offsets[g1]) - off_at(group_offsets[0]));
-        const double scale = (double)total_bytes / (double)done_bytes;
         const size_t est_k = (size_t)((double)(base_k + r.n_kmers) * scale * 1.05) + 4096;
         const size_t est_e = (size_t)((double)(base_e + r.n_edges) * scale * 1.05) + 4096;
         const size_t need_k = (size_t)(base_k + r.n_kmers);
@@ -931,6 +1278,7 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
         tmark(s_out);
         r.off.release(); r.lo.release(); r.hi.release(); r.exts.release(); r.counts.release();
         r.stats.release(); r.rowptr.release(); r.cols.release();
+        }
         // timings of this chunk (waits for its compute; the next chunk's input copy is already in flight)
         CK(cudaEventSynchronize(ctx->ev[3]));
         float ms = 0;
@@ -998,7 +1346,42 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
     out->ms_csr = ms_csr;
     out->ms_stats = ms_stats;
     host_guard.armed = false;   // the blocks now belong to the batch
+    post_guard.armed = false;
     CK(cudaGetLastError());
+}
+
+// assemble_sequences(method = compression) on the overlapped host path: true when it ran (large host-resident input), false when the
+// caller should take the plain route.  `post` receives the strings in page-locked blocks the caller adopts.
+bool assemble_compression_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets, int64_t n_groups, int64_t k,
+                                  uint32_t min_coverage, uint32_t flags, ChunkPost &post, rogtk_graph_batch *info)
+{
+    if ((flags & (ROGTK_INPUT_ON_DEVICE | ROGTK_OUTPUT_ON_DEVICE)) || n_groups <= 1 || !reads || !group_offsets) return false;
+    int64_t total = 0;
+    if (reads->layout == ROGTK_UTF8_VIEW) {
+        for (int b = 0; b < reads->n_buffers && reads->data_len; b++) total += std::max<int64_t>(0, reads->data_len[b]);
+        total = std::max<int64_t>(total, reads->n_rows * 12);
+    } else if (reads->n_buffers == 1 && reads->data && reads->data_len) {
+        total = reads->data_len[0];
+    }
+    if (total <= (int64_t)ctx->chunk_bytes + (int64_t)(ctx->chunk_bytes >> 1)) return false;
+    const int K = (flags & ROGTK_EXACT_K) ? (int)k : k_eff_host(k);
+    if (K < 1 || K > 64 || !reads->offsets_or_views || reads->n_rows < 0) return false;
+    {   // the host indexes with the group offsets: same check as count_prune_impl
+        int64_t prev = group_offsets[0];
+        bool ok = prev >= 0;
+        for (int64_t g = 1; g <= n_groups && ok; g++) {
+            ok = group_offsets[g] >= prev;
+            prev = group_offsets[g];
+        }
+        if (!ok || prev > reads->n_rows) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: group_offsets not monotone or outside the rows;"};
+    }
+    CK(cudaSetDevice(ctx->device));
+    memset(info, 0, sizeof(*info));
+    BatchOwner own;   // the node arrays never reach the host on this route: nothing to adopt but the offsets block
+    run_chunked(ctx, reads, group_offsets, n_groups, K, min_coverage, flags & ~(ROGTK_EMIT_CSR | ROGTK_EMIT_STATS), info, &own, &post);
+    for (void *p : own.ptrs) pinned_put(ctx, p);
+    info->k_eff = K;
+    return true;
 }
 
 int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_t *group_offsets, int64_t n_groups, int64_t k,
@@ -1041,11 +1424,19 @@ int count_prune_impl(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, const int64_
         }
         if (!ok || prev > reads->n_rows) throw ArgFail{ROGTK_ERR_INVALID_ARG, "malformed input: group_offsets not monotone or outside the rows;"};
     }
-    // host input + host output of a large offsets-layout column: chunked, copies overlapped with compute
-    if (!in_dev && !out_dev && (reads->layout == ROGTK_UTF8_I32 || reads->layout == ROGTK_UTF8_I64) && reads->n_buffers == 1 &&
-        reads->data && reads->data_len && n_groups > 1 && reads->data_len[0] > (int64_t)ctx->chunk_bytes + (ctx->chunk_bytes >> 1)) {
-        run_chunked(ctx, reads, group_offsets, n_groups, K, min_coverage, flags, out, own);
-        return ROGTK_OK;
+    // host input + host output of a large column: chunked, copies overlapped with compute
+    if (!in_dev && !out_dev && n_groups > 1) {
+        int64_t total = 0;
+        if (reads->layout == ROGTK_UTF8_VIEW) {
+            for (int b = 0; b < reads->n_buffers && reads->data_len; b++) total += std::max<int64_t>(0, reads->data_len[b]);
+            total = std::max<int64_t>(total, reads->n_rows * 12);   // (short rows live inside the views)
+        } else if (reads->n_buffers == 1 && reads->data && reads->data_len) {
+            total = reads->data_len[0];
+        }
+        if (total > (int64_t)ctx->chunk_bytes + (int64_t)(ctx->chunk_bytes >> 1)) {
+            run_chunked(ctx, reads, group_offsets, n_groups, K, min_coverage, flags, out, own);
+            return ROGTK_OK;
+        }
     }
 
     Staged in;
@@ -1417,7 +1808,7 @@ void unitig_fused(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_l
     k_unitig_largest<<<blocks_for(ng, 256), 256, 0, st>>>(ng, uoff.as<int64_t>(), ulen.as<int32_t>(), ucyc.as<uint8_t>(), min_length,
                                                           largest.as<int64_t>(), lflags.as<uint8_t>());
     ctx->launches++;
-    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaEventRecord(ctx->ev[13], st));
     out->n_groups = ng;
     out->n_unitigs = nu;
     out->n_bases = nb;
@@ -1446,6 +1837,110 @@ void unitig_fused(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_l
 
 }  // namespace
 
+namespace {
+// (no lock, no argument checks: callers hold ctx->mu.  Records ev[12] / ev[13] around the device work.)
+void compress_unitigs_impl(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_length, uint32_t flags, rogtk_contig_batch *out,
+                           BatchOwner *own)
+{
+    const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[12], st));
+    const int64_t n = in->n_kmers, ng = in->n_groups;
+    const int K = in->k_eff;
+    const size_t nn = (size_t)std::max<int64_t>(n, 1);
+    // every group small enough for one CTA's shared memory: fused per-group kernels (two passes), else node-parallel kernels
+    unsigned long long max_n = 0;
+    if (n > 0 && ng > 0 && !(flags & ROGTK_UNITIG_NODE_PARALLEL)) {
+        DevBuf mx(8, st);
+        CK(cudaMemsetAsync(mx.p, 0, 8, st));
+        k_max_group<<<ctx->sm_count * 4, 256, 0, st>>>(in->kmer_offsets, ng, mx.as<unsigned long long>());
+        Peek pk0(ctx->peek_slot, st, &ctx->launches);
+        pk0.add(mx.p, 8, &max_n);
+        pk0.sync();
+        ctx->launches++;
+    }
+    const bool fused = max_n > 0 && max_n <= (unsigned long long)UG_BIG_NMAX;
+    if (fused) {
+        unitig_fused(ctx, in, min_length, max_n <= (unsigned long long)UG_SMALL_NMAX, out_dev, own, out);
+    } else {
+    DevBuf fx(nn + 4, st), nxt(nn * 4, st), fl(nn, st), hlen(nn * 4, st), hcnt(nn * 2, st), hext(nn, st), is_head(nn * 4, st),
+        upos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st), uoff((size_t)(ng + 1) * 8, st);
+    CK(cudaMemsetAsync(fl.p, 0, nn, st));
+    CK(cudaMemsetAsync(fx.p, 0, nn + 4, st));
+    UnitigArgs a{};
+    a.n = n; a.n_groups = ng; a.offsets = in->kmer_offsets;
+    a.lo = in->kmers_lo; a.hi = K > 32 ? in->kmers_hi : nullptr; a.exts = in->exts; a.counts = in->counts; a.K = K;
+    a.fx = fx.as<uint8_t>(); a.nxt = nxt.as<int32_t>(); a.flags = fl.as<uint8_t>(); a.hlen = hlen.as<int32_t>();
+    a.hcnt = hcnt.as<uint16_t>(); a.hext = hext.as<uint8_t>();
+    if (n > 0) {
+        const unsigned gb = blocks_for(n, 256);
+        k_unitig_links<<<gb, 256, 0, st>>>(a);
+        k_unitig_fixleft<<<gb, 256, 0, st>>>(a);
+        k_unitig_next<<<gb, 256, 0, st>>>(a);
+        k_unitig_heads<<<gb, 256, 0, st>>>(a);
+        k_unitig_cycles<<<gb, 256, 0, st>>>(a);
+        k_unitig_headflags<<<gb, 256, 0, st>>>(a.flags, n, is_head.as<int32_t>());
+        ctx->launches += 6;
+    }
+    exclusive_scan<int32_t>(is_head.as<int32_t>(), n, upos.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
+    k_thr_offsets<<<blocks_for(ng + 1, 256), 256, 0, st>>>(in->kmer_offsets, ng, upos.as<int64_t>(), uoff.as<int64_t>());
+    int64_t nu = 0;
+    Peek pk(ctx->peek_slot, st, &ctx->launches);
+    pk.add(upos.as<int64_t>() + n, 8, &nu);
+    pk.sync();
+    const size_t nun = (size_t)std::max<int64_t>(nu, 1);
+    DevBuf uhead(nun * 8, st), ulen(nun * 4, st), ucnt(nun * 2, st), uext(nun, st), ucyc(nun, st), soff((nun + 1) * 8, st),
+        scr2(scan_scratch_bytes(nu), st), largest((size_t)std::max<int64_t>(ng, 1) * 8, st), lflags((size_t)std::max<int64_t>(ng, 1), st);
+    if (n > 0)
+        k_unitig_compact<<<blocks_for(n, 256), 256, 0, st>>>(a, upos.as<int64_t>(), uhead.as<int64_t>(), ulen.as<int32_t>(),
+                                                             ucnt.as<uint16_t>(), uext.as<uint8_t>(), ucyc.as<uint8_t>());
+    exclusive_scan<int32_t>(ulen.as<int32_t>(), nu, soff.as<int64_t>(), scr2.as<int64_t>(), st, &ctx->launches);
+    int64_t nb = 0;
+    pk.add(soff.as<int64_t>() + nu, 8, &nb);
+    pk.sync();
+    DevBuf seq((size_t)std::max<int64_t>(nb, 1) + 8, st);
+    if (nu > 0)
+        k_unitig_emit<<<blocks_for(nu, 128), 128, 0, st>>>(a, nu, uhead.as<int64_t>(), ulen.as<int32_t>(), soff.as<int64_t>(),
+                                                           seq.as<uint8_t>());
+    if (ng > 0)
+        k_unitig_largest<<<blocks_for(ng, 256), 256, 0, st>>>(ng, uoff.as<int64_t>(), ulen.as<int32_t>(), ucyc.as<uint8_t>(),
+                                                              min_length, largest.as<int64_t>(), lflags.as<uint8_t>());
+    ctx->launches += 4;
+    CK(cudaEventRecord(ctx->ev[13], st));
+    out->n_groups = ng;
+    out->n_unitigs = nu;
+    out->n_bases = nb;
+    out->k_eff = K;
+    out->on_device = out_dev ? 1 : 0;
+    auto give = [&](DevBuf &b, size_t bytes) -> void * {
+        if (out_dev) {
+            void *p = b.detach();
+            own->ptrs.push_back(p);
+            return p;
+        }
+        void *h = pinned_get(ctx, bytes);
+        own->ptrs.push_back(h);
+        if (bytes) CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, st));
+        return h;
+    };
+    out->unitig_offsets = (int64_t *)give(uoff, (size_t)(ng + 1) * 8);
+    out->seq_offsets = (int64_t *)give(soff, (size_t)(nu + 1) * 8);
+    out->seq = (uint8_t *)give(seq, (size_t)nb);
+    out->counts = (uint16_t *)give(ucnt, (size_t)nu * 2);
+    out->exts = (uint8_t *)give(uext, (size_t)nu);
+    out->cyclic = (uint8_t *)give(ucyc, (size_t)nu);
+    out->largest = (int64_t *)give(largest, (size_t)ng * 8);
+    out->largest_flags = (uint8_t *)give(lflags, (size_t)ng);
+    }
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+    out->ms_total = ms;
+    CK(cudaGetLastError());
+}
+}  // namespace
+
 extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *in, int64_t min_length, uint32_t flags,
                                           rogtk_contig_batch *out)
 {
@@ -1461,101 +1956,7 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
     out->_owner = own;
     int rc = ROGTK_OK;
     try {
-        CK(cudaSetDevice(ctx->device));
-        cudaStream_t st = ctx->stream;
-        CK(cudaEventRecord(ctx->ev[0], st));
-        const int64_t n = in->n_kmers, ng = in->n_groups;
-        const int K = in->k_eff;
-        const size_t nn = (size_t)std::max<int64_t>(n, 1);
-        // every group small enough for one CTA's shared memory: fused per-group kernels (two passes), else node-parallel kernels
-        unsigned long long max_n = 0;
-        if (n > 0 && ng > 0 && !(flags & ROGTK_UNITIG_NODE_PARALLEL)) {
-            DevBuf mx(8, st);
-            CK(cudaMemsetAsync(mx.p, 0, 8, st));
-            k_max_group<<<ctx->sm_count * 4, 256, 0, st>>>(in->kmer_offsets, ng, mx.as<unsigned long long>());
-            Peek pk0(ctx->peek_slot, st, &ctx->launches);
-            pk0.add(mx.p, 8, &max_n);
-            pk0.sync();
-            ctx->launches++;
-        }
-        const bool fused = max_n > 0 && max_n <= (unsigned long long)UG_BIG_NMAX;
-        if (fused) {
-            unitig_fused(ctx, in, min_length, max_n <= (unsigned long long)UG_SMALL_NMAX, out_dev, own, out);
-        } else {
-        DevBuf fx(nn + 4, st), nxt(nn * 4, st), fl(nn, st), hlen(nn * 4, st), hcnt(nn * 2, st), hext(nn, st), is_head(nn * 4, st),
-            upos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st), uoff((size_t)(ng + 1) * 8, st);
-        CK(cudaMemsetAsync(fl.p, 0, nn, st));
-        CK(cudaMemsetAsync(fx.p, 0, nn + 4, st));
-        UnitigArgs a{};
-        a.n = n; a.n_groups = ng; a.offsets = in->kmer_offsets;
-        a.lo = in->kmers_lo; a.hi = K > 32 ? in->kmers_hi : nullptr; a.exts = in->exts; a.counts = in->counts; a.K = K;
-        a.fx = fx.as<uint8_t>(); a.nxt = nxt.as<int32_t>(); a.flags = fl.as<uint8_t>(); a.hlen = hlen.as<int32_t>();
-        a.hcnt = hcnt.as<uint16_t>(); a.hext = hext.as<uint8_t>();
-        if (n > 0) {
-            const unsigned gb = blocks_for(n, 256);
-            k_unitig_links<<<gb, 256, 0, st>>>(a);
-            k_unitig_fixleft<<<gb, 256, 0, st>>>(a);
-            k_unitig_next<<<gb, 256, 0, st>>>(a);
-            k_unitig_heads<<<gb, 256, 0, st>>>(a);
-            k_unitig_cycles<<<gb, 256, 0, st>>>(a);
-            k_unitig_headflags<<<gb, 256, 0, st>>>(a.flags, n, is_head.as<int32_t>());
-            ctx->launches += 6;
-        }
-        exclusive_scan<int32_t>(is_head.as<int32_t>(), n, upos.as<int64_t>(), scr.as<int64_t>(), st, &ctx->launches);
-        k_thr_offsets<<<blocks_for(ng + 1, 256), 256, 0, st>>>(in->kmer_offsets, ng, upos.as<int64_t>(), uoff.as<int64_t>());
-        int64_t nu = 0;
-        Peek pk(ctx->peek_slot, st, &ctx->launches);
-        pk.add(upos.as<int64_t>() + n, 8, &nu);
-        pk.sync();
-        const size_t nun = (size_t)std::max<int64_t>(nu, 1);
-        DevBuf uhead(nun * 8, st), ulen(nun * 4, st), ucnt(nun * 2, st), uext(nun, st), ucyc(nun, st), soff((nun + 1) * 8, st),
-            scr2(scan_scratch_bytes(nu), st), largest((size_t)std::max<int64_t>(ng, 1) * 8, st), lflags((size_t)std::max<int64_t>(ng, 1), st);
-        if (n > 0)
-            k_unitig_compact<<<blocks_for(n, 256), 256, 0, st>>>(a, upos.as<int64_t>(), uhead.as<int64_t>(), ulen.as<int32_t>(),
-                                                                 ucnt.as<uint16_t>(), uext.as<uint8_t>(), ucyc.as<uint8_t>());
-        exclusive_scan<int32_t>(ulen.as<int32_t>(), nu, soff.as<int64_t>(), scr2.as<int64_t>(), st, &ctx->launches);
-        int64_t nb = 0;
-        pk.add(soff.as<int64_t>() + nu, 8, &nb);
-        pk.sync();
-        DevBuf seq((size_t)std::max<int64_t>(nb, 1) + 8, st);
-        if (nu > 0)
-            k_unitig_emit<<<blocks_for(nu, 128), 128, 0, st>>>(a, nu, uhead.as<int64_t>(), ulen.as<int32_t>(), soff.as<int64_t>(),
-                                                               seq.as<uint8_t>());
-        if (ng > 0)
-            k_unitig_largest<<<blocks_for(ng, 256), 256, 0, st>>>(ng, uoff.as<int64_t>(), ulen.as<int32_t>(), ucyc.as<uint8_t>(),
-                                                                  min_length, largest.as<int64_t>(), lflags.as<uint8_t>());
-        ctx->launches += 4;
-        CK(cudaEventRecord(ctx->ev[3], st));
-        out->n_groups = ng;
-        out->n_unitigs = nu;
-        out->n_bases = nb;
-        out->k_eff = K;
-        out->on_device = out_dev ? 1 : 0;
-        auto give = [&](DevBuf &b, size_t bytes) -> void * {
-            if (out_dev) {
-                void *p = b.detach();
-                own->ptrs.push_back(p);
-                return p;
-            }
-            void *h = pinned_get(ctx, bytes);
-            own->ptrs.push_back(h);
-            if (bytes) CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, st));
-            return h;
-        };
-        out->unitig_offsets = (int64_t *)give(uoff, (size_t)(ng + 1) * 8);
-        out->seq_offsets = (int64_t *)give(soff, (size_t)(nu + 1) * 8);
-        out->seq = (uint8_t *)give(seq, (size_t)nb);
-        out->counts = (uint16_t *)give(ucnt, (size_t)nu * 2);
-        out->exts = (uint8_t *)give(uext, (size_t)nu);
-        out->cyclic = (uint8_t *)give(ucyc, (size_t)nu);
-        out->largest = (int64_t *)give(largest, (size_t)ng * 8);
-        out->largest_flags = (uint8_t *)give(lflags, (size_t)ng);
-        }
-        CK(cudaStreamSynchronize(st));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
-        out->ms_total = ms;
-        CK(cudaGetLastError());
+        compress_unitigs_impl(ctx, in, min_length, flags, out, own);
     } catch (...) {
         rc = fail_code(ctx);
     }

@@ -186,3 +186,32 @@ def test_optimize_matches_recounting(engine, oracle, method, explore_k, prioriti
         with pytest.raises(rogtk_b200.RogtkGpuError) as ei:
             engine.optimize_assembly(data, offs, goff, sa, ea, method=m, validity=val)
         assert "should not be provided" in str(ei.value)
+
+
+def test_assemble_compression_on_the_overlapped_path(oracle, monkeypatch):
+    """Large host-resident input: assemble_sequences(method="compression") runs chunk by chunk (count -> unitigs -> contig choice on the
+    device, only the strings come back).  Same rows as the plain route and as the oracle; only_largest False lists every contig."""
+    import rogtk_b200
+    from rogtk_b200 import synth
+    data, offs, goff = synth.synth_reads(synth.config_seed(2), 40, 600, 20, 150, 400)
+    with rogtk_b200.Engine(device=0) as eng:
+        plain = {ol: eng.assemble_sequences(data, offs, goff, k=31, min_coverage=2, method="compression", min_length=60, only_largest=ol)
+                 for ol in (True, False)}
+    monkeypatch.setenv("ROGTK_CHUNK_BYTES", "100000")
+    with rogtk_b200.Engine(device=0) as eng:
+        for ol in (True, False):
+            got = eng.assemble_sequences(data, offs, goff, k=31, min_coverage=2, method="compression", min_length=60, only_largest=ol)
+            assert got.n_count_passes == 1
+            assert got.strings() == plain[ol].strings()
+            assert (got.flags == plain[ol].flags).all()
+        got = eng.assemble_sequences(data, offs, goff, k=31, min_coverage=2, method="compression", min_length=60)
+    s = got.strings()
+    n_checked = 0
+    for g in range(0, 600, 7):
+        reads = [data[offs[r]:offs[r + 1]].tobytes().decode() for r in range(goff[g], goff[g + 1])]
+        want, info = oracle.assemble_sequences_py(reads, 31, 2, "compression", min_length=60, only_largest=True)
+        if info["tie"]:
+            continue
+        assert s[g] == (want[0] if want else ""), g
+        n_checked += 1
+    assert n_checked > 50

@@ -107,6 +107,60 @@ def test_utf8view_layout(engine, oracle):
         assert_batches_equal(got, ref, ctx=f"view k={k}")
 
 
+def test_views_and_pageable_input_on_the_chunked_path(oracle, monkeypatch):
+    """Large host input that is not page-locked (numpy arrays, like the buffers Polars / pyarrow own) and the Utf8View layout go
+    through the bounce buffers of the overlapped path (a staging thread gathers views into the offsets layout one chunk ahead):
+    many small chunks, nulls, inline and out-of-line rows over three data buffers, CSR + stats, and a malformed view in a late chunk."""
+    import rogtk_b200
+    monkeypatch.setenv("ROGTK_CHUNK_BYTES", "16384")
+    monkeypatch.setenv("ROGTK_STAGE_THREADS", "3")
+    rng = np.random.default_rng(21)
+    groups = random_groups(rng, 300, max_reads=14, max_len=90, tmpl_len=120, p_null=0.05)
+    flat = [r for g in groups for r in g]
+    goff = np.zeros(len(groups) + 1, dtype=np.int64)
+    np.cumsum([len(g) for g in groups], out=goff[1:])
+    bufs = [bytearray(), bytearray(), bytearray()]
+    views = np.zeros((len(flat), 16), dtype=np.uint8)
+    valid = np.ones(len(flat), dtype=bool)
+    for i, r in enumerate(flat):
+        if r is None:
+            valid[i] = False
+            views[i, 0:4] = np.frombuffer(np.uint32(77).tobytes(), dtype=np.uint8)   # a null row's view is never dereferenced
+            views[i, 8:12] = np.frombuffer(np.uint32(9).tobytes(), dtype=np.uint8)
+            continue
+        b = r.encode()
+        views[i, 0:4] = np.frombuffer(np.uint32(len(b)).tobytes(), dtype=np.uint8)
+        if len(b) <= 12:
+            views[i, 4:4 + len(b)] = np.frombuffer(b, dtype=np.uint8)
+        else:
+            which = (i * 7) % 3
+            off = len(bufs[which])
+            bufs[which] += b
+            views[i, 4:8] = np.frombuffer(b[:4], dtype=np.uint8)
+            views[i, 8:12] = np.frombuffer(np.uint32(which).tobytes(), dtype=np.uint8)
+            views[i, 12:16] = np.frombuffer(np.uint32(off).tobytes(), dtype=np.uint8)
+    validity = None if valid.all() else np.packbits(valid, bitorder="little")
+    nbufs = [np.frombuffer(bytes(b), dtype=np.uint8) for b in bufs]
+    data, offs, v2, _ = groups_to_arrow(groups)
+    with rogtk_b200.Engine(device=0) as eng:
+        for k, mc in ((8, 1), (17, 2), (40, 1)):
+            ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=v2, emit_csr=True)
+            got = eng.count_prune_views(views, nbufs, goff, k, mc, validity=validity, flags=EMIT_STATS | EMIT_CSR)
+            assert_batches_equal(got, ref, check_csr=True, ctx=f"chunked views k={k}")
+            got = eng.count_prune(data, offs, goff, k, mc, validity=v2, flags=EMIT_STATS | EMIT_CSR)      # pageable offsets layout
+            assert_batches_equal(got, ref, check_csr=True, ctx=f"chunked pageable k={k}")
+            got = eng.count_prune(data, offs.astype(np.int32), goff, k, mc, validity=v2, flags=EMIT_STATS)
+            assert_batches_equal(got, ref, ctx=f"chunked pageable int32 offsets k={k}")
+        bad = views.copy()
+        j = max(i for i, r in enumerate(flat) if r is not None and len(r) > 12)
+        bad[j, 12:16] = np.frombuffer(np.uint32(1 << 30).tobytes(), dtype=np.uint8)
+        with pytest.raises(rogtk_b200.RogtkGpuError) as ei:
+            eng.count_prune_views(bad, nbufs, goff, 17, 2, validity=validity)
+        assert ei.value.code == -1
+        ref = oracle.count_prune_batch(data, offs, goff, 17, 2, validity=v2)
+        assert_batches_equal(eng.count_prune_views(views, nbufs, goff, 17, 2, validity=validity, flags=EMIT_STATS), ref, ctx="after error")
+
+
 def test_count_saturation_and_long_reads(engine, oracle):
     # one k-mer observed > 65535 times (u16 saturation, SURVEY A.6); read longer than any staging tile
     reads = ["A" * 70000, "ACGT" * 3000, "A" * 40 + "C" + "A" * 40]
