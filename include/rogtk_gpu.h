@@ -126,6 +126,16 @@ int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *reads, c
                                 rogtk_graph_batch *out);
 void rogtk_gpu_free_batch(rogtk_gpu_ctx *ctx, rogtk_graph_batch *batch);
 
+/* ---- one host frame on several GPUs of this process (BASELINE configs[3]) --------------------------------------------
+ * ctxs: one context per device (rogtk_gpu_create(device d, ..)).  Whole groups go to device rogtk_gpu_shard_of(umi_ids[g], n_ctx)
+ * (umi_ids NULL: the group index is hashed); every device gets its groups as one gathered page-locked sub-column, runs
+ * rogtk_gpu_count_prune_batch on its own context from its own host thread, and the results come back in ORIGINAL group order
+ * (host arrays, released with rogtk_gpu_free_batch(ctxs[0], out)).  No collective, no peer access: groups are independent.
+ * shard_of_group (optional, [n_groups]) receives the device every group ran on.  Offsets layouts only. */
+int rogtk_gpu_count_prune_multi(rogtk_gpu_ctx *const *ctxs, int n_ctx, const rogtk_strcol *reads, const int64_t *group_offsets,
+                                int64_t n_groups, const uint64_t *umi_ids, int64_t k, uint32_t min_coverage, uint32_t flags,
+                                rogtk_graph_batch *out, int32_t *shard_of_group);
+
 /* ---- threshold re-use -------------------------------------------------------------------------------------------
  * `in` is a device-resident batch (ROGTK_OUTPUT_ON_DEVICE) counted at min_coverage <= min_coverage2.  Produces the batch the
  * hot path would return for min_coverage2 without touching the reads again: what sweep_assembly_params_expr

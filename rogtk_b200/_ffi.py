@@ -38,7 +38,7 @@ SYMBOLS = [
     "rogtk_gpu_spectrum_owner", "rogtk_gpu_spectrum_split", "rogtk_gpu_spectrum_merge", "rogtk_gpu_rethreshold",
     "rogtk_gpu_compress_unitigs", "rogtk_gpu_free_contigs",
     "rogtk_gpu_assemble_batch", "rogtk_gpu_free_strings", "rogtk_gpu_sweep_batch", "rogtk_gpu_free_sweep",
-    "rogtk_gpu_optimize_batch", "rogtk_gpu_free_optimize", "rogtk_host_shortest_path",
+    "rogtk_gpu_optimize_batch", "rogtk_gpu_free_optimize", "rogtk_host_shortest_path", "rogtk_gpu_count_prune_multi",
 ]
 METHODS = {"compression": 0, "shortest_path": 1, "shortest_path_auto": 2}
 
@@ -252,6 +252,9 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_free_optimize.argtypes = [vp, ctypes.POINTER(OptimizeResultC)]
     lib.rogtk_host_shortest_path.argtypes = [ctypes.c_int, i32, vp, vp, vp, vp, vp, vp, ctypes.c_char_p, ctypes.c_char_p, vp, i64]
     lib.rogtk_host_shortest_path.restype = i64
+    lib.rogtk_gpu_count_prune_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(StrCol), vp, i64, vp, i64, u32, u32,
+                                                ctypes.POINTER(GraphBatchC), vp]
+    lib.rogtk_gpu_count_prune_multi.restype = ctypes.c_int
     lib.rogtk_gpu_flush_l2.argtypes = [vp]
     lib.rogtk_gpu_flush_l2.restype = ctypes.c_int
     _lib = lib

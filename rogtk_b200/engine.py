@@ -654,3 +654,23 @@ class Engine:
             data_bufs = [np.frombuffer(b, dtype=np.uint8) if b is not None else np.zeros(0, np.uint8) for b in bufs[2:]]
             return self.count_prune_views(views, data_bufs, goff, k, min_coverage, validity=validity, flags=flags)
         raise TypeError(f"unsupported child type {ct}")
+
+
+def count_prune_multi(engines: list, data, offsets, group_offsets, k: int, min_coverage: int, umi_ids=None, validity=None,
+                      validity_bit_offset: int = 0, flags: int = 0):
+    """One host frame on several GPUs of this process (rogtk_gpu_count_prune_multi; SURVEY 8e, BASELINE configs[3]): whole groups go to
+    the engine rogtk_gpu_shard_of(umi_id) names, every engine counts its share on its own device, the batch comes back in the
+    original group order.  Returns (GraphBatch, shard_of_group int32[n_groups])."""
+    e0 = engines[0]
+    col, keep = e0._host_col(data, offsets, validity, validity_bit_offset)
+    goff = np.ascontiguousarray(group_offsets, dtype=np.int64)
+    ng = len(goff) - 1
+    ctxs = (ctypes.c_void_p * len(engines))(*[e._ctx for e in engines])
+    ids = np.ascontiguousarray(umi_ids, dtype=np.uint64) if umi_ids is not None else None
+    shard = np.zeros(max(ng, 1), dtype=np.int32)
+    out = _ffi.GraphBatchC()
+    rc = e0._lib.rogtk_gpu_count_prune_multi(ctxs, len(engines), ctypes.byref(col), goff.ctypes.data, ng,
+                                             ids.ctypes.data if ids is not None else None, int(k), int(min_coverage),
+                                             int(flags) & ~(_ffi.INPUT_ON_DEVICE | _ffi.OUTPUT_ON_DEVICE), ctypes.byref(out), shard.ctypes.data)
+    e0._check(rc)
+    return e0._to_numpy(out), shard[:ng]

@@ -7,6 +7,8 @@ import pytest
 
 from util import groups_to_arrow, random_groups
 
+EMIT_CSR, EMIT_STATS = 1, 2
+
 pytestmark = pytest.mark.gpu
 
 
@@ -215,3 +217,45 @@ def test_assemble_compression_on_the_overlapped_path(oracle, monkeypatch):
         assert s[g] == (want[0] if want else ""), g
         n_checked += 1
     assert n_checked > 50
+
+
+def test_one_frame_on_several_gpus(oracle):
+    """rogtk_gpu_count_prune_multi (BASELINE configs[3] as written): whole groups to the device their UMI id hashes to, one context +
+    host thread per device, no collective, results in the original group order.  Two contexts on device 0 exercise the whole path
+    on a one-GPU box; with a second GPU present the same frame also runs across devices 0 and 1."""
+    import rogtk_b200
+    from rogtk_b200 import synth, sharding
+    from util import assert_batches_equal
+    rp = np.concatenate([np.full(150, 12), np.array([1, 2, 300, 45, 0, 260, 90, 3])])
+    data, offs, goff = synth.synth_reads(synth.config_seed(3), 5, len(rp), rp, 150, 500)
+    umi_ids = np.arange(len(rp), dtype=np.uint64) * 7919 + 13
+    valid = np.ones(len(offs) - 1, dtype=bool)
+    valid[::17] = False
+    validity = np.packbits(valid, bitorder="little")
+    devs = [[0, 0], [0, 0, 0]]
+    if rogtk_b200.ffi.load().rogtk_gpu_device_count() >= 2:
+        devs.append([0, 1])
+    for dl in devs:
+        engines = [rogtk_b200.Engine(device=d) for d in dl]
+        try:
+            for k, mc, fl in ((31, 2, EMIT_STATS | EMIT_CSR), (47, 1, EMIT_STATS), (80, 1, 0)):
+                got, shard = rogtk_b200.count_prune_multi(engines, data, offs, goff, k, mc, umi_ids=umi_ids, validity=validity, flags=fl)
+                ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity, emit_csr=bool(fl & EMIT_CSR))
+                if k <= 64:
+                    assert_batches_equal(got, ref, check_csr=bool(fl & EMIT_CSR), ctx=f"multi {dl} k={k}")
+                else:
+                    assert got.k_eff == -1 and len(got.kmers_lo) == 0
+                assert (shard == sharding.shard_ids(umi_ids, len(dl))).all()
+                assert len(set(shard.tolist())) == len(dl)
+            # the group index is hashed when there are no ids
+            got, shard = rogtk_b200.count_prune_multi(engines, data, offs.astype(np.int32), goff, 17, 2)
+            assert_batches_equal(got, oracle.count_prune_batch(data, offs, goff, 17, 2), ctx="multi, no ids, int32 offsets")
+            assert (shard == sharding.shard_ids(np.arange(len(rp), dtype=np.uint64), len(dl))).all()
+            bad = offs.copy()
+            bad[40] = bad[39] - 3
+            with pytest.raises(rogtk_b200.RogtkGpuError) as ei:
+                rogtk_b200.count_prune_multi(engines, data, bad, goff, 17, 2)
+            assert ei.value.code == -1
+        finally:
+            for e in engines:
+                e.close()
