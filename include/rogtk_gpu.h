@@ -298,6 +298,26 @@ int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_kmers_lo, con
                              const uint8_t *d_exts, int64_t n, int k_eff, uint32_t min_coverage, uint32_t flags,
                              rogtk_graph_batch *out);
 
+/* The exchange inside the library: NCCL point-to-point over NVLink / NVSwitch, reached through dlopen("libnccl.so.2") (no link-time
+ * dependency; single-GPU users need no NCCL).  One communicator per context:
+ *   rank 0: rogtk_gpu_nccl_unique_id(id) -> the 128 bytes reach every rank by any means (rogtk_b200/spectrum.py uses a TCP socket)
+ *   all:    rogtk_gpu_nccl_init(ctx, id, rank, n_ranks) ... rogtk_gpu_nccl_finalize(ctx)
+ * rogtk_gpu_spectrum_exchange = steps 2-4 above in one call: `local` is this rank's device-resident one-group batch (step 1),
+ * `carry` (optional) the device-resident share of the spectrum this rank owns from earlier rounds.  Per peer ONE grouped
+ * ncclSend/ncclRecv of a packed stream (k-mer words, [high words,] u16 partial counts, exts bytes: 11 / 19 bytes per record) after
+ * a size exchange; then the merge.  Without a communicator (or n_ranks == 1) it is the single-rank merge. */
+typedef struct rogtk_exchange_stats {
+    int64_t n_sent, n_received;          /* records that left / reached this rank over NCCL */
+    int64_t bytes_sent, bytes_received;  /* payload bytes over NCCL (blocks are padded to 16 bytes) */
+    float ms_exchange;                   /* device time of the grouped send/recv (CUDA events on the context stream) */
+    int32_t n_ranks;
+} rogtk_exchange_stats;
+int rogtk_gpu_nccl_unique_id(uint8_t *id128);
+int rogtk_gpu_nccl_init(rogtk_gpu_ctx *ctx, const uint8_t *id128, int rank, int n_ranks);
+int rogtk_gpu_nccl_finalize(rogtk_gpu_ctx *ctx);
+int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *local, const rogtk_graph_batch *carry, uint32_t min_coverage,
+                                uint32_t flags, rogtk_graph_batch *out, rogtk_exchange_stats *stats);
+
 /* ---- bench / test utilities (not part of the reference surface) ------------------------------------------------ */
 /* Synthetic reads of SURVEY 8(d) generated directly in HBM: n_umis groups x reads_per_umi reads of read_len bases
  * drawn from a per-UMI random template of template_len bases with iid substitution errors (err_per_64k / 65536).

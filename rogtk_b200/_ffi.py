@@ -38,7 +38,8 @@ SYMBOLS = [
     "rogtk_gpu_spectrum_owner", "rogtk_gpu_spectrum_split", "rogtk_gpu_spectrum_merge", "rogtk_gpu_rethreshold",
     "rogtk_gpu_compress_unitigs", "rogtk_gpu_free_contigs",
     "rogtk_gpu_assemble_batch", "rogtk_gpu_free_strings", "rogtk_gpu_sweep_batch", "rogtk_gpu_free_sweep",
-    "rogtk_gpu_optimize_batch", "rogtk_gpu_free_optimize", "rogtk_host_shortest_path", "rogtk_gpu_count_prune_multi",
+    "rogtk_gpu_optimize_batch", "rogtk_gpu_free_optimize", "rogtk_host_shortest_path", "rogtk_gpu_count_prune_multi", "rogtk_gpu_nccl_unique_id", "rogtk_gpu_nccl_init",
+    "rogtk_gpu_nccl_finalize", "rogtk_gpu_spectrum_exchange",
 ]
 METHODS = {"compression": 0, "shortest_path": 1, "shortest_path_auto": 2}
 
@@ -255,6 +256,14 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_count_prune_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(StrCol), vp, i64, vp, i64, u32, u32,
                                                 ctypes.POINTER(GraphBatchC), vp]
     lib.rogtk_gpu_count_prune_multi.restype = ctypes.c_int
+    lib.rogtk_gpu_nccl_unique_id.argtypes = [vp]
+    lib.rogtk_gpu_nccl_unique_id.restype = ctypes.c_int
+    lib.rogtk_gpu_nccl_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    lib.rogtk_gpu_nccl_init.restype = ctypes.c_int
+    lib.rogtk_gpu_nccl_finalize.argtypes = [vp]
+    lib.rogtk_gpu_nccl_finalize.restype = ctypes.c_int
+    lib.rogtk_gpu_spectrum_exchange.argtypes = [vp, ctypes.POINTER(GraphBatchC), ctypes.POINTER(GraphBatchC), u32, u32, ctypes.POINTER(GraphBatchC), vp]
+    lib.rogtk_gpu_spectrum_exchange.restype = ctypes.c_int
     lib.rogtk_gpu_flush_l2.argtypes = [vp]
     lib.rogtk_gpu_flush_l2.restype = ctypes.c_int
     _lib = lib

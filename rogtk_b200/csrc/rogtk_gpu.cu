@@ -2097,3 +2097,4 @@ extern "C" int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx)
 
 #include "assemble_host.cuh"
 #include "multi_host.cuh"
+#include "spectrum_nccl.cuh"

@@ -4,88 +4,159 @@ The reference has no multi-process form; its closest call is the same expression
 `filter_kmers` over all reads (reference src/fracture.rs:110-116), which internally walks the 256 first-4-base buckets in
 ascending order.  Here every rank
   1. counts its own reads as one group with min_coverage=1 (distinct k-mers, partial u16-saturated counts, exts) on its GPU,
-  2. splits the ascending result at the owner boundaries (owner = contiguous range of first-4-base buckets),
-  3. exchanges the four arrays with one all-to-all (NCCL over NVLink when the process group is NCCL),
-  4. merges what it received: sums partial counts (saturating), ORs exts, applies min_coverage.
+  2. hands the device-resident result to ``rogtk_gpu_spectrum_exchange``: split at the owner boundaries (owner = contiguous
+     range of first-4-base buckets), one grouped ncclSend/ncclRecv per peer of a packed record stream over NVLink, merge of what
+     arrived (sum partial counts saturating, OR exts, apply min_coverage) -- all inside the C library.
 Rank-ordered concatenation of the per-rank outputs is the single-process answer (ascending), bit for bit.
+
+No torch here: the NCCL communicator belongs to the library (dlopen'ed libnccl); the 128-byte unique id and the two scalars the
+driver needs from every rank travel over a plain TCP socket through rank 0 (`Rendezvous`).
 """
 from __future__ import annotations
+
+import ctypes
+import socket
+import struct
+import time
 
 import numpy as np
 
 from . import _ffi
-from .engine import Engine, GraphBatch
+from .engine import DeviceBatch, Engine, GraphBatch
 
 
-class _DevArray:
-    """Zero-copy torch view of a raw device pointer owned by the C library."""
+class Rendezvous:
+    """Star-shaped control channel through rank 0 (a few bytes per call; data never goes here)."""
 
-    def __init__(self, ptr: int, n: int, typestr: str):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+    def __init__(self, rank: int, world: int, addr: str = "127.0.0.1", port: int = 29577, timeout: float = 120.0):
+        self.rank, self.world = rank, world
+        self.peers = []
+        self.sock = None
+        if world == 1:
+            return
+        if rank == 0:
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((addr, port))
+            srv.listen(world)
+            srv.settimeout(timeout)
+            got = {}
+            while len(got) < world - 1:
+                c, _ = srv.accept()
+                c.settimeout(timeout)
+                r = struct.unpack("<i", self._recv(c, 4))[0]
+                got[r] = c
+            self.peers = [got[r] for r in range(1, world)]
+            srv.close()
+        else:
+            t0 = time.time()
+            while True:
+                try:
+                    s = socket.create_connection((addr, port), timeout=5.0)
+                    break
+                except OSError:
+                    if time.time() - t0 > timeout:
+                        raise
+                    time.sleep(0.1)
+            s.settimeout(timeout)
+            s.sendall(struct.pack("<i", rank))
+            self.sock = s
+
+    @staticmethod
+    def _recv(s, n):
+        buf = b""
+        while len(buf) < n:
+            part = s.recv(n - len(buf))
+            if not part:
+                raise ConnectionError("rendezvous peer closed")
+            buf += part
+        return buf
+
+    def broadcast(self, payload: bytes | None, n: int) -> bytes:
+        if self.world == 1:
+            return payload
+        if self.rank == 0:
+            for p in self.peers:
+                p.sendall(payload)
+            return payload
+        return self._recv(self.sock, n)
+
+    def allreduce(self, value: int, op: str = "sum") -> int:
+        if self.world == 1:
+            return int(value)
+        if self.rank == 0:
+            vals = [int(value)] + [struct.unpack("<q", self._recv(p, 8))[0] for p in self.peers]
+            r = max(vals) if op == "max" else sum(vals)
+            for p in self.peers:
+                p.sendall(struct.pack("<q", r))
+            return r
+        self.sock.sendall(struct.pack("<q", int(value)))
+        return struct.unpack("<q", self._recv(self.sock, 8))[0]
+
+    def barrier(self):
+        self.allreduce(0)
+
+    def close(self):
+        for p in self.peers:
+            p.close()
+        if self.sock is not None:
+            self.sock.close()
 
 
-def _as_tensor(ptr, n, typestr, torch_dtype, device):
-    import torch
-    if n == 0:
-        return torch.empty(0, dtype=torch_dtype, device=device)
-    return torch.as_tensor(_DevArray(ptr, n, typestr), device=device).view(torch_dtype)
+class ExchangeStats(ctypes.Structure):
+    _fields_ = [("n_sent", ctypes.c_int64), ("n_received", ctypes.c_int64), ("bytes_sent", ctypes.c_int64),
+                ("bytes_received", ctypes.c_int64), ("ms_exchange", ctypes.c_float), ("n_ranks", ctypes.c_int32)]
 
 
-def _exchange(send, send_counts, group, device):
-    """all-to-all of a 1-D device tensor with per-destination counts; returns (recv tensor, recv_counts).
-    Payloads travel as bytes (NCCL has no 16-bit integer type)."""
-    import torch
-    import torch.distributed as dist
-    if send.dtype != torch.uint8:
-        isz = send.element_size()
-        dt = send.dtype
-        recv, rc = _exchange(send.view(torch.uint8), [c * isz for c in send_counts], group, device)
-        return recv.view(dt), [c // isz for c in rc]
-    world = dist.get_world_size(group)
-    sc = torch.tensor(send_counts, dtype=torch.int64, device=device if dist.get_backend(group) == "nccl" else "cpu")
-    rc = torch.empty_like(sc)
-    dist.all_to_all_single(rc, sc, group=group)
-    recv_counts = [int(x) for x in rc.cpu()]
-    if dist.get_backend(group) == "nccl":
-        recv = torch.empty(sum(recv_counts), dtype=send.dtype, device=device)
-        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
-        return recv, recv_counts
-    # gloo (CPU tests / single-GPU emulation): stage through host memory
-    s_cpu = send.cpu()
-    r_cpu = torch.empty(sum(recv_counts), dtype=send.dtype)
-    dist.all_to_all_single(r_cpu, s_cpu, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
-    return r_cpu.to(device), recv_counts
+def init_comm(engine: Engine, rdv: Rendezvous):
+    """Create the library-owned NCCL communicator of this rank (rogtk_gpu_nccl_init); no-op for one rank."""
+    if rdv.world == 1:
+        return
+    lib = engine._lib
+    ident = (ctypes.c_uint8 * 128)()
+    if rdv.rank == 0:
+        engine._check(lib.rogtk_gpu_nccl_unique_id(ident))
+    raw = rdv.broadcast(bytes(ident) if rdv.rank == 0 else None, 128)
+    ident = (ctypes.c_uint8 * 128).from_buffer_copy(raw)
+    engine._check(lib.rogtk_gpu_nccl_init(engine._ctx, ident, rdv.rank, rdv.world))
 
 
-def global_spectrum(engine: Engine, data: np.ndarray, offsets: np.ndarray, k: int, min_coverage: int, group=None,
-                    validity: np.ndarray | None = None, flags: int = 0, chunk_rows: int | None = None) -> GraphBatch:
-    """This rank's share of the global spectrum of all ranks' reads.  `group` is a torch.distributed process group
-    (None = default group; if torch.distributed is not initialised the call is the single-rank form).
+def finalize_comm(engine: Engine):
+    engine._lib.rogtk_gpu_nccl_finalize(engine._ctx)
+
+
+def _exchange(engine: Engine, local: DeviceBatch, carry: DeviceBatch | None, min_coverage: int, flags: int, on_device: bool):
+    out = _ffi.GraphBatchC()
+    st = ExchangeStats()
+    f = (int(flags) | _ffi.OUTPUT_ON_DEVICE) if on_device else (int(flags) & ~_ffi.OUTPUT_ON_DEVICE)
+    engine._check(engine._lib.rogtk_gpu_spectrum_exchange(engine._ctx, ctypes.byref(local._c), ctypes.byref(carry._c) if carry is not None else None,
+                                                          int(min_coverage), f, ctypes.byref(out), ctypes.byref(st)))
+    if not on_device:
+        return engine._to_numpy(out), st
+    return DeviceBatch(k_eff=int(out.k_eff), n_groups=int(out.n_groups), n_kmers=int(out.n_kmers), n_edges=int(out.n_edges),
+                       n_observations=int(out.n_observations), ms_total=float(out.ms_total), ms_count=float(out.ms_count),
+                       ms_hot_kernel=float(out.ms_hot_kernel), n_spilled_groups=0, n_multipass_groups=0, _c=out, _engine=engine), st
+
+
+def global_spectrum(engine: Engine, data: np.ndarray, offsets: np.ndarray, k: int, min_coverage: int, rdv: Rendezvous | None = None,
+                    validity: np.ndarray | None = None, flags: int = 0, chunk_rows: int | None = None, stats_out: dict | None = None) -> GraphBatch:
+    """This rank's share of the global spectrum of all ranks' reads.  `rdv` is the control channel of the job (None = one rank);
+    call init_comm(engine, rdv) once before.
 
     `chunk_rows` bounds the reads counted at a time: the local table of a round is sized by the round's reads, not by the
     whole input, and the rank's share of the spectrum (distinct k-mers it owns, counts saturating at 65535, exts) is carried in
-    HBM from round to round; min_coverage is applied in the last round only.  Every rank runs the same number of rounds."""
-    import torch
-    import torch.distributed as dist
-    multi = dist.is_available() and dist.is_initialized()
-    world = dist.get_world_size(group) if multi else 1
-    nccl = multi and dist.get_backend(group) == "nccl"
-    device = torch.device("cuda", engine.device)
+    HBM from round to round; min_coverage is applied in the last round only.  Every rank runs the same number of rounds.
+    stats_out (optional dict) receives the NCCL byte / time totals of the exchanges."""
+    rdv = rdv or Rendezvous(0, 1)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n_rows = len(offsets) - 1
     step = n_rows if not chunk_rows or chunk_rows <= 0 else int(chunk_rows)
-    rounds = max(1, -(-n_rows // max(step, 1)))
-    if world > 1:
-        t = torch.tensor([rounds], dtype=torch.int64, device=device if nccl else "cpu")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        rounds = int(t.item())
+    rounds = rdv.allreduce(max(1, -(-n_rows // max(step, 1))), "max")
     if validity is not None and rounds > 1:
         raise ValueError("chunk_rows with a validity bitmap is not supported: drop the null rows first")
-
-    carry = None        # device-resident share of the spectrum after the previous rounds (C batch, min_coverage 1)
-    carry_t = None      # torch views of it
+    carry = None        # device-resident share of the spectrum after the previous rounds (min_coverage 1)
     n_obs = 0
-    K = None
+    tot = dict(bytes_sent=0, bytes_received=0, ms_exchange=0.0, n_sent=0, n_received=0, rounds=rounds, ms_local=0.0, ms_merge=0.0)
     try:
         for r in range(rounds):
             a, b = min(n_rows, r * step), min(n_rows, (r + 1) * step)
@@ -94,52 +165,28 @@ def global_spectrum(engine: Engine, data: np.ndarray, offsets: np.ndarray, k: in
             local = engine.count_prune_to_device(d, o, np.array([0, b - a], dtype=np.int64), k, 1,
                                                  validity=validity if rounds == 1 else None, flags=flags & _ffi.EXACT_K)
             try:
-                K = local.k_eff
-                if K < 0:   # k > 64: empty result (reference src/fracture.rs:212-215)
+                if local.k_eff < 0:   # k > 64: empty result (reference src/fracture.rs:212-215)
                     return local.to_host()
                 n_obs += local.n_observations
-                c, n = local._c, local.n_kmers
-                bounds = engine.spectrum_split(c.kmers_lo, c.kmers_hi, n, K, world)
-                send_counts = [int(bounds[i + 1] - bounds[i]) for i in range(world)]
-                lo = _as_tensor(c.kmers_lo, n, "<i8", torch.int64, device)
-                hi = _as_tensor(c.kmers_hi, n, "<i8", torch.int64, device) if K > 32 else None
-                cnt = _as_tensor(c.counts, n, "<i2", torch.int16, device)
-                ext = _as_tensor(c.exts, n, "|u1", torch.uint8, device)
-                if world > 1:
-                    r_lo, _ = _exchange(lo, send_counts, group, device)
-                    r_hi = _exchange(hi, send_counts, group, device)[0] if hi is not None else None
-                    r_cnt, _ = _exchange(cnt, send_counts, group, device)
-                    r_ext, _ = _exchange(ext, send_counts, group, device)
-                else:
-                    r_lo, r_hi, r_cnt, r_ext = lo, hi, cnt, ext
-                if carry_t is not None:   # what this rank owns so far joins the merge as one more source
-                    r_lo = torch.cat([carry_t[0], r_lo])
-                    r_hi = torch.cat([carry_t[1], r_hi]) if r_hi is not None else None
-                    r_cnt = torch.cat([carry_t[2], r_cnt])
-                    r_ext = torch.cat([carry_t[3], r_ext])
-                torch.cuda.synchronize(device)
+                tot["ms_local"] += local.ms_total
                 last = r == rounds - 1
-                ptr = lambda t_: t_.data_ptr() if t_ is not None and t_.numel() else 0
-                merged = engine.spectrum_merge(ptr(r_lo), ptr(r_hi), ptr(r_cnt), ptr(r_ext), int(r_lo.numel()), K,
-                                               min_coverage if last else 1, flags=flags & _ffi.EMIT_STATS if last else 0,
-                                               on_device=not last)
+                merged, st = _exchange(engine, local, carry, min_coverage if last else 1, (flags & _ffi.EMIT_STATS) if last else 0,
+                                       on_device=not last)
+                for key in ("bytes_sent", "bytes_received", "n_sent", "n_received"):
+                    tot[key] += int(getattr(st, key))
+                tot["ms_exchange"] += float(st.ms_exchange)
+                tot["ms_merge"] += float(merged.ms_total)
             finally:
                 local.free()
             if carry is not None:
                 carry.free()
-                carry, carry_t = None, None
+                carry = None
             if last:
-                if world > 1:   # observations of the whole job (a size, not data)
-                    t = torch.tensor([n_obs], dtype=torch.int64, device=device if nccl else "cpu")
-                    dist.all_reduce(t, group=group)
-                    n_obs = int(t.item())
-                merged.n_observations = n_obs
+                merged.n_observations = rdv.allreduce(n_obs)   # observations of the whole job (a size, not data)
+                if stats_out is not None:
+                    stats_out.update(tot)
                 return merged
             carry = merged
-            cc, m = carry._c, carry.n_kmers
-            carry_t = (_as_tensor(cc.kmers_lo, m, "<i8", torch.int64, device),
-                       _as_tensor(cc.kmers_hi, m, "<i8", torch.int64, device) if K > 32 else None,
-                       _as_tensor(cc.counts, m, "<i2", torch.int16, device), _as_tensor(cc.exts, m, "|u1", torch.uint8, device))
     finally:
         if carry is not None:
             carry.free()

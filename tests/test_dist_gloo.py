@@ -92,7 +92,21 @@ def _spectrum_worker(rank, world, port, tmpdir):
     import rogtk_b200
     from oracle import dbg_oracle
     from rogtk_b200 import synth
-    from rogtk_b200.spectrum import _exchange
+
+    def _exchange(send, send_counts, group, device):
+        """all-to-all of a 1-D tensor with per-destination counts over gloo (on the GPU the library does this step itself with grouped
+        ncclSend / ncclRecv, rogtk_gpu_spectrum_exchange; the protocol around it is what this CPU test covers)"""
+        if send.dtype != torch.uint8:   # payloads travel as bytes (no 16-bit integer type on the wire)
+            isz, dt = send.element_size(), send.dtype
+            recv, rcnt = _exchange(send.view(torch.uint8), [c * isz for c in send_counts], group, device)
+            return recv.view(dt), [c // isz for c in rcnt]
+        sc = torch.tensor(send_counts, dtype=torch.int64)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=group)
+        recv_counts = [int(x) for x in rc]
+        recv = torch.empty(sum(recv_counts), dtype=send.dtype)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+        return recv, recv_counts
     data, offs, _ = synth.synth_reads(synth.config_seed(5), 0, 30, 20, 100, 300)
     n_rows, L = len(offs) - 1, 100
     rows = np.arange(rank, n_rows, world)

@@ -389,16 +389,25 @@ def test_chunked_overlapped_host_path(oracle, monkeypatch):
 def test_global_spectrum_single_rank_and_emulated_sources(engine, oracle):
     """Global k-mer-spectrum mode: the merge of per-source partial (k-mer, count, exts) lists must equal one
     un-grouped filter_kmers call.  Sources are emulated on one GPU: every "rank" counts its stripe of the reads, the lists are
-    split by owner and concatenated per owner exactly as the all-to-all would deliver them."""
-    import torch
+    split by owner and concatenated per owner exactly as the exchange would deliver them."""
     from rogtk_b200 import spectrum, synth
     data, offs, _ = synth.synth_reads(synth.config_seed(5), 0, 40, 25, 150, 500)   # 1000 reads from 40 templates
     n_rows = len(offs) - 1
+
+    def to_dev(a):
+        a = np.ascontiguousarray(a)
+        p = engine.device_alloc(max(a.nbytes, 16))
+        if a.nbytes:
+            engine.h2d(p, a.view(np.uint8))
+        return p
+
     for k, mc in ((31, 2), (13, 1), (40, 2)):
         ref = oracle.count_prune_batch(data, offs, np.array([0, n_rows]), k, mc)
-        # single rank
-        got = spectrum.global_spectrum(engine, data, offs, k, mc, flags=EMIT_STATS)
+        # single rank (rogtk_gpu_spectrum_exchange without a communicator)
+        st = {}
+        got = spectrum.global_spectrum(engine, data, offs, k, mc, flags=EMIT_STATS, stats_out=st)
         assert_batches_equal(got, ref, ctx=f"spectrum 1 rank k={k}")
+        assert st["bytes_sent"] == 0 and st["rounds"] == 1
         # the same in rounds of 130 reads: the share of the spectrum is carried in HBM between the rounds
         got = spectrum.global_spectrum(engine, data, offs, k, mc, flags=EMIT_STATS, chunk_rows=130)
         assert_batches_equal(got, ref, ctx=f"spectrum 1 rank, 8 rounds, k={k}")
@@ -421,14 +430,12 @@ def test_global_spectrum_single_rank_and_emulated_sources(engine, oracle):
             hi = np.concatenate([b.kmers_hi[m] for b, m in sel]) if ref.kmers_hi is not None else None
             ct = np.concatenate([b.counts[m] for b, m in sel])
             ex = np.concatenate([b.exts[m] for b, m in sel])
-            t_lo = torch.from_numpy(lo.view(np.int64)).cuda()
-            t_hi = torch.from_numpy(hi.view(np.int64)).cuda() if hi is not None else None
-            t_ct = torch.from_numpy(ct.view(np.int16)).cuda()
-            t_ex = torch.from_numpy(ex).cuda()
-            torch.cuda.synchronize()
-            pieces.append(engine.spectrum_merge(t_lo.data_ptr() if len(lo) else 0, t_hi.data_ptr() if t_hi is not None and len(lo) else 0,
-                                                t_ct.data_ptr() if len(lo) else 0, t_ex.data_ptr() if len(lo) else 0, len(lo),
-                                                ref.k_eff, mc))
+            ptrs = [to_dev(lo), to_dev(hi) if hi is not None else 0, to_dev(ct), to_dev(ex)]
+            pieces.append(engine.spectrum_merge(ptrs[0] if len(lo) else 0, ptrs[1] if hi is not None and len(lo) else 0,
+                                                ptrs[2] if len(lo) else 0, ptrs[3] if len(lo) else 0, len(lo), ref.k_eff, mc))
+            for p in ptrs:
+                if p:
+                    engine.device_free(p)
         assert np.array_equal(np.concatenate([p.kmers_lo for p in pieces]), ref.kmers_lo)
         if ref.kmers_hi is not None:
             assert np.array_equal(np.concatenate([p.kmers_hi for p in pieces]), ref.kmers_hi)
