@@ -52,6 +52,7 @@ extern "C" {
 #define ROGTK_OUTPUT_ON_DEVICE (1u << 4) /* leave the result arrays in device memory */
 #define ROGTK_FORCE_SPILL (1u << 5)      /* testing: bypass the shared-memory tables, use the HBM tables only */
 #define ROGTK_NO_MULTIPASS (1u << 6)     /* testing: groups beyond one shared-memory table go straight to the HBM tables */
+#define ROGTK_NO_PARTITION (1u << 8)     /* testing: groups beyond the multi-pass kernel skip the partition-then-count tier (HBM tables take them) */
 #define ROGTK_UNITIG_NODE_PARALLEL (1u << 7) /* testing: rogtk_gpu_compress_unitigs uses the node-parallel kernels for every batch */
 
 typedef struct rogtk_gpu_ctx rogtk_gpu_ctx;
@@ -326,6 +327,10 @@ int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *loc
 int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t reads_per_umi,
                           int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data,
                           int64_t *d_offsets, int64_t *d_group_offsets);
+/* the same generator with a read count per UMI (BASELINE configs[2], skewed groups): d_group_offsets [n_umis+1] is an input */
+int rogtk_gpu_synth_reads_var(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, const int64_t *d_group_offsets,
+                              int64_t n_reads, int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data,
+                              int64_t *d_offsets);
 /* raw device/pinned memory for harnesses that must not depend on torch */
 void *rogtk_gpu_device_alloc(rogtk_gpu_ctx *ctx, size_t bytes);
 void rogtk_gpu_device_free(rogtk_gpu_ctx *ctx, void *p);

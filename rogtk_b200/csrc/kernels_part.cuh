@@ -1,0 +1,518 @@
+// kernels_part.cuh -- partition-then-count: the tier for groups beyond the multi-pass kernel (more than SM_PMAX * SM_PASS_OBS
+// bases: UMIs with thousands of reads, BASELINE configs[2]).  Same semantics as debruijn::filter::filter_kmers + CountFilter at
+// reference src/fracture.rs:110-116, which itself walks the k-mer space bucket range by bucket range.
+//
+// Round 1 sent these groups to open-addressing tables in HBM (kernels_table.cuh): one L2/HBM atomic per observation on random
+// addresses, a scan of 2x obs slots to extract, a library sort of the records -- 1.3 x 10^10 obs/s on configs[2], where they hold
+// most of the observations.  Here the k-mer space of a group is cut into P equal ranges (the multi-pass kernel's pass_of) so that
+// one range's distinct k-mers fit a shared-memory table, and
+//   k_part_scatter  stages slabs of the group's reads exactly like the hot kernel (128-bit loads, 2-bit pack) and runs twice:
+//                   HIST = true counts the slab's observations per range (-> exact bucket sizes: the true k-mers of a deep UMI
+//                   carry thousands of observations each, so range loads are far from uniform and no fixed slack fits them);
+//                   HIST = false appends (k-mer, exts) records to the range buckets in HBM: a slab's records of one range form one
+//                   contiguous run reserved with ONE global atomic per (slab, range), not one per observation;
+//   k_part_count    one CTA per (group, range): reads the bucket with coalesced loads, counts it in a shared-memory table, prunes,
+//                   and leaves the survivors in the pool as one segment (SegRec), exactly what a pass of the multi-pass kernel
+//                   leaves -- ranges ascend, so ordering every segment in place orders the group (k_sort_small<W, true>).
+// A group whose bucket or table overflows (extremely repetitive reads) is handed to the HBM tables, which hold anything.
+#pragma once
+
+namespace rogtk {
+
+constexpr int PT_PMAX = 128;             // ranges per group at most
+constexpr int64_t PT_TARGET = 8192;      // observations per range the plan aims at (table: 8192 slots; about half of the observations repeat a k-mer)
+constexpr int PT_NT = 384;
+constexpr int PT_NW = PT_NT / 32;
+constexpr int PT_MAX_BASES = 16384;      // staged bases per slab (incl. alignment slack)
+constexpr int PT_PK_WORDS = PT_MAX_BASES / 16 + 8;
+
+struct PartArgs {
+    ColView col;
+    const uint8_t *data_begin, *data_end;
+    const int64_t *group_offsets;
+    const int32_t *ids;          // listed groups
+    int64_t n_list;
+    const int32_t *np;           // [n_list] ranges of entry e
+    const int32_t *rows_per_slab;// [n_list]
+    const int64_t *slab_off;     // [n_list+1] first slab item of entry e
+    const int64_t *bucket_off;   // [n_list+1] first bucket of entry e
+    const int64_t *rec_off;      // [n_buckets+1] first record slot of bucket b
+    unsigned int *cursor;        // [n_buckets] HIST: records of the bucket; scatter: records appended so far
+    uint32_t *slab_cnt;          // [n_slabs * PT_PMAX] observations per (slab, range), written by HIST, read by the scatter
+    uint64_t *rec_lo, *rec_hi;
+    uint8_t *rec_ex;
+    int32_t *failed;             // [n_list]
+    int K;
+    uint32_t min_cov;
+    unsigned long long *ticket;
+    // count kernel
+    unsigned long long *pool_cursor;
+    int64_t pool_cap;
+    uint64_t *pool_lo, *pool_hi;
+    uint8_t *pool_exts;
+    uint16_t *pool_counts;
+    SegRec *segs;                // [n_list * PT_PMAX]
+    // prefix kernel
+    int32_t *seg_count;          // [n_list]
+    int64_t *nsurv;              // [n_groups]
+    unsigned long long *n_obs;
+    int32_t *failed_ids;         // groups handed to the HBM tables
+    unsigned long long *n_failed;
+};
+
+// per listed group: observation upper bound -> ranges, rows per slab, slabs, bucket capacities
+__global__ void k_part_plan(ColView col, const int64_t *group_offsets, const int32_t *ids, int64_t n_list, int K, int32_t *np, int32_t *rows_per_slab,
+                            int64_t *slabs, int64_t *bucket_cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = warp; e < n_list; e += n_warps) {
+        const int64_t g = ids[e];
+        const int64_t r0 = group_offsets[g], r1 = group_offsets[g + 1];
+        unsigned long long obs = 0;
+        long long maxlen = 1;
+        for (int64_t r = r0 + lane; r < r1; r += 32) {
+            const int64_t len = col_off(col, r + 1) - col_off(col, r);
+            if (len >= K) obs += (unsigned long long)(len - K + 1);
+            maxlen = len > maxlen ? len : maxlen;
+        }
+        for (int d = 16; d; d >>= 1) {
+            obs += __shfl_xor_sync(0xffffffffu, obs, d);
+            const long long o = __shfl_xor_sync(0xffffffffu, maxlen, d);
+            maxlen = o > maxlen ? o : maxlen;
+        }
+        if (lane == 0) {
+            int64_t P = ((int64_t)obs + PT_TARGET - 1) / PT_TARGET;
+            P = P < 1 ? 1 : (P > PT_PMAX ? PT_PMAX : P);
+            if (2 * K <= 12) P = 1;   // at most 4096 distinct k-mers
+            // rows per slab: every slab of rps rows fits the staged span whatever the reads' lengths (0 = a read longer than a slab)
+            int64_t rps = (PT_MAX_BASES - 32) / maxlen;
+            rps = rps > SM_MAXR ? SM_MAXR : rps;
+            np[e] = (int32_t)P;
+            rows_per_slab[e] = (int32_t)rps;
+            slabs[e] = rps > 0 ? (r1 - r0 + rps - 1) / rps : 0;
+            bucket_cap[e] = (int64_t)obs;   // records of the whole entry at most (wave planning)
+        }
+    }
+}
+template <int W>
+constexpr size_t part_scatter_smem() { return (size_t)PT_PK_WORDS * 4 + (size_t)(SM_MAXR + 1) * 4 + SM_MAXR + (size_t)PT_PMAX * 4 * 3 + 64 * 4 + 64; }
+
+// one slab of one listed group per iteration: stage, bin the observations by range, append the bins to the range buckets
+template <int W, bool HIST>
+__global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n_items)
+{
+    constexpr int NT = PT_NT;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *pk = scratch + 1;
+    uint32_t *rstart = scratch + PT_PK_WORDS;
+    uint32_t *cnt = rstart + SM_MAXR + 1;         // [PT_PMAX] observations of the slab per range
+    uint32_t *base = cnt + PT_PMAX;               // [PT_PMAX] first record of the slab's bin inside the bucket
+    uint32_t *fill = base + PT_PMAX;              // [PT_PMAX] records of the bin written so far
+    uint32_t *ws = fill + PT_PMAX;                // 64 words
+    uint8_t *bad = reinterpret_cast<uint8_t *>(ws + 64);
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const int K = a.K;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long t = atomicAdd(a.ticket, 1ull);
+            ws[0] = (uint32_t)t;
+            ws[1] = (uint32_t)(t >> 32);
+        }
+        __syncthreads();
+        const int64_t item = (int64_t)(((unsigned long long)ws[1] << 32) | ws[0]);
+        if (item >= n_items) break;
+        // entry of this slab item: last e with slab_off[e] <= item
+        int64_t lo_e = 0, hi_e = a.n_list;
+        while (hi_e - lo_e > 1) {
+            const int64_t m = (lo_e + hi_e) >> 1;
+            if (a.slab_off[m] <= item) lo_e = m; else hi_e = m;
+        }
+        const int64_t e = lo_e;
+        const int64_t g = a.ids[e];
+        const int rps = a.rows_per_slab[e];
+        const int P = a.np[e];
+        const int64_t r0 = a.group_offsets[g] + (item - a.slab_off[e]) * rps;
+        const int64_t r1g = a.group_offsets[g + 1];
+        const int64_t r1 = r0 + rps < r1g ? r0 + rps : r1g;
+        const int nr = (int)(r1 - r0);
+        const int64_t sb0 = col_off(a.col, r0), sb1 = col_off(a.col, r1);
+        const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.col.data + sb0);
+        const uint32_t slack = (uint32_t)(addr0 & 15u);
+        const uint32_t span = (uint32_t)((sb1 - sb0) + slack);
+        for (int r = tid; r <= nr; r += NT) rstart[r] = (uint32_t)(col_off(a.col, r0 + r) - sb0) + slack;
+        if (tid < nr) bad[tid] = col_valid(a.col, r0 + tid) ? 0 : 1;
+        const int64_t bucket0 = a.bucket_off[e];
+        for (int p = tid; p < PT_PMAX; p += NT) {
+            cnt[p] = 0;
+            fill[p] = 0;
+            if (!HIST) {   // the slab's run inside every range bucket: one global atomic per (slab, range)
+                const uint32_t c = p < P ? a.slab_cnt[item * PT_PMAX + p] : 0u;
+                base[p] = c ? atomicAdd(&a.cursor[bucket0 + p], c) : 0u;
+            }
+        }
+        __syncthreads();
+        // ---- ingest: 16-byte chunks -> one packed u32 (16 bases, first base in the top bits) --------------------------
+        {
+            const uint8_t *a0 = reinterpret_cast<const uint8_t *>(addr0 - slack);
+            const int nchunks = (int)((span + 15u) >> 4);
+            for (int c = tid; c < nchunks; c += NT) {
+                const uint8_t *p = a0 + 16 * c;
+                uint4 v;
+                if (p >= a.data_begin && p + 16 <= a.data_end) {
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+                } else {
+                    v = load_chunk_guarded(p, a.data_begin, a.data_end);
+                }
+                pk[c] = (pack4(v.x) << 24) | (pack4(v.y) << 16) | (pack4(v.z) << 8) | pack4(v.w);
+                const bool ok = valid4(v.x) & valid4(v.y) & valid4(v.z) & valid4(v.w);
+                if (!ok) mark_bad_reads(v, 16u * c, slack, span, rstart, nr, bad);
+            }
+        }
+        __syncthreads();
+        // ---- one sweep over the windows (a warp per read): HIST counts per range, the scatter writes ----------------------------------
+        for (int r = (int)warp; r < nr; r += PT_NW) {
+            const uint32_t rs = rstart[r], len = rstart[r + 1] - rs;
+            if (bad[r] || len < (uint32_t)K) continue;
+            const uint32_t nk = len - (uint32_t)K + 1u;
+            for (uint32_t p = lane; p < nk; p += 32u) {
+                const uint32_t q = rs + p;
+                Key<W> key = Key<W>::zero();
+                load_window(pk, q, K, key);
+                const uint32_t range = P > 1 ? pass_of(key_top32(key, 2 * K), (uint32_t)P) : 0u;
+                if (HIST) {
+                    atomicAdd(&cnt[range], 1u);
+                } else {
+                    const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
+                    const uint32_t ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
+                    const int64_t at = a.rec_off[bucket0 + range] + base[range] + atomicAdd(&fill[range], 1u);
+                    a.rec_lo[at] = key.lo;
+                    if (W == 2) a.rec_hi[at] = key.hi_word();
+                    a.rec_ex[at] = (uint8_t)ex;
+                }
+            }
+        }
+        if (HIST) {
+            __syncthreads();
+            for (int p = tid; p < P; p += NT) {
+                const uint32_t c = cnt[p];
+                a.slab_cnt[item * PT_PMAX + p] = c;
+                if (c) atomicAdd(&a.cursor[bucket0 + p], c);
+            }
+        }
+    }
+}
+
+template <int W>
+constexpr size_t part_count_smem() { return (size_t)table_slots<W>() * (sizeof(typename KeySlot<W>::T) + 4) + 64 * 4; }
+
+// one (group, range) bucket per iteration: count it in shared memory, prune, leave the survivors in the pool as one segment
+template <int W>
+__global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs a, int64_t n_buckets)
+{
+    constexpr int NT = PT_NT, TS = table_slots<W>();
+    using S = KeySlot<W>;
+    using KT = typename S::T;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    KT *tkey = reinterpret_cast<KT *>(smem_raw);
+    uint32_t *tval = reinterpret_cast<uint32_t *>(tkey + TS);
+    uint32_t *ws = tval + TS;   // [0],[1] ticket [2] all-ones k-mer value [3] abort [4],[5] pool base [6] survivors
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t thr = a.min_cov > 65535u ? 0xffffffffu : (a.min_cov > 1u ? a.min_cov : 1u);
+    int64_t cta_pool_pos = 0, cta_pool_end = 0;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long t = atomicAdd(a.ticket, 1ull);
+            ws[0] = (uint32_t)t;
+            ws[1] = (uint32_t)(t >> 32);
+            ws[2] = 0;
+            ws[3] = 0;
+            ws[6] = 0;
+        }
+        __syncthreads();
+        const int64_t b = (int64_t)(((unsigned long long)ws[1] << 32) | ws[0]);
+        if (b >= n_buckets) break;
+        int64_t lo_e = 0, hi_e = a.n_list;
+        while (hi_e - lo_e > 1) {
+            const int64_t m = (lo_e + hi_e) >> 1;
+            if (a.bucket_off[m] <= b) lo_e = m; else hi_e = m;
+        }
+        const int64_t e = lo_e;
+        const int pass = (int)(b - a.bucket_off[e]);
+        if (a.failed[e]) continue;
+        const int64_t rec0 = a.rec_off[b];
+        const uint32_t n = (uint32_t)(a.rec_off[b + 1] - rec0);
+        // table sized to the bucket
+        uint32_t tsize = (uint32_t)TS;
+        if (W == 1) {
+            int tb = 8;
+            while (tb < SM_TBITS && (1u << tb) < 2u * n) tb++;
+            tsize = 1u << tb;
+        }
+        {
+            uint4 *kq = reinterpret_cast<uint4 *>(tkey);
+            for (int j = tid; j < (int)(tsize * sizeof(KT) / 16); j += NT) kq[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+            uint4 *vq = reinterpret_cast<uint4 *>(tval);
+            for (int j = tid; j < (int)(tsize / 4); j += NT) vq[j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        // (measured and dropped: merging equal k-mers inside a warp with __match_any_sync before the probe -- a range of a deep UMI
+        //  holds a handful of true k-mers that carry most of its records -- made this kernel 2.4x slower: 62 -> 147 ms on configs[2])
+        for (uint32_t i = tid; i < n; i += NT) {
+            Key<W> key = Key<W>::zero();
+            key.lo = a.rec_lo[rec0 + i];
+            if constexpr (W == 2) key.hi = a.rec_hi[rec0 + i];
+            const uint32_t ex = a.rec_ex[rec0 + i];
+            const KT kp = S::pack(key);
+            if (kp == S::empty()) {   // the all-ones k-mer is the table's EMPTY marker: side word
+                val_add(&ws[2], ex);
+                continue;
+            }
+            uint32_t h = W == 2 ? __umulhi(hash32(key), tsize) : (hash32(key) >> (32 - __ffs((int)tsize) + 1));
+            uint32_t guard = 0;
+            while (true) {
+                KT cur = tkey[h];
+                if (cur == S::empty()) cur = atomicCAS(&tkey[h], S::empty(), kp);
+                if (cur == kp || cur == S::empty()) {
+                    val_add(&tval[h], ex);
+                    break;
+                }
+                h = h + 1u == tsize ? 0u : h + 1u;
+                if (++guard > tsize) {
+                    ws[3] = 1;
+                    break;
+                }
+            }
+        }
+        if (tid == 0) {
+            if (cta_pool_pos + (int64_t)(TS + 1) > cta_pool_end) {
+                cta_pool_pos = (int64_t)atomicAdd(a.pool_cursor, (unsigned long long)SM_POOL_CHUNK);
+                cta_pool_end = cta_pool_pos + (int64_t)SM_POOL_CHUNK;
+            }
+            ws[4] = (uint32_t)cta_pool_pos;
+            ws[5] = (uint32_t)((uint64_t)cta_pool_pos >> 32);
+        }
+        __syncthreads();
+        const int64_t pb = (int64_t)(((unsigned long long)ws[5] << 32) | ws[4]);
+        if (ws[3] || pb + (int64_t)(TS + 1) > a.pool_cap) {   // table full / pool exhausted: the group is handed on
+            if (tid == 0) a.failed[e] = 1;
+            continue;
+        }
+        // prune + compact (as in k_smem_count)
+        {
+            const uint32_t nq = tsize / 4;
+            const uint4 *tval4 = reinterpret_cast<const uint4 *>(tval);
+            for (uint32_t j0 = 0; j0 < nq; j0 += NT) {
+                const uint32_t j = j0 + (uint32_t)tid;
+                uint4 vv = make_uint4(0u, 0u, 0u, 0u);
+                if (j < nq) vv = tval4[j];
+                const uint32_t c[4] = {vv.x, vv.y, vv.z, vv.w};
+                uint32_t cntk = ((c[0] >> 8) >= thr) + ((c[1] >> 8) >= thr) + ((c[2] >> 8) >= thr) + ((c[3] >> 8) >= thr);
+                uint32_t incl = cntk;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += y;
+                }
+                uint32_t wbase = 0;
+                if (lane == 31u && incl) wbase = atomicAdd(&ws[6], incl);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                int64_t pos = pb + (int64_t)(wbase + incl - cntk);
+                if (cntk) {
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if ((c[t] >> 8) >= thr) {
+                            const Key<W> k = S::unpack(tkey[4 * j + t]);
+                            a.pool_lo[pos] = k.lo;
+                            if (W == 2) a.pool_hi[pos] = k.hi_word();
+                            a.pool_exts[pos] = (uint8_t)c[t];
+                            a.pool_counts[pos] = (uint16_t)((c[t] >> 8) > 65535u ? 65535u : (c[t] >> 8));
+                            pos++;
+                        }
+                }
+            }
+            if (tid == 0) {
+                const uint32_t sv = ws[2];
+                if ((sv >> 8) >= thr) {
+                    const int64_t pos = pb + (int64_t)atomicAdd(&ws[6], 1u);
+                    a.pool_lo[pos] = ~0ull;
+                    if (W == 2) a.pool_hi[pos] = ~0ull;
+                    a.pool_exts[pos] = (uint8_t)sv;
+                    a.pool_counts[pos] = (uint16_t)((sv >> 8) > 65535u ? 65535u : (sv >> 8));
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_out = ws[6];
+        if (tid == 0) {
+            cta_pool_pos += n_out;
+            if (n_out > (uint32_t)SM_TSIZE) a.failed[e] = 1;   // more than the ordering kernels hold
+            a.segs[e * PT_PMAX + pass] = SegRec{pb, (int32_t)n_out, 0};
+        }
+    }
+}
+
+// per listed group: prefix of its segments, survivor total, observations; failed groups go to the next list
+__global__ void k_part_finish(PartArgs a)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_list) return;
+    const int64_t g = a.ids[e];
+    const int P = a.np[e];
+    if (a.failed[e] || a.rows_per_slab[e] <= 0) {
+        a.seg_count[e] = 0;
+        a.failed_ids[atomicAdd(a.n_failed, 1ull)] = (int32_t)g;
+        return;
+    }
+    int64_t pre = 0;
+    unsigned long long obs = 0;
+    for (int p = 0; p < P; p++) {
+        SegRec &r = a.segs[e * PT_PMAX + p];
+        r.prefix = (int32_t)pre;
+        pre += r.n;
+        obs += (unsigned long long)(a.rec_off[a.bucket_off[e] + p + 1] - a.rec_off[a.bucket_off[e] + p]);
+    }
+    a.seg_count[e] = P;
+    a.nsurv[g] = pre;
+    if (obs) atomicAdd(a.n_obs, obs);
+}
+
+}  // namespace rogtk
+
+// -----------------------------------------------------------------------------------------------------------------------------
+// host side
+// -----------------------------------------------------------------------------------------------------------------------------
+namespace rogtk {
+
+struct PartResult {
+    int64_t n_entries = 0;            // listed groups (segment sets of PT_PMAX slots each)
+    const int32_t *seg_list = nullptr;
+    const SegRec *segs = nullptr;
+    const int32_t *seg_count = nullptr;
+    const int32_t *failed_ids = nullptr;
+    int64_t n_failed = 0;
+    std::vector<DevBuf> keep;
+};
+
+inline void part_path_configure()
+{
+    auto cfg = [](auto kernel, size_t bytes) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    };
+    cfg(k_part_scatter<1, true>, part_scatter_smem<1>());
+    cfg(k_part_scatter<2, true>, part_scatter_smem<2>());
+    cfg(k_part_scatter<1, false>, part_scatter_smem<1>());
+    cfg(k_part_scatter<2, false>, part_scatter_smem<2>());
+    cfg(k_part_count<1>, part_count_smem<1>());
+    cfg(k_part_count<2>, part_count_smem<2>());
+}
+
+// d_ids: n_list listed groups (device).  Survivors go to the shared pool (pool_* / pool_cursor of the shared-memory path).
+template <int W>
+inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, size_t workspace_bytes, const ColView &col, const uint8_t *data_begin,
+                            const uint8_t *data_end, const int64_t *d_group_offsets, const int32_t *d_ids, int64_t n_list, int K, uint32_t min_cov,
+                            unsigned long long *d_nobs, int64_t *d_nsurv, unsigned long long *pool_cursor, int64_t pool_cap, uint64_t *pool_lo,
+                            uint64_t *pool_hi, uint8_t *pool_exts, uint16_t *pool_counts, PartResult &res, int64_t *launches)
+{
+    res.n_entries = n_list;
+    res.seg_list = d_ids;
+    if (n_list == 0) return;
+    auto blocks = [](int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); };
+    res.keep.emplace_back((size_t)n_list * PT_PMAX * sizeof(SegRec), st);
+    SegRec *d_segs = res.keep.back().as<SegRec>();
+    res.keep.emplace_back((size_t)n_list * 4, st);
+    int32_t *d_segc = res.keep.back().as<int32_t>();
+    res.keep.emplace_back((size_t)n_list * 4, st);
+    int32_t *d_failed_ids = res.keep.back().as<int32_t>();
+    CK(cudaMemsetAsync(d_segc, 0, (size_t)n_list * 4, st));
+    DevBuf np((size_t)n_list * 4, st), rps((size_t)n_list * 4, st), slabs((size_t)n_list * 8, st), bcap((size_t)n_list * 8, st),
+        failed((size_t)n_list * 4, st), ctr(64, st);
+    CK(cudaMemsetAsync(failed.p, 0, (size_t)n_list * 4, st));
+    CK(cudaMemsetAsync(ctr.p, 0, 64, st));
+    unsigned long long *d_ctr = ctr.as<unsigned long long>();   // [0] scatter ticket [1] count ticket [2] n_failed
+    k_part_plan<<<(unsigned)std::min<int64_t>(blocks(n_list * 32, 256), (int64_t)sm_count * 16), 256, 0, st>>>(
+        col, d_group_offsets, d_ids, n_list, K, np.as<int32_t>(), rps.as<int32_t>(), slabs.as<int64_t>(), bcap.as<int64_t>());
+    if (launches) *launches += 1;
+    // waves bounded by the workspace: records of a wave = sum over its entries of np * capacity
+    std::vector<int32_t> h_np((size_t)n_list);
+    std::vector<int64_t> h_bcap((size_t)n_list);
+    CK(cudaMemcpyAsync(h_np.data(), np.p, (size_t)n_list * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_bcap.data(), bcap.p, (size_t)n_list * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const size_t rec_bytes = (W == 2 ? 17 : 9);
+    const int64_t budget = std::max<int64_t>(1 << 20, (int64_t)(workspace_bytes / 2 / rec_bytes));
+    int64_t e0 = 0;
+    while (e0 < n_list) {
+        int64_t e1 = e0, recs = 0;
+        while (e1 < n_list && (e1 == e0 || recs + h_bcap[(size_t)e1] <= budget)) {
+            recs += h_bcap[(size_t)e1];
+            e1++;
+        }
+        const int64_t nl = e1 - e0;
+        DevBuf slab_off((size_t)(nl + 1) * 8, st), bucket_off((size_t)(nl + 1) * 8, st), scr(scan_scratch_bytes(nl), st);
+        exclusive_scan<int64_t>(slabs.as<int64_t>() + e0, nl, slab_off.as<int64_t>(), scr.as<int64_t>(), st, launches);
+        exclusive_scan<int32_t>(np.as<int32_t>() + e0, nl, bucket_off.as<int64_t>(), scr.as<int64_t>(), st, launches);
+        int64_t h_tot[2] = {0, 0};
+        Peek pk(peek_slot, st, launches);
+        pk.add(slab_off.as<int64_t>() + nl, 8, &h_tot[0]);
+        pk.add(bucket_off.as<int64_t>() + nl, 8, &h_tot[1]);
+        pk.sync();
+        const int64_t n_slabs = h_tot[0], n_buckets = h_tot[1];
+        DevBuf rec_off((size_t)(n_buckets + 1) * 8, st), scr2(scan_scratch_bytes(n_buckets), st), cursor((size_t)std::max<int64_t>(n_buckets, 1) * 4, st),
+            slab_cnt((size_t)std::max<int64_t>(n_slabs, 1) * PT_PMAX * 4, st);
+        CK(cudaMemsetAsync(cursor.p, 0, cursor.bytes, st));
+        PartArgs a{};
+        a.col = col; a.data_begin = data_begin; a.data_end = data_end; a.group_offsets = d_group_offsets;
+        a.ids = d_ids + e0; a.n_list = nl;
+        a.np = np.as<int32_t>() + e0; a.rows_per_slab = rps.as<int32_t>() + e0;
+        a.slab_off = slab_off.as<int64_t>(); a.bucket_off = bucket_off.as<int64_t>(); a.rec_off = rec_off.as<int64_t>();
+        a.cursor = cursor.as<unsigned int>();
+        a.slab_cnt = slab_cnt.as<uint32_t>();
+        a.failed = failed.as<int32_t>() + e0;
+        a.K = K; a.min_cov = min_cov;
+        a.pool_cursor = pool_cursor; a.pool_cap = pool_cap; a.pool_lo = pool_lo; a.pool_hi = pool_hi; a.pool_exts = pool_exts; a.pool_counts = pool_counts;
+        a.segs = d_segs + e0 * PT_PMAX; a.seg_count = d_segc + e0; a.nsurv = d_nsurv; a.n_obs = d_nobs;
+        a.failed_ids = d_failed_ids; a.n_failed = d_ctr + 2;
+        CK(cudaMemsetAsync(d_ctr, 0, 16, st));
+        const unsigned sgrid = (unsigned)std::min<int64_t>(std::max<int64_t>(n_slabs, 1), (int64_t)sm_count * 2);
+        a.ticket = d_ctr;
+        if (n_slabs > 0) k_part_scatter<W, true><<<sgrid, PT_NT, part_scatter_smem<W>(), st>>>(a, n_slabs);
+        // exact bucket sizes -> record offsets; the cursors restart at zero for the scatter
+        exclusive_scan<uint32_t>(cursor.as<uint32_t>(), n_buckets, rec_off.as<int64_t>(), scr2.as<int64_t>(), st, launches);
+        int64_t n_recs = 0;
+        pk.add(rec_off.as<int64_t>() + n_buckets, 8, &n_recs);
+        pk.sync();
+        CK(cudaMemsetAsync(cursor.p, 0, cursor.bytes, st));
+        CK(cudaMemsetAsync(d_ctr, 0, 8, st));
+        DevBuf rlo((size_t)std::max<int64_t>(n_recs, 1) * 8, st), rhi(W == 2 ? (size_t)std::max<int64_t>(n_recs, 1) * 8 : 0, st),
+            rex((size_t)std::max<int64_t>(n_recs, 1), st);
+        a.rec_lo = rlo.as<uint64_t>(); a.rec_hi = W == 2 ? rhi.as<uint64_t>() : nullptr; a.rec_ex = rex.as<uint8_t>();
+        if (n_slabs > 0) k_part_scatter<W, false><<<sgrid, PT_NT, part_scatter_smem<W>(), st>>>(a, n_slabs);
+        if (n_buckets > 0) {
+            a.ticket = d_ctr + 1;
+            const unsigned grid = (unsigned)std::min<int64_t>(n_buckets, (int64_t)sm_count * (W == 1 ? 2 : 1));
+            k_part_count<W><<<grid, PT_NT, part_count_smem<W>(), st>>>(a, n_buckets);
+        }
+        k_part_finish<<<blocks(nl, 128), 128, 0, st>>>(a);
+        if (launches) *launches += 5;
+        // (the wave's buffers are released in stream order when they go out of scope)
+        e0 = e1;
+    }
+    unsigned long long nf = 0;
+    Peek pk(peek_slot, st, launches);
+    pk.add(d_ctr + 2, 8, &nf);
+    pk.sync();
+    res.segs = d_segs;
+    res.seg_count = d_segc;
+    res.failed_ids = d_failed_ids;
+    res.n_failed = (int64_t)nf;
+    res.keep.push_back(std::move(ctr));
+}
+
+}  // namespace rogtk

@@ -458,6 +458,36 @@ __host__ __device__ __forceinline__ uint8_t synth_base(uint64_t seed, int64_t um
     return (uint8_t)("ACGT"[b]);
 }
 
+// the same generator with a per-UMI read count (BASELINE configs[2]: skewed groups): group_offsets is given, one thread per 4 bases
+__global__ void k_synth_var(uint64_t seed, int64_t umi_base, int64_t n_umis, const int64_t *group_offsets, int32_t L, int32_t T, uint32_t err,
+                            uint8_t *data, int64_t *offsets)
+{
+    const int64_t n_reads = group_offsets[n_umis];
+    const int64_t total = n_reads * (int64_t)L;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= n_reads) offsets[t] = t * (int64_t)L;
+    const int64_t q0 = t * 4;
+    if (q0 >= total) return;
+    uint8_t out[4] = {0, 0, 0, 0};
+    int64_t cur_read = -1, u = 0;
+    for (int x = 0; x < 4; x++) {
+        const int64_t q = q0 + x;
+        if (q >= total) break;
+        const int64_t read = q / L;
+        if (read != cur_read) {   // last u with group_offsets[u] <= read
+            int64_t a = 0, b = n_umis;
+            while (b - a > 1) {
+                const int64_t m = (a + b) >> 1;
+                if (group_offsets[m] <= read) a = m; else b = m;
+            }
+            u = a;
+            cur_read = read;
+        }
+        out[x] = synth_base(seed, umi_base + u, (int32_t)(read - group_offsets[u]), (int32_t)(q - read * L), L, T, err);
+    }
+    for (int x = 0; x < 4 && q0 + x < total; x++) data[q0 + x] = out[x];
+}
+
 __global__ void k_synth(uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t R, int32_t L, int32_t T, uint32_t err,
                         uint8_t *data, int64_t *offsets, int64_t *group_offsets)
 {

@@ -62,7 +62,8 @@ __device__ __forceinline__ uint32_t prev_slot(uint32_t h, uint32_t tsize)
 constexpr int SM_SORT_BITS = 10;
 constexpr int SM_SORT_BUCKETS = 1 << SM_SORT_BITS;
 constexpr int SM_POOL_CHUNK = 65536;   // survivors a CTA reserves from the pool at a time (a group needs room for SM_TSIZE + 1)
-constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this -> bitonic kernel
+constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this: the bucket is ordered by a warp (odd-even transposition)
+constexpr int SM_MAX_BUCKET_WARP = 512;   // ... and beyond this the item goes to the bitonic kernel
 // Multi-pass variant for groups that do not fit one table / one staged span (MULTI = true): the k-mer space is cut into
 // P equal ranges (range of a k-mer = floor(top 32 bits * P / 2^32)); pass p re-reads the group's reads in slabs of
 // <= SM_MAX_BASES bases and counts only the k-mers of range p, so every pass needs a table for about 1/P of the distinct
@@ -994,6 +995,7 @@ struct SortArgs {
     const SegRec *segs;
     const int32_t *seg_count;
     const int32_t *seg_list;
+    int seg_stride;                // segment slots per list entry (SM_PMAX for multi-pass groups, PT_PMAX for partitioned ones)
 };
 
 // Counting sort of one work item per CTA pass: survivors are read once into registers, counted per bucket (top 10 k-mer bits),
@@ -1023,15 +1025,15 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
         const int kb = a.kbits;
         uint32_t seg_np = 1, seg_first = 0;   // SEG: passes of the group, first top-32 value of this segment's k-mer range
         if (SEG) {
-            const int64_t e = it / SM_PMAX;
+            const int64_t e = it / a.seg_stride;
             const int np = a.seg_count[e];
-            if ((int)(it % SM_PMAX) >= np) continue;
+            if ((int)(it % a.seg_stride) >= np) continue;
             const SegRec r = a.segs[it];
             ps = r.pool_start;
             o = a.kmer_offsets[a.seg_list[e]] + r.prefix;
             n = r.n;
             seg_np = (uint32_t)np;
-            seg_first = pass_first((uint32_t)(it % SM_PMAX), seg_np);
+            seg_first = pass_first((uint32_t)(it % a.seg_stride), seg_np);
         } else {
             ps = a.pool_start[it];
             if (ps < 0) continue;
@@ -1081,7 +1083,8 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
                 sum += loc[t];
                 mx = loc[t] > mx ? loc[t] : mx;
             }
-            if (mx > (uint32_t)SM_MAX_BUCKET) s_flag = 1;
+            if (mx > (uint32_t)SM_MAX_BUCKET_WARP) s_flag = 2;
+            else if (mx > (uint32_t)SM_MAX_BUCKET) atomicMax(&s_flag, 1);
             uint32_t x = sum;
             const unsigned lane = tid & 31u, warp = tid >> 5;
 #pragma unroll
@@ -1101,10 +1104,11 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
             }
         }
         __syncthreads();
-        if (s_flag) {   // a crowded bucket (low-complexity k-mers): bitonic kernel
+        if (s_flag == 2) {   // a very crowded bucket (low-complexity k-mers): bitonic kernel
             if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)it;
             continue;
         }
+        const bool crowded = s_flag == 1;
         // ---- registers -> shared memory in bucket order (arrival order inside a bucket) ----------------------------------------------
 #pragma unroll
         for (int t = 0; t < EPT; t++) {
@@ -1116,14 +1120,41 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
             }
         }
         __syncthreads();
-        // s_hist[b] is now the END of bucket b.  Every survivor ranks itself inside its (tiny) bucket -- final position = bucket
-        // start + number of bucket members with a smaller k-mer (k-mers are distinct) -- and goes straight to the dense output.
+        // s_hist[b] is now the END of bucket b.
+        if (crowded) {
+            // Deep UMIs: every true k-mer drags ~3K single-error variants along that share its leading bases, i.e. its bucket.  A warp
+            // orders such a bucket in place (odd-even transposition, no block barrier); round 1 sent the whole item to the bitonic kernel.
+            const unsigned lane = tid & 31u, warp = tid >> 5;
+            for (uint32_t b = warp; b < (uint32_t)SM_SORT_BUCKETS; b += NT / 32) {
+                const uint32_t st = b ? s_hist[b - 1] : 0u, en = s_hist[b];
+                const uint32_t sz = en - st;
+                if (sz <= (uint32_t)SM_MAX_BUCKET) continue;
+                for (uint32_t phase = 0; phase < sz; phase++) {
+                    for (uint32_t i = st + (phase & 1u) + 2u * lane; i + 1u < en; i += 64u) {
+                        const uint64_t la = s_lo[i], lb = s_lo[i + 1];
+                        const uint64_t ha = (W == 2) ? s_hi[i] : 0ull, hb = (W == 2) ? s_hi[i + 1] : 0ull;
+                        if (ha > hb || (ha == hb && la > lb)) {
+                            s_lo[i] = lb; s_lo[i + 1] = la;
+                            if (W == 2) { s_hi[i] = hb; s_hi[i + 1] = ha; }
+                            const uint32_t va = s_val[i];
+                            s_val[i] = s_val[i + 1]; s_val[i + 1] = va;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        }
+        // Every survivor ranks itself inside its (tiny) bucket -- final position = bucket start + number of bucket members with a
+        // smaller k-mer (k-mers are distinct) -- and goes straight to the dense output; members of a warp-ordered bucket are in place.
         for (int j = tid; j < n; j += NT) {
             const uint64_t lj = s_lo[j], hj = (W == 2) ? s_hi[j] : 0ull;
             const uint32_t b = bucket_of(lj, hj);
             const uint32_t st = b ? s_hist[b - 1] : 0u, en = s_hist[b];
             uint32_t r = st;
-            if (en - st > 1u) {
+            if (en - st > (uint32_t)SM_MAX_BUCKET) {
+                r = (uint32_t)j;
+            } else if (en - st > 1u) {
                 for (uint32_t i = st; i < en; i++) {
                     const uint64_t li = s_lo[i], hi_i = (W == 2) ? s_hi[i] : 0ull;
                     r += (hi_i < hj || (hi_i == hj && li < lj)) ? 1u : 0u;
@@ -1159,7 +1190,7 @@ __global__ void __launch_bounds__(SORT_BIG_NT) k_sort_big(SortArgs a, int64_t n_
             const int64_t it = a.big_ids[i];
             const SegRec r = a.segs[it];
             ps = r.pool_start;
-            o = a.kmer_offsets[a.seg_list[it / SM_PMAX]] + r.prefix;
+            o = a.kmer_offsets[a.seg_list[it / a.seg_stride]] + r.prefix;
             n = r.n;
         } else {
             const int64_t g = a.big_ids[i];
@@ -1219,7 +1250,7 @@ inline void run_sort_gather_w(cudaStream_t st, uint8_t *peek_slot, int sm_count,
                               int64_t *launches)
 {
     constexpr int SMALL = sort_small_max<W>();
-    const int64_t n_seg_items = n_seg_groups * SM_PMAX;
+    const int64_t n_seg_items = n_seg_groups * (int64_t)a.seg_stride;
     // lists: [0] groups small->mid, [1] segments small->mid, [2] groups mid->bitonic, [3] segments mid->bitonic
     DevBuf ctr(32, st), l0((size_t)n_groups * 4 + 16, st), l1((size_t)n_seg_items * 4 + 16, st);
     CK(cudaMemsetAsync(ctr.p, 0, 32, st));
@@ -1227,7 +1258,7 @@ inline void run_sort_gather_w(cudaStream_t st, uint8_t *peek_slot, int sm_count,
     SortArgs g = a, s = a;
     g.big_ids = l0.as<int32_t>(); g.n_big = d_n;
     s.big_ids = l1.as<int32_t>(); s.n_big = d_n + 1;
-    {
+    if (n_groups > 0) {
         const unsigned grid = (unsigned)std::min<int64_t>(n_groups, (int64_t)sm_count * 16);
         k_sort_small<W, false, SMALL, SORT_NT, false><<<grid, SORT_NT, sort_count_smem<W, SMALL>(), st>>>(g, n_groups, nullptr);
         if (launches) *launches += 1;
@@ -1276,7 +1307,8 @@ inline void run_sort_gather_w(cudaStream_t st, uint8_t *peek_slot, int sm_count,
 inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, int K, int64_t n_groups, const int64_t *pool_start, const int64_t *kmer_offsets,
                             const uint64_t *p_lo, const uint64_t *p_hi, const uint8_t *p_exts, const uint16_t *p_counts, uint64_t *o_lo,
                             uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts, int64_t *launches, const SegRec *segs = nullptr,
-                            const int32_t *seg_count = nullptr, const int32_t *seg_list = nullptr, int64_t n_seg_groups = 0)
+                            const int32_t *seg_count = nullptr, const int32_t *seg_list = nullptr, int64_t n_seg_groups = 0,
+                            int seg_stride = SM_PMAX, bool groups_too = true)
 {
     SortArgs a{};
     a.n_groups = n_groups;
@@ -1288,8 +1320,9 @@ inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, i
     a.segs = segs;
     a.seg_count = seg_count;
     a.seg_list = seg_list;
-    if (K > 32) run_sort_gather_w<2>(st, peek_slot, sm_count, a, n_groups, n_seg_groups, launches);
-    else run_sort_gather_w<1>(st, peek_slot, sm_count, a, n_groups, n_seg_groups, launches);
+    a.seg_stride = seg_stride;
+    if (K > 32) run_sort_gather_w<2>(st, peek_slot, sm_count, a, groups_too ? n_groups : 0, n_seg_groups, launches);
+    else run_sort_gather_w<1>(st, peek_slot, sm_count, a, groups_too ? n_groups : 0, n_seg_groups, launches);
 }
 
 }  // namespace rogtk
@@ -1314,6 +1347,8 @@ struct SmemResult {
     const uint64_t *pool_lo = nullptr, *pool_hi = nullptr;
     const uint8_t *pool_exts = nullptr;
     const uint16_t *pool_counts = nullptr;
+    unsigned long long *pool_cursor = nullptr;   // the partition tier appends its segments to the same pool
+    int64_t pool_cap = 0;
     std::vector<DevBuf> keep;
     float ms_kernel = 0.f;
     // multi-pass groups: list entries, their segments (SM_PMAX per entry) and passes used
@@ -1378,7 +1413,7 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     int64_t pool_cap = (int64_t)(ub / (min_cov > 1 ? min_cov : 1)) + 1;
     pool_cap = std::min<int64_t>(pool_cap, (int64_t)(workspace_bytes / 2 / entry));
     // per-CTA chunking leaves unused tails: one open chunk per running CTA, up to SM_TSIZE + 1 entries at every chunk switch
-    pool_cap += pool_cap / 4 + std::min<int64_t>(n_groups, first_ctas) * 2 * SM_POOL_CHUNK;
+    pool_cap += pool_cap / 4 + (std::min<int64_t>(n_groups, first_ctas) * 2 + (int64_t)sm_count * 2) * SM_POOL_CHUNK;
     pool_cap = std::max<int64_t>(pool_cap, 1024);
     if (tune.debug_pool_cap) pool_cap = std::max<int64_t>(1024, tune.debug_pool_cap);   // tests: exhaust the pool
     res.keep.emplace_back((size_t)pool_cap * 8, st);
@@ -1492,6 +1527,8 @@ inline void run_smem_path(cudaStream_t st, uint8_t *peek_slot, int sm_count, siz
     res.pool_hi = p_hi;
     res.pool_exts = p_exts;
     res.pool_counts = p_counts;
+    res.pool_cursor = d_ctr + 1;
+    res.pool_cap = pool_cap;
     res.keep.push_back(std::move(ctr));
 }
 

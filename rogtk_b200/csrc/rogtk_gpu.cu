@@ -33,6 +33,7 @@
 #include "kernels_table.cuh"
 #include "kernels_unitig.cuh"
 #include "scan.cuh"
+#include "kernels_part.cuh"
 
 using namespace rogtk;
 
@@ -412,6 +413,7 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         uint64_t thr = UINT64_MAX;
         CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         smem_path_configure();
+        part_path_configure();
     } catch (const CudaFail &f) {
         fprintf(stderr, "rogtk_gpu_create: %s: %s\n", f.what, cudaGetErrorString(f.e));
         cudaGetLastError();
@@ -679,6 +681,22 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
         d_spill_ids = sm.deferred_ids;
         n_spill = sm.n_deferred;
     }
+    // groups beyond the multi-pass kernel: partition-then-count in shared memory (kernels_part.cuh); what overflows there goes on
+    PartResult part;
+    if (n_spill > 0 && sm.pool_cursor && !(flags & (ROGTK_FORCE_SPILL | ROGTK_NO_MULTIPASS | ROGTK_NO_PARTITION))) {
+        if (K <= 32)
+            run_part_path_w<1>(st, ctx->peek_slot, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_begin, in.data_end, in.group_offsets, d_spill_ids,
+                               n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), sm.pool_cursor, sm.pool_cap, const_cast<uint64_t *>(sm.pool_lo),
+                               const_cast<uint64_t *>(sm.pool_hi), const_cast<uint8_t *>(sm.pool_exts), const_cast<uint16_t *>(sm.pool_counts), part,
+                               &ctx->launches);
+        else
+            run_part_path_w<2>(st, ctx->peek_slot, ctx->sm_count, ctx->workspace_bytes, in.col, in.data_begin, in.data_end, in.group_offsets, d_spill_ids,
+                               n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), sm.pool_cursor, sm.pool_cap, const_cast<uint64_t *>(sm.pool_lo),
+                               const_cast<uint64_t *>(sm.pool_hi), const_cast<uint8_t *>(sm.pool_exts), const_cast<uint16_t *>(sm.pool_counts), part,
+                               &ctx->launches);
+        d_spill_ids = part.failed_ids;
+        n_spill = part.n_failed;
+    }
     if (n_spill > 0) {
         if (K <= 32)
             run_spill<1>(ctx, in.col, in.group_offsets, d_spill_ids, n_spill, K, min_coverage, d_nobs, nsurv.as<int64_t>(), waves);
@@ -708,6 +726,10 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
         run_sort_gather(st, ctx->peek_slot, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
                         sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches,
                         sm.segs, sm.seg_count, sm.seg_list, sm.n_seg_groups);
+    if (part.n_entries > 0)   // segments of the partitioned groups (same pool, PT_PMAX segment slots per group)
+        run_sort_gather(st, ctx->peek_slot, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
+                        sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches, part.segs,
+                        part.seg_count, part.seg_list, part.n_entries, PT_PMAX, false);
     for (auto &wv : waves) {
         if (wv.n_recs == 0) continue;
         k_spill_scatter<<<blocks_for(wv.n_recs, 256), 256, 0, st>>>(wv.recs.as<SpillRec>(), wv.n_recs, d_spill_ids, wv.list_base,
@@ -741,7 +763,7 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
     r.n_edges = n_edges;
     r.n_obs = (int64_t)h_nobs;
     r.n_spill = n_spill;
-    r.n_multi = sm.n_seg_groups - (sm.n_seg_groups ? sm.n_deferred : 0);
+    r.n_multi = sm.n_seg_groups - (sm.n_seg_groups ? sm.n_deferred : 0) + (part.n_entries - part.n_failed);
     r.ms_hot = sm.ms_kernel;
 }
 
@@ -2000,6 +2022,27 @@ extern "C" int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t 
         const int64_t threads = std::max<int64_t>((total + 3) / 4, n_umis * (int64_t)reads_per_umi + 1);
         k_synth<<<blocks_for(threads, 256), 256, 0, ctx->stream>>>(seed, umi_base, n_umis, reads_per_umi, read_len, template_len,
                                                                    err_per_64k, d_data, d_offsets, d_group_offsets);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+    } catch (...) {
+        return fail_code(ctx);
+    }
+    return ROGTK_OK;
+}
+
+extern "C" int rogtk_gpu_synth_reads_var(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, const int64_t *d_group_offsets,
+                                         int64_t n_reads, int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data,
+                                         int64_t *d_offsets)
+{
+    if (!ctx || n_umis < 0 || n_reads < 0 || read_len < 1 || template_len < read_len || !d_group_offsets) return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    try {
+        CK(cudaSetDevice(ctx->device));
+        const int64_t total = n_reads * (int64_t)read_len;
+        const int64_t threads = std::max<int64_t>((total + 3) / 4, n_reads + 1);
+        k_synth_var<<<blocks_for(threads, 256), 256, 0, ctx->stream>>>(seed, umi_base, n_umis, d_group_offsets, read_len, template_len, err_per_64k,
+                                                                       d_data, d_offsets);
         ctx->launches++;
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());

@@ -261,6 +261,21 @@ class Engine:
                                                     ctypes.c_void_p(d_off), ctypes.c_void_p(d_goff)))
         return d_data, d_off, d_goff, n_bytes
 
+    def synth_reads_device_var(self, seed: int, umi_base: int, reads_per_umi: np.ndarray, read_len: int, template_len: int, err_per_64k: int):
+        """synth_reads_device with a read count per UMI (BASELINE configs[2]); same bytes as synth.synth_reads."""
+        rp = np.asarray(reads_per_umi, dtype=np.int64)
+        goff = np.zeros(len(rp) + 1, dtype=np.int64)
+        np.cumsum(rp, out=goff[1:])
+        n_reads = int(goff[-1])
+        n_bytes = n_reads * read_len
+        d_data = self.device_alloc(n_bytes + 16)
+        d_off = self.device_alloc((n_reads + 1) * 8)
+        d_goff = self.device_alloc((len(rp) + 1) * 8)
+        self.h2d(d_goff, goff.view(np.uint8))
+        self._check(self._lib.rogtk_gpu_synth_reads_var(self._ctx, seed & 0xFFFFFFFFFFFFFFFF, umi_base, len(rp), ctypes.c_void_p(d_goff), n_reads,
+                                                        read_len, template_len, err_per_64k, ctypes.c_void_p(d_data), ctypes.c_void_p(d_off)))
+        return d_data, d_off, d_goff, n_bytes, n_reads
+
     # ---- the hot path ----------------------------------------------------------------------------------------------------
     def _call(self, col: _ffi.StrCol, goff_ptr, n_groups: int, k: int, min_coverage: int, flags: int):
         out = _ffi.GraphBatchC()

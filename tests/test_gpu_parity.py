@@ -8,6 +8,7 @@ from util import assert_batches_equal, check_invariants, groups_to_arrow, load_g
 pytestmark = pytest.mark.gpu
 
 EMIT_CSR, EMIT_STATS, EXACT_K, FORCE_SPILL, NO_MULTIPASS = 1, 2, 4, 32, 64
+NO_PARTITION = 256
 
 
 def _both(engine, oracle, data, offs, goff, k, mc, validity=None, exact=False, spill=False, csr=True, ctx="", extra_flags=0):
@@ -201,14 +202,18 @@ def test_groups_too_big_for_one_table(engine, oracle):
 @pytest.mark.parametrize("k,exact", [(31, False), (16, False), (47, False), (33, True), (6, True), (1, True)])
 def test_multipass_groups(engine, oracle, k, exact):
     """mid-size groups: 60..430 reads of 300 bp around a 1000 bp template (1..8 passes), a group of unrelated reads (every pass
-    near its table limit), null / invalid / short reads inside slabs, and a group beyond the multi-pass limit (HBM tables)."""
+    near its table limit), null / invalid / short reads inside slabs, and a group beyond the multi-pass limit (partition-then-count;
+    the HBM tables with ROGTK_NO_PARTITION)."""
     from rogtk_b200 import synth
     rp = np.array([60, 5, 130, 280, 0, 430, 90, 600])
     data, offs, goff = synth.synth_reads(synth.config_seed(2), 7, len(rp), rp, 300, 1000)
     for mc in (1, 2, 3):
         got, ref = _both(engine, oracle, data, offs, goff, k, mc, exact=exact, csr=(mc == 2), ctx=f"multipass k={k} mc={mc}")
-        assert got.n_multipass_groups >= 4
-        assert got.n_spilled_groups == 1           # 600 x 300 bases is beyond 8 passes
+        assert got.n_multipass_groups >= 5
+        assert got.n_spilled_groups == 0           # 600 x 300 bases is beyond 8 passes: partition-then-count
+        alt = engine.count_prune(data, offs, goff, k, mc, flags=EMIT_STATS | NO_PARTITION | (EXACT_K if exact else 0))
+        assert alt.n_spilled_groups == 1
+        assert_batches_equal(alt, ref, ctx=f"multipass k={k} mc={mc}, HBM tables for the largest group")
     rng = np.random.default_rng(k)
     groups = []
     # unrelated reads: ~ as many distinct k-mers as observations
@@ -277,14 +282,18 @@ def test_baseline_config_subsets(engine, oracle, cfg):
 @pytest.mark.parametrize("k", [11, 16, 17, 31, 33, 63])
 def test_baseline_config3_subset(engine, oracle, k):
     """BASELINE configs[2]: skewed reads per UMI (log-uniform 1..5000; the first 40 UMIs hold groups of 3028, 2120 and 3962
-    reads), L=150, T=500, min_cov=2, k sweep over K = 16 / 32 / 64 -- all three counting paths in one batch."""
+    reads), L=150, T=500, min_cov=2, k sweep over K = 16 / 32 / 64 -- single table, multi-pass and partition-then-count in one batch,
+    and the same batch with the largest groups in the HBM tables (ROGTK_NO_PARTITION)."""
     from rogtk_b200 import synth
     seed = synth.config_seed(3)
     rp = synth.skewed_reads_per_umi(seed, 40)
     data, offs, goff = synth.synth_reads(seed, 0, len(rp), rp, 150, 500)
     got, ref = _both(engine, oracle, data, offs, goff, k, 2, csr=(k == 31), ctx=f"cfg3 k={k}")
-    assert got.n_spilled_groups >= 3 and got.n_multipass_groups >= 5
+    assert got.n_spilled_groups == 0 and got.n_multipass_groups >= 8
     check_invariants(got, 2)
+    alt = engine.count_prune(data, offs, goff, k, 2, flags=EMIT_STATS | NO_PARTITION)
+    assert alt.n_spilled_groups >= 3 and alt.n_multipass_groups >= 5
+    assert_batches_equal(alt, ref, ctx=f"cfg3 k={k}, HBM tables")
 
 
 def test_device_resident_path_and_invariants_at_scale(engine, oracle):
@@ -671,6 +680,42 @@ def test_three_counting_paths_agree_on_skewed_batches(engine, k, exact):
         for other, name in ((b, "no multipass"), (c, "hbm tables only")):
             assert_batches_equal(other, a, check_csr=True, ctx=f"paths k={k} mc={mc}: {name}")
         check_invariants(a, mc)
+
+
+def test_partition_then_count_tier(engine, oracle):
+    """Groups beyond the multi-pass kernel (more than 131 072 bases: UMIs with thousands of reads, BASELINE configs[2]) are cut
+    into k-mer ranges, their observations scattered to range buckets in HBM and every bucket counted in shared memory
+    (kernels_part.cuh).  Bit-exact against the oracle for K = 16 / 32 / 64 and small K (one range), nulls and invalid reads
+    inside; identical to the HBM-table path (ROGTK_NO_PARTITION); buckets are sized exactly, so a group whose reads are one k-mer
+    repeated 119 000 times (count saturates at 65535) stays in this tier."""
+    from rogtk_b200 import synth
+    rp = np.array([1200, 3, 2500, 950, 1, 4000, 60])
+    data, offs, goff = synth.synth_reads(synth.config_seed(3), 17, len(rp), rp, 150, 500)
+    data = data.copy()
+    data[offs[5] + 7] = ord("N")                # an invalid read inside a partitioned group
+    data[offs[1300]:offs[1301]] |= 0x20         # a lower-case read
+    valid = np.ones(len(offs) - 1, dtype=bool)
+    valid[[10, 2000, 4400]] = False
+    validity = np.packbits(valid, bitorder="little")
+    for k, mc in ((31, 2), (13, 1), (47, 2), (5, 3), (63, 1)):
+        ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity, emit_csr=True)
+        got = engine.count_prune(data, offs, goff, k, mc, validity=validity, flags=EMIT_STATS | EMIT_CSR)
+        assert_batches_equal(got, ref, check_csr=True, ctx=f"partition tier k={k} mc={mc}")
+        assert got.n_observations == ref.n_observations
+        assert got.n_spilled_groups == 0 and got.n_multipass_groups >= 4
+        alt = engine.count_prune(data, offs, goff, k, mc, validity=validity, flags=EMIT_STATS | EMIT_CSR | NO_PARTITION)
+        assert alt.n_spilled_groups >= 4
+        assert_batches_equal(alt, got, check_csr=True, ctx=f"partition tier vs HBM tables k={k}")
+    # a low-complexity giant group: 1000 reads of poly-A (one 32-mer observed ~119 000 times -> count saturates) + a normal big group
+    reads = ["A" * 150] * 1000 + ["ACGT" * 37 + "AC"] * 900
+    d2, o2, _ = oracle.strings_to_arrow(reads)
+    g2 = np.array([0, 1000, 1900])
+    for k in (31, 40):
+        ref = oracle.count_prune_batch(d2, o2, g2, k, 2)
+        got = engine.count_prune(d2, o2, g2, k, 2, flags=EMIT_STATS)
+        assert_batches_equal(got, ref, ctx=f"partition tier, low-complexity giant groups k={k}")
+        assert got.n_spilled_groups == 0
+        assert int(got.counts.max()) == 65535
 
 
 def _check_unitigs(engine, oracle, data, offs, goff, k, mc, min_length, validity=None, ctx=""):
