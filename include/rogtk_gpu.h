@@ -104,6 +104,8 @@ int rogtk_gpu_device_count(void);
 /* workspace_bytes: upper bound for transient HBM tables + pools (0 = 25% of free device memory) */
 rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, int *err);
 void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx);
+/* hand the context's cached device memory (its private stream-ordered pool) and cached page-locked blocks back to the system */
+int rogtk_gpu_trim(rogtk_gpu_ctx *ctx);
 const char *rogtk_gpu_last_error(rogtk_gpu_ctx *ctx);
 
 /* ---- host helpers that mirror reference host logic (no GPU needed) ------------------------------------------ */

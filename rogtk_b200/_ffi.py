@@ -32,7 +32,7 @@ NO_PARTITION = 1 << 8
 
 # every symbol include/rogtk_gpu.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
-    "rogtk_gpu_abi_version", "rogtk_gpu_device_count", "rogtk_gpu_create", "rogtk_gpu_destroy", "rogtk_gpu_last_error",
+    "rogtk_gpu_abi_version", "rogtk_gpu_device_count", "rogtk_gpu_create", "rogtk_gpu_destroy", "rogtk_gpu_trim", "rogtk_gpu_last_error",
     "rogtk_gpu_k_eff", "rogtk_gpu_estimate_k", "rogtk_gpu_shard_of", "rogtk_gpu_count_prune_batch", "rogtk_gpu_free_batch",
     "rogtk_gpu_synth_reads", "rogtk_gpu_synth_reads_var", "rogtk_gpu_device_alloc", "rogtk_gpu_device_free", "rogtk_gpu_pinned_alloc",
     "rogtk_gpu_pinned_free", "rogtk_gpu_memcpy_h2d", "rogtk_gpu_memcpy_d2h", "rogtk_gpu_launch_count", "rogtk_gpu_flush_l2", "rogtk_gpu_debug_phase_cycles",
@@ -202,6 +202,8 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_create.argtypes = [ctypes.c_int, sz, ctypes.POINTER(ctypes.c_int)]
     lib.rogtk_gpu_create.restype = vp
     lib.rogtk_gpu_destroy.argtypes = [vp]
+    lib.rogtk_gpu_trim.argtypes = [vp]
+    lib.rogtk_gpu_trim.restype = ctypes.c_int
     lib.rogtk_gpu_last_error.argtypes = [vp]
     lib.rogtk_gpu_last_error.restype = ctypes.c_char_p
     lib.rogtk_gpu_k_eff.argtypes = [i64]

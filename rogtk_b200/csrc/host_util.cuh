@@ -22,6 +22,20 @@ struct ArgFail {
     std::string msg;
 };
 
+// The memory pool stream-ordered allocations of this thread come from: every context owns one (created in rogtk_gpu_create,
+// destroyed with the context), so a context neither pins freed memory in the device's default pool for the rest of the process
+// nor trims other users' cached memory when it goes away.  Entry points set it for their duration (PoolScope).
+inline thread_local cudaMemPool_t tl_pool = nullptr;
+struct PoolScope {
+    cudaMemPool_t prev;
+    explicit PoolScope(cudaMemPool_t p) : prev(tl_pool) { tl_pool = p; }
+    ~PoolScope() { tl_pool = prev; }
+};
+inline cudaError_t pool_malloc(void **p, size_t n, cudaStream_t s)
+{
+    return tl_pool ? cudaMallocFromPoolAsync(p, n, tl_pool, s) : cudaMallocAsync(p, n, s);
+}
+
 // stream-ordered device buffer
 struct DevBuf {
     void *p = nullptr;
@@ -43,7 +57,7 @@ struct DevBuf {
         release();
         st = s;
         bytes = n;
-        CK(cudaMallocAsync(&p, n ? n : 16, s));
+        CK(pool_malloc(&p, n ? n : 16, s));
     }
     void release()
     {

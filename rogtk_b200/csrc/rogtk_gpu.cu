@@ -43,6 +43,7 @@ using namespace rogtk;
 struct rogtk_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;   // this context's stream-ordered allocations (host_util.cuh: PoolScope)
     cudaStream_t copy_stream = nullptr;
     cudaStream_t out_stream = nullptr;
     size_t chunk_bytes = (size_t)256 << 20;   // read bytes per chunk of the overlapped host->host path
@@ -408,10 +409,16 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         ctx->workspace_bytes = workspace_bytes ? workspace_bytes : free_b / 4;
-        cudaMemPool_t pool;
-        CK(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t thr = UINT64_MAX;
-        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        {   // a private pool: freed blocks stay cached for the next batch of THIS context only (rogtk_gpu_trim hands them back)
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            CK(cudaMemPoolCreate(&ctx->pool, &props));
+            uint64_t thr = UINT64_MAX;
+            CK(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        }
         smem_path_configure();
         part_path_configure();
     } catch (const CudaFail &f) {
@@ -432,9 +439,9 @@ extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
     for (auto &kv : ctx->pinned_size) cudaFreeHost(kv.first);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->peek_slot) cudaFreeHost(ctx->peek_slot);
-    {   // hand the stream-ordered pool's cached memory back to the device
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    if (ctx->pool) {   // the context's own pool goes away with it (nobody else's cached memory is touched)
+        cudaDeviceSynchronize();
+        cudaMemPoolDestroy(ctx->pool);
     }
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -442,6 +449,25 @@ extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     delete ctx;
+}
+
+extern "C" int rogtk_gpu_trim(rogtk_gpu_ctx *ctx)
+{
+    if (!ctx) return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->pool) cudaMemPoolTrimTo(ctx->pool, 0);
+    {
+        std::lock_guard<std::mutex> plk(ctx->pin_mu);
+        for (auto &kv : ctx->pinned_free) {
+            ctx->pinned_size.erase(kv.second);
+            cudaFreeHost(kv.second);
+        }
+        ctx->pinned_free.clear();
+        ctx->pinned_cached = 0;
+    }
+    return ROGTK_OK;
 }
 
 extern "C" const char *rogtk_gpu_last_error(rogtk_gpu_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
@@ -562,7 +588,7 @@ void fill_empty_batch(rogtk_gpu_ctx *ctx, int64_t n_groups, bool out_dev, uint32
     const size_t ob = (size_t)(n_groups + 1) * 8;
     if (out_dev) {
         void *p;
-        CK(cudaMallocAsync(&p, ob, ctx->stream));
+        CK(pool_malloc(&p, ob, ctx->stream));
         CK(cudaMemsetAsync(p, 0, ob, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         out->kmer_offsets = (int64_t *)p;
@@ -1521,6 +1547,7 @@ extern "C" void rogtk_gpu_free_batch(rogtk_gpu_ctx *ctx, rogtk_graph_batch *b)
 {
     if (!ctx || !b || !b->_owner) return;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     BatchOwner *own = reinterpret_cast<BatchOwner *>(b->_owner);
     cudaSetDevice(ctx->device);
     for (void *p : own->ptrs) {
@@ -1537,6 +1564,7 @@ extern "C" int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strco
 {
     if (!ctx) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     int rc = ROGTK_ERR_INTERNAL;
     try {
         rc = count_prune_impl(ctx, reads, group_offsets, n_groups, k, min_coverage, flags, out);
@@ -1565,6 +1593,7 @@ extern "C" int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch
         (in->n_kmers > 0 && (!in->kmers_lo || !in->exts || !in->counts)) || (in->k_eff > 32 && in->n_kmers > 0 && !in->kmers_hi))
         return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     memset(out, 0, sizeof(*out));
     BatchOwner *own = new BatchOwner();
     const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
@@ -1665,6 +1694,7 @@ extern "C" int rogtk_gpu_spectrum_split(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
     if (!ctx || !h_bounds || n < 0 || k_eff < 1 || k_eff > 64 || n_ranks < 1 || n_ranks > 256 || (n > 0 && !d_lo))
         return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     try {
         CK(cudaSetDevice(ctx->device));
         DevBuf b((size_t)(n_ranks + 1) * 8, ctx->stream);
@@ -1686,6 +1716,7 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
     if (!ctx || !out || n < 0 || k_eff < 1 || k_eff > 64 || (n > 0 && (!d_lo || !d_counts || !d_exts)) || (k_eff > 32 && n > 0 && !d_hi))
         return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     memset(out, 0, sizeof(*out));
     BatchOwner *own = new BatchOwner();
     const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
@@ -1971,6 +2002,7 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
         (in->k_eff > 32 && in->n_kmers > 0 && !in->kmers_hi))
         return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     memset(out, 0, sizeof(*out));
     BatchOwner *own = new BatchOwner();
     const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
@@ -1997,6 +2029,7 @@ extern "C" void rogtk_gpu_free_contigs(rogtk_gpu_ctx *ctx, rogtk_contig_batch *b
 {
     if (!ctx || !b || !b->_owner) return;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     BatchOwner *own = reinterpret_cast<BatchOwner *>(b->_owner);
     cudaSetDevice(ctx->device);
     for (void *p : own->ptrs) {
@@ -2016,6 +2049,7 @@ extern "C" int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t 
 {
     if (!ctx || n_umis < 0 || reads_per_umi < 1 || read_len < 1 || template_len < read_len) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     try {
         CK(cudaSetDevice(ctx->device));
         const int64_t total = n_umis * (int64_t)reads_per_umi * read_len;
@@ -2037,6 +2071,7 @@ extern "C" int rogtk_gpu_synth_reads_var(rogtk_gpu_ctx *ctx, uint64_t seed, int6
 {
     if (!ctx || n_umis < 0 || n_reads < 0 || read_len < 1 || template_len < read_len || !d_group_offsets) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     try {
         CK(cudaSetDevice(ctx->device));
         const int64_t total = n_reads * (int64_t)read_len;
@@ -2116,6 +2151,7 @@ extern "C" int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint
 {
     if (!ctx) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     ctx->phase_enabled = enable != 0;
     if (out16) memcpy(out16, ctx->phase_cycles, sizeof(ctx->phase_cycles));
     return ROGTK_OK;
@@ -2125,6 +2161,7 @@ extern "C" int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx)
 {
     if (!ctx) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PoolScope pool_scope(ctx->pool);
     cudaSetDevice(ctx->device);
     if (!ctx->flush_buf) {
         ctx->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
