@@ -45,7 +45,7 @@ void compression_rows(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *db, int64_t m
     } fr{ctx, &cb};
     if (ms_device) *ms_device += cb.ms_total;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t ngn = (size_t)std::max<int64_t>(ng, 1);
@@ -308,7 +308,7 @@ void hand_over_strings(rogtk_gpu_ctx *ctx, const HostStrings &hs, rogtk_string_b
     out->n_rows = ng;
     out->n_bytes = hs.off.empty() ? 0 : hs.off.back();
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     int64_t *o = (int64_t *)pinned_get(ctx, (size_t)(ng + 1) * 8);
     own->ptrs.push_back(o);
     uint8_t *d = (uint8_t *)pinned_get(ctx, (size_t)std::max<int64_t>(out->n_bytes, 1));
@@ -327,7 +327,7 @@ void release_owner(rogtk_gpu_ctx *ctx, void *owner)
 {
     if (!owner) return;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     BatchOwner *own = reinterpret_cast<BatchOwner *>(owner);
     for (void *p : own->ptrs) pinned_put(ctx, p);
     delete own;
@@ -401,7 +401,7 @@ extern "C" int rogtk_gpu_assemble_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
             bool ran = false;
             {
                 std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
                 ran = assemble_compression_chunked(ctx, reads, group_offsets, n_groups, p->k, p->min_coverage, flags, post, &info);
                 if (ran) {
                     for (HostArr *h : {&post.h_soff, &post.h_sdata, &post.h_sflags})
@@ -418,7 +418,7 @@ extern "C" int rogtk_gpu_assemble_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
                 out->n_count_passes = 1;
                 if (!out->data) {   // no contig at all: still a valid (empty) data buffer
                     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
                     out->data = (uint8_t *)pinned_get(ctx, 16);
                     own->ptrs.push_back(out->data);
                 }
@@ -531,7 +531,7 @@ extern "C" int rogtk_gpu_sweep_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *rea
         const size_t total = (size_t)std::max<int64_t>(1, n_groups * n_cells);
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
             out->k = (int64_t *)pinned_get(ctx, total * 8); own->ptrs.push_back(out->k);
             out->min_coverage = (int64_t *)pinned_get(ctx, total * 8); own->ptrs.push_back(out->min_coverage);
             out->contig_length = (int64_t *)pinned_get(ctx, total * 8); own->ptrs.push_back(out->contig_length);
@@ -772,7 +772,7 @@ extern "C" int rogtk_gpu_optimize_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
         rows.data.resize((size_t)rows.off[(size_t)n_groups]);
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
             const size_t nb = (size_t)std::max<int64_t>(n_groups, 1) * 4;
             out->k = (uint32_t *)pinned_get(ctx, nb); own->ptrs.push_back(out->k);
             out->min_coverage = (uint32_t *)pinned_get(ctx, nb); own->ptrs.push_back(out->min_coverage);

@@ -43,7 +43,7 @@ using namespace rogtk;
 struct rogtk_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaMemPool_t pool = nullptr;   // this context's stream-ordered allocations (host_util.cuh: PoolScope)
+    DevCache *cache = nullptr;      // this context's device memory (host_util.cuh: DevCache / CacheScope)
     cudaStream_t copy_stream = nullptr;
     cudaStream_t out_stream = nullptr;
     size_t chunk_bytes = (size_t)256 << 20;   // read bytes per chunk of the overlapped host->host path
@@ -409,16 +409,7 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         ctx->workspace_bytes = workspace_bytes ? workspace_bytes : free_b / 4;
-        {   // a private pool: freed blocks stay cached for the next batch of THIS context only (rogtk_gpu_trim hands them back)
-            cudaMemPoolProps props{};
-            props.allocType = cudaMemAllocationTypePinned;
-            props.handleTypes = cudaMemHandleTypeNone;
-            props.location.type = cudaMemLocationTypeDevice;
-            props.location.id = device;
-            CK(cudaMemPoolCreate(&ctx->pool, &props));
-            uint64_t thr = UINT64_MAX;
-            CK(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        }
+        ctx->cache = new DevCache();
         smem_path_configure();
         part_path_configure();
     } catch (const CudaFail &f) {
@@ -439,9 +430,9 @@ extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
     for (auto &kv : ctx->pinned_size) cudaFreeHost(kv.first);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->peek_slot) cudaFreeHost(ctx->peek_slot);
-    if (ctx->pool) {   // the context's own pool goes away with it (nobody else's cached memory is touched)
+    if (ctx->cache) {   // the context's device memory goes away with it (nobody else's cached memory is touched)
         cudaDeviceSynchronize();
-        cudaMemPoolDestroy(ctx->pool);
+        delete ctx->cache;
     }
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -457,7 +448,7 @@ extern "C" int rogtk_gpu_trim(rogtk_gpu_ctx *ctx)
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->pool) cudaMemPoolTrimTo(ctx->pool, 0);
+    if (ctx->cache) ctx->cache->release_idle();
     {
         std::lock_guard<std::mutex> plk(ctx->pin_mu);
         for (auto &kv : ctx->pinned_free) {
@@ -588,7 +579,7 @@ void fill_empty_batch(rogtk_gpu_ctx *ctx, int64_t n_groups, bool out_dev, uint32
     const size_t ob = (size_t)(n_groups + 1) * 8;
     if (out_dev) {
         void *p;
-        CK(pool_malloc(&p, ob, ctx->stream));
+        CK(dev_alloc(&p, ob, ctx->stream));
         CK(cudaMemsetAsync(p, 0, ob, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         out->kmer_offsets = (int64_t *)p;
@@ -1263,10 +1254,10 @@ void run_chunked(rogtk_gpu_ctx *ctx, const rogtk_strcol *c, const int64_t *group
                 compress_unitigs_impl(ctx, &view, post->min_length, ROGTK_OUTPUT_ON_DEVICE, &cb, &cown);
                 contig_rows_device(ctx, cb, post->min_length, post->only_largest, roff, rows, rflags, nb);
             } catch (...) {
-                for (void *p : cown.ptrs) cudaFreeAsync(p, s_comp);
+                for (void *p : cown.ptrs) dev_free(p, s_comp);
                 throw;
             }
-            for (void *p : cown.ptrs) cudaFreeAsync(p, s_comp);
+            for (void *p : cown.ptrs) dev_free(p, s_comp);
             if (post->n_bytes) k_add_i64<<<blocks_for(ng + 1, 256), 256, 0, s_comp>>>(roff.as<int64_t>(), ng + 1, post->n_bytes);
             CK(cudaEventRecord(comp_done, s_comp));
             CK(cudaEventRecord(x.consumed, s_comp));
@@ -1547,11 +1538,11 @@ extern "C" void rogtk_gpu_free_batch(rogtk_gpu_ctx *ctx, rogtk_graph_batch *b)
 {
     if (!ctx || !b || !b->_owner) return;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     BatchOwner *own = reinterpret_cast<BatchOwner *>(b->_owner);
     cudaSetDevice(ctx->device);
     for (void *p : own->ptrs) {
-        if (own->on_device) cudaFreeAsync(p, ctx->stream);
+        if (own->on_device) dev_free(p, ctx->stream);
         else pinned_put(ctx, p);
     }
     delete own;
@@ -1564,7 +1555,7 @@ extern "C" int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strco
 {
     if (!ctx) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     int rc = ROGTK_ERR_INTERNAL;
     try {
         rc = count_prune_impl(ctx, reads, group_offsets, n_groups, k, min_coverage, flags, out);
@@ -1574,7 +1565,7 @@ extern "C" int rogtk_gpu_count_prune_batch(rogtk_gpu_ctx *ctx, const rogtk_strco
     if (rc != ROGTK_OK && out && out->_owner) {
         BatchOwner *own = reinterpret_cast<BatchOwner *>(out->_owner);
         for (void *p : own->ptrs) {
-            if (own->on_device) cudaFreeAsync(p, ctx->stream);
+            if (own->on_device) dev_free(p, ctx->stream);
             else pinned_put(ctx, p);
         }
         delete own;
@@ -1593,7 +1584,7 @@ extern "C" int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch
         (in->n_kmers > 0 && (!in->kmers_lo || !in->exts || !in->counts)) || (in->k_eff > 32 && in->n_kmers > 0 && !in->kmers_hi))
         return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     memset(out, 0, sizeof(*out));
     BatchOwner *own = new BatchOwner();
     const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
@@ -1670,7 +1661,7 @@ extern "C" int rogtk_gpu_rethreshold(rogtk_gpu_ctx *ctx, const rogtk_graph_batch
     }
     if (rc != ROGTK_OK) {
         for (void *p : own->ptrs) {
-            if (own->on_device) cudaFreeAsync(p, ctx->stream);
+            if (own->on_device) dev_free(p, ctx->stream);
             else pinned_put(ctx, p);
         }
         delete own;
@@ -1694,7 +1685,7 @@ extern "C" int rogtk_gpu_spectrum_split(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
     if (!ctx || !h_bounds || n < 0 || k_eff < 1 || k_eff > 64 || n_ranks < 1 || n_ranks > 256 || (n > 0 && !d_lo))
         return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     try {
         CK(cudaSetDevice(ctx->device));
         DevBuf b((size_t)(n_ranks + 1) * 8, ctx->stream);
@@ -1716,7 +1707,7 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
     if (!ctx || !out || n < 0 || k_eff < 1 || k_eff > 64 || (n > 0 && (!d_lo || !d_counts || !d_exts)) || (k_eff > 32 && n > 0 && !d_hi))
         return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     memset(out, 0, sizeof(*out));
     BatchOwner *own = new BatchOwner();
     const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
@@ -1789,7 +1780,7 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
     }
     if (rc != ROGTK_OK) {
         for (void *p : own->ptrs) {
-            if (own->on_device) cudaFreeAsync(p, ctx->stream);
+            if (own->on_device) dev_free(p, ctx->stream);
             else pinned_put(ctx, p);
         }
         delete own;
@@ -2002,7 +1993,7 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
         (in->k_eff > 32 && in->n_kmers > 0 && !in->kmers_hi))
         return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     memset(out, 0, sizeof(*out));
     BatchOwner *own = new BatchOwner();
     const bool out_dev = flags & ROGTK_OUTPUT_ON_DEVICE;
@@ -2016,7 +2007,7 @@ extern "C" int rogtk_gpu_compress_unitigs(rogtk_gpu_ctx *ctx, const rogtk_graph_
     }
     if (rc != ROGTK_OK) {
         for (void *p : own->ptrs) {
-            if (own->on_device) cudaFreeAsync(p, ctx->stream);
+            if (own->on_device) dev_free(p, ctx->stream);
             else pinned_put(ctx, p);
         }
         delete own;
@@ -2029,11 +2020,11 @@ extern "C" void rogtk_gpu_free_contigs(rogtk_gpu_ctx *ctx, rogtk_contig_batch *b
 {
     if (!ctx || !b || !b->_owner) return;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     BatchOwner *own = reinterpret_cast<BatchOwner *>(b->_owner);
     cudaSetDevice(ctx->device);
     for (void *p : own->ptrs) {
-        if (own->on_device) cudaFreeAsync(p, ctx->stream);
+        if (own->on_device) dev_free(p, ctx->stream);
         else pinned_put(ctx, p);
     }
     delete own;
@@ -2049,7 +2040,7 @@ extern "C" int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t 
 {
     if (!ctx || n_umis < 0 || reads_per_umi < 1 || read_len < 1 || template_len < read_len) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     try {
         CK(cudaSetDevice(ctx->device));
         const int64_t total = n_umis * (int64_t)reads_per_umi * read_len;
@@ -2071,7 +2062,7 @@ extern "C" int rogtk_gpu_synth_reads_var(rogtk_gpu_ctx *ctx, uint64_t seed, int6
 {
     if (!ctx || n_umis < 0 || n_reads < 0 || read_len < 1 || template_len < read_len || !d_group_offsets) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     try {
         CK(cudaSetDevice(ctx->device));
         const int64_t total = n_reads * (int64_t)read_len;
@@ -2151,7 +2142,7 @@ extern "C" int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint
 {
     if (!ctx) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     ctx->phase_enabled = enable != 0;
     if (out16) memcpy(out16, ctx->phase_cycles, sizeof(ctx->phase_cycles));
     return ROGTK_OK;
@@ -2161,7 +2152,7 @@ extern "C" int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx)
 {
     if (!ctx) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     cudaSetDevice(ctx->device);
     if (!ctx->flush_buf) {
         ctx->flush_bytes = (size_t)256 << 20;   // > 126 MB L2

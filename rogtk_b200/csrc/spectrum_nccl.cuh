@@ -102,7 +102,7 @@ extern "C" int rogtk_gpu_nccl_init(rogtk_gpu_ctx *ctx, const uint8_t *id128, int
 {
     if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     try {
         NcclApi &api = nccl_api();
         if (!api.error.empty()) throw ArgFail{ROGTK_ERR_UNSUPPORTED, api.error};
@@ -125,7 +125,7 @@ extern "C" int rogtk_gpu_nccl_finalize(rogtk_gpu_ctx *ctx)
 {
     if (!ctx) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
     std::lock_guard<std::mutex> l(g_nccl_mu);
     auto it = g_nccl.find(ctx);
     if (it == g_nccl.end()) return ROGTK_OK;
@@ -151,7 +151,7 @@ extern "C" int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph
     rogtk_exchange_stats xs{};
     try {
         std::lock_guard<std::mutex> lk(ctx->mu);
-    PoolScope pool_scope(ctx->pool);
+    CacheScope cache_scope(ctx->cache);
         CK(cudaSetDevice(ctx->device));
         cudaStream_t st = ctx->stream;
         const int64_t n = local->n_kmers;

@@ -185,6 +185,10 @@ class Engine:
             raise RogtkGpuError(err.value, "rogtk_gpu_create failed (no usable sm_100 GPU?) - there is no CPU fallback")
         self.device = device
 
+    def trim(self):
+        """Return the context's cached device blocks and page-locked buffers to the driver (rogtk_gpu_trim)."""
+        self._check(self._lib.rogtk_gpu_trim(self._ctx))
+
     def close(self):
         if getattr(self, "_ctx", None):
             self._lib.rogtk_gpu_destroy(self._ctx)

@@ -849,6 +849,27 @@ def test_survivor_pool_exhaustion_falls_back(engine, oracle, monkeypatch):
     assert got.n_spilled_groups == 0
 
 
+def test_device_cache_reuse_and_trim(oracle):
+    """The context's caching allocator (host_util.cuh DevCache): batches of changing shape and flags reuse cached blocks, trim()
+    returns them to the driver, results stay the oracle's before and after; two contexts on one device do not share blocks."""
+    import rogtk_b200
+    import torch
+    from rogtk_b200 import synth
+    with rogtk_b200.Engine(device=0) as a, rogtk_b200.Engine(device=0) as b:
+        free0 = torch.cuda.mem_get_info(0)[0]
+        for i, (n, k, mc, fl) in enumerate(((300, 31, 2, 0), (500, 17, 1, EMIT_CSR), (120, 47, 2, EMIT_STATS | EMIT_CSR), (300, 31, 2, EMIT_CSR))):
+            data, offs, goff = synth.synth_reads(synth.config_seed(2), 10 * i, n, 20, 150, 400)
+            ref = oracle.count_prune_batch(data, offs, goff, k, mc, emit_csr=bool(fl & EMIT_CSR))
+            for eng in (a, b):
+                assert_batches_equal(eng.count_prune(data, offs, goff, k, mc, flags=fl | EMIT_STATS), ref, check_csr=bool(fl & EMIT_CSR), ctx=f"round {i}")
+            if i == 1:
+                a.trim()
+        held = free0 - torch.cuda.mem_get_info(0)[0]
+        a.trim()
+        b.trim()
+        assert free0 - torch.cuda.mem_get_info(0)[0] < max(held, 1)   # cached blocks went back
+
+
 @pytest.mark.parametrize("rl", [3, 5])
 def test_link_walk_kernel_matches_oracle(oracle, monkeypatch, rl):
     """The experimental first-tier kernel k_walk_count (ROGTK_WALK_RL, read when a context is created): 8-byte
