@@ -4,5 +4,6 @@ from .engine import (ContigBatch, DeviceBatch, Engine, GraphBatch, RogtkGpuError
                      shard_of)
 from . import _ffi as ffi  # noqa: F401
 from . import sharding, spectrum, synth  # noqa: F401
+from .fracture import fracture_fasta, fracture_sequences  # noqa: F401
 
-__all__ = ["Engine", "GraphBatch", "DeviceBatch", "ContigBatch", "StringBatch", "count_prune_multi", "RogtkGpuError", "k_eff", "estimate_k", "shard_of", "ffi", "synth", "sharding", "spectrum"]
+__all__ = ["Engine", "GraphBatch", "DeviceBatch", "ContigBatch", "StringBatch", "count_prune_multi", "fracture_sequences", "fracture_fasta", "RogtkGpuError", "k_eff", "estimate_k", "shard_of", "ffi", "synth", "sharding", "spectrum"]

@@ -401,7 +401,7 @@ extern "C" int rogtk_gpu_assemble_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
             bool ran = false;
             {
                 std::lock_guard<std::mutex> lk(ctx->mu);
-    CacheScope cache_scope(ctx->cache);
+                CacheScope cache_scope(ctx->cache);
                 ran = assemble_compression_chunked(ctx, reads, group_offsets, n_groups, p->k, p->min_coverage, flags, post, &info);
                 if (ran) {
                     for (HostArr *h : {&post.h_soff, &post.h_sdata, &post.h_sflags})
@@ -418,7 +418,7 @@ extern "C" int rogtk_gpu_assemble_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
                 out->n_count_passes = 1;
                 if (!out->data) {   // no contig at all: still a valid (empty) data buffer
                     std::lock_guard<std::mutex> lk(ctx->mu);
-    CacheScope cache_scope(ctx->cache);
+                    CacheScope cache_scope(ctx->cache);
                     out->data = (uint8_t *)pinned_get(ctx, 16);
                     own->ptrs.push_back(out->data);
                 }
@@ -531,7 +531,7 @@ extern "C" int rogtk_gpu_sweep_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *rea
         const size_t total = (size_t)std::max<int64_t>(1, n_groups * n_cells);
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
-    CacheScope cache_scope(ctx->cache);
+            CacheScope cache_scope(ctx->cache);
             out->k = (int64_t *)pinned_get(ctx, total * 8); own->ptrs.push_back(out->k);
             out->min_coverage = (int64_t *)pinned_get(ctx, total * 8); own->ptrs.push_back(out->min_coverage);
             out->contig_length = (int64_t *)pinned_get(ctx, total * 8); own->ptrs.push_back(out->contig_length);
@@ -772,7 +772,7 @@ extern "C" int rogtk_gpu_optimize_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
         rows.data.resize((size_t)rows.off[(size_t)n_groups]);
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
-    CacheScope cache_scope(ctx->cache);
+            CacheScope cache_scope(ctx->cache);
             const size_t nb = (size_t)std::max<int64_t>(n_groups, 1) * 4;
             out->k = (uint32_t *)pinned_get(ctx, nb); own->ptrs.push_back(out->k);
             out->min_coverage = (uint32_t *)pinned_get(ctx, nb); own->ptrs.push_back(out->min_coverage);

@@ -151,7 +151,7 @@ extern "C" int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph
     rogtk_exchange_stats xs{};
     try {
         std::lock_guard<std::mutex> lk(ctx->mu);
-    CacheScope cache_scope(ctx->cache);
+        CacheScope cache_scope(ctx->cache);
         CK(cudaSetDevice(ctx->device));
         cudaStream_t st = ctx->stream;
         const int64_t n = local->n_kmers;

@@ -23,6 +23,7 @@ class RogtkGpuError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"rogtk_gpu error {code} ({_ERR.get(code, '?')}): {msg}")
         self.code = code
+        self.msg = msg
 
 
 @dataclass

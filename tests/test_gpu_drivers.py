@@ -259,3 +259,53 @@ def test_one_frame_on_several_gpus(oracle):
         finally:
             for e in engines:
                 e.close()
+
+
+_REF_FASTA = [   # reference src/fracture.rs:573-584 (create_test_fasta)
+    "ATGCATGCATGCTAGCTGATCGATCGTAGCTAGCTAGCTGATCGATCGTACGTACGTACGTAGCTACGTACGTACGTAGCTAGCTGATCGTAGCTACGTAGCTAGCTAGCTGATCGTACGTACGT",
+    "GTAGCTAGCTAGCTGATCGATCGTACGTACGTACGTAGCTACGTACGTACGTAGCTAGCTGATCGTAGCTACGTAGCTAGCTAGCTGATCGTACGTACGTAGCTGATCGATCGTAGCTACGTACGT",
+    "GTACGTACGTACGTAGCTACGTACGTACGTAGCTAGCTGATCGTAGCTACGTAGCTAGCTAGCTGATCGTACGTACGTAGCTGATCGATCGTAGCTACGTACGTACGTAGCTACGTACGTACGTAG",
+    "TACGTACGTACGTAGCTAGCTGATCGTAGCTACGTAGCTAGCTAGCTGATCGTACGTACGTAGCTGATCGATCGTAGCTACGTACGTACGTAGCTACGTACGTACGTAGCTAGCTGATCGTAGCT",
+]
+
+
+def test_fracture_entries_mirror_the_pyo3_functions(engine, oracle, tmp_path):
+    """fracture_sequences / fracture_fasta (reference src/fracture.rs:468-564) with the reference's own test inputs
+    (src/fracture.rs:593-607 FASTA, :621-679 two reads + anchors, :681-707 absent anchors) and its error types."""
+    import rogtk_b200
+    reads = ["GAGACTGCATGGGCTGGTGGGCGTCCGTCTGC", "GGGCTGGTGGGCGTCCGTCTGCTTTAGTGAGGGT"]
+    got = rogtk_b200.fracture_sequences(reads, 13, 1, min_length=None, method="shortest_path", start_anchor="GAGACTGCATGG",
+                                        end_anchor="TTTAGTGAGGGT", export_graphs=True, auto_k=False, prefix="test_prefix", engine=engine)
+    assert got == "GAGACTGCATGGGCTGGTGGGCGTCCGTCTGCTTTAGTGAGGGT"   # the 44-bp answer in the comment at src/fracture.rs:611
+    assert rogtk_b200.fracture_sequences(["AAAACCCCCAAAAA", "TTTTTGGGGGTTTT"], 4, 1, min_length=None, method="shortest_path",
+                                         start_anchor="NONEXISTENT", end_anchor="ALSONOTHERE", engine=engine) == ""
+    # default min_length = 200 hides the 44-bp contig; compression is the default method
+    assert rogtk_b200.fracture_sequences(reads, 13, 1, engine=engine) == ""
+    assert rogtk_b200.fracture_sequences(reads, 13, 1, min_length=10, engine=engine) == "GAGACTGCATGGGCTGGTGGGCGTCCGTCTGCTTTAGTGAGGGT"
+    with pytest.raises(ValueError, match="Both start_anchor and end_anchor are required"):
+        rogtk_b200.fracture_sequences(reads, 13, 1, method="shortest_path", engine=engine)
+    with pytest.raises(ValueError, match="Invalid assembly method"):
+        rogtk_b200.fracture_sequences(reads, 13, 1, method="greedy", engine=engine)
+
+    # FASTA: wrapped lines, lower case, a record with an N (dropped), a blank line
+    fa = tmp_path / "reads.fa"
+    with open(fa, "w") as fh:
+        for i, r in enumerate(_REF_FASTA):
+            fh.write(f">read{i + 1} some description\n")
+            body = r.lower() if i == 1 else r
+            for j in range(0, len(body), 60):
+                fh.write(body[j:j + 60] + "\n")
+        fh.write(">bad\nACGTNACGT\n\n")
+    assert [s.upper() for s in map(bytes.decode, rogtk_b200.fracture.read_fasta_sequences(fa))][:4] == _REF_FASTA
+    want_all, _ = oracle.assemble_sequences_py(_REF_FASTA + ["ACGTNACGT"], 20, 1, "compression", min_length=0, only_largest=False)
+    # (the reference test asserts a first contig > 150 bp, src/fracture.rs:603-606; no reading of the crate's semantics yields
+    #  one from these four reads -- tools/parity_sensitivity.py, DESIGN.md 3 -- so the unitigs of 79 and 125 bp are what is compared)
+    assert sorted(len(c) for c in want_all) == [79, 125]
+    want, info = oracle.assemble_sequences_py(_REF_FASTA, 20, 1, "compression", min_length=100, only_largest=True)
+    assert not info["tie"]
+    assert rogtk_b200.fracture_fasta(str(fa), 20, 1, min_length=100, engine=engine) == want[0]
+    assert sorted(rogtk_b200.fracture_sequences(_REF_FASTA, 20, 1, min_length=0, engine=engine).split("\n")) == sorted(want_all)
+    with pytest.raises(ValueError, match="No contigs found with length >= 5000"):
+        rogtk_b200.fracture_fasta(str(fa), 20, 1, min_length=5000, engine=engine)
+    with pytest.raises(ValueError, match="No contigs found"):
+        rogtk_b200.fracture_fasta(str(fa), 70, 1, min_length=1, engine=engine)   # k > 64: no contigs (src/fracture.rs:286-289)
