@@ -19,8 +19,15 @@
 
 namespace rogtk {
 
-constexpr int PT_PMAX = 128;             // ranges per group at most
+constexpr int PT_PMAX = 128;             // ranges per group at most (per-UMI groups; a batch holds thousands of them)
 constexpr int64_t PT_TARGET = 8192;      // observations per range the plan aims at (table: 8192 slots; about half of the observations repeat a k-mer)
+// One very large group (the un-grouped column of the global-spectrum mode, SURVEY 8e row 2: 10^8 observations in one group) gets
+// up to PT_PBIG ranges of PT_TARGET_BIG observations -- most k-mers of such a group are seen once or twice, so a range's table must
+// hold about as many k-mers as the range has observations -- and every scatter item covers PT_SUB_BIG slabs, so that an item's
+// records of one range still form a run (about 16 x 16384 / P records) behind ONE global atomic.
+constexpr int PT_PBIG = 49152;     // 192 KB of shared-memory bins: one scatter CTA per SM
+constexpr int64_t PT_TARGET_BIG = 4096;
+constexpr int PT_SUB_BIG = 16;
 constexpr int PT_NT = 384;
 constexpr int PT_NW = PT_NT / 32;
 constexpr int PT_MAX_BASES = 16384;      // staged bases per slab (incl. alignment slack)
@@ -34,11 +41,13 @@ struct PartArgs {
     int64_t n_list;
     const int32_t *np;           // [n_list] ranges of entry e
     const int32_t *rows_per_slab;// [n_list]
+    int sub_slabs;               // slabs per scatter item (1, or PT_SUB_BIG for a wave holding one large group)
+    int pcap;                    // ranges per entry at most in this wave: stride of slab_cnt, size of the shared-memory bins
     const int64_t *slab_off;     // [n_list+1] first slab item of entry e
     const int64_t *bucket_off;   // [n_list+1] first bucket of entry e
     const int64_t *rec_off;      // [n_buckets+1] first record slot of bucket b
     unsigned int *cursor;        // [n_buckets] HIST: records of the bucket; scatter: records appended so far
-    uint32_t *slab_cnt;          // [n_slabs * PT_PMAX] observations per (slab, range), written by HIST, read by the scatter
+    uint32_t *slab_cnt;          // [n_items * pcap] observations per (item, range), written by HIST, read by the scatter
     uint64_t *rec_lo, *rec_hi;
     uint8_t *rec_ex;
     int32_t *failed;             // [n_list]
@@ -51,7 +60,7 @@ struct PartArgs {
     uint64_t *pool_lo, *pool_hi;
     uint8_t *pool_exts;
     uint16_t *pool_counts;
-    SegRec *segs;                // [n_list * PT_PMAX]
+    SegRec *segs;                // [n_list * pcap]
     // prefix kernel
     int32_t *seg_count;          // [n_list]
     int64_t *nsurv;              // [n_groups]
@@ -83,20 +92,26 @@ __global__ void k_part_plan(ColView col, const int64_t *group_offsets, const int
         }
         if (lane == 0) {
             int64_t P = ((int64_t)obs + PT_TARGET - 1) / PT_TARGET;
-            P = P < 1 ? 1 : (P > PT_PMAX ? PT_PMAX : P);
-            if (2 * K <= 12) P = 1;   // at most 4096 distinct k-mers
             // rows per slab: every slab of rps rows fits the staged span whatever the reads' lengths (0 = a read longer than a slab)
             int64_t rps = (PT_MAX_BASES - 32) / maxlen;
             rps = rps > SM_MAXR ? SM_MAXR : rps;
+            int64_t sub = 1;
+            if (P > PT_PMAX && 2 * K > 24) {   // a large group (beyond 128 x 8192 observations)
+                P = ((int64_t)obs + PT_TARGET_BIG - 1) / PT_TARGET_BIG;
+                sub = PT_SUB_BIG;
+                if (P > PT_PBIG) rps = 0;      // more than the bins hold: the HBM tables take it (callers bound their rounds below this)
+            }
+            P = P < 1 ? 1 : (P > PT_PBIG ? PT_PBIG : P);
+            if (sub == 1 && P > PT_PMAX) P = PT_PMAX;
+            if (2 * K <= 12) P = 1;   // at most 4096 distinct k-mers
             np[e] = (int32_t)P;
             rows_per_slab[e] = (int32_t)rps;
-            slabs[e] = rps > 0 ? (r1 - r0 + rps - 1) / rps : 0;
+            slabs[e] = rps > 0 ? (r1 - r0 + rps * sub - 1) / (rps * sub) : 0;   // scatter items
             bucket_cap[e] = (int64_t)obs;   // records of the whole entry at most (wave planning)
         }
     }
 }
-template <int W>
-constexpr size_t part_scatter_smem() { return (size_t)PT_PK_WORDS * 4 + (size_t)(SM_MAXR + 1) * 4 + SM_MAXR + (size_t)PT_PMAX * 4 * 3 + 64 * 4 + 64; }
+inline size_t part_scatter_smem(int pcap) { return (size_t)PT_PK_WORDS * 4 + (size_t)(SM_MAXR + 1) * 4 + (size_t)pcap * 4 + 64 * 4 + SM_MAXR + 64; }
 
 // one slab of one listed group per iteration: stage, bin the observations by range, append the bins to the range buckets
 template <int W, bool HIST>
@@ -107,10 +122,9 @@ __global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n
     uint32_t *scratch = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *pk = scratch + 1;
     uint32_t *rstart = scratch + PT_PK_WORDS;
-    uint32_t *cnt = rstart + SM_MAXR + 1;         // [PT_PMAX] observations of the slab per range
-    uint32_t *base = cnt + PT_PMAX;               // [PT_PMAX] first record of the slab's bin inside the bucket
-    uint32_t *fill = base + PT_PMAX;              // [PT_PMAX] records of the bin written so far
-    uint32_t *ws = fill + PT_PMAX;                // 64 words
+    uint32_t *bin = rstart + SM_MAXR + 1;         // [pcap] HIST: observations of the item per range; scatter: next record slot of the
+                                                  //        item's run inside the range bucket
+    uint32_t *ws = bin + a.pcap;                  // 64 words
     uint8_t *bad = reinterpret_cast<uint8_t *>(ws + 64);
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
@@ -135,71 +149,75 @@ __global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n
         const int64_t g = a.ids[e];
         const int rps = a.rows_per_slab[e];
         const int P = a.np[e];
-        const int64_t r0 = a.group_offsets[g] + (item - a.slab_off[e]) * rps;
         const int64_t r1g = a.group_offsets[g + 1];
-        const int64_t r1 = r0 + rps < r1g ? r0 + rps : r1g;
-        const int nr = (int)(r1 - r0);
-        const int64_t sb0 = col_off(a.col, r0), sb1 = col_off(a.col, r1);
-        const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.col.data + sb0);
-        const uint32_t slack = (uint32_t)(addr0 & 15u);
-        const uint32_t span = (uint32_t)((sb1 - sb0) + slack);
-        for (int r = tid; r <= nr; r += NT) rstart[r] = (uint32_t)(col_off(a.col, r0 + r) - sb0) + slack;
-        if (tid < nr) bad[tid] = col_valid(a.col, r0 + tid) ? 0 : 1;
         const int64_t bucket0 = a.bucket_off[e];
-        for (int p = tid; p < PT_PMAX; p += NT) {
-            cnt[p] = 0;
-            fill[p] = 0;
-            if (!HIST) {   // the slab's run inside every range bucket: one global atomic per (slab, range)
-                const uint32_t c = p < P ? a.slab_cnt[item * PT_PMAX + p] : 0u;
-                base[p] = c ? atomicAdd(&a.cursor[bucket0 + p], c) : 0u;
+        for (int p = tid; p < P; p += NT) {
+            if (HIST) {
+                bin[p] = 0;
+            } else {   // the item's run inside every range bucket: one global atomic per (item, range)
+                const uint32_t c = a.slab_cnt[item * a.pcap + p];
+                bin[p] = c ? atomicAdd(&a.cursor[bucket0 + p], c) : 0u;
             }
         }
-        __syncthreads();
-        // ---- ingest: 16-byte chunks -> one packed u32 (16 bases, first base in the top bits) --------------------------
-        {
-            const uint8_t *a0 = reinterpret_cast<const uint8_t *>(addr0 - slack);
-            const int nchunks = (int)((span + 15u) >> 4);
-            for (int c = tid; c < nchunks; c += NT) {
-                const uint8_t *p = a0 + 16 * c;
-                uint4 v;
-                if (p >= a.data_begin && p + 16 <= a.data_end) {
-                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-                } else {
-                    v = load_chunk_guarded(p, a.data_begin, a.data_end);
+        for (int sub = 0; sub < a.sub_slabs; sub++) {
+            const int64_t r0 = a.group_offsets[g] + ((item - a.slab_off[e]) * a.sub_slabs + sub) * rps;
+            if (r0 >= r1g) break;
+            const int64_t r1 = r0 + rps < r1g ? r0 + rps : r1g;
+            const int nr = (int)(r1 - r0);
+            const int64_t sb0 = col_off(a.col, r0), sb1 = col_off(a.col, r1);
+            const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.col.data + sb0);
+            const uint32_t slack = (uint32_t)(addr0 & 15u);
+            const uint32_t span = (uint32_t)((sb1 - sb0) + slack);
+            __syncthreads();   // the previous slab's staged bases are no longer read
+            for (int r = tid; r <= nr; r += NT) rstart[r] = (uint32_t)(col_off(a.col, r0 + r) - sb0) + slack;
+            if (tid < nr) bad[tid] = col_valid(a.col, r0 + tid) ? 0 : 1;
+            __syncthreads();
+            // ---- ingest: 16-byte chunks -> one packed u32 (16 bases, first base in the top bits) --------------------------
+            {
+                const uint8_t *a0 = reinterpret_cast<const uint8_t *>(addr0 - slack);
+                const int nchunks = (int)((span + 15u) >> 4);
+                for (int c = tid; c < nchunks; c += NT) {
+                    const uint8_t *p = a0 + 16 * c;
+                    uint4 v;
+                    if (p >= a.data_begin && p + 16 <= a.data_end) {
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+                    } else {
+                        v = load_chunk_guarded(p, a.data_begin, a.data_end);
+                    }
+                    pk[c] = (pack4(v.x) << 24) | (pack4(v.y) << 16) | (pack4(v.z) << 8) | pack4(v.w);
+                    const bool ok = valid4(v.x) & valid4(v.y) & valid4(v.z) & valid4(v.w);
+                    if (!ok) mark_bad_reads(v, 16u * c, slack, span, rstart, nr, bad);
                 }
-                pk[c] = (pack4(v.x) << 24) | (pack4(v.y) << 16) | (pack4(v.z) << 8) | pack4(v.w);
-                const bool ok = valid4(v.x) & valid4(v.y) & valid4(v.z) & valid4(v.w);
-                if (!ok) mark_bad_reads(v, 16u * c, slack, span, rstart, nr, bad);
             }
-        }
-        __syncthreads();
-        // ---- one sweep over the windows (a warp per read): HIST counts per range, the scatter writes ----------------------------------
-        for (int r = (int)warp; r < nr; r += PT_NW) {
-            const uint32_t rs = rstart[r], len = rstart[r + 1] - rs;
-            if (bad[r] || len < (uint32_t)K) continue;
-            const uint32_t nk = len - (uint32_t)K + 1u;
-            for (uint32_t p = lane; p < nk; p += 32u) {
-                const uint32_t q = rs + p;
-                Key<W> key = Key<W>::zero();
-                load_window(pk, q, K, key);
-                const uint32_t range = P > 1 ? pass_of(key_top32(key, 2 * K), (uint32_t)P) : 0u;
-                if (HIST) {
-                    atomicAdd(&cnt[range], 1u);
-                } else {
-                    const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
-                    const uint32_t ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
-                    const int64_t at = a.rec_off[bucket0 + range] + base[range] + atomicAdd(&fill[range], 1u);
-                    a.rec_lo[at] = key.lo;
-                    if (W == 2) a.rec_hi[at] = key.hi_word();
-                    a.rec_ex[at] = (uint8_t)ex;
+            __syncthreads();
+            // ---- one sweep over the windows (a warp per read): HIST counts per range, the scatter writes ----------------------------------
+            for (int r = (int)warp; r < nr; r += PT_NW) {
+                const uint32_t rs = rstart[r], len = rstart[r + 1] - rs;
+                if (bad[r] || len < (uint32_t)K) continue;
+                const uint32_t nk = len - (uint32_t)K + 1u;
+                for (uint32_t p = lane; p < nk; p += 32u) {
+                    const uint32_t q = rs + p;
+                    Key<W> key = Key<W>::zero();
+                    load_window(pk, q, K, key);
+                    const uint32_t range = P > 1 ? pass_of(key_top32(key, 2 * K), (uint32_t)P) : 0u;
+                    if (HIST) {
+                        atomicAdd(&bin[range], 1u);
+                    } else {
+                        const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
+                        const uint32_t ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
+                        const int64_t at = a.rec_off[bucket0 + range] + atomicAdd(&bin[range], 1u);
+                        a.rec_lo[at] = key.lo;
+                        if (W == 2) a.rec_hi[at] = key.hi_word();
+                        a.rec_ex[at] = (uint8_t)ex;
+                    }
                 }
             }
         }
         if (HIST) {
             __syncthreads();
             for (int p = tid; p < P; p += NT) {
-                const uint32_t c = cnt[p];
-                a.slab_cnt[item * PT_PMAX + p] = c;
+                const uint32_t c = bin[p];
+                a.slab_cnt[item * a.pcap + p] = c;
                 if (c) atomicAdd(&a.cursor[bucket0 + p], c);
             }
         }
@@ -352,7 +370,7 @@ __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs
         if (tid == 0) {
             cta_pool_pos += n_out;
             if (n_out > (uint32_t)SM_TSIZE) a.failed[e] = 1;   // more than the ordering kernels hold
-            a.segs[e * PT_PMAX + pass] = SegRec{pb, (int32_t)n_out, 0};
+            a.segs[e * a.pcap + pass] = SegRec{pb, (int32_t)n_out, 0};
         }
     }
 }
@@ -372,7 +390,7 @@ __global__ void k_part_finish(PartArgs a)
     int64_t pre = 0;
     unsigned long long obs = 0;
     for (int p = 0; p < P; p++) {
-        SegRec &r = a.segs[e * PT_PMAX + p];
+        SegRec &r = a.segs[e * a.pcap + p];
         r.prefix = (int32_t)pre;
         pre += r.n;
         obs += (unsigned long long)(a.rec_off[a.bucket_off[e] + p + 1] - a.rec_off[a.bucket_off[e] + p]);
@@ -382,6 +400,49 @@ __global__ void k_part_finish(PartArgs a)
     if (obs) atomicAdd(a.n_obs, obs);
 }
 
+// the same for a wave holding ONE large group (thousands of segments): one block, chunked scan
+__global__ void __launch_bounds__(1024) k_part_finish_one(PartArgs a)
+{
+    __shared__ long long part[1024];
+    const int tid = threadIdx.x;
+    const int64_t g = a.ids[0];
+    const int P = a.np[0];
+    if (a.failed[0] || a.rows_per_slab[0] <= 0) {
+        if (tid == 0) {
+            a.seg_count[0] = 0;
+            a.failed_ids[atomicAdd(a.n_failed, 1ull)] = (int32_t)g;
+        }
+        return;
+    }
+    const int per = (P + 1023) / 1024;
+    const int p0 = tid * per, p1 = p0 + per < P ? p0 + per : P;
+    long long sum = 0;
+    for (int p = p0; p < p1; p++) sum += a.segs[p].n;
+    part[tid] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const long long y = tid >= d ? part[tid - d] : 0;
+        __syncthreads();
+        part[tid] += y;
+        __syncthreads();
+    }
+    long long pre = part[tid] - sum;
+    for (int p = p0; p < p1; p++) {
+        a.segs[p].prefix = (int32_t)pre;
+        pre += a.segs[p].n;
+    }
+    if (tid == 1023) {
+        a.seg_count[0] = P;
+        a.nsurv[g] = part[1023];
+        const unsigned long long obs = (unsigned long long)(a.rec_off[a.bucket_off[0] + P] - a.rec_off[a.bucket_off[0]]);
+        if (obs) atomicAdd(a.n_obs, obs);
+        if (part[1023] > 0x7fffffffll) {   // (prefixes are 32-bit)
+            a.seg_count[0] = 0;
+            a.failed_ids[atomicAdd(a.n_failed, 1ull)] = (int32_t)g;
+        }
+    }
+}
+
 }  // namespace rogtk
 
 // -----------------------------------------------------------------------------------------------------------------------------
@@ -389,11 +450,17 @@ __global__ void k_part_finish(PartArgs a)
 // -----------------------------------------------------------------------------------------------------------------------------
 namespace rogtk {
 
-struct PartResult {
-    int64_t n_entries = 0;            // listed groups (segment sets of PT_PMAX slots each)
+struct PartSegSet {   // segments of a run of listed groups: seg slot = (entry - first) * stride + range
     const int32_t *seg_list = nullptr;
     const SegRec *segs = nullptr;
     const int32_t *seg_count = nullptr;
+    int64_t n_entries = 0;
+    int stride = PT_PMAX;
+};
+
+struct PartResult {
+    int64_t n_entries = 0;            // listed groups
+    std::vector<PartSegSet> sets;
     const int32_t *failed_ids = nullptr;
     int64_t n_failed = 0;
     std::vector<DevBuf> keep;
@@ -405,10 +472,10 @@ inline void part_path_configure()
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     };
-    cfg(k_part_scatter<1, true>, part_scatter_smem<1>());
-    cfg(k_part_scatter<2, true>, part_scatter_smem<2>());
-    cfg(k_part_scatter<1, false>, part_scatter_smem<1>());
-    cfg(k_part_scatter<2, false>, part_scatter_smem<2>());
+    cfg(k_part_scatter<1, true>, part_scatter_smem(PT_PBIG));
+    cfg(k_part_scatter<2, true>, part_scatter_smem(PT_PBIG));
+    cfg(k_part_scatter<1, false>, part_scatter_smem(PT_PBIG));
+    cfg(k_part_scatter<2, false>, part_scatter_smem(PT_PBIG));
     cfg(k_part_count<1>, part_count_smem<1>());
     cfg(k_part_count<2>, part_count_smem<2>());
 }
@@ -421,11 +488,8 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
                             uint64_t *pool_hi, uint8_t *pool_exts, uint16_t *pool_counts, PartResult &res, int64_t *launches)
 {
     res.n_entries = n_list;
-    res.seg_list = d_ids;
     if (n_list == 0) return;
     auto blocks = [](int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); };
-    res.keep.emplace_back((size_t)n_list * PT_PMAX * sizeof(SegRec), st);
-    SegRec *d_segs = res.keep.back().as<SegRec>();
     res.keep.emplace_back((size_t)n_list * 4, st);
     int32_t *d_segc = res.keep.back().as<int32_t>();
     res.keep.emplace_back((size_t)n_list * 4, st);
@@ -449,12 +513,20 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
     const int64_t budget = std::max<int64_t>(1 << 20, (int64_t)(workspace_bytes / 2 / rec_bytes));
     int64_t e0 = 0;
     while (e0 < n_list) {
+        // a wave: a run of per-UMI entries (<= PT_PMAX ranges each) within the record budget, or ONE large group on its own
+        const bool big = h_np[(size_t)e0] > PT_PMAX;
         int64_t e1 = e0, recs = 0;
-        while (e1 < n_list && (e1 == e0 || recs + h_bcap[(size_t)e1] <= budget)) {
+        while (e1 < n_list && (e1 == e0 || (!big && h_np[(size_t)e1] <= PT_PMAX && recs + h_bcap[(size_t)e1] <= budget))) {
             recs += h_bcap[(size_t)e1];
             e1++;
         }
         const int64_t nl = e1 - e0;
+        const int pcap = big ? h_np[(size_t)e0] : PT_PMAX;
+        res.keep.emplace_back((size_t)nl * pcap * sizeof(SegRec), st);
+        SegRec *d_segs = res.keep.back().as<SegRec>();
+        PartSegSet set;
+        set.seg_list = d_ids + e0; set.segs = d_segs; set.seg_count = d_segc + e0; set.n_entries = nl; set.stride = pcap;
+        res.sets.push_back(set);
         DevBuf slab_off((size_t)(nl + 1) * 8, st), bucket_off((size_t)(nl + 1) * 8, st), scr(scan_scratch_bytes(nl), st);
         exclusive_scan<int64_t>(slabs.as<int64_t>() + e0, nl, slab_off.as<int64_t>(), scr.as<int64_t>(), st, launches);
         exclusive_scan<int32_t>(np.as<int32_t>() + e0, nl, bucket_off.as<int64_t>(), scr.as<int64_t>(), st, launches);
@@ -465,24 +537,26 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
         pk.sync();
         const int64_t n_slabs = h_tot[0], n_buckets = h_tot[1];
         DevBuf rec_off((size_t)(n_buckets + 1) * 8, st), scr2(scan_scratch_bytes(n_buckets), st), cursor((size_t)std::max<int64_t>(n_buckets, 1) * 4, st),
-            slab_cnt((size_t)std::max<int64_t>(n_slabs, 1) * PT_PMAX * 4, st);
+            slab_cnt((size_t)std::max<int64_t>(n_slabs, 1) * pcap * 4, st);
         CK(cudaMemsetAsync(cursor.p, 0, cursor.bytes, st));
         PartArgs a{};
         a.col = col; a.data_begin = data_begin; a.data_end = data_end; a.group_offsets = d_group_offsets;
         a.ids = d_ids + e0; a.n_list = nl;
         a.np = np.as<int32_t>() + e0; a.rows_per_slab = rps.as<int32_t>() + e0;
+        a.sub_slabs = big ? PT_SUB_BIG : 1; a.pcap = pcap;
         a.slab_off = slab_off.as<int64_t>(); a.bucket_off = bucket_off.as<int64_t>(); a.rec_off = rec_off.as<int64_t>();
         a.cursor = cursor.as<unsigned int>();
         a.slab_cnt = slab_cnt.as<uint32_t>();
         a.failed = failed.as<int32_t>() + e0;
         a.K = K; a.min_cov = min_cov;
         a.pool_cursor = pool_cursor; a.pool_cap = pool_cap; a.pool_lo = pool_lo; a.pool_hi = pool_hi; a.pool_exts = pool_exts; a.pool_counts = pool_counts;
-        a.segs = d_segs + e0 * PT_PMAX; a.seg_count = d_segc + e0; a.nsurv = d_nsurv; a.n_obs = d_nobs;
+        a.segs = d_segs; a.seg_count = d_segc + e0; a.nsurv = d_nsurv; a.n_obs = d_nobs;
         a.failed_ids = d_failed_ids; a.n_failed = d_ctr + 2;
         CK(cudaMemsetAsync(d_ctr, 0, 16, st));
+        const size_t ssmem = part_scatter_smem(pcap);
         const unsigned sgrid = (unsigned)std::min<int64_t>(std::max<int64_t>(n_slabs, 1), (int64_t)sm_count * 2);
         a.ticket = d_ctr;
-        if (n_slabs > 0) k_part_scatter<W, true><<<sgrid, PT_NT, part_scatter_smem<W>(), st>>>(a, n_slabs);
+        if (n_slabs > 0) k_part_scatter<W, true><<<sgrid, PT_NT, ssmem, st>>>(a, n_slabs);
         // exact bucket sizes -> record offsets; the cursors restart at zero for the scatter
         exclusive_scan<uint32_t>(cursor.as<uint32_t>(), n_buckets, rec_off.as<int64_t>(), scr2.as<int64_t>(), st, launches);
         int64_t n_recs = 0;
@@ -493,13 +567,14 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
         DevBuf rlo((size_t)std::max<int64_t>(n_recs, 1) * 8, st), rhi(W == 2 ? (size_t)std::max<int64_t>(n_recs, 1) * 8 : 0, st),
             rex((size_t)std::max<int64_t>(n_recs, 1), st);
         a.rec_lo = rlo.as<uint64_t>(); a.rec_hi = W == 2 ? rhi.as<uint64_t>() : nullptr; a.rec_ex = rex.as<uint8_t>();
-        if (n_slabs > 0) k_part_scatter<W, false><<<sgrid, PT_NT, part_scatter_smem<W>(), st>>>(a, n_slabs);
+        if (n_slabs > 0) k_part_scatter<W, false><<<sgrid, PT_NT, ssmem, st>>>(a, n_slabs);
         if (n_buckets > 0) {
             a.ticket = d_ctr + 1;
             const unsigned grid = (unsigned)std::min<int64_t>(n_buckets, (int64_t)sm_count * (W == 1 ? 2 : 1));
             k_part_count<W><<<grid, PT_NT, part_count_smem<W>(), st>>>(a, n_buckets);
         }
-        k_part_finish<<<blocks(nl, 128), 128, 0, st>>>(a);
+        if (big) k_part_finish_one<<<1, 1024, 0, st>>>(a);
+        else k_part_finish<<<blocks(nl, 128), 128, 0, st>>>(a);
         if (launches) *launches += 5;
         // (the wave's buffers are released in stream order when they go out of scope)
         e0 = e1;
@@ -508,8 +583,6 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
     Peek pk(peek_slot, st, launches);
     pk.add(d_ctr + 2, 8, &nf);
     pk.sync();
-    res.segs = d_segs;
-    res.seg_count = d_segc;
     res.failed_ids = d_failed_ids;
     res.n_failed = (int64_t)nf;
     res.keep.push_back(std::move(ctr));

@@ -743,10 +743,10 @@ void run_pipeline(rogtk_gpu_ctx *ctx, const Staged &in, int64_t n_groups, int K,
         run_sort_gather(st, ctx->peek_slot, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
                         sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches,
                         sm.segs, sm.seg_count, sm.seg_list, sm.n_seg_groups);
-    if (part.n_entries > 0)   // segments of the partitioned groups (same pool, PT_PMAX segment slots per group)
+    for (const PartSegSet &ps : part.sets)   // segments of the partitioned groups (same pool; ps.stride segment slots per group)
         run_sort_gather(st, ctx->peek_slot, ctx->sm_count, K, n_groups, sm.pool_start, r.off.as<int64_t>(), sm.pool_lo, sm.pool_hi, sm.pool_exts,
-                        sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches, part.segs,
-                        part.seg_count, part.seg_list, part.n_entries, PT_PMAX, false);
+                        sm.pool_counts, r.lo.as<uint64_t>(), p_hi, r.exts.as<uint8_t>(), r.counts.as<uint16_t>(), &ctx->launches, ps.segs,
+                        ps.seg_count, ps.seg_list, ps.n_entries, ps.stride, false);
     for (auto &wv : waves) {
         if (wv.n_recs == 0) continue;
         k_spill_scatter<<<blocks_for(wv.n_recs, 256), 256, 0, st>>>(wv.recs.as<SpillRec>(), wv.n_recs, d_spill_ids, wv.list_base,

@@ -718,6 +718,24 @@ def test_partition_then_count_tier(engine, oracle):
         assert int(got.counts.max()) == 65535
 
 
+def test_partition_tier_one_large_group(engine, oracle):
+    """One group far beyond 128 x 8192 observations (the un-grouped column of the global-spectrum mode): thousands of k-mer ranges,
+    scatter items of several slabs (kernels_part.cuh PT_PBIG / PT_SUB_BIG).  Reads drawn from many templates, so most k-mers are
+    seen a few times only.  Bit-exact against the oracle, no HBM tables, next to ordinary groups in the same batch."""
+    from rogtk_b200 import synth
+    data, offs, _ = synth.synth_reads(synth.config_seed(5), 0, 700, 20, 150, 500)    # 14 000 reads of 700 templates
+    n = len(offs) - 1
+    goff = np.array([0, 30, n - 40, n - 40, n])    # a small group, the large one (1.66 M observations at K = 32), an empty one, a small one
+    data = data.copy()
+    data[offs[5000] + 3] = ord("N")
+    for k, mc in ((31, 2), (31, 1), (47, 2), (15, 1)):
+        ref = oracle.count_prune_batch(data, offs, goff, k, mc, emit_csr=(k == 31))
+        got = engine.count_prune(data, offs, goff, k, mc, flags=EMIT_STATS | (EMIT_CSR if k == 31 else 0))
+        assert_batches_equal(got, ref, check_csr=(k == 31), ctx=f"one large group k={k} mc={mc}")
+        assert got.n_observations == ref.n_observations
+        assert got.n_spilled_groups == 0, (k, mc)
+
+
 def _check_unitigs(engine, oracle, data, offs, goff, k, mc, min_length, validity=None, ctx=""):
     ref = oracle.count_prune_batch(data, offs, goff, k, mc, validity=validity)
     got = engine.assemble(data, offs, goff, k, mc, min_length=min_length, validity=validity)
