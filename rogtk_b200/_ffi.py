@@ -35,7 +35,7 @@ SYMBOLS = [
     "rogtk_gpu_abi_version", "rogtk_gpu_device_count", "rogtk_gpu_create", "rogtk_gpu_destroy", "rogtk_gpu_trim", "rogtk_gpu_last_error",
     "rogtk_gpu_k_eff", "rogtk_gpu_estimate_k", "rogtk_gpu_shard_of", "rogtk_gpu_count_prune_batch", "rogtk_gpu_free_batch",
     "rogtk_gpu_synth_reads", "rogtk_gpu_synth_reads_var", "rogtk_gpu_device_alloc", "rogtk_gpu_device_free", "rogtk_gpu_pinned_alloc",
-    "rogtk_gpu_pinned_free", "rogtk_gpu_memcpy_h2d", "rogtk_gpu_memcpy_d2h", "rogtk_gpu_launch_count", "rogtk_gpu_flush_l2", "rogtk_gpu_debug_phase_cycles",
+    "rogtk_gpu_pinned_free", "rogtk_gpu_memcpy_h2d", "rogtk_gpu_memcpy_d2h", "rogtk_gpu_launch_count", "rogtk_gpu_flush_l2", "rogtk_gpu_debug_phase_cycles", "rogtk_gpu_debug_cache_stats",
     "rogtk_gpu_spectrum_owner", "rogtk_gpu_spectrum_split", "rogtk_gpu_spectrum_merge", "rogtk_gpu_rethreshold",
     "rogtk_gpu_compress_unitigs", "rogtk_gpu_free_contigs",
     "rogtk_gpu_assemble_batch", "rogtk_gpu_free_strings", "rogtk_gpu_sweep_batch", "rogtk_gpu_free_sweep",
@@ -234,6 +234,8 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_launch_count.restype = i64
     lib.rogtk_gpu_debug_phase_cycles.argtypes = [vp, ctypes.c_int, vp]
     lib.rogtk_gpu_debug_phase_cycles.restype = ctypes.c_int
+    lib.rogtk_gpu_debug_cache_stats.argtypes = [vp, vp]
+    lib.rogtk_gpu_debug_cache_stats.restype = ctypes.c_int
     lib.rogtk_gpu_spectrum_owner.argtypes = [u64, u64, ctypes.c_int, ctypes.c_int]
     lib.rogtk_gpu_spectrum_owner.restype = ctypes.c_int
     lib.rogtk_gpu_spectrum_split.argtypes = [vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp]

@@ -156,15 +156,16 @@ struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     cudaStream_t st = nullptr;
+    DevCache *cache = nullptr;   // where p came from (a buffer may outlive the CacheScope it was allocated under)
     DevBuf() = default;
     DevBuf(size_t n, cudaStream_t s) { alloc(n, s); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), st(o.st) { o.p = nullptr; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), st(o.st), cache(o.cache) { o.p = nullptr; }
     DevBuf &operator=(DevBuf &&o) noexcept
     {
         release();
-        p = o.p; bytes = o.bytes; st = o.st; o.p = nullptr;
+        p = o.p; bytes = o.bytes; st = o.st; cache = o.cache; o.p = nullptr;
         return *this;
     }
     void alloc(size_t n, cudaStream_t s)
@@ -172,11 +173,12 @@ struct DevBuf {
         release();
         st = s;
         bytes = n;
+        cache = tl_cache;
         CK(dev_alloc(&p, n ? n : 16, s));
     }
     void release()
     {
-        if (p) dev_free(p, st);
+        if (p && cache) cache->free(p, st);
         p = nullptr;
     }
     void *detach()

@@ -61,6 +61,13 @@ struct PartArgs {
     uint8_t *pool_exts;
     uint16_t *pool_counts;
     SegRec *segs;                // [n_list * pcap]
+    // merge mode (k_part_count<W, true>): the records of range b are the slices [m_bnd[r * m_stride + b], m_bnd[r * m_stride + b + 1])
+    // of m_runs ascending runs (k-mer, partial count, exts) laid out one after the other in m_lo / m_hi / m_cnt / m_ext
+    const uint64_t *m_lo, *m_hi;
+    const uint16_t *m_cnt;
+    const uint8_t *m_ext;
+    const int64_t *m_bnd;
+    int m_runs, m_stride;
     // prefix kernel
     int32_t *seg_count;          // [n_list]
     int64_t *nsurv;              // [n_groups]
@@ -228,7 +235,9 @@ template <int W>
 constexpr size_t part_count_smem() { return (size_t)table_slots<W>() * (sizeof(typename KeySlot<W>::T) + 4) + 64 * 4; }
 
 // one (group, range) bucket per iteration: count it in shared memory, prune, leave the survivors in the pool as one segment
-template <int W>
+// MERGE = true: the same table fed by slices of already counted ascending runs -- partial counts add up (saturating at 65535 when
+// written out), exts are OR-ed: the merge step of the global-spectrum exchange (spectrum_nccl.cuh), one list entry, bucket = range.
+template <int W, bool MERGE>
 __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs a, int64_t n_buckets)
 {
     constexpr int NT = PT_NT, TS = table_slots<W>();
@@ -255,16 +264,28 @@ __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs
         __syncthreads();
         const int64_t b = (int64_t)(((unsigned long long)ws[1] << 32) | ws[0]);
         if (b >= n_buckets) break;
-        int64_t lo_e = 0, hi_e = a.n_list;
+        int64_t lo_e = 0, hi_e = MERGE ? 1 : a.n_list;
         while (hi_e - lo_e > 1) {
             const int64_t m = (lo_e + hi_e) >> 1;
             if (a.bucket_off[m] <= b) lo_e = m; else hi_e = m;
         }
         const int64_t e = lo_e;
-        const int pass = (int)(b - a.bucket_off[e]);
+        const int pass = MERGE ? (int)b : (int)(b - a.bucket_off[e]);
         if (a.failed[e]) continue;
-        const int64_t rec0 = a.rec_off[b];
-        const uint32_t n = (uint32_t)(a.rec_off[b + 1] - rec0);
+        int64_t rec0 = 0;
+        uint32_t n = 0;
+        if (MERGE) {
+            int64_t tot = 0;
+            for (int r = 0; r < a.m_runs; r++) tot += a.m_bnd[(int64_t)r * a.m_stride + b + 1] - a.m_bnd[(int64_t)r * a.m_stride + b];
+            if (tot > (int64_t)(TS - TS / 8)) {   // more records than the table takes for sure: the caller falls back to its sort
+                if (tid == 0) a.failed[e] = 1;
+                continue;
+            }
+            n = (uint32_t)tot;
+        } else {
+            rec0 = a.rec_off[b];
+            n = (uint32_t)(a.rec_off[b + 1] - rec0);
+        }
         // table sized to the bucket
         uint32_t tsize = (uint32_t)TS;
         if (W == 1) {
@@ -281,15 +302,12 @@ __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs
         __syncthreads();
         // (measured and dropped: merging equal k-mers inside a warp with __match_any_sync before the probe -- a range of a deep UMI
         //  holds a handful of true k-mers that carry most of its records -- made this kernel 2.4x slower: 62 -> 147 ms on configs[2])
-        for (uint32_t i = tid; i < n; i += NT) {
-            Key<W> key = Key<W>::zero();
-            key.lo = a.rec_lo[rec0 + i];
-            if constexpr (W == 2) key.hi = a.rec_hi[rec0 + i];
-            const uint32_t ex = a.rec_ex[rec0 + i];
+        auto insert = [&](const Key<W> &key, uint32_t ex, uint32_t weight) {
             const KT kp = S::pack(key);
             if (kp == S::empty()) {   // the all-ones k-mer is the table's EMPTY marker: side word
-                val_add(&ws[2], ex);
-                continue;
+                const uint32_t old = atomicAdd(&ws[2], weight << 8);
+                if (ex & ~old) atomicOr(&ws[2], ex);
+                return;
             }
             uint32_t h = W == 2 ? __umulhi(hash32(key), tsize) : (hash32(key) >> (32 - __ffs((int)tsize) + 1));
             uint32_t guard = 0;
@@ -297,7 +315,8 @@ __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs
                 KT cur = tkey[h];
                 if (cur == S::empty()) cur = atomicCAS(&tkey[h], S::empty(), kp);
                 if (cur == kp || cur == S::empty()) {
-                    val_add(&tval[h], ex);
+                    const uint32_t old = atomicAdd(&tval[h], weight << 8);
+                    if (ex & ~old) atomicOr(&tval[h], ex);
                     break;
                 }
                 h = h + 1u == tsize ? 0u : h + 1u;
@@ -305,6 +324,25 @@ __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs
                     ws[3] = 1;
                     break;
                 }
+            }
+        };
+        if (MERGE) {
+            // (partial counts are at most 65535 and at most 257 runs meet in a table word: the 24-bit count field cannot overflow)
+            for (int r = 0; r < a.m_runs; r++) {
+                const int64_t s0 = a.m_bnd[(int64_t)r * a.m_stride + b], s1 = a.m_bnd[(int64_t)r * a.m_stride + b + 1];
+                for (int64_t i = s0 + tid; i < s1; i += NT) {
+                    Key<W> key = Key<W>::zero();
+                    key.lo = a.m_lo[i];
+                    if constexpr (W == 2) key.hi = a.m_hi[i];
+                    insert(key, a.m_ext[i], a.m_cnt[i]);
+                }
+            }
+        } else {
+            for (uint32_t i = tid; i < n; i += NT) {
+                Key<W> key = Key<W>::zero();
+                key.lo = a.rec_lo[rec0 + i];
+                if constexpr (W == 2) key.hi = a.rec_hi[rec0 + i];
+                insert(key, a.rec_ex[rec0 + i], 1u);
             }
         }
         if (tid == 0) {
@@ -434,13 +472,41 @@ __global__ void __launch_bounds__(1024) k_part_finish_one(PartArgs a)
     if (tid == 1023) {
         a.seg_count[0] = P;
         a.nsurv[g] = part[1023];
-        const unsigned long long obs = (unsigned long long)(a.rec_off[a.bucket_off[0] + P] - a.rec_off[a.bucket_off[0]]);
-        if (obs) atomicAdd(a.n_obs, obs);
+        if (a.rec_off) {
+            const unsigned long long obs = (unsigned long long)(a.rec_off[a.bucket_off[0] + P] - a.rec_off[a.bucket_off[0]]);
+            if (obs) atomicAdd(a.n_obs, obs);
+        }
         if (part[1023] > 0x7fffffffll) {   // (prefixes are 32-bit)
             a.seg_count[0] = 0;
             a.failed_ids[atomicAdd(a.n_failed, 1ull)] = (int32_t)g;
         }
     }
+}
+
+// merge mode: first record of every (run, range): bnd[r * stride + j] = first index in run r (ascending k-mers, [run_off[r],
+// run_off[r+1]) of the concatenated arrays) whose range is >= base + j, j in [0, n_ranges]
+template <int W>
+__global__ void k_merge_bounds(const uint64_t *lo, const uint64_t *hi, const int64_t *run_off, int n_runs, int kbits, uint32_t total, uint32_t base,
+                               int n_ranges, int64_t *bnd)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)n_ranges + 1;
+    if (i >= (int64_t)n_runs * stride) return;
+    const int r = (int)(i / stride), j = (int)(i % stride);
+    int64_t a = run_off[r], b = run_off[r + 1];
+    if (j == n_ranges) {
+        bnd[i] = b;
+        return;
+    }
+    const uint32_t want = base + (uint32_t)j;
+    while (a < b) {
+        const int64_t m = (a + b) >> 1;
+        Key<W> key = Key<W>::zero();
+        key.lo = lo[m];
+        if constexpr (W == 2) key.hi = hi[m];
+        if (pass_of(key_top32(key, kbits), total) < want) a = m + 1; else b = m;
+    }
+    bnd[i] = a;
 }
 
 }  // namespace rogtk
@@ -476,8 +542,10 @@ inline void part_path_configure()
     cfg(k_part_scatter<2, true>, part_scatter_smem(PT_PBIG));
     cfg(k_part_scatter<1, false>, part_scatter_smem(PT_PBIG));
     cfg(k_part_scatter<2, false>, part_scatter_smem(PT_PBIG));
-    cfg(k_part_count<1>, part_count_smem<1>());
-    cfg(k_part_count<2>, part_count_smem<2>());
+    cfg(k_part_count<1, false>, part_count_smem<1>());
+    cfg(k_part_count<2, false>, part_count_smem<2>());
+    cfg(k_part_count<1, true>, part_count_smem<1>());
+    cfg(k_part_count<2, true>, part_count_smem<2>());
 }
 
 // d_ids: n_list listed groups (device).  Survivors go to the shared pool (pool_* / pool_cursor of the shared-memory path).
@@ -571,7 +639,7 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
         if (n_buckets > 0) {
             a.ticket = d_ctr + 1;
             const unsigned grid = (unsigned)std::min<int64_t>(n_buckets, (int64_t)sm_count * (W == 1 ? 2 : 1));
-            k_part_count<W><<<grid, PT_NT, part_count_smem<W>(), st>>>(a, n_buckets);
+            k_part_count<W, false><<<grid, PT_NT, part_count_smem<W>(), st>>>(a, n_buckets);
         }
         if (big) k_part_finish_one<<<1, 1024, 0, st>>>(a);
         else k_part_finish<<<blocks(nl, 128), 128, 0, st>>>(a);
@@ -586,6 +654,69 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
     res.failed_ids = d_failed_ids;
     res.n_failed = (int64_t)nf;
     res.keep.push_back(std::move(ctr));
+}
+
+// Merge of R ascending runs of counted k-mers that all lie in ranges [base, base + n_ranges) of `total` equal ranges of the k-mer
+// space: per range one shared-memory table (k_part_count<W, true>), survivors ordered by the segment sort.  Returns false when a
+// range does not fit a table (skewed k-mers): nothing is written and the caller uses its generic sort-based merge.
+// d_run_off: device [n_runs + 1].  Outputs (allocated here): o_* with n_out survivors, ascending.
+template <int W>
+inline bool merge_sorted_runs_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, const uint64_t *m_lo, const uint64_t *m_hi, const uint16_t *m_cnt,
+                                const uint8_t *m_ext, const int64_t *d_run_off, int n_runs, int64_t n_in, int K, uint32_t min_cov, uint32_t total,
+                                uint32_t base, int n_ranges, DevBuf &o_lo, DevBuf &o_hi, DevBuf &o_exts, DevBuf &o_counts, int64_t &n_out,
+                                int64_t *launches)
+{
+    auto blocks = [](int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); };
+    const int64_t stride = (int64_t)n_ranges + 1;
+    DevBuf bnd((size_t)n_runs * stride * 8, st), segs((size_t)n_ranges * sizeof(SegRec), st), misc(256, st), boff(16, st);
+    CK(cudaMemsetAsync(misc.p, 0, 256, st));
+    k_merge_bounds<W><<<blocks((int64_t)n_runs * stride, 256), 256, 0, st>>>(m_lo, m_hi, d_run_off, n_runs, 2 * K, total, base, n_ranges, bnd.as<int64_t>());
+    // words of misc: [0] ticket [1] pool cursor [2] n_failed [3] nsurv [4] n_obs (unused) ; 32-bit: np, rows_per_slab, failed, seg_count, ids, failed_ids
+    unsigned long long *d_ctr = misc.as<unsigned long long>();
+    int32_t *d_i32 = reinterpret_cast<int32_t *>(d_ctr + 8);
+    const int32_t h_i32[6] = {n_ranges, 1, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(d_i32, h_i32, sizeof(h_i32), cudaMemcpyHostToDevice, st));
+    const int64_t h_boff[2] = {0, n_ranges};
+    CK(cudaMemcpyAsync(boff.p, h_boff, 16, cudaMemcpyHostToDevice, st));
+    const unsigned grid = (unsigned)std::min<int64_t>(n_ranges, (int64_t)sm_count * (W == 1 ? 2 : 1));
+    const int64_t pool_cap = n_in + n_in / 4 + (int64_t)(grid + 2) * (SM_POOL_CHUNK + table_slots<W>() + 1);
+    DevBuf p_lo((size_t)pool_cap * 8, st), p_hi(W == 2 ? (size_t)pool_cap * 8 : 0, st), p_exts((size_t)pool_cap, st), p_counts((size_t)pool_cap * 2, st);
+    PartArgs a{};
+    a.n_list = 1;
+    a.ids = d_i32 + 4; a.np = d_i32; a.rows_per_slab = d_i32 + 1; a.failed = d_i32 + 2; a.seg_count = d_i32 + 3; a.failed_ids = d_i32 + 5;
+    a.bucket_off = boff.as<int64_t>();
+    a.pcap = n_ranges;
+    a.min_cov = min_cov; a.K = K;
+    a.ticket = d_ctr; a.pool_cursor = d_ctr + 1; a.n_failed = d_ctr + 2; a.nsurv = reinterpret_cast<int64_t *>(d_ctr + 3); a.n_obs = d_ctr + 4;
+    a.pool_cap = pool_cap; a.pool_lo = p_lo.as<uint64_t>(); a.pool_hi = W == 2 ? p_hi.as<uint64_t>() : nullptr;
+    a.pool_exts = p_exts.as<uint8_t>(); a.pool_counts = p_counts.as<uint16_t>();
+    a.segs = segs.as<SegRec>();
+    a.m_lo = m_lo; a.m_hi = m_hi; a.m_cnt = m_cnt; a.m_ext = m_ext; a.m_bnd = bnd.as<int64_t>(); a.m_runs = n_runs; a.m_stride = (int)stride;
+    k_part_count<W, true><<<grid, PT_NT, part_count_smem<W>(), st>>>(a, n_ranges);
+    k_part_finish_one<<<1, 1024, 0, st>>>(a);
+    if (launches) *launches += 3;
+    unsigned long long nf = 0;
+    int64_t ns = 0;
+    Peek pk(peek_slot, st, launches);
+    pk.add(d_ctr + 2, 8, &nf);
+    pk.add(d_ctr + 3, 8, &ns);
+    pk.sync();
+    if (nf) return false;
+    n_out = ns;
+    const size_t no = (size_t)std::max<int64_t>(n_out, 1);
+    o_lo.alloc(no * 8, st);
+    if (W == 2) o_hi.alloc(no * 8, st);
+    o_exts.alloc(no, st);
+    o_counts.alloc(no * 2, st);
+    DevBuf koff(16, st);
+    const int64_t h_koff[2] = {0, n_out};
+    CK(cudaMemcpyAsync(koff.p, h_koff, 16, cudaMemcpyHostToDevice, st));
+    if (n_out > 0)
+        run_sort_gather(st, peek_slot, sm_count, K, 1, nullptr, koff.as<int64_t>(), a.pool_lo, a.pool_hi, a.pool_exts, a.pool_counts, o_lo.as<uint64_t>(),
+                        W == 2 ? o_hi.as<uint64_t>() : nullptr, o_exts.as<uint8_t>(), o_counts.as<uint16_t>(), launches, a.segs, a.seg_count, a.ids, 1,
+                        n_ranges, false, total, base);
+    CK(cudaStreamSynchronize(st));   // h_* staging arrays above are on this frame
+    return true;
 }
 
 }  // namespace rogtk

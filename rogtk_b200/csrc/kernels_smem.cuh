@@ -996,6 +996,7 @@ struct SortArgs {
     const int32_t *seg_count;
     const int32_t *seg_list;
     int seg_stride;                // segment slots per list entry (SM_PMAX for multi-pass groups, PT_PMAX for partitioned ones)
+    uint32_t seg_total, seg_base;  // seg_total != 0: slot p is range seg_base + p of seg_total equal ranges of the k-mer space (merge of owned ranges)
 };
 
 // Counting sort of one work item per CTA pass: survivors are read once into registers, counted per bucket (top 10 k-mer bits),
@@ -1032,8 +1033,8 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
             ps = r.pool_start;
             o = a.kmer_offsets[a.seg_list[e]] + r.prefix;
             n = r.n;
-            seg_np = (uint32_t)np;
-            seg_first = pass_first((uint32_t)(it % a.seg_stride), seg_np);
+            seg_np = a.seg_total ? a.seg_total : (uint32_t)np;
+            seg_first = pass_first((uint32_t)(it % a.seg_stride) + a.seg_base, seg_np);
         } else {
             ps = a.pool_start[it];
             if (ps < 0) continue;
@@ -1308,7 +1309,7 @@ inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, i
                             const uint64_t *p_lo, const uint64_t *p_hi, const uint8_t *p_exts, const uint16_t *p_counts, uint64_t *o_lo,
                             uint64_t *o_hi, uint8_t *o_exts, uint16_t *o_counts, int64_t *launches, const SegRec *segs = nullptr,
                             const int32_t *seg_count = nullptr, const int32_t *seg_list = nullptr, int64_t n_seg_groups = 0,
-                            int seg_stride = SM_PMAX, bool groups_too = true)
+                            int seg_stride = SM_PMAX, bool groups_too = true, uint32_t seg_total = 0, uint32_t seg_base = 0)
 {
     SortArgs a{};
     a.n_groups = n_groups;
@@ -1321,6 +1322,8 @@ inline void run_sort_gather(cudaStream_t st, uint8_t *peek_slot, int sm_count, i
     a.seg_count = seg_count;
     a.seg_list = seg_list;
     a.seg_stride = seg_stride;
+    a.seg_total = seg_total;
+    a.seg_base = seg_base;
     if (K > 32) run_sort_gather_w<2>(st, peek_slot, sm_count, a, groups_too ? n_groups : 0, n_seg_groups, launches);
     else run_sort_gather_w<1>(st, peek_slot, sm_count, a, groups_too ? n_groups : 0, n_seg_groups, launches);
 }

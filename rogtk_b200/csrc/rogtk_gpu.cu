@@ -1700,9 +1700,16 @@ extern "C" int rogtk_gpu_spectrum_split(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
     return ROGTK_OK;
 }
 
-extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo, const uint64_t *d_hi, const uint16_t *d_counts,
-                                        const uint8_t *d_exts, int64_t n, int k_eff, uint32_t min_coverage, uint32_t flags,
-                                        rogtk_graph_batch *out)
+// What the merge knows when its input is the exchange's: R ascending runs, all inside ranges [base, base + n_ranges) of `total`
+// equal ranges of the k-mer space (this rank's share).  Then the merge is one shared-memory table per range (kernels_part.cuh).
+struct MergeRuns {
+    std::vector<int64_t> run_off;   // [R + 1]
+    uint32_t total = 0, base = 0;
+    int n_ranges = 0;
+};
+
+static int spectrum_merge_impl(rogtk_gpu_ctx *ctx, const uint64_t *d_lo, const uint64_t *d_hi, const uint16_t *d_counts, const uint8_t *d_exts,
+                               int64_t n, int k_eff, uint32_t min_coverage, uint32_t flags, rogtk_graph_batch *out, const MergeRuns *runs)
 {
     if (!ctx || !out || n < 0 || k_eff < 1 || k_eff > 64 || (n > 0 && (!d_lo || !d_counts || !d_exts)) || (k_eff > 32 && n > 0 && !d_hi))
         return ROGTK_ERR_INVALID_ARG;
@@ -1719,8 +1726,22 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
         cudaStream_t st = ctx->stream;
         CK(cudaEventRecord(ctx->ev[0], st));
         const size_t nn = (size_t)std::max<int64_t>(n, 1);
-        DevBuf recs(nn * sizeof(SpecRec), st), keep(nn * 4, st), pos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st);
         int64_t n_out = 0;
+        DevBuf o_lo, o_hi, o_exts, o_counts, o_off(16, st), o_stats(16, st);
+        bool merged = false;
+        if (runs && n > 0 && runs->n_ranges > 0 && !(flags & ROGTK_FORCE_SPILL)) {
+            const int R = (int)runs->run_off.size() - 1;
+            DevBuf d_ro((size_t)(R + 1) * 8, st);
+            CK(cudaMemcpyAsync(d_ro.p, runs->run_off.data(), (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, st));
+            if (k_eff > 32)
+                merged = merge_sorted_runs_w<2>(st, ctx->peek_slot, ctx->sm_count, d_lo, d_hi, d_counts, d_exts, d_ro.as<int64_t>(), R, n, k_eff, min_coverage,
+                                                runs->total, runs->base, runs->n_ranges, o_lo, o_hi, o_exts, o_counts, n_out, &ctx->launches);
+            else
+                merged = merge_sorted_runs_w<1>(st, ctx->peek_slot, ctx->sm_count, d_lo, nullptr, d_counts, d_exts, d_ro.as<int64_t>(), R, n, k_eff, min_coverage,
+                                                runs->total, runs->base, runs->n_ranges, o_lo, o_hi, o_exts, o_counts, n_out, &ctx->launches);
+        }
+        if (!merged) {
+        DevBuf recs(nn * sizeof(SpecRec), st), keep(nn * 4, st), pos((nn + 1) * 8, st), scr(scan_scratch_bytes(n), st);
         if (n > 0) {
             k_spec_pack<<<blocks_for(n, 256), 256, 0, st>>>(d_lo, k_eff > 32 ? d_hi : nullptr, d_counts, d_exts, n, recs.as<SpecRec>());
             {
@@ -1735,12 +1756,17 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
             ctx->launches += 5;
         }
         const size_t no = (size_t)std::max<int64_t>(n_out, 1);
-        DevBuf o_lo(no * 8, st), o_hi(k_eff > 32 ? no * 8 : 0, st), o_exts(no, st), o_counts(no * 2, st), o_off(16, st), o_stats(16, st);
+        o_lo.alloc(no * 8, st);
+        if (k_eff > 32) o_hi.alloc(no * 8, st);
+        o_exts.alloc(no, st);
+        o_counts.alloc(no * 2, st);
+
         if (n > 0) {
             k_spec_emit<<<blocks_for(n, 256), 256, 0, st>>>(recs.as<SpecRec>(), n, keep.as<int32_t>(), pos.as<int64_t>(), o_lo.as<uint64_t>(),
                                                             k_eff > 32 ? o_hi.as<uint64_t>() : nullptr, o_exts.as<uint8_t>(),
                                                             o_counts.as<uint16_t>());
             ctx->launches++;
+        }
         }
         const int64_t h_off[2] = {0, n_out};
         CK(cudaMemcpyAsync(o_off.p, h_off, 16, cudaMemcpyHostToDevice, st));
@@ -1787,6 +1813,13 @@ extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo
         memset(out, 0, sizeof(*out));
     }
     return rc;
+}
+
+extern "C" int rogtk_gpu_spectrum_merge(rogtk_gpu_ctx *ctx, const uint64_t *d_lo, const uint64_t *d_hi, const uint16_t *d_counts,
+                                        const uint8_t *d_exts, int64_t n, int k_eff, uint32_t min_coverage, uint32_t flags,
+                                        rogtk_graph_batch *out)
+{
+    return spectrum_merge_impl(ctx, d_lo, d_hi, d_counts, d_exts, n, k_eff, min_coverage, flags, out, nullptr);
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -2137,6 +2170,19 @@ extern "C" int rogtk_gpu_memcpy_d2h(rogtk_gpu_ctx *ctx, void *dst, const void *s
     return ROGTK_OK;
 }
 extern "C" int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int rogtk_gpu_debug_cache_stats(rogtk_gpu_ctx *ctx, int64_t *out6)
+{
+    if (!ctx || !out6 || !ctx->cache) return ROGTK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->cache->mu);
+    out6[0] = ctx->cache->n_malloc;
+    out6[1] = ctx->cache->n_reuse;
+    out6[2] = (int64_t)ctx->cache->idle_bytes;
+    out6[3] = (int64_t)ctx->cache->live_bytes;
+    out6[4] = (int64_t)ctx->cache->peak_bytes;
+    out6[5] = (int64_t)ctx->cache->idle.size();
+    return ROGTK_OK;
+}
 
 extern "C" int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint64_t *out16)
 {

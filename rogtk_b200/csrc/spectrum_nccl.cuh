@@ -148,6 +148,7 @@ extern "C" int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph
     const int world = ns ? ns->world : 1, rank = ns ? ns->rank : 0;
     DevBuf m_lo, m_hi, m_cnt, m_ext;   // what the merge reads: carry + every received slice
     int64_t n_merge = 0;
+    MergeRuns runs;                    // ... as ascending runs inside this rank's share of the k-mer space
     rogtk_exchange_stats xs{};
     try {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -233,7 +234,9 @@ extern "C" int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph
         m_cnt.alloc(nm * 2, st);
         m_ext.alloc(nm, st);
         int64_t at = 0;
+        runs.run_off.push_back(0);
         auto append = [&](const uint64_t *lo, const uint64_t *hi, const uint16_t *cnt, const uint8_t *ext, int64_t c) {
+            runs.run_off.push_back(at + c);
             if (c == 0) return;
             CK(cudaMemcpyAsync(m_lo.as<uint64_t>() + at, lo, (size_t)c * 8, cudaMemcpyDeviceToDevice, st));
             if (two) CK(cudaMemcpyAsync(m_hi.as<uint64_t>() + at, hi, (size_t)c * 8, cudaMemcpyDeviceToDevice, st));
@@ -269,7 +272,21 @@ extern "C" int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph
         return fail_code(ctx);
     }
     if (stats) *stats = xs;
+    if (2 * K > 24 && n_merge > 0) {
+        // this rank owns the first-4-base buckets [b0, b1) (spectrum_owner); cut each into m equal ranges of about 3000 records
+        const uint32_t b0 = (uint32_t)((256u * (uint32_t)rank + (uint32_t)world - 1u) / (uint32_t)world);
+        const uint32_t b1 = (uint32_t)((256u * (uint32_t)(rank + 1) + (uint32_t)world - 1u) / (uint32_t)world);
+        const int64_t want = (n_merge + 2999) / 3000;
+        const uint32_t nb = b1 > b0 ? b1 - b0 : 1u;
+        uint32_t m = (uint32_t)((want + nb - 1) / nb);
+        m = m < 1u ? 1u : m;
+        if ((int64_t)m * nb <= (1 << 22)) {
+            runs.total = 256u * m;
+            runs.base = b0 * m;
+            runs.n_ranges = (int)(nb * m);
+        }
+    }
     // (takes the context lock itself)
-    return rogtk_gpu_spectrum_merge(ctx, m_lo.as<uint64_t>(), two ? m_hi.as<uint64_t>() : nullptr, m_cnt.as<uint16_t>(), m_ext.as<uint8_t>(), n_merge, K,
-                                    min_coverage, flags, out);
+    return spectrum_merge_impl(ctx, m_lo.as<uint64_t>(), two ? m_hi.as<uint64_t>() : nullptr, m_cnt.as<uint16_t>(), m_ext.as<uint8_t>(), n_merge, K,
+                               min_coverage, flags, out, &runs);
 }

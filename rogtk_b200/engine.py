@@ -221,6 +221,12 @@ class Engine:
         self._check(self._lib.rogtk_gpu_debug_phase_cycles(self._ctx, int(enable), out.ctypes.data))
         return out
 
+    def cache_stats(self) -> dict:
+        """Counters of the context's device-memory cache (rogtk_gpu_debug_cache_stats)."""
+        out = np.zeros(6, dtype=np.int64)
+        self._check(self._lib.rogtk_gpu_debug_cache_stats(self._ctx, out.ctypes.data))
+        return dict(zip(("n_malloc", "n_reuse", "idle_bytes", "live_bytes", "peak_bytes", "idle_blocks"), map(int, out)))
+
     def flush_l2(self):
         self._check(self._lib.rogtk_gpu_flush_l2(self._ctx))
 

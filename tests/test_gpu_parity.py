@@ -452,6 +452,28 @@ def test_global_spectrum_single_rank_and_emulated_sources(engine, oracle):
         assert np.array_equal(np.concatenate([p.counts for p in pieces]), ref.counts)
 
 
+def test_global_spectrum_merge_tables_and_their_fallback(engine, oracle):
+    """The merge of the exchange (ascending runs -> one shared-memory table per k-mer range, kernels_part.cuh k_part_count<W, true>)
+    on a spectrum large enough for hundreds of ranges, in several rounds (carry + own slice = two runs), and on reads whose k-mers
+    crowd one range (12 000 distinct k-mers share their first 16 bases): the range does not fit a table, the sort-based merge
+    takes over, the result is the same."""
+    from rogtk_b200 import spectrum, synth
+    data, offs, _ = synth.synth_reads(synth.config_seed(5), 3, 1500, 8, 150, 500)    # 12 000 reads, 1500 templates: ~1.4 M observations
+    n_rows = len(offs) - 1
+    for k, mc in ((31, 2), (45, 1)):
+        ref = oracle.count_prune_batch(data, offs, np.array([0, n_rows]), k, mc)
+        for chunk in (None, 5000):
+            got = spectrum.global_spectrum(engine, data, offs, k, mc, flags=EMIT_STATS, chunk_rows=chunk)
+            assert_batches_equal(got, ref, ctx=f"spectrum merge k={k} chunk={chunk}")
+    rng = np.random.default_rng(5)
+    reads = ["A" * 16 + "".join(rng.choice(list("ACGT"), 22)) for _ in range(12000)]
+    d2, o2, _ = oracle.strings_to_arrow(reads)
+    ref = oracle.count_prune_batch(d2, o2, np.array([0, len(reads)]), 31, 1)
+    for chunk in (None, 7000):
+        got = spectrum.global_spectrum(engine, d2, o2, 31, 1, flags=EMIT_STATS, chunk_rows=chunk)
+        assert_batches_equal(got, ref, ctx=f"spectrum merge, crowded range, chunk={chunk}")
+
+
 def test_threshold_reuse_matches_recount(engine, oracle):
     """one count at min_coverage=1 serves every higher threshold of the sweep / optimise drivers
     (reference src/expressions.rs:901-941, src/fracture_opt.rs:163-218) bit-for-bit."""
@@ -882,6 +904,18 @@ def test_device_cache_reuse_and_trim(oracle):
                 assert_batches_equal(eng.count_prune(data, offs, goff, k, mc, flags=fl | EMIT_STATS), ref, check_csr=bool(fl & EMIT_CSR), ctx=f"round {i}")
             if i == 1:
                 a.trim()
+        # nothing stays allocated behind a finished call (buffers that outlive an entry point's scope included: the exchange's
+        # merge input), and the steady state allocates nothing new
+        from rogtk_b200 import spectrum
+        data, offs, goff = synth.synth_reads(synth.config_seed(5), 0, 30, 20, 150, 400)
+        for it in range(3):
+            spectrum.global_spectrum(a, data, offs, 31, 2, chunk_rows=250)
+            st = a.cache_stats()
+            assert st["live_bytes"] == 0, st
+            if it == 1:
+                mallocs = st["n_malloc"]
+        assert st["n_malloc"] == mallocs and st["n_reuse"] > 0
+        assert b.cache_stats()["live_bytes"] == 0
         held = free0 - torch.cuda.mem_get_info(0)[0]
         a.trim()
         b.trim()
