@@ -34,7 +34,7 @@ NO_PARTITION = 1 << 8
 SYMBOLS = [
     "rogtk_gpu_abi_version", "rogtk_gpu_device_count", "rogtk_gpu_create", "rogtk_gpu_destroy", "rogtk_gpu_trim", "rogtk_gpu_last_error",
     "rogtk_gpu_k_eff", "rogtk_gpu_estimate_k", "rogtk_gpu_shard_of", "rogtk_gpu_count_prune_batch", "rogtk_gpu_free_batch",
-    "rogtk_gpu_synth_reads", "rogtk_gpu_synth_reads_var", "rogtk_gpu_device_alloc", "rogtk_gpu_device_free", "rogtk_gpu_pinned_alloc",
+    "rogtk_gpu_synth_reads", "rogtk_gpu_synth_reads_from", "rogtk_gpu_synth_reads_var", "rogtk_gpu_device_alloc", "rogtk_gpu_device_free", "rogtk_gpu_pinned_alloc",
     "rogtk_gpu_pinned_free", "rogtk_gpu_memcpy_h2d", "rogtk_gpu_memcpy_d2h", "rogtk_gpu_launch_count", "rogtk_gpu_flush_l2", "rogtk_gpu_debug_phase_cycles", "rogtk_gpu_debug_cache_stats",
     "rogtk_gpu_spectrum_owner", "rogtk_gpu_spectrum_split", "rogtk_gpu_spectrum_merge", "rogtk_gpu_rethreshold",
     "rogtk_gpu_compress_unitigs", "rogtk_gpu_free_contigs",
@@ -218,6 +218,8 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_free_batch.argtypes = [vp, ctypes.POINTER(GraphBatchC)]
     lib.rogtk_gpu_synth_reads.argtypes = [vp, u64, i64, i64, i32, i32, i32, u32, vp, vp, vp]
     lib.rogtk_gpu_synth_reads.restype = ctypes.c_int
+    lib.rogtk_gpu_synth_reads_from.argtypes = [vp, u64, i64, i64, i32, i32, i32, i32, u32, vp, vp, vp]
+    lib.rogtk_gpu_synth_reads_from.restype = ctypes.c_int
     lib.rogtk_gpu_synth_reads_var.argtypes = [vp, u64, i64, i64, vp, i64, i32, i32, u32, vp, vp]
     lib.rogtk_gpu_synth_reads_var.restype = ctypes.c_int
     lib.rogtk_gpu_device_alloc.argtypes = [vp, sz]

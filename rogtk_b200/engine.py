@@ -259,7 +259,7 @@ class Engine:
         return out
 
     def synth_reads_device(self, seed: int, umi_base: int, n_umis: int, reads_per_umi: int, read_len: int,
-                           template_len: int, err_per_64k: int):
+                           template_len: int, err_per_64k: int, read_base: int = 0):
         """Generate the SURVEY 8(d) synthetic reads directly in HBM.  Returns (d_data, d_offsets, d_group_offsets,
         n_bytes) as raw device pointers (free with device_free)."""
         n_reads = n_umis * reads_per_umi
@@ -267,9 +267,9 @@ class Engine:
         d_data = self.device_alloc(n_bytes + 16)
         d_off = self.device_alloc((n_reads + 1) * 8)
         d_goff = self.device_alloc((n_umis + 1) * 8)
-        self._check(self._lib.rogtk_gpu_synth_reads(self._ctx, seed & 0xFFFFFFFFFFFFFFFF, umi_base, n_umis, reads_per_umi,
-                                                    read_len, template_len, err_per_64k, ctypes.c_void_p(d_data),
-                                                    ctypes.c_void_p(d_off), ctypes.c_void_p(d_goff)))
+        self._check(self._lib.rogtk_gpu_synth_reads_from(self._ctx, seed & 0xFFFFFFFFFFFFFFFF, umi_base, n_umis, reads_per_umi, read_base,
+                                                         read_len, template_len, err_per_64k, ctypes.c_void_p(d_data),
+                                                         ctypes.c_void_p(d_off), ctypes.c_void_p(d_goff)))
         return d_data, d_off, d_goff, n_bytes
 
     def synth_reads_device_var(self, seed: int, umi_base: int, reads_per_umi: np.ndarray, read_len: int, template_len: int, err_per_64k: int):

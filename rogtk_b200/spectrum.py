@@ -138,6 +138,53 @@ def _exchange(engine: Engine, local: DeviceBatch, carry: DeviceBatch | None, min
                        ms_hot_kernel=float(out.ms_hot_kernel), n_spilled_groups=0, n_multipass_groups=0, _c=out, _engine=engine), st
 
 
+def global_spectrum_device(engine: Engine, d_data: int, n_bytes: int, d_offsets: int, n_rows: int, k: int, min_coverage: int,
+                           rdv: Rendezvous | None = None, flags: int = 0, chunk_rows: int | None = None, stats_out: dict | None = None,
+                           keep_on_device: bool = False):
+    """global_spectrum for reads already resident in HBM (one LargeUtf8 column: d_data bytes, d_offsets int64[n_rows + 1]).
+    Rounds of chunk_rows reads address the same column through an advanced offsets pointer -- nothing is copied.
+    keep_on_device=True returns the rank's share as a DeviceBatch (free it), else a host GraphBatch."""
+    rdv = rdv or Rendezvous(0, 1)
+    step = n_rows if not chunk_rows or chunk_rows <= 0 else int(chunk_rows)
+    rounds = rdv.allreduce(max(1, -(-n_rows // max(step, 1))), "max")
+    d_goff = engine.device_alloc(16)
+    carry = None
+    n_obs = 0
+    tot = dict(bytes_sent=0, bytes_received=0, ms_exchange=0.0, n_sent=0, n_received=0, rounds=rounds, ms_local=0.0, ms_merge=0.0)
+    try:
+        for r in range(rounds):
+            a, b = min(n_rows, r * step), min(n_rows, (r + 1) * step)
+            engine.h2d(d_goff, np.array([0, b - a], dtype=np.int64).view(np.uint8))
+            local = engine.count_prune_device(d_data, n_bytes, d_offsets + 8 * a, b - a, d_goff, 1, k, 1, flags=flags & _ffi.EXACT_K)
+            try:
+                if local.k_eff < 0:
+                    return local.to_host()
+                n_obs += local.n_observations
+                tot["ms_local"] += local.ms_total
+                last = r == rounds - 1
+                merged, st = _exchange(engine, local, carry, min_coverage if last else 1, (flags & _ffi.EMIT_STATS) if last else 0,
+                                       on_device=(not last) or keep_on_device)
+                for key in ("bytes_sent", "bytes_received", "n_sent", "n_received"):
+                    tot[key] += int(getattr(st, key))
+                tot["ms_exchange"] += float(st.ms_exchange)
+                tot["ms_merge"] += float(merged.ms_total)
+            finally:
+                local.free()
+            if carry is not None:
+                carry.free()
+                carry = None
+            if last:
+                merged.n_observations = rdv.allreduce(n_obs)
+                if stats_out is not None:
+                    stats_out.update(tot)
+                return merged
+            carry = merged
+    finally:
+        if carry is not None:
+            carry.free()
+        engine.device_free(d_goff)
+
+
 def global_spectrum(engine: Engine, data: np.ndarray, offsets: np.ndarray, k: int, min_coverage: int, rdv: Rendezvous | None = None,
                     validity: np.ndarray | None = None, flags: int = 0, chunk_rows: int | None = None, stats_out: dict | None = None) -> GraphBatch:
     """This rank's share of the global spectrum of all ranks' reads.  `rdv` is the control channel of the job (None = one rank);

@@ -23,25 +23,28 @@ if PARITY:
     rows = np.arange(rank, n_rows, world)                       # reads striped round-robin over ranks
     d = data.reshape(n_rows, L)[rows].reshape(-1)
 else:
-    # large runs: the rank draws reads_per / world reads of EVERY template (same templates on all ranks, different reads)
+    # timing runs: every rank draws ITS reads_per / world reads of EVERY template straight into HBM (same templates on all ranks,
+    # different reads), and the whole mode runs device-resident: the reads never exist on the host
     per = max(1, reads_per // world)
-    d, o_, _ = synth.synth_reads_chunked(synth.config_seed(5) + 1000 * rank, 0, n_tmpl, per, L, T, 655, template_seed=synth.config_seed(5)) \
-        if hasattr(synth, "synth_reads_chunked") and "template_seed" in synth.synth_reads_chunked.__code__.co_varnames else (None, None, None)
-    if d is None:
-        data, offs, _ = synth.synth_reads(synth.config_seed(5), 0, n_tmpl, reads_per, L, T)
-        n_rows = len(offs) - 1
-        rows = np.arange(rank, n_rows, world)
-        d = data.reshape(n_rows, L)[rows].reshape(-1)
-    n_rows = n_tmpl * reads_per
-    rows = np.arange(len(d) // L)
-o = np.arange(len(d) // L + 1, dtype=np.int64) * L
+    d_data, d_off, d_goff, n_bytes = eng.synth_reads_device(synth.config_seed(5), 0, n_tmpl, per, L, T, 655, read_base=rank * per)
+    n_local = n_tmpl * per
+    n_rows = n_local * world
+if PARITY:
+    o = np.arange(len(d) // L + 1, dtype=np.int64) * L
 k, mc = 31, 2
 st = {}
-for it in range(3):
+for it in range(3 if PARITY else 4):
     rdv.barrier(); t0 = time.perf_counter()
-    got = spectrum.global_spectrum(eng, d, o, k, mc, rdv=rdv, chunk_rows=CHUNK, stats_out=st)
+    if PARITY:
+        got = spectrum.global_spectrum(eng, d, o, k, mc, rdv=rdv, chunk_rows=CHUNK, stats_out=st)
+        n_mine = len(got.kmers_lo)
+    else:
+        got = spectrum.global_spectrum_device(eng, d_data, n_bytes, d_off, n_local, k, mc, rdv=rdv, chunk_rows=CHUNK, stats_out=st,
+                                              keep_on_device=True)
+        n_mine = got.n_kmers
+        got.free()
     rdv.barrier(); dt = time.perf_counter() - t0
-tot_surv = rdv.allreduce(len(got.kmers_lo))
+tot_surv = rdv.allreduce(n_mine)
 max_bytes = rdv.allreduce(st["bytes_sent"], "max")
 max_ms = rdv.allreduce(int(st["ms_exchange"] * 1000), "max") / 1000.0
 ok = None
@@ -61,7 +64,8 @@ if rank == 0:
                       "observations": int(got.n_observations), "survivors": int(tot_surv), "parity_vs_oracle": ok, "wall_ms": dt * 1e3,
                       "obs_per_s": got.n_observations / dt, "nccl_bytes_sent_max_rank": int(max_bytes), "nccl_ms_max_rank": max_ms,
                       "nvlink_GBps_per_dir": nv, "nvlink_frac_of_900": (nv / 900.0) if nv else None,
-                      "stage_ms_rank0": {k_: round(v, 2) for k_, v in st.items() if k_.startswith("ms_")}}))
+                      "stage_ms_rank0": {k_: round(v, 2) for k_, v in st.items() if k_.startswith("ms_")},
+                      "input": "host numpy (parity run)" if PARITY else "synthesized in HBM, result left in HBM"}))
     assert ok is not False
 spectrum.finalize_comm(eng)
 rdv.close()
