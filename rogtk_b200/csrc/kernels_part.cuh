@@ -76,15 +76,19 @@ struct PartArgs {
     unsigned long long *n_failed;
 };
 
-// per listed group: observation upper bound -> ranges, rows per slab, slabs, bucket capacities
-__global__ void k_part_plan(ColView col, const int64_t *group_offsets, const int32_t *ids, int64_t n_list, int K, int32_t *np, int32_t *rows_per_slab,
-                            int64_t *slabs, int64_t *bucket_cap)
+// per listed group: observation upper bound and longest read, accumulated by `parts` warps per group (a batch of thousands of
+// groups: one warp each; one group of millions of reads: thousands of warps), ...
+__global__ void k_part_plan_rows(ColView col, const int64_t *group_offsets, const int32_t *ids, int64_t n_list, int K, int parts,
+                                 unsigned long long *obs_acc, int *maxlen_acc)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t e = warp; e < n_list; e += n_warps) {
+    for (int64_t u = warp; u < n_list * parts; u += n_warps) {
+        const int64_t e = u / parts, part = u % parts;
         const int64_t g = ids[e];
-        const int64_t r0 = group_offsets[g], r1 = group_offsets[g + 1];
+        const int64_t g0 = group_offsets[g], g1 = group_offsets[g + 1];
+        const int64_t per = (g1 - g0 + parts - 1) / parts;
+        const int64_t r0 = g0 + part * per, r1 = r0 + per < g1 ? r0 + per : g1;
         unsigned long long obs = 0;
         long long maxlen = 1;
         for (int64_t r = r0 + lane; r < r1; r += 32) {
@@ -97,26 +101,39 @@ __global__ void k_part_plan(ColView col, const int64_t *group_offsets, const int
             const long long o = __shfl_xor_sync(0xffffffffu, maxlen, d);
             maxlen = o > maxlen ? o : maxlen;
         }
-        if (lane == 0) {
-            int64_t P = ((int64_t)obs + PT_TARGET - 1) / PT_TARGET;
-            // rows per slab: every slab of rps rows fits the staged span whatever the reads' lengths (0 = a read longer than a slab)
-            int64_t rps = (PT_MAX_BASES - 32) / maxlen;
-            rps = rps > SM_MAXR ? SM_MAXR : rps;
-            int64_t sub = 1;
-            if (P > PT_PMAX && 2 * K > 24) {   // a large group (beyond 128 x 8192 observations)
-                P = ((int64_t)obs + PT_TARGET_BIG - 1) / PT_TARGET_BIG;
-                sub = PT_SUB_BIG;
-                if (P > PT_PBIG) rps = 0;      // more than the bins hold: the HBM tables take it (callers bound their rounds below this)
-            }
-            P = P < 1 ? 1 : (P > PT_PBIG ? PT_PBIG : P);
-            if (sub == 1 && P > PT_PMAX) P = PT_PMAX;
-            if (2 * K <= 12) P = 1;   // at most 4096 distinct k-mers
-            np[e] = (int32_t)P;
-            rows_per_slab[e] = (int32_t)rps;
-            slabs[e] = rps > 0 ? (r1 - r0 + rps * sub - 1) / (rps * sub) : 0;   // scatter items
-            bucket_cap[e] = (int64_t)obs;   // records of the whole entry at most (wave planning)
+        if (lane == 0 && r0 < r1) {
+            atomicAdd(&obs_acc[e], obs);
+            atomicMax(&maxlen_acc[e], (int)(maxlen > 0x7fffffffll ? 0x7fffffffll : maxlen));
         }
     }
+}
+// ... -> ranges, rows per slab, scatter items, record capacity
+__global__ void k_part_plan(const int64_t *group_offsets, const int32_t *ids, int64_t n_list, int K, const unsigned long long *obs_acc,
+                            const int *maxlen_acc, int32_t *np, int32_t *rows_per_slab, int64_t *slabs, int64_t *bucket_cap)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_list) return;
+    const int64_t g = ids[e];
+    const int64_t r0 = group_offsets[g], r1 = group_offsets[g + 1];
+    const unsigned long long obs = obs_acc[e];
+    const long long maxlen = maxlen_acc[e] > 1 ? maxlen_acc[e] : 1;
+    int64_t P = ((int64_t)obs + PT_TARGET - 1) / PT_TARGET;
+    // rows per slab: every slab of rps rows fits the staged span whatever the reads' lengths (0 = a read longer than a slab)
+    int64_t rps = (PT_MAX_BASES - 32) / maxlen;
+    rps = rps > SM_MAXR ? SM_MAXR : rps;
+    int64_t sub = 1;
+    if (P > PT_PMAX && 2 * K > 24) {   // a large group (beyond 128 x 8192 observations)
+        P = ((int64_t)obs + PT_TARGET_BIG - 1) / PT_TARGET_BIG;
+        sub = PT_SUB_BIG;
+        if (P > PT_PBIG) rps = 0;      // more than the bins hold: the HBM tables take it (callers bound their rounds below this)
+    }
+    P = P < 1 ? 1 : (P > PT_PBIG ? PT_PBIG : P);
+    if (sub == 1 && P > PT_PMAX) P = PT_PMAX;
+    if (2 * K <= 12) P = 1;   // at most 4096 distinct k-mers
+    np[e] = (int32_t)P;
+    rows_per_slab[e] = (int32_t)rps;
+    slabs[e] = rps > 0 ? (r1 - r0 + rps * sub - 1) / (rps * sub) : 0;   // scatter items
+    bucket_cap[e] = (int64_t)obs;   // records of the whole entry at most (wave planning)
 }
 inline size_t part_scatter_smem(int pcap) { return (size_t)PT_PK_WORDS * 4 + (size_t)(SM_MAXR + 1) * 4 + (size_t)pcap * 4 + 64 * 4 + SM_MAXR + 64; }
 
@@ -568,9 +585,19 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
     CK(cudaMemsetAsync(failed.p, 0, (size_t)n_list * 4, st));
     CK(cudaMemsetAsync(ctr.p, 0, 64, st));
     unsigned long long *d_ctr = ctr.as<unsigned long long>();   // [0] scatter ticket [1] count ticket [2] n_failed
-    k_part_plan<<<(unsigned)std::min<int64_t>(blocks(n_list * 32, 256), (int64_t)sm_count * 16), 256, 0, st>>>(
-        col, d_group_offsets, d_ids, n_list, K, np.as<int32_t>(), rps.as<int32_t>(), slabs.as<int64_t>(), bcap.as<int64_t>());
-    if (launches) *launches += 1;
+    {
+        DevBuf acc((size_t)n_list * 12, st);   // u64 observations, then int longest read, per entry
+        CK(cudaMemsetAsync(acc.p, 0, (size_t)n_list * 12, st));
+        unsigned long long *obs_acc = acc.as<unsigned long long>();
+        int *maxlen_acc = reinterpret_cast<int *>(obs_acc + n_list);
+        const int64_t warps = (int64_t)sm_count * 16 * 8;
+        const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(4096, warps / n_list));
+        k_part_plan_rows<<<(unsigned)std::min<int64_t>(blocks(n_list * parts * 32, 256), (int64_t)sm_count * 16), 256, 0, st>>>(
+            col, d_group_offsets, d_ids, n_list, K, parts, obs_acc, maxlen_acc);
+        k_part_plan<<<blocks(n_list, 128), 128, 0, st>>>(d_group_offsets, d_ids, n_list, K, obs_acc, maxlen_acc, np.as<int32_t>(), rps.as<int32_t>(),
+                                                         slabs.as<int64_t>(), bcap.as<int64_t>());
+        if (launches) *launches += 2;
+    }
     // waves bounded by the workspace: records of a wave = sum over its entries of np * capacity
     std::vector<int32_t> h_np((size_t)n_list);
     std::vector<int64_t> h_bcap((size_t)n_list);
