@@ -62,8 +62,7 @@ __device__ __forceinline__ uint32_t prev_slot(uint32_t h, uint32_t tsize)
 constexpr int SM_SORT_BITS = 10;
 constexpr int SM_SORT_BUCKETS = 1 << SM_SORT_BITS;
 constexpr int SM_POOL_CHUNK = 65536;   // survivors a CTA reserves from the pool at a time (a group needs room for SM_TSIZE + 1)
-constexpr int SM_MAX_BUCKET = 32;     // survivors sharing a sort prefix beyond this: the bucket is ordered by a warp (odd-even transposition)
-constexpr int SM_MAX_BUCKET_WARP = 512;   // ... and beyond this the item goes to the bitonic kernel
+constexpr int SM_MAX_BUCKET_WARP = 512;   // survivors sharing a sort prefix beyond this (all-pairs ranking gets quadratic): the item goes to the bitonic kernel
 // Multi-pass variant for groups that do not fit one table / one staged span (MULTI = true): the k-mer space is cut into
 // P equal ranges (range of a k-mer = floor(top 32 bits * P / 2^32)); pass p re-reads the group's reads in slabs of
 // <= SM_MAX_BASES bases and counts only the k-mers of range p, so every pass needs a table for about 1/P of the distinct
@@ -1085,7 +1084,6 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
                 mx = loc[t] > mx ? loc[t] : mx;
             }
             if (mx > (uint32_t)SM_MAX_BUCKET_WARP) s_flag = 2;
-            else if (mx > (uint32_t)SM_MAX_BUCKET) atomicMax(&s_flag, 1);
             uint32_t x = sum;
             const unsigned lane = tid & 31u, warp = tid >> 5;
 #pragma unroll
@@ -1109,7 +1107,6 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
             if (tid == 0) a.big_ids[atomicAdd(a.n_big, 1ull)] = (int32_t)it;
             continue;
         }
-        const bool crowded = s_flag == 1;
         // ---- registers -> shared memory in bucket order (arrival order inside a bucket) ----------------------------------------------
 #pragma unroll
         for (int t = 0; t < EPT; t++) {
@@ -1122,30 +1119,10 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
         }
         __syncthreads();
         // s_hist[b] is now the END of bucket b.
-        if (crowded) {
-            // Deep UMIs: every true k-mer drags ~3K single-error variants along that share its leading bases, i.e. its bucket.  A warp
-            // orders such a bucket in place (odd-even transposition, no block barrier); round 1 sent the whole item to the bitonic kernel.
-            const unsigned lane = tid & 31u, warp = tid >> 5;
-            for (uint32_t b = warp; b < (uint32_t)SM_SORT_BUCKETS; b += NT / 32) {
-                const uint32_t st = b ? s_hist[b - 1] : 0u, en = s_hist[b];
-                const uint32_t sz = en - st;
-                if (sz <= (uint32_t)SM_MAX_BUCKET) continue;
-                for (uint32_t phase = 0; phase < sz; phase++) {
-                    for (uint32_t i = st + (phase & 1u) + 2u * lane; i + 1u < en; i += 64u) {
-                        const uint64_t la = s_lo[i], lb = s_lo[i + 1];
-                        const uint64_t ha = (W == 2) ? s_hi[i] : 0ull, hb = (W == 2) ? s_hi[i + 1] : 0ull;
-                        if (ha > hb || (ha == hb && la > lb)) {
-                            s_lo[i] = lb; s_lo[i + 1] = la;
-                            if (W == 2) { s_hi[i] = hb; s_hi[i + 1] = ha; }
-                            const uint32_t va = s_val[i];
-                            s_val[i] = s_val[i + 1]; s_val[i + 1] = va;
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-        }
+        // Deep UMIs: every true k-mer drags ~3K single-error variants along that share its leading bases, i.e. its bucket (dozens to
+        // hundreds of members).  Such a bucket is ranked like the tiny ones -- all pairs: consecutive threads hold members of the
+        // same bucket, so the inner loop's shared-memory reads are broadcasts.  (An earlier version had one warp order each crowded
+        // bucket by odd-even transposition: `size` dependent phases per bucket; 39 ms of BASELINE configs[2]'s 205 ms.)
         // Every survivor ranks itself inside its (tiny) bucket -- final position = bucket start + number of bucket members with a
         // smaller k-mer (k-mers are distinct) -- and goes straight to the dense output; members of a warp-ordered bucket are in place.
         for (int j = tid; j < n; j += NT) {
@@ -1153,9 +1130,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 && W == 1 ? 8 : 1)) k_sort_smal
             const uint32_t b = bucket_of(lj, hj);
             const uint32_t st = b ? s_hist[b - 1] : 0u, en = s_hist[b];
             uint32_t r = st;
-            if (en - st > (uint32_t)SM_MAX_BUCKET) {
-                r = (uint32_t)j;
-            } else if (en - st > 1u) {
+            if (en - st > 1u) {
                 for (uint32_t i = st; i < en; i++) {
                     const uint64_t li = s_lo[i], hi_i = (W == 2) ? s_hi[i] : 0ull;
                     r += (hi_i < hj || (hi_i == hj && li < lj)) ? 1u : 0u;
