@@ -43,8 +43,11 @@ struct PartArgs {
     const int32_t *rows_per_slab;// [n_list]
     int sub_slabs;               // slabs per scatter item (1, or PT_SUB_BIG for a wave holding one large group)
     int pcap;                    // ranges per entry at most in this wave: stride of slab_cnt, size of the shared-memory bins
+    int stage_cap;               // scatter: records of an item staged in shared memory and written out as whole runs (0: written directly)
     const int64_t *slab_off;     // [n_list+1] first slab item of entry e
     const int64_t *bucket_off;   // [n_list+1] first bucket of entry e
+    const int32_t *item_entry;   // [n_items] entry of scatter item i   } one load instead of a binary search over slab_off / bucket_off:
+    const int32_t *bucket_entry; // [n_buckets] entry of bucket b       } 16 dependent L2 round trips per item on a CTA that has the SM to itself
     const int64_t *rec_off;      // [n_buckets+1] first record slot of bucket b
     unsigned int *cursor;        // [n_buckets] HIST: records of the bucket; scatter: records appended so far
     uint32_t *slab_cnt;          // [n_items * pcap] observations per (item, range), written by HIST, read by the scatter
@@ -135,13 +138,24 @@ __global__ void k_part_plan(const int64_t *group_offsets, const int32_t *ids, in
     slabs[e] = rps > 0 ? (r1 - r0 + rps * sub - 1) / (rps * sub) : 0;   // scatter items
     bucket_cap[e] = (int64_t)obs;   // records of the whole entry at most (wave planning)
 }
-inline size_t part_scatter_smem(int pcap) { return (size_t)PT_PK_WORDS * 4 + (size_t)(SM_MAXR + 1) * 4 + (size_t)pcap * 4 + 64 * 4 + SM_MAXR + 64; }
+__host__ __device__ inline size_t part_scatter_smem(int pcap) { return (size_t)PT_PK_WORDS * 4 + (size_t)(SM_MAXR + 1) * 4 + (size_t)pcap * 4 + 64 * 4 + SM_MAXR + 64; }
+// ... plus the staging area of the scatter pass: per-range start / fill words and `cap` records
+template <int W>
+constexpr int part_stage_cap() { return W == 2 ? 11264 : PT_MAX_BASES; }
+template <int W>
+inline size_t part_scatter_smem_staged(int pcap)
+{
+    return ((part_scatter_smem(pcap) + 15) & ~(size_t)15) + (size_t)(2 * pcap + 2) * 4 + 8 + (size_t)part_stage_cap<W>() * (8 * W + 1);
+}
 
 // one slab of one listed group per iteration: stage, bin the observations by range, append the bins to the range buckets
+// (the HIST pass runs two CTAs of 384 threads per SM; the scatter pass holds the staging area or the bins of a large group, has the
+//  SM to itself and runs 768 threads -- with 384 its sweep was latency-bound: 62 -> 53 ms on configs[2] from the staging alone)
+constexpr int PT_NT_SCATTER = 768;
 template <int W, bool HIST>
-__global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n_items)
+__global__ void __launch_bounds__(HIST ? PT_NT : PT_NT_SCATTER, HIST ? 2 : 1) k_part_scatter(PartArgs a, int64_t n_items)
 {
-    constexpr int NT = PT_NT;
+    constexpr int NT = HIST ? PT_NT : PT_NT_SCATTER, NWARP = NT / 32;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *scratch = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *pk = scratch + 1;
@@ -150,6 +164,14 @@ __global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n
                                                   //        item's run inside the range bucket
     uint32_t *ws = bin + a.pcap;                  // 64 words
     uint8_t *bad = reinterpret_cast<uint8_t *>(ws + 64);
+    // staging area (scatter pass, a.stage_cap > 0): an item's records are binned in shared memory first and leave as whole runs --
+    // written directly, the 32 lanes of a store hit 32 different sectors, and the pass ran at the L2's sector-write rate
+    uint8_t *stg = smem_raw + ((part_scatter_smem(a.pcap) + 15) & ~(size_t)15);
+    uint32_t *soff = reinterpret_cast<uint32_t *>(stg);            // [pcap + 1] first staged slot of range p
+    uint32_t *lfill = soff + a.pcap + 1;                             // [pcap] next staged slot of range p
+    uint64_t *s_lo = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(lfill + a.pcap) + 7) & ~(uintptr_t)7);
+    uint64_t *s_hi = s_lo + (W == 2 ? a.stage_cap : 0);
+    uint8_t *s_ex = reinterpret_cast<uint8_t *>(s_hi + a.stage_cap);
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
     const int K = a.K;
@@ -163,13 +185,7 @@ __global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n
         __syncthreads();
         const int64_t item = (int64_t)(((unsigned long long)ws[1] << 32) | ws[0]);
         if (item >= n_items) break;
-        // entry of this slab item: last e with slab_off[e] <= item
-        int64_t lo_e = 0, hi_e = a.n_list;
-        while (hi_e - lo_e > 1) {
-            const int64_t m = (lo_e + hi_e) >> 1;
-            if (a.slab_off[m] <= item) lo_e = m; else hi_e = m;
-        }
-        const int64_t e = lo_e;
+        const int64_t e = a.item_entry[item];
         const int64_t g = a.ids[e];
         const int rps = a.rows_per_slab[e];
         const int P = a.np[e];
@@ -181,7 +197,41 @@ __global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n
             } else {   // the item's run inside every range bucket: one global atomic per (item, range)
                 const uint32_t c = a.slab_cnt[item * a.pcap + p];
                 bin[p] = c ? atomicAdd(&a.cursor[bucket0 + p], c) : 0u;
+                if (a.stage_cap) soff[p + 1] = c;
             }
+        }
+        bool staged = false;
+        if (!HIST && a.stage_cap) {   // staged slots: exclusive prefix of the per-range counts (P <= 128: one warp)
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t c[4], sum = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int p = (int)lane * 4 + t;
+                    c[t] = p < P ? soff[p + 1] : 0u;
+                    sum += c[t];
+                }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += y;
+                }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int p = (int)lane * 4 + t;
+                    if (p < P) {
+                        soff[p] = run;       // (soff[p + 1] of the last range is rewritten below)
+                        lfill[p] = run;
+                    }
+                    run += c[t];
+                }
+                if (lane == 31u) ws[2] = incl;
+            }
+            __syncthreads();
+            if (tid == 0) soff[P] = ws[2];
+            staged = ws[2] <= (uint32_t)a.stage_cap;
         }
         for (int sub = 0; sub < a.sub_slabs; sub++) {
             const int64_t r0 = a.group_offsets[g] + ((item - a.slab_off[e]) * a.sub_slabs + sub) * rps;
@@ -215,7 +265,7 @@ __global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n
             }
             __syncthreads();
             // ---- one sweep over the windows (a warp per read): HIST counts per range, the scatter writes ----------------------------------
-            for (int r = (int)warp; r < nr; r += PT_NW) {
+            for (int r = (int)warp; r < nr; r += NWARP) {
                 const uint32_t rs = rstart[r], len = rstart[r + 1] - rs;
                 if (bad[r] || len < (uint32_t)K) continue;
                 const uint32_t nk = len - (uint32_t)K + 1u;
@@ -229,10 +279,17 @@ __global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n
                     } else {
                         const uint32_t lb = base_of(pk, q - 1u), rb = base_of(pk, q + (uint32_t)K);
                         const uint32_t ex = (p ? (1u << lb) : 0u) | ((p + 1u < nk) ? (16u << rb) : 0u);
-                        const int64_t at = a.rec_off[bucket0 + range] + atomicAdd(&bin[range], 1u);
-                        a.rec_lo[at] = key.lo;
-                        if (W == 2) a.rec_hi[at] = key.hi_word();
-                        a.rec_ex[at] = (uint8_t)ex;
+                        if (staged) {
+                            const uint32_t slot = atomicAdd(&lfill[range], 1u);
+                            s_lo[slot] = key.lo;
+                            if (W == 2) s_hi[slot] = key.hi_word();
+                            s_ex[slot] = (uint8_t)ex;
+                        } else {
+                            const int64_t at = a.rec_off[bucket0 + range] + atomicAdd(&bin[range], 1u);
+                            a.rec_lo[at] = key.lo;
+                            if (W == 2) a.rec_hi[at] = key.hi_word();
+                            a.rec_ex[at] = (uint8_t)ex;
+                        }
                     }
                 }
             }
@@ -243,6 +300,17 @@ __global__ void __launch_bounds__(PT_NT, 2) k_part_scatter(PartArgs a, int64_t n
                 const uint32_t c = bin[p];
                 a.slab_cnt[item * a.pcap + p] = c;
                 if (c) atomicAdd(&a.cursor[bucket0 + p], c);
+            }
+        } else if (staged) {   // a warp per range: the run leaves as coalesced stores
+            __syncthreads();
+            for (int p = (int)warp; p < P; p += NWARP) {
+                const uint32_t s0 = soff[p], n = soff[p + 1] - s0;
+                const int64_t dst = a.rec_off[bucket0 + p] + bin[p];
+                for (uint32_t i = lane; i < n; i += 32u) {
+                    a.rec_lo[dst + i] = s_lo[s0 + i];
+                    if (W == 2) a.rec_hi[dst + i] = s_hi[s0 + i];
+                    a.rec_ex[dst + i] = s_ex[s0 + i];
+                }
             }
         }
     }
@@ -281,12 +349,7 @@ __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs
         __syncthreads();
         const int64_t b = (int64_t)(((unsigned long long)ws[1] << 32) | ws[0]);
         if (b >= n_buckets) break;
-        int64_t lo_e = 0, hi_e = MERGE ? 1 : a.n_list;
-        while (hi_e - lo_e > 1) {
-            const int64_t m = (lo_e + hi_e) >> 1;
-            if (a.bucket_off[m] <= b) lo_e = m; else hi_e = m;
-        }
-        const int64_t e = lo_e;
+        const int64_t e = MERGE ? 0 : (int64_t)a.bucket_entry[b];
         const int pass = MERGE ? (int)b : (int)(b - a.bucket_off[e]);
         if (a.failed[e]) continue;
         int64_t rec0 = 0;
@@ -430,6 +493,17 @@ __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs
     }
 }
 
+// item -> entry and bucket -> entry maps of a wave (a warp per entry)
+__global__ void k_part_maps(const int64_t *slab_off, const int64_t *bucket_off, int64_t n_list, int32_t *item_entry, int32_t *bucket_entry)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = warp; e < n_list; e += n_warps) {
+        for (int64_t i = slab_off[e] + lane; i < slab_off[e + 1]; i += 32) item_entry[i] = (int32_t)e;
+        for (int64_t b = bucket_off[e] + lane; b < bucket_off[e + 1]; b += 32) bucket_entry[b] = (int32_t)e;
+    }
+}
+
 // per listed group: prefix of its segments, survivor total, observations; failed groups go to the next list
 __global__ void k_part_finish(PartArgs a)
 {
@@ -557,8 +631,8 @@ inline void part_path_configure()
     };
     cfg(k_part_scatter<1, true>, part_scatter_smem(PT_PBIG));
     cfg(k_part_scatter<2, true>, part_scatter_smem(PT_PBIG));
-    cfg(k_part_scatter<1, false>, part_scatter_smem(PT_PBIG));
-    cfg(k_part_scatter<2, false>, part_scatter_smem(PT_PBIG));
+    cfg(k_part_scatter<1, false>, std::max(part_scatter_smem(PT_PBIG), part_scatter_smem_staged<1>(PT_PMAX)));
+    cfg(k_part_scatter<2, false>, std::max(part_scatter_smem(PT_PBIG), part_scatter_smem_staged<2>(PT_PMAX)));
     cfg(k_part_count<1, false>, part_count_smem<1>());
     cfg(k_part_count<2, false>, part_count_smem<2>());
     cfg(k_part_count<1, true>, part_count_smem<1>());
@@ -634,7 +708,12 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
         DevBuf rec_off((size_t)(n_buckets + 1) * 8, st), scr2(scan_scratch_bytes(n_buckets), st), cursor((size_t)std::max<int64_t>(n_buckets, 1) * 4, st),
             slab_cnt((size_t)std::max<int64_t>(n_slabs, 1) * pcap * 4, st);
         CK(cudaMemsetAsync(cursor.p, 0, cursor.bytes, st));
+        DevBuf item_entry((size_t)std::max<int64_t>(n_slabs, 1) * 4, st), bucket_entry((size_t)std::max<int64_t>(n_buckets, 1) * 4, st);
+        k_part_maps<<<(unsigned)std::min<int64_t>(blocks(nl * 32, 256), (int64_t)sm_count * 16), 256, 0, st>>>(
+            slab_off.as<int64_t>(), bucket_off.as<int64_t>(), nl, item_entry.as<int32_t>(), bucket_entry.as<int32_t>());
+        if (launches) *launches += 1;
         PartArgs a{};
+        a.item_entry = item_entry.as<int32_t>(); a.bucket_entry = bucket_entry.as<int32_t>();
         a.col = col; a.data_begin = data_begin; a.data_end = data_end; a.group_offsets = d_group_offsets;
         a.ids = d_ids + e0; a.n_list = nl;
         a.np = np.as<int32_t>() + e0; a.rows_per_slab = rps.as<int32_t>() + e0;
@@ -662,7 +741,12 @@ inline void run_part_path_w(cudaStream_t st, uint8_t *peek_slot, int sm_count, s
         DevBuf rlo((size_t)std::max<int64_t>(n_recs, 1) * 8, st), rhi(W == 2 ? (size_t)std::max<int64_t>(n_recs, 1) * 8 : 0, st),
             rex((size_t)std::max<int64_t>(n_recs, 1), st);
         a.rec_lo = rlo.as<uint64_t>(); a.rec_hi = W == 2 ? rhi.as<uint64_t>() : nullptr; a.rec_ex = rex.as<uint8_t>();
-        if (n_slabs > 0) k_part_scatter<W, false><<<sgrid, PT_NT, ssmem, st>>>(a, n_slabs);
+        if (n_slabs > 0) {
+            // per-UMI waves stage an item's records in shared memory (one CTA per SM); one large group has too many ranges for runs
+            a.stage_cap = big ? 0 : part_stage_cap<W>();
+            const unsigned grid2 = (unsigned)std::min<int64_t>(n_slabs, (int64_t)sm_count);
+            k_part_scatter<W, false><<<grid2, PT_NT_SCATTER, big ? ssmem : part_scatter_smem_staged<W>(pcap), st>>>(a, n_slabs);
+        }
         if (n_buckets > 0) {
             a.ticket = d_ctr + 1;
             const unsigned grid = (unsigned)std::min<int64_t>(n_buckets, (int64_t)sm_count * (W == 1 ? 2 : 1));
