@@ -418,11 +418,30 @@ __global__ void __launch_bounds__(PT_NT, (W == 1 ? 2 : 1)) k_part_count(PartArgs
                 }
             }
         } else {
-            for (uint32_t i = tid; i < n; i += NT) {
-                Key<W> key = Key<W>::zero();
-                key.lo = a.rec_lo[rec0 + i];
-                if constexpr (W == 2) key.hi = a.rec_hi[rec0 + i];
-                insert(key, a.rec_ex[rec0 + i], 1u);
+            // four records per thread in flight: with one, the loop ran at the latency of its global loads
+            for (uint32_t i0 = tid; i0 < n; i0 += 4u * NT) {
+                uint64_t lo4[4], hi4[4];
+                uint32_t ex4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + (uint32_t)u * NT;
+                    lo4[u] = hi4[u] = 0ull;
+                    ex4[u] = 0u;
+                    if (i < n) {
+                        lo4[u] = a.rec_lo[rec0 + i];
+                        if constexpr (W == 2) hi4[u] = a.rec_hi[rec0 + i];
+                        ex4[u] = a.rec_ex[rec0 + i];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (i0 + (uint32_t)u * NT < n) {
+                        Key<W> key = Key<W>::zero();
+                        key.lo = lo4[u];
+                        if constexpr (W == 2) key.hi = hi4[u];
+                        insert(key, ex4[u], 1u);
+                    }
+                }
             }
         }
         if (tid == 0) {
