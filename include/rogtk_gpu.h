@@ -352,8 +352,9 @@ int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx);
  * also event counts: 8 walked windows, 9 densely inserted windows, 10 range heads, 11 probe steps, 12 dense warp steps,
  * 13 walk warp steps, 14 k-mer compares through a reference, 15 ranges whose walk broke.  out16: 16 words */
 int rogtk_gpu_debug_phase_cycles(rogtk_gpu_ctx *ctx, int enable, uint64_t *out16);
-/* device-memory cache of the context: out6 = cudaMalloc calls, reuses of a cached block, idle bytes, live bytes, peak bytes, idle blocks */
-int rogtk_gpu_debug_cache_stats(rogtk_gpu_ctx *ctx, int64_t *out6);
+/* device-memory cache of the context: out7 = cudaMalloc calls, reuses of a cached block, idle bytes, live bytes, peak bytes, idle blocks,
+   times its idle blocks were released because an allocation on the device failed */
+int rogtk_gpu_debug_cache_stats(rogtk_gpu_ctx *ctx, int64_t *out7);
 /* write a >L2 scratch buffer (L2 flush between timed iterations) */
 int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx);
 

@@ -7,6 +7,8 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
+#include <cstdlib>
 
 namespace rogtk {
 
@@ -38,6 +40,20 @@ struct ArgFail {
 //
 // Ordering: free(p, s) records an event on s; a later alloc on another stream waits for it (same stream: program order suffices).
 // Entry points set the cache of the calling thread for their duration (CacheScope).
+//
+// Several contexts may live in one process (one per Polars worker thread): when cudaMalloc fails, the idle blocks
+// of EVERY cache on the device are released before the request is retried (registry below; never two cache locks held at once), and
+// ROGTK_DEVICE_CACHE_BYTES bounds the idle bytes a cache keeps (largest blocks go first).
+struct DevCache;
+struct DevCacheRegistry {
+    std::mutex mu;
+    std::vector<DevCache *> all;
+    static DevCacheRegistry &get()
+    {
+        static DevCacheRegistry r;
+        return r;
+    }
+};
 struct DevCache {
     struct Block {
         void *p;
@@ -49,7 +65,29 @@ struct DevCache {
     std::multimap<size_t, Block> idle;            // by size
     std::unordered_map<void *, Block> live;
     size_t idle_bytes = 0, live_bytes = 0, peak_bytes = 0;
-    int64_t n_malloc = 0, n_reuse = 0;
+    size_t idle_limit = ~(size_t)0;
+    int64_t n_malloc = 0, n_reuse = 0, n_released_for_others = 0;
+    int device = 0;
+
+    explicit DevCache(int dev = 0) : device(dev)
+    {
+        if (const char *e = getenv("ROGTK_DEVICE_CACHE_BYTES")) idle_limit = (size_t)strtoull(e, nullptr, 10);
+        DevCacheRegistry &r = DevCacheRegistry::get();
+        std::lock_guard<std::mutex> lk(r.mu);
+        r.all.push_back(this);
+    }
+    // cudaMalloc failed: hand every cache's idle blocks on this device back to the driver (caller holds no cache lock)
+    static void release_all_idle(int dev)
+    {
+        DevCacheRegistry &r = DevCacheRegistry::get();
+        std::lock_guard<std::mutex> lk(r.mu);
+        for (DevCache *c : r.all) {
+            if (c->device != dev) continue;
+            std::lock_guard<std::mutex> cl(c->mu);
+            if (!c->idle.empty()) c->n_released_for_others++;
+            c->release_idle_locked();
+        }
+    }
 
     static size_t size_class(size_t n)
     {
@@ -59,6 +97,14 @@ struct DevCache {
         return (n + step - 1) & ~(step - 1);
     }
     cudaError_t alloc(void **out, size_t n, cudaStream_t s)
+    {
+        cudaError_t e = alloc_once(out, n, s);
+        if (e != cudaErrorMemoryAllocation) return e;
+        cudaGetLastError();
+        release_all_idle(device);
+        return alloc_once(out, n, s);
+    }
+    cudaError_t alloc_once(void **out, size_t n, cudaStream_t s)
     {
         const size_t sz = size_class(n);
         std::lock_guard<std::mutex> lk(mu);
@@ -79,12 +125,7 @@ struct DevCache {
         }
         Block b{nullptr, sz, nullptr, s};
         cudaError_t e = cudaMalloc(&b.p, sz);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            release_idle_locked();
-            e = cudaMalloc(&b.p, sz);
-            if (e != cudaSuccess) return e;
-        }
+        if (e != cudaSuccess) return e;
         e = cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             cudaFree(b.p);
@@ -109,6 +150,14 @@ struct DevCache {
         cudaEventRecord(b.ev, s);
         idle_bytes += b.sz;
         idle.emplace(b.sz, b);
+        while (idle_bytes > idle_limit && !idle.empty()) {   // bounded cache: the largest idle block goes back to the driver
+            auto last = std::prev(idle.end());
+            cudaEventSynchronize(last->second.ev);
+            cudaEventDestroy(last->second.ev);
+            cudaFree(last->second.p);
+            idle_bytes -= last->second.sz;
+            idle.erase(last);
+        }
     }
     void release_idle_locked()
     {
@@ -127,6 +176,11 @@ struct DevCache {
     }
     ~DevCache()
     {
+        {
+            DevCacheRegistry &r = DevCacheRegistry::get();
+            std::lock_guard<std::mutex> lk(r.mu);
+            r.all.erase(std::remove(r.all.begin(), r.all.end(), this), r.all.end());
+        }
         release_idle();
         for (auto &kv : live) {   // blocks the caller never freed go with the context
             cudaEventDestroy(kv.second.ev);

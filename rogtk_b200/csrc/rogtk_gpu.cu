@@ -409,7 +409,7 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         ctx->workspace_bytes = workspace_bytes ? workspace_bytes : free_b / 4;
-        ctx->cache = new DevCache();
+        ctx->cache = new DevCache(device);
         smem_path_configure();
         part_path_configure();
     } catch (const CudaFail &f) {
@@ -2179,16 +2179,17 @@ extern "C" int rogtk_gpu_memcpy_d2h(rogtk_gpu_ctx *ctx, void *dst, const void *s
 }
 extern "C" int64_t rogtk_gpu_launch_count(rogtk_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" int rogtk_gpu_debug_cache_stats(rogtk_gpu_ctx *ctx, int64_t *out6)
+extern "C" int rogtk_gpu_debug_cache_stats(rogtk_gpu_ctx *ctx, int64_t *out7)
 {
-    if (!ctx || !out6 || !ctx->cache) return ROGTK_ERR_INVALID_ARG;
+    if (!ctx || !out7 || !ctx->cache) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->cache->mu);
-    out6[0] = ctx->cache->n_malloc;
-    out6[1] = ctx->cache->n_reuse;
-    out6[2] = (int64_t)ctx->cache->idle_bytes;
-    out6[3] = (int64_t)ctx->cache->live_bytes;
-    out6[4] = (int64_t)ctx->cache->peak_bytes;
-    out6[5] = (int64_t)ctx->cache->idle.size();
+    out7[0] = ctx->cache->n_malloc;
+    out7[1] = ctx->cache->n_reuse;
+    out7[2] = (int64_t)ctx->cache->idle_bytes;
+    out7[3] = (int64_t)ctx->cache->live_bytes;
+    out7[4] = (int64_t)ctx->cache->peak_bytes;
+    out7[5] = (int64_t)ctx->cache->idle.size();
+    out7[6] = ctx->cache->n_released_for_others;
     return ROGTK_OK;
 }
 

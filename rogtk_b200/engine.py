@@ -223,9 +223,9 @@ class Engine:
 
     def cache_stats(self) -> dict:
         """Counters of the context's device-memory cache (rogtk_gpu_debug_cache_stats)."""
-        out = np.zeros(6, dtype=np.int64)
+        out = np.zeros(7, dtype=np.int64)
         self._check(self._lib.rogtk_gpu_debug_cache_stats(self._ctx, out.ctypes.data))
-        return dict(zip(("n_malloc", "n_reuse", "idle_bytes", "live_bytes", "peak_bytes", "idle_blocks"), map(int, out)))
+        return dict(zip(("n_malloc", "n_reuse", "idle_bytes", "live_bytes", "peak_bytes", "idle_blocks", "n_released_for_others"), map(int, out)))
 
     def flush_l2(self):
         self._check(self._lib.rogtk_gpu_flush_l2(self._ctx))

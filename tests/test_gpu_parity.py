@@ -922,6 +922,36 @@ def test_device_cache_reuse_and_trim(oracle):
         assert free0 - torch.cuda.mem_get_info(0)[0] < max(held, 1)   # cached blocks went back
 
 
+def test_device_cache_gives_way_under_memory_pressure(oracle, monkeypatch):
+    """Two contexts on one device (one per worker thread in the plugin): when a cudaMalloc fails, the idle blocks of EVERY context's
+    cache go back to the driver and the request is retried; ROGTK_DEVICE_CACHE_BYTES bounds what a context keeps."""
+    import rogtk_b200
+    import torch
+    from rogtk_b200 import synth
+    data, offs, goff = synth.synth_reads(synth.config_seed(2), 0, 4000, 50, 300, 1000)      # 60 MB of reads, ~0.5 GB of working set
+    small = synth.synth_reads(synth.config_seed(2), 0, 50, 50, 300, 1000)
+    ref = oracle.count_prune_batch(*small, 31, 2)
+    with rogtk_b200.Engine(device=0) as a, rogtk_b200.Engine(device=0) as b:
+        a.count_prune(data, offs, goff, 31, 2)                      # a's cache now holds a few hundred MB of idle blocks
+        held = a.cache_stats()["idle_bytes"]
+        assert held > 100 << 20
+        free_now = torch.cuda.mem_get_info(0)[0]
+        hog = torch.empty(free_now - (64 << 20), dtype=torch.uint8, device="cuda:0")      # leave 64 MB: less than b needs
+        try:
+            got = b.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)                  # must take a's idle memory
+            assert a.cache_stats()["n_released_for_others"] >= 1 and a.cache_stats()["idle_bytes"] < held
+            assert got.n_groups == 4000
+            assert_batches_equal(b.count_prune(*small, 31, 2, flags=EMIT_STATS), ref, ctx="after giving way")
+        finally:
+            del hog
+            torch.cuda.empty_cache()
+    monkeypatch.setenv("ROGTK_DEVICE_CACHE_BYTES", str(32 << 20))
+    with rogtk_b200.Engine(device=0) as c:
+        c.count_prune(data, offs, goff, 31, 2)
+        assert c.cache_stats()["idle_bytes"] <= 32 << 20
+        assert_batches_equal(c.count_prune(*small, 31, 2, flags=EMIT_STATS), ref, ctx="bounded cache")
+
+
 @pytest.mark.parametrize("rl", [3, 5])
 def test_link_walk_kernel_matches_oracle(oracle, monkeypatch, rl):
     """The experimental first-tier kernel k_walk_count (ROGTK_WALK_RL, read when a context is created): 8-byte
