@@ -320,6 +320,12 @@ int rogtk_gpu_nccl_init(rogtk_gpu_ctx *ctx, const uint8_t *id128, int rank, int 
 int rogtk_gpu_nccl_finalize(rogtk_gpu_ctx *ctx);
 int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *local, const rogtk_graph_batch *carry, uint32_t min_coverage,
                                 uint32_t flags, rogtk_graph_batch *out, rogtk_exchange_stats *stats);
+/* merge of several device-resident shares of the spectrum this rank owns (one-group batches as rogtk_gpu_spectrum_exchange leaves
+ * them with ROGTK_OUTPUT_ON_DEVICE; at most 64) into one: partial counts add (saturating), exts OR, min_coverage on the way out.  No
+ * communication.  For drivers that keep the carried share in levels (rogtk_b200/spectrum.py) instead of re-merging all of it
+ * every round. */
+int rogtk_gpu_spectrum_merge_runs(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *const *parts, int n_parts, uint32_t min_coverage,
+                                  uint32_t flags, rogtk_graph_batch *out);
 
 /* ---- bench / test utilities (not part of the reference surface) ------------------------------------------------ */
 /* Synthetic reads of SURVEY 8(d) generated directly in HBM: n_umis groups x reads_per_umi reads of read_len bases

@@ -40,7 +40,7 @@ SYMBOLS = [
     "rogtk_gpu_compress_unitigs", "rogtk_gpu_free_contigs",
     "rogtk_gpu_assemble_batch", "rogtk_gpu_free_strings", "rogtk_gpu_sweep_batch", "rogtk_gpu_free_sweep",
     "rogtk_gpu_optimize_batch", "rogtk_gpu_free_optimize", "rogtk_host_shortest_path", "rogtk_gpu_count_prune_multi", "rogtk_gpu_nccl_unique_id", "rogtk_gpu_nccl_init",
-    "rogtk_gpu_nccl_finalize", "rogtk_gpu_spectrum_exchange",
+    "rogtk_gpu_nccl_finalize", "rogtk_gpu_spectrum_exchange", "rogtk_gpu_spectrum_merge_runs",
 ]
 METHODS = {"compression": 0, "shortest_path": 1, "shortest_path_auto": 2}
 
@@ -273,6 +273,8 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_nccl_finalize.restype = ctypes.c_int
     lib.rogtk_gpu_spectrum_exchange.argtypes = [vp, ctypes.POINTER(GraphBatchC), ctypes.POINTER(GraphBatchC), u32, u32, ctypes.POINTER(GraphBatchC), vp]
     lib.rogtk_gpu_spectrum_exchange.restype = ctypes.c_int
+    lib.rogtk_gpu_spectrum_merge_runs.argtypes = [vp, vp, ctypes.c_int, u32, u32, ctypes.POINTER(GraphBatchC)]
+    lib.rogtk_gpu_spectrum_merge_runs.restype = ctypes.c_int
     lib.rogtk_gpu_flush_l2.argtypes = [vp]
     lib.rogtk_gpu_flush_l2.restype = ctypes.c_int
     _lib = lib

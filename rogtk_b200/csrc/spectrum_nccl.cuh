@@ -136,6 +136,76 @@ extern "C" int rogtk_gpu_nccl_finalize(rogtk_gpu_ctx *ctx)
     return ROGTK_OK;
 }
 
+// this rank owns the first-4-base buckets [b0, b1) (spectrum_owner); cut each into m equal ranges of about 3000 records
+static void plan_merge_ranges(MergeRuns &runs, int64_t n_merge, int K, int rank, int world)
+{
+    if (2 * K <= 24 || n_merge <= 0) return;
+    const uint32_t b0 = (uint32_t)((256u * (uint32_t)rank + (uint32_t)world - 1u) / (uint32_t)world);
+    const uint32_t b1 = (uint32_t)((256u * (uint32_t)(rank + 1) + (uint32_t)world - 1u) / (uint32_t)world);
+    const int64_t want = (n_merge + 2999) / 3000;
+    const uint32_t nb = b1 > b0 ? b1 - b0 : 1u;
+    uint32_t m = (uint32_t)((want + nb - 1) / nb);
+    m = m < 1u ? 1u : m;
+    if ((int64_t)m * nb <= (1 << 22)) {
+        runs.total = 256u * m;
+        runs.base = b0 * m;
+        runs.n_ranges = (int)(nb * m);
+    }
+}
+
+// Merge of several device-resident shares of the spectrum this rank owns (each ascending, one group, same K): what a driver that
+// keeps its carried share in LEVELS calls -- a level is merged with the next one only when it has grown to its size, so a record
+// is re-read O(log rounds) times instead of once per round.  No communication.
+extern "C" int rogtk_gpu_spectrum_merge_runs(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *const *parts, int n_parts, uint32_t min_coverage,
+                                             uint32_t flags, rogtk_graph_batch *out)
+{
+    if (!ctx || !parts || n_parts < 1 || n_parts > 64 || !out) return ROGTK_ERR_INVALID_ARG;
+    const int K = parts[0]->k_eff;
+    for (int i = 0; i < n_parts; i++)
+        if (!parts[i] || !parts[i]->on_device || parts[i]->n_groups != 1 || parts[i]->k_eff != K || K < 1 || K > 64) return ROGTK_ERR_INVALID_ARG;
+    const bool two = K > 32;
+    NcclState *ns = nccl_state(ctx);
+    const int world = ns ? ns->world : 1, rank = ns ? ns->rank : 0;
+    DevBuf m_lo, m_hi, m_cnt, m_ext;
+    MergeRuns runs;
+    int64_t n_merge = 0, n_obs = 0;
+    try {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CacheScope cache_scope(ctx->cache);
+        CK(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        for (int i = 0; i < n_parts; i++) {
+            n_merge += parts[i]->n_kmers;
+            n_obs += parts[i]->n_observations;
+        }
+        const size_t nm = (size_t)std::max<int64_t>(n_merge, 1);
+        m_lo.alloc(nm * 8, st);
+        if (two) m_hi.alloc(nm * 8, st);
+        m_cnt.alloc(nm * 2, st);
+        m_ext.alloc(nm, st);
+        int64_t at = 0;
+        runs.run_off.push_back(0);
+        for (int i = 0; i < n_parts; i++) {
+            const int64_t c = parts[i]->n_kmers;
+            runs.run_off.push_back(at + c);
+            if (c == 0) continue;
+            CK(cudaMemcpyAsync(m_lo.as<uint64_t>() + at, parts[i]->kmers_lo, (size_t)c * 8, cudaMemcpyDeviceToDevice, st));
+            if (two) CK(cudaMemcpyAsync(m_hi.as<uint64_t>() + at, parts[i]->kmers_hi, (size_t)c * 8, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(m_cnt.as<uint16_t>() + at, parts[i]->counts, (size_t)c * 2, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(m_ext.as<uint8_t>() + at, parts[i]->exts, (size_t)c, cudaMemcpyDeviceToDevice, st));
+            at += c;
+        }
+        CK(cudaStreamSynchronize(st));
+    } catch (...) {
+        return fail_code(ctx);
+    }
+    plan_merge_ranges(runs, n_merge, K, rank, world);
+    const int rc = spectrum_merge_impl(ctx, m_lo.as<uint64_t>(), two ? m_hi.as<uint64_t>() : nullptr, m_cnt.as<uint16_t>(), m_ext.as<uint8_t>(), n_merge, K,
+                                       min_coverage, flags, out, &runs);
+    if (rc == ROGTK_OK) out->n_observations = n_obs;
+    return rc;
+}
+
 extern "C" int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *local, const rogtk_graph_batch *carry,
                                            uint32_t min_coverage, uint32_t flags, rogtk_graph_batch *out, rogtk_exchange_stats *stats)
 {
@@ -272,20 +342,7 @@ extern "C" int rogtk_gpu_spectrum_exchange(rogtk_gpu_ctx *ctx, const rogtk_graph
         return fail_code(ctx);
     }
     if (stats) *stats = xs;
-    if (2 * K > 24 && n_merge > 0) {
-        // this rank owns the first-4-base buckets [b0, b1) (spectrum_owner); cut each into m equal ranges of about 3000 records
-        const uint32_t b0 = (uint32_t)((256u * (uint32_t)rank + (uint32_t)world - 1u) / (uint32_t)world);
-        const uint32_t b1 = (uint32_t)((256u * (uint32_t)(rank + 1) + (uint32_t)world - 1u) / (uint32_t)world);
-        const int64_t want = (n_merge + 2999) / 3000;
-        const uint32_t nb = b1 > b0 ? b1 - b0 : 1u;
-        uint32_t m = (uint32_t)((want + nb - 1) / nb);
-        m = m < 1u ? 1u : m;
-        if ((int64_t)m * nb <= (1 << 22)) {
-            runs.total = 256u * m;
-            runs.base = b0 * m;
-            runs.n_ranges = (int)(nb * m);
-        }
-    }
+    plan_merge_ranges(runs, n_merge, K, rank, world);
     // (takes the context lock itself)
     return spectrum_merge_impl(ctx, m_lo.as<uint64_t>(), two ? m_hi.as<uint64_t>() : nullptr, m_cnt.as<uint16_t>(), m_ext.as<uint8_t>(), n_merge, K,
                                min_coverage, flags, out, &runs);

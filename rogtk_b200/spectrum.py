@@ -138,6 +138,82 @@ def _exchange(engine: Engine, local: DeviceBatch, carry: DeviceBatch | None, min
                        ms_hot_kernel=float(out.ms_hot_kernel), n_spilled_groups=0, n_multipass_groups=0, _c=out, _engine=engine), st
 
 
+def _device_batch(engine: Engine, out: "_ffi.GraphBatchC") -> DeviceBatch:
+    return DeviceBatch(k_eff=int(out.k_eff), n_groups=int(out.n_groups), n_kmers=int(out.n_kmers), n_edges=int(out.n_edges),
+                       n_observations=int(out.n_observations), ms_total=float(out.ms_total), ms_count=float(out.ms_count),
+                       ms_hot_kernel=float(out.ms_hot_kernel), n_spilled_groups=0, n_multipass_groups=0, _c=out, _engine=engine)
+
+
+def _merge_levels(engine: Engine, parts: list, min_coverage: int, flags: int, on_device: bool):
+    """rogtk_gpu_spectrum_merge_runs over device-resident shares (no communication)."""
+    arr = (ctypes.c_void_p * len(parts))(*[ctypes.addressof(p._c) for p in parts])
+    out = _ffi.GraphBatchC()
+    f = (int(flags) | _ffi.OUTPUT_ON_DEVICE) if on_device else (int(flags) & ~_ffi.OUTPUT_ON_DEVICE)
+    engine._check(engine._lib.rogtk_gpu_spectrum_merge_runs(engine._ctx, arr, len(parts), int(min_coverage), f, ctypes.byref(out)))
+    return _device_batch(engine, out) if on_device else engine._to_numpy(out)
+
+
+def _run_rounds(engine: Engine, rdv: Rendezvous, rounds: int, count_round, min_coverage: int, flags: int, keep_on_device: bool,
+                stats_out: dict | None):
+    """The rounds of the mode.  count_round(r) -> this rank's reads of round r counted as one group (DeviceBatch, min_coverage 1).
+    The share of the spectrum this rank owns is carried in HBM as LEVELS.  The exchange of a round merges what arrives with the
+    newest level while that level is small (up to 3 rounds' worth: the merge runs inside the exchange call, no extra pass), else
+    it leaves a new level; two levels are merged when the newer one has reached 3/4 of the older one.  A carried record is
+    re-read O(log rounds) times instead of once per round (20 rounds: about half the merge traffic, 100 rounds: a sixth);
+    min_coverage is applied by the last merge."""
+    levels: list[DeviceBatch] = []
+    n_obs = 0
+    unit = None   # records one round adds to this rank's share (first round's result)
+    tot = dict(bytes_sent=0, bytes_received=0, ms_exchange=0.0, n_sent=0, n_received=0, rounds=rounds, ms_local=0.0, ms_merge=0.0,
+               level_merges=0)
+    try:
+        for r in range(rounds):
+            local = count_round(r)
+            try:
+                if local.k_eff < 0:   # k > 64: empty result (reference src/fracture.rs:212-215)
+                    return local.to_host()
+                n_obs += local.n_observations
+                tot["ms_local"] += local.ms_total
+                last = r == rounds - 1
+                carry = levels[-1] if levels and unit is not None and levels[-1].n_kmers <= 3 * unit else None
+                closing = last and len(levels) == (1 if carry is not None else 0)    # this exchange produces the final result
+                merged, st = _exchange(engine, local, carry, min_coverage if closing else 1, (flags & _ffi.EMIT_STATS) if closing else 0,
+                                       on_device=(not closing) or keep_on_device)
+                for key in ("bytes_sent", "bytes_received", "n_sent", "n_received"):
+                    tot[key] += int(getattr(st, key))
+                tot["ms_exchange"] += float(st.ms_exchange)
+                tot["ms_merge"] += float(merged.ms_total)
+            finally:
+                local.free()
+            if carry is not None:
+                levels.pop().free()
+            if closing:
+                merged.n_observations = rdv.allreduce(n_obs)   # observations of the whole job (a size, not data)
+                if stats_out is not None:
+                    stats_out.update(tot)
+                return merged
+            if unit is None:
+                unit = max(1, merged.n_kmers)
+            levels.append(merged)
+            while len(levels) >= 2 and 4 * levels[-1].n_kmers >= 3 * levels[-2].n_kmers:
+                m = _merge_levels(engine, levels[-2:], 1, 0, True)
+                tot["ms_merge"] += float(m.ms_total)
+                tot["level_merges"] += 1
+                levels.pop().free()
+                levels.pop().free()
+                levels.append(m)
+        final = _merge_levels(engine, levels, min_coverage, flags & _ffi.EMIT_STATS, keep_on_device)
+        tot["ms_merge"] += float(final.ms_total)
+        tot["level_merges"] += 1
+        final.n_observations = rdv.allreduce(n_obs)
+        if stats_out is not None:
+            stats_out.update(tot)
+        return final
+    finally:
+        for lv in levels:
+            lv.free()
+
+
 def global_spectrum_device(engine: Engine, d_data: int, n_bytes: int, d_offsets: int, n_rows: int, k: int, min_coverage: int,
                            rdv: Rendezvous | None = None, flags: int = 0, chunk_rows: int | None = None, stats_out: dict | None = None,
                            keep_on_device: bool = False):
@@ -148,40 +224,15 @@ def global_spectrum_device(engine: Engine, d_data: int, n_bytes: int, d_offsets:
     step = n_rows if not chunk_rows or chunk_rows <= 0 else int(chunk_rows)
     rounds = rdv.allreduce(max(1, -(-n_rows // max(step, 1))), "max")
     d_goff = engine.device_alloc(16)
-    carry = None
-    n_obs = 0
-    tot = dict(bytes_sent=0, bytes_received=0, ms_exchange=0.0, n_sent=0, n_received=0, rounds=rounds, ms_local=0.0, ms_merge=0.0)
+
+    def count_round(r):
+        a, b = min(n_rows, r * step), min(n_rows, (r + 1) * step)
+        engine.h2d(d_goff, np.array([0, b - a], dtype=np.int64).view(np.uint8))
+        return engine.count_prune_device(d_data, n_bytes, d_offsets + 8 * a, b - a, d_goff, 1, k, 1, flags=flags & _ffi.EXACT_K)
+
     try:
-        for r in range(rounds):
-            a, b = min(n_rows, r * step), min(n_rows, (r + 1) * step)
-            engine.h2d(d_goff, np.array([0, b - a], dtype=np.int64).view(np.uint8))
-            local = engine.count_prune_device(d_data, n_bytes, d_offsets + 8 * a, b - a, d_goff, 1, k, 1, flags=flags & _ffi.EXACT_K)
-            try:
-                if local.k_eff < 0:
-                    return local.to_host()
-                n_obs += local.n_observations
-                tot["ms_local"] += local.ms_total
-                last = r == rounds - 1
-                merged, st = _exchange(engine, local, carry, min_coverage if last else 1, (flags & _ffi.EMIT_STATS) if last else 0,
-                                       on_device=(not last) or keep_on_device)
-                for key in ("bytes_sent", "bytes_received", "n_sent", "n_received"):
-                    tot[key] += int(getattr(st, key))
-                tot["ms_exchange"] += float(st.ms_exchange)
-                tot["ms_merge"] += float(merged.ms_total)
-            finally:
-                local.free()
-            if carry is not None:
-                carry.free()
-                carry = None
-            if last:
-                merged.n_observations = rdv.allreduce(n_obs)
-                if stats_out is not None:
-                    stats_out.update(tot)
-                return merged
-            carry = merged
+        return _run_rounds(engine, rdv, rounds, count_round, min_coverage, flags, keep_on_device, stats_out)
     finally:
-        if carry is not None:
-            carry.free()
         engine.device_free(d_goff)
 
 
@@ -192,8 +243,8 @@ def global_spectrum(engine: Engine, data: np.ndarray, offsets: np.ndarray, k: in
 
     `chunk_rows` bounds the reads counted at a time: the local table of a round is sized by the round's reads, not by the
     whole input, and the rank's share of the spectrum (distinct k-mers it owns, counts saturating at 65535, exts) is carried in
-    HBM from round to round; min_coverage is applied in the last round only.  Every rank runs the same number of rounds.
-    stats_out (optional dict) receives the NCCL byte / time totals of the exchanges."""
+    HBM from round to round (in levels, see _run_rounds); min_coverage is applied at the end.  Every rank runs the same number of
+    rounds.  stats_out (optional dict) receives the NCCL byte / time totals of the exchanges."""
     rdv = rdv or Rendezvous(0, 1)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n_rows = len(offsets) - 1
@@ -201,39 +252,12 @@ def global_spectrum(engine: Engine, data: np.ndarray, offsets: np.ndarray, k: in
     rounds = rdv.allreduce(max(1, -(-n_rows // max(step, 1))), "max")
     if validity is not None and rounds > 1:
         raise ValueError("chunk_rows with a validity bitmap is not supported: drop the null rows first")
-    carry = None        # device-resident share of the spectrum after the previous rounds (min_coverage 1)
-    n_obs = 0
-    tot = dict(bytes_sent=0, bytes_received=0, ms_exchange=0.0, n_sent=0, n_received=0, rounds=rounds, ms_local=0.0, ms_merge=0.0)
-    try:
-        for r in range(rounds):
-            a, b = min(n_rows, r * step), min(n_rows, (r + 1) * step)
-            d = data[offsets[a]:offsets[b]]
-            o = offsets[a:b + 1] - offsets[a]
-            local = engine.count_prune_to_device(d, o, np.array([0, b - a], dtype=np.int64), k, 1,
-                                                 validity=validity if rounds == 1 else None, flags=flags & _ffi.EXACT_K)
-            try:
-                if local.k_eff < 0:   # k > 64: empty result (reference src/fracture.rs:212-215)
-                    return local.to_host()
-                n_obs += local.n_observations
-                tot["ms_local"] += local.ms_total
-                last = r == rounds - 1
-                merged, st = _exchange(engine, local, carry, min_coverage if last else 1, (flags & _ffi.EMIT_STATS) if last else 0,
-                                       on_device=not last)
-                for key in ("bytes_sent", "bytes_received", "n_sent", "n_received"):
-                    tot[key] += int(getattr(st, key))
-                tot["ms_exchange"] += float(st.ms_exchange)
-                tot["ms_merge"] += float(merged.ms_total)
-            finally:
-                local.free()
-            if carry is not None:
-                carry.free()
-                carry = None
-            if last:
-                merged.n_observations = rdv.allreduce(n_obs)   # observations of the whole job (a size, not data)
-                if stats_out is not None:
-                    stats_out.update(tot)
-                return merged
-            carry = merged
-    finally:
-        if carry is not None:
-            carry.free()
+
+    def count_round(r):
+        a, b = min(n_rows, r * step), min(n_rows, (r + 1) * step)
+        d = data[offsets[a]:offsets[b]]
+        o = offsets[a:b + 1] - offsets[a]
+        return engine.count_prune_to_device(d, o, np.array([0, b - a], dtype=np.int64), k, 1,
+                                            validity=validity if rounds == 1 else None, flags=flags & _ffi.EXACT_K)
+
+    return _run_rounds(engine, rdv, rounds, count_round, min_coverage, flags, False, stats_out)

@@ -33,7 +33,8 @@ if PARITY:
     o = np.arange(len(d) // L + 1, dtype=np.int64) * L
 k, mc = 31, 2
 st = {}
-for it in range(3 if PARITY else 4):
+ITERS = int(sys.argv[4]) if len(sys.argv) > 4 else (3 if PARITY else 4)
+for it in range(ITERS):
     rdv.barrier(); t0 = time.perf_counter()
     if PARITY:
         got = spectrum.global_spectrum(eng, d, o, k, mc, rdv=rdv, chunk_rows=CHUNK, stats_out=st)
@@ -64,7 +65,7 @@ if rank == 0:
                       "observations": int(got.n_observations), "survivors": int(tot_surv), "parity_vs_oracle": ok, "wall_ms": dt * 1e3,
                       "obs_per_s": got.n_observations / dt, "nccl_bytes_sent_max_rank": int(max_bytes), "nccl_ms_max_rank": max_ms,
                       "nvlink_GBps_per_dir": nv, "nvlink_frac_of_900": (nv / 900.0) if nv else None,
-                      "stage_ms_rank0": {k_: round(v, 2) for k_, v in st.items() if k_.startswith("ms_")},
+                      "stage_ms_rank0": {k_: round(v, 2) for k_, v in st.items() if k_.startswith("ms_")}, "level_merges_rank0": st.get("level_merges"),
                       "input": "host numpy (parity run)" if PARITY else "synthesized in HBM, result left in HBM"}))
     assert ok is not False
 spectrum.finalize_comm(eng)
