@@ -616,7 +616,7 @@ def main():
             "config": {"workload": workload, "parallelism": f"umi-sharded x{world}, no collective",
                        "l2": "inputs (15 GB/GPU) far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the library stream around the whole device pipeline, max over ranks"},
-            "roofline": roofline, "value_with_csr": value_with_csr, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "value_with_csr": value_with_csr, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "device_cache": eng.cache_stats(),
             "clocks": clocks,
             "survivors_per_step": int(n_kmers), "spilled_groups": int(n_spill), "observations_per_step": int(obs_all),
             "next_rows": next_rows})

@@ -76,19 +76,40 @@ struct DevCache {
         std::lock_guard<std::mutex> lk(r.mu);
         r.all.push_back(this);
     }
-    // cudaMalloc failed: hand every cache's idle blocks on this device back to the driver (caller holds no cache lock)
-    static void release_all_idle(int dev)
+    // cudaMalloc failed: hand idle blocks of the caches on this device back to the driver, largest first, until about twice the
+    // request has been freed (everything when need == 0); the caller holds no cache lock
+    static void release_all_idle(int dev, size_t need = 0)
     {
         DevCacheRegistry &r = DevCacheRegistry::get();
         std::lock_guard<std::mutex> lk(r.mu);
-        for (DevCache *c : r.all) {
-            if (c->device != dev) continue;
-            std::lock_guard<std::mutex> cl(c->mu);
-            if (!c->idle.empty()) c->n_released_for_others++;
-            c->release_idle_locked();
+        cudaDeviceSynchronize();
+        size_t freed = 0;
+        while (true) {
+            DevCache *best = nullptr;
+            size_t best_sz = 0;
+            for (DevCache *c : r.all) {
+                if (c->device != dev) continue;
+                std::lock_guard<std::mutex> cl(c->mu);
+                if (!c->idle.empty() && std::prev(c->idle.end())->first > best_sz) {
+                    best = c;
+                    best_sz = std::prev(c->idle.end())->first;
+                }
+            }
+            if (!best) break;
+            {
+                std::lock_guard<std::mutex> cl(best->mu);
+                if (best->idle.empty()) continue;
+                auto last = std::prev(best->idle.end());
+                cudaEventDestroy(last->second.ev);
+                cudaFree(last->second.p);
+                freed += last->second.sz;
+                best->idle_bytes -= last->second.sz;
+                best->idle.erase(last);
+                best->n_released_for_others++;
+            }
+            if (need && freed >= 2 * need) break;
         }
     }
-
     static size_t size_class(size_t n)
     {
         if (n < 512) return 512;
@@ -101,7 +122,11 @@ struct DevCache {
         cudaError_t e = alloc_once(out, n, s);
         if (e != cudaErrorMemoryAllocation) return e;
         cudaGetLastError();
-        release_all_idle(device);
+        release_all_idle(device, size_class(n));       // enough for this request ...
+        e = alloc_once(out, n, s);
+        if (e != cudaErrorMemoryAllocation) return e;
+        cudaGetLastError();
+        release_all_idle(device);                      // ... or everything (fragmented address space)
         return alloc_once(out, n, s);
     }
     cudaError_t alloc_once(void **out, size_t n, cudaStream_t s)

@@ -922,7 +922,7 @@ def test_device_cache_reuse_and_trim(oracle):
         assert free0 - torch.cuda.mem_get_info(0)[0] < max(held, 1)   # cached blocks went back
 
 
-def test_device_cache_gives_way_under_memory_pressure(oracle, monkeypatch):
+def test_device_cache_gives_way_under_memory_pressure(engine, oracle, monkeypatch):
     """Two contexts on one device (one per worker thread in the plugin): when a cudaMalloc fails, the idle blocks of EVERY context's
     cache go back to the driver and the request is retried; ROGTK_DEVICE_CACHE_BYTES bounds what a context keeps."""
     import rogtk_b200
@@ -933,13 +933,16 @@ def test_device_cache_gives_way_under_memory_pressure(oracle, monkeypatch):
     ref = oracle.count_prune_batch(*small, 31, 2)
     with rogtk_b200.Engine(device=0) as a, rogtk_b200.Engine(device=0) as b:
         a.count_prune(data, offs, goff, 31, 2)                      # a's cache now holds a few hundred MB of idle blocks
-        held = a.cache_stats()["idle_bytes"]
-        assert held > 100 << 20
+        assert a.cache_stats()["idle_bytes"] > 100 << 20
+        # (the session's context is a third cache on the device: blocks go largest first, whoever holds them)
+        held = a.cache_stats()["idle_bytes"] + engine.cache_stats()["idle_bytes"]
+        rel0 = a.cache_stats()["n_released_for_others"] + engine.cache_stats()["n_released_for_others"]
         free_now = torch.cuda.mem_get_info(0)[0]
         hog = torch.empty(free_now - (64 << 20), dtype=torch.uint8, device="cuda:0")      # leave 64 MB: less than b needs
         try:
             got = b.count_prune(data, offs, goff, 31, 2, flags=EMIT_STATS)                  # must take a's idle memory
-            assert a.cache_stats()["n_released_for_others"] >= 1 and a.cache_stats()["idle_bytes"] < held
+            assert a.cache_stats()["n_released_for_others"] + engine.cache_stats()["n_released_for_others"] > rel0
+            assert a.cache_stats()["idle_bytes"] + engine.cache_stats()["idle_bytes"] < held
             assert got.n_groups == 4000
             assert_batches_equal(b.count_prune(*small, 31, 2, flags=EMIT_STATS), ref, ctx="after giving way")
         finally:
