@@ -286,7 +286,16 @@ def main():
     n_umis, R, L = cfg["n_umis"], cfg["reads"], cfg["read_len"]
     n_reads = n_umis * R
     # each rank owns a disjoint range of UMI indices (its hash shard, materialised as a contiguous range)
-    d_data, d_off, d_goff, n_bytes = eng.synth_reads_device(seed, rank * n_umis, n_umis, R, L, cfg["template"], cfg["err64k"])
+    # each rank owns the UMIs its hash names: the first n_umis ids u >= 0 with rogtk_gpu_shard_of(u, world) == rank (what a host
+    # that shards a frame by rogtk_gpu_shard_of hands to this GPU); one rank: ids 0 .. n_umis - 1
+    shard_ids_ = None
+    if world > 1:
+        from rogtk_b200 import sharding
+        pop = np.arange(int(world * n_umis * 1.02) + 4096, dtype=np.int64)
+        shard_ids_ = pop[sharding.shard_ids(pop, world) == rank][:n_umis]
+        assert len(shard_ids_) == n_umis
+        del pop
+    d_data, d_off, d_goff, n_bytes = eng.synth_reads_device(seed, rank * n_umis, n_umis, R, L, cfg["template"], cfg["err64k"], umi_ids=shard_ids_)
 
     stage_acc = {}
 
@@ -613,7 +622,7 @@ def main():
         line = dict(base)
         line.update({
             "value": value, "ms_per_step": ms_dev_max, "wall_ms_per_step": wall_max, "umi_groups_per_s": groups_all / (ms_dev_max * 1e-3),
-            "config": {"workload": workload, "parallelism": f"umi-sharded x{world}, no collective",
+            "config": {"workload": workload, "parallelism": f"umi-sharded x{world} by rogtk_gpu_shard_of(umi_id) (splitmix64 mod ranks), no collective",
                        "l2": "inputs (15 GB/GPU) far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the library stream around the whole device pipeline, max over ranks"},
             "roofline": roofline, "value_with_csr": value_with_csr, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "device_cache": eng.cache_stats(),

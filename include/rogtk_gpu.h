@@ -336,10 +336,10 @@ int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, i
                           int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data,
                           int64_t *d_offsets, int64_t *d_group_offsets);
 /* the same, reads read_base .. read_base + reads_per_umi - 1 of every template (ranks of the global-spectrum mode draw different reads
-   of the same templates) */
+   of the same templates); d_umi_ids (device, [n_umis], or NULL) names the UMIs instead of umi_base + i (a rank's hash shard) */
 int rogtk_gpu_synth_reads_from(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t reads_per_umi, int32_t read_base,
                                int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data, int64_t *d_offsets,
-                               int64_t *d_group_offsets);
+                               int64_t *d_group_offsets, const int64_t *d_umi_ids);
 /* the same generator with a read count per UMI (BASELINE configs[2], skewed groups): d_group_offsets [n_umis+1] is an input */
 int rogtk_gpu_synth_reads_var(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, const int64_t *d_group_offsets,
                               int64_t n_reads, int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data,

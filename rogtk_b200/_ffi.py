@@ -218,7 +218,7 @@ def load() -> ctypes.CDLL:
     lib.rogtk_gpu_free_batch.argtypes = [vp, ctypes.POINTER(GraphBatchC)]
     lib.rogtk_gpu_synth_reads.argtypes = [vp, u64, i64, i64, i32, i32, i32, u32, vp, vp, vp]
     lib.rogtk_gpu_synth_reads.restype = ctypes.c_int
-    lib.rogtk_gpu_synth_reads_from.argtypes = [vp, u64, i64, i64, i32, i32, i32, i32, u32, vp, vp, vp]
+    lib.rogtk_gpu_synth_reads_from.argtypes = [vp, u64, i64, i64, i32, i32, i32, i32, u32, vp, vp, vp, vp]
     lib.rogtk_gpu_synth_reads_from.restype = ctypes.c_int
     lib.rogtk_gpu_synth_reads_var.argtypes = [vp, u64, i64, i64, vp, i64, i32, i32, u32, vp, vp]
     lib.rogtk_gpu_synth_reads_var.restype = ctypes.c_int

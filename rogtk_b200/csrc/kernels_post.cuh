@@ -489,7 +489,7 @@ __global__ void k_synth_var(uint64_t seed, int64_t umi_base, int64_t n_umis, con
 }
 
 __global__ void k_synth(uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t R, int32_t L, int32_t T, uint32_t err,
-                        uint8_t *data, int64_t *offsets, int64_t *group_offsets, int32_t read_base)
+                        uint8_t *data, int64_t *offsets, int64_t *group_offsets, int32_t read_base, const int64_t *umi_ids)
 {
     const int64_t total = n_umis * (int64_t)R * L;
     const int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -508,7 +508,7 @@ __global__ void k_synth(uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t
             int32_t j = (int32_t)(q - read * L);
             int64_t u = read / R;
             int32_t r = (int32_t)(read - u * R);
-            out[x] = synth_base(seed, umi_base + u, r + read_base, j, L, T, err);
+            out[x] = synth_base(seed, umi_ids ? umi_ids[u] : umi_base + u, r + read_base, j, L, T, err);
         } else {
             out[x] = 0;
         }

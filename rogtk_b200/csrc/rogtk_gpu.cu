@@ -2069,7 +2069,7 @@ extern "C" void rogtk_gpu_free_contigs(rogtk_gpu_ctx *ctx, rogtk_contig_batch *b
 // -----------------------------------------------------------------------------------------------------------------
 extern "C" int rogtk_gpu_synth_reads_from(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, int32_t reads_per_umi,
                                           int32_t read_base, int32_t read_len, int32_t template_len, uint32_t err_per_64k, uint8_t *d_data,
-                                          int64_t *d_offsets, int64_t *d_group_offsets)
+                                          int64_t *d_offsets, int64_t *d_group_offsets, const int64_t *d_umi_ids)
 {
     if (!ctx || n_umis < 0 || reads_per_umi < 1 || read_base < 0 || read_len < 1 || template_len < read_len) return ROGTK_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -2079,7 +2079,7 @@ extern "C" int rogtk_gpu_synth_reads_from(rogtk_gpu_ctx *ctx, uint64_t seed, int
         const int64_t total = n_umis * (int64_t)reads_per_umi * read_len;
         const int64_t threads = std::max<int64_t>((total + 3) / 4, n_umis * (int64_t)reads_per_umi + 1);
         k_synth<<<blocks_for(threads, 256), 256, 0, ctx->stream>>>(seed, umi_base, n_umis, reads_per_umi, read_len, template_len,
-                                                                   err_per_64k, d_data, d_offsets, d_group_offsets, read_base);
+                                                                   err_per_64k, d_data, d_offsets, d_group_offsets, read_base, d_umi_ids);
         ctx->launches++;
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
@@ -2094,7 +2094,7 @@ extern "C" int rogtk_gpu_synth_reads(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t 
                                      int64_t *d_offsets, int64_t *d_group_offsets)
 {
     return rogtk_gpu_synth_reads_from(ctx, seed, umi_base, n_umis, reads_per_umi, 0, read_len, template_len, err_per_64k, d_data, d_offsets,
-                                      d_group_offsets);
+                                      d_group_offsets, nullptr);
 }
 
 extern "C" int rogtk_gpu_synth_reads_var(rogtk_gpu_ctx *ctx, uint64_t seed, int64_t umi_base, int64_t n_umis, const int64_t *d_group_offsets,

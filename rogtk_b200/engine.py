@@ -259,7 +259,7 @@ class Engine:
         return out
 
     def synth_reads_device(self, seed: int, umi_base: int, n_umis: int, reads_per_umi: int, read_len: int,
-                           template_len: int, err_per_64k: int, read_base: int = 0):
+                           template_len: int, err_per_64k: int, read_base: int = 0, umi_ids: np.ndarray | None = None):
         """Generate the SURVEY 8(d) synthetic reads directly in HBM.  Returns (d_data, d_offsets, d_group_offsets,
         n_bytes) as raw device pointers (free with device_free)."""
         n_reads = n_umis * reads_per_umi
@@ -267,9 +267,19 @@ class Engine:
         d_data = self.device_alloc(n_bytes + 16)
         d_off = self.device_alloc((n_reads + 1) * 8)
         d_goff = self.device_alloc((n_umis + 1) * 8)
-        self._check(self._lib.rogtk_gpu_synth_reads_from(self._ctx, seed & 0xFFFFFFFFFFFFFFFF, umi_base, n_umis, reads_per_umi, read_base,
-                                                         read_len, template_len, err_per_64k, ctypes.c_void_p(d_data),
-                                                         ctypes.c_void_p(d_off), ctypes.c_void_p(d_goff)))
+        d_ids = None
+        if umi_ids is not None:   # the UMIs of a hash shard instead of a contiguous range
+            ids = np.ascontiguousarray(umi_ids, dtype=np.int64)
+            assert len(ids) == n_umis
+            d_ids = self.device_alloc(max(ids.nbytes, 16))
+            self.h2d(d_ids, ids.view(np.uint8))
+        try:
+            self._check(self._lib.rogtk_gpu_synth_reads_from(self._ctx, seed & 0xFFFFFFFFFFFFFFFF, umi_base, n_umis, reads_per_umi, read_base,
+                                                             read_len, template_len, err_per_64k, ctypes.c_void_p(d_data),
+                                                             ctypes.c_void_p(d_off), ctypes.c_void_p(d_goff), ctypes.c_void_p(d_ids) if d_ids else None))
+        finally:
+            if d_ids:
+                self.device_free(d_ids)
         return d_data, d_off, d_goff, n_bytes
 
     def synth_reads_device_var(self, seed: int, umi_base: int, reads_per_umi: np.ndarray, read_len: int, template_len: int, err_per_64k: int):
@@ -597,38 +607,61 @@ class Engine:
         return res
 
     # ---- Arrow-native entry: one call per frame ----------------------------------------------------------------------
-    def assemble_arrow(self, reads, k: int, min_coverage: int, min_length: int = 0):
-        """The batched form of assemble_sequences_expr(method="compression") (reference src/expressions.rs:695-762): `reads` is a
-        pyarrow List(String) array with one row per group; returns (pyarrow LargeStringArray with the contig of every group, ""
-        where the reference returns no contig; uint8 flags per group: bit 0 tie in length, bit 1 cyclic -- recompute those groups
-        with the reference if its tie-break matters).  Reads -> nodes -> unitigs -> choice all happen on the device."""
+    def _arrow_col(self, child):
+        """rogtk_strcol over the buffers of a pyarrow String / LargeString / Binary / StringView array -- no re-encoding, no copy
+        (a sliced view array is re-based, pyarrow keeps its variadic buffers whole).  Returns (StrCol, keep-alive objects)."""
         import pyarrow as pa
-        goff, child = self._arrow_groups(reads)
         ct = child.type
-        if not (pa.types.is_large_string(ct) or pa.types.is_large_binary(ct)):
-            child = child.cast(pa.large_string())   # one host copy for Utf8 / Utf8View children (this entry only)
         bufs = child.buffers()
         validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None
-        offs = np.frombuffer(bufs[1], dtype=np.int64)[child.offset:child.offset + len(child) + 1]
-        data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None else np.zeros(0, np.uint8)
-        db = self.count_prune_to_device(data, offs, goff, k, min_coverage, validity=validity, validity_bit_offset=child.offset)
-        try:
-            ng = len(goff) - 1
-            if db.k_eff < 0:
-                return pa.array([""] * ng, type=pa.large_string()), np.zeros(ng, np.uint8)
-            cb = self.compress_unitigs(db, min_length)
-        finally:
-            db.free()
-        u = cb.largest
-        has = u >= 0
-        starts = np.where(has, cb.seq_offsets[np.maximum(u, 0)], 0)
-        lens = np.where(has, cb.seq_offsets[np.maximum(u, 0) + 1] - starts, 0)
-        out_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        out = np.empty(int(out_off[-1]), dtype=np.uint8)
-        for g in np.nonzero(has)[0]:   # (a gather; groups are few compared with bases)
-            out[out_off[g]:out_off[g + 1]] = cb.seq[starts[g]:starts[g] + lens[g]]
-        arr = pa.LargeStringArray.from_buffers(ng, pa.py_buffer(out_off), pa.py_buffer(out))
-        return arr, cb.largest_flags
+        if pa.types.is_string(ct) or pa.types.is_large_string(ct) or pa.types.is_binary(ct) or pa.types.is_large_binary(ct):
+            sdt = np.int64 if (pa.types.is_large_string(ct) or pa.types.is_large_binary(ct)) else np.int32
+            offs = np.frombuffer(bufs[1], dtype=sdt)[child.offset:child.offset + len(child) + 1] if bufs[1] is not None else np.zeros(1, sdt)
+            data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None else np.zeros(0, np.uint8)
+            col, keep = self._host_col(data, offs, validity, child.offset)
+            return col, keep + (child,)
+        if hasattr(pa.types, "is_string_view") and (pa.types.is_string_view(ct) or pa.types.is_binary_view(ct)):
+            if child.offset:
+                child = pa.concat_arrays([child])   # re-base a sliced view array
+                bufs = child.buffers()
+                validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None
+            views = np.frombuffer(bufs[1], dtype=np.uint8)[:len(child) * 16].reshape(-1, 16) if bufs[1] is not None else np.zeros((0, 16), np.uint8)
+            # (a null variadic buffer keeps its place: the views name buffers by index)
+            data_bufs = [np.frombuffer(b_, dtype=np.uint8) if b_ is not None else np.zeros(0, np.uint8) for b_ in bufs[2:]]
+            nb = len(data_bufs)
+            dptr = (ctypes.c_void_p * max(nb, 1))(*[b_.ctypes.data if b_.size else None for b_ in data_bufs])
+            dlen = (ctypes.c_int64 * max(nb, 1))(*[b_.size for b_ in data_bufs])
+            col = _ffi.StrCol(layout=_ffi.UTF8_VIEW, n_buffers=nb, n_rows=views.shape[0],
+                              validity=validity.ctypes.data if validity is not None else None, validity_bit_offset=0,
+                              offsets_or_views=views.ctypes.data, data=dptr, data_len=dlen)
+            return col, (views, data_bufs, validity, dptr, dlen, child)
+        raise TypeError(f"unsupported child type {ct}")
+
+    def assemble_arrow(self, reads, k: int, min_coverage: int, min_length: int = 0, method: str = "compression",
+                       start_anchor: str | None = None, end_anchor: str | None = None, auto_k: bool = False):
+        """The batched form of assemble_sequences_expr (reference src/expressions.rs:695-762): `reads` is a pyarrow List(String)
+        array with one row per group (String / LargeString / StringView children go to the C ABI as they are); returns (pyarrow
+        LargeStringArray with the contig of every group, "" where the reference returns no contig; uint8 flags per group: bit 0
+        tie in length, bit 1 cyclic -- recompute those groups with the reference if its tie-break matters).  One call of
+        rogtk_gpu_assemble_batch: reads -> nodes -> unitigs / paths -> choice; the result buffers become the Arrow array as they
+        are."""
+        import pyarrow as pa
+        goff, child = self._arrow_groups(reads)
+        col, keep = self._arrow_col(child)
+        if method not in _ffi.METHODS:
+            raise RogtkGpuError(-1, "Invalid assembly method. Must be 'compression', 'shortest_path', or 'shortest_path_auto'")
+        p = _ffi.AssemblyParamsC(k=int(k), min_coverage=int(min_coverage), method=_ffi.METHODS[method],
+                                 start_anchor=start_anchor.encode() if start_anchor is not None else None,
+                                 end_anchor=end_anchor.encode() if end_anchor is not None else None,
+                                 min_length=int(min_length or 0), only_largest=1, auto_k=int(bool(auto_k)))
+        out = _ffi.StringBatchC()
+        self._check(self._lib.rogtk_gpu_assemble_batch(self._ctx, ctypes.byref(col), goff.ctypes.data, len(goff) - 1, ctypes.byref(p), 0,
+                                                       ctypes.byref(out)))
+        res = self._strings_out(out)
+        self._lib.rogtk_gpu_free_strings(self._ctx, ctypes.byref(out))
+        del keep
+        arr = pa.LargeStringArray.from_buffers(len(goff) - 1, pa.py_buffer(res.offsets), pa.py_buffer(res.data))
+        return arr, res.flags
 
     def _arrow_groups(self, reads):
         """(group_offsets int64, child string array) of a List(String) array; null lists become empty groups."""
@@ -659,27 +692,11 @@ class Engine:
         `df.group_by("umi").agg(pl.col("seq"))` hands to a batched plugin call), or a ChunkedArray of those.  The list
         offsets are the group offsets; the child string buffers go to the C ABI without re-encoding.  Null lists are empty
         groups, null strings are dropped (reference src/expressions.rs:737-740)."""
-        import pyarrow as pa
         goff, child = self._arrow_groups(reads)
-        ct = child.type
-        bufs = child.buffers()
-        validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None
-        if pa.types.is_string(ct) or pa.types.is_large_string(ct) or pa.types.is_binary(ct) or pa.types.is_large_binary(ct):
-            sdt = np.int64 if (pa.types.is_large_string(ct) or pa.types.is_large_binary(ct)) else np.int32
-            offs = np.frombuffer(bufs[1], dtype=sdt)[child.offset:child.offset + len(child) + 1]
-            data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None else np.zeros(0, np.uint8)
-            return self.count_prune(data, offs, goff, k, min_coverage, validity=validity, validity_bit_offset=child.offset,
-                                    flags=flags)
-        if hasattr(pa.types, "is_string_view") and (pa.types.is_string_view(ct) or pa.types.is_binary_view(ct)):
-            if child.offset or validity is not None and child.offset:
-                child = pa.concat_arrays([child])   # re-base a sliced view array
-                bufs = child.buffers()
-                validity = np.frombuffer(bufs[0], dtype=np.uint8) if bufs[0] is not None and child.null_count else None
-            views = np.frombuffer(bufs[1], dtype=np.uint8)[:len(child) * 16].reshape(-1, 16)
-            # (a null variadic buffer keeps its place: the views name buffers by index)
-            data_bufs = [np.frombuffer(b, dtype=np.uint8) if b is not None else np.zeros(0, np.uint8) for b in bufs[2:]]
-            return self.count_prune_views(views, data_bufs, goff, k, min_coverage, validity=validity, flags=flags)
-        raise TypeError(f"unsupported child type {ct}")
+        col, keep = self._arrow_col(child)
+        c = self._call(col, goff.ctypes.data, len(goff) - 1, k, min_coverage, flags & ~(_ffi.INPUT_ON_DEVICE | _ffi.OUTPUT_ON_DEVICE))
+        del keep
+        return self._to_numpy(c)
 
 
 def count_prune_multi(engines: list, data, offsets, group_offsets, k: int, min_coverage: int, umi_ids=None, validity=None,

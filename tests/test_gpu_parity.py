@@ -261,6 +261,23 @@ def test_device_generator_matches_numpy(engine):
     assert np.array_equal(engine.d2h(d_goff, 51 * 8, np.int64), goff)
     for p in (d_data, d_off, d_goff):
         engine.device_free(p)
+    # the UMIs of a hash shard (bench.py, N > 1) and a read offset (the ranks of the global-spectrum mode): same generator
+    from rogtk_b200 import sharding
+    pop = np.arange(400, dtype=np.int64)
+    ids = pop[sharding.shard_ids(pop, 4) == 2][:40]
+    assert len(ids) == 40 and all(engine._lib.rogtk_gpu_shard_of(int(u), 4) == 2 for u in ids[:10])
+    d_data, d_off, d_goff, nbytes = engine.synth_reads_device(seed, 0, 40, 7, 150, 500, 655, umi_ids=ids)
+    got = engine.d2h(d_data, nbytes).reshape(40, 7 * 150)
+    for i, u in enumerate(ids):
+        assert np.array_equal(got[i], synth.synth_reads(seed, int(u), 1, 7, 150, 500, 655)[0]), u
+    for p in (d_data, d_off, d_goff):
+        engine.device_free(p)
+    d_data, d_off, d_goff, nbytes = engine.synth_reads_device(seed, 9, 5, 3, 150, 500, 655, read_base=4)
+    got = engine.d2h(d_data, nbytes).reshape(5, 3 * 150)
+    full = synth.synth_reads(seed, 9, 5, 7, 150, 500, 655)[0].reshape(5, 7 * 150)
+    assert np.array_equal(got, full[:, 4 * 150:])
+    for p in (d_data, d_off, d_goff):
+        engine.device_free(p)
 
 
 @pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
