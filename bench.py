@@ -102,12 +102,13 @@ class ClockSampler:
 
 
 def kernel_build_id() -> str:
-    """sha1 over the CUDA sources: ncu-derived counters are only quoted for the build they were captured on"""
+    """sha1 over the kernel sources (kernels_*.cuh and the device headers they share; the host-side files -- C ABI, drivers, path
+    finding, plugin -- do not change a kernel): ncu-derived counters are only quoted for the build they were captured on"""
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(ROOT, "rogtk_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
+        if f.startswith("kernels_") or f in ("common.cuh", "scan.cuh"):
             with open(os.path.join(d, f), "rb") as fh:
                 h.update(f.encode() + b"\0" + fh.read())
     return h.hexdigest()[:16]
@@ -436,6 +437,20 @@ def main():
         except Exception as exc:
             next_rows = dict(next_rows or {})
             next_rows["sweep"] = {"error": str(exc)[:200]}
+        try:   # the reference's default method on the same 20 000 groups: nodes + CSR on the device, path search on the host's cores
+            eng.assemble_sequences(sd[:R * L * 200], so[:R * 200 + 1], sg[:201], k=31, min_coverage=2, method="shortest_path_auto")
+            t0 = time.perf_counter()
+            sp = eng.assemble_sequences(sd, so, sg, k=31, min_coverage=2, method="shortest_path_auto")
+            dt_sp = time.perf_counter() - t0
+            lens = np.diff(sp.offsets)
+            next_rows["shortest_path_auto"] = {"umis": n_s, "wall_ms": dt_sp * 1e3, "ms_device": sp.ms_device, "ms_host_search": sp.ms_host,
+                                               "host_threads": os.cpu_count(), "groups_with_contig": int((lens > 0).sum()),
+                                               "mean_contig_bp": float(lens[lens > 0].mean()) if (lens > 0).any() else 0.0,
+                                               "api": "rogtk_gpu_assemble_batch(method=shortest_path_auto): count + CSR on the GPU, "
+                                                      "petgraph-exact search per group on the host (csrc/pathfind_host.h)"}
+        except Exception as exc:
+            next_rows = dict(next_rows or {})
+            next_rows["shortest_path_auto"] = {"error": str(exc)[:200]}
     if world > 1:
         spec = None
         try:

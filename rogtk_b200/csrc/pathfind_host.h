@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -77,8 +78,25 @@ struct PetGraph {
     std::vector<int32_t> out_head, in_head, out_next, in_next;
 };
 
+// -ln((cov_from + cov_to) / 2) for every possible sum of two u16 counts: the same libm call the per-edge expression makes (the sum
+// of two integers below 2^17 halves exactly in f64), computed once per process -- std::log was a third of a group's search time
+inline const double *edge_weight_table()
+{
+    static std::vector<double> tab;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        tab.resize(2 * 65535 + 1);
+        for (size_t sum = 0; sum < tab.size(); sum++) {
+            const double mean_cov = (double)sum / 2.0;
+            tab[sum] = -std::log(mean_cov);
+        }
+    });
+    return tab.data();
+}
+
 inline void build_petgraph(const GroupGraph &g, PetGraph &pg)
 {
+    const double *wtab = edge_weight_table();
     const int32_t n = g.n;
     pg.n = n;
     pg.node_of_pid.assign((size_t)n, 0);
@@ -94,12 +112,9 @@ inline void build_petgraph(const GroupGraph &g, PetGraph &pg)
     pg.out_next.clear(); pg.in_next.clear();
     for (int32_t pid = 0; pid < n; pid++) {   // djfind.rs:92-118: from nodes in id order, right edges in base order
         const int32_t i = pg.node_of_pid[(size_t)pid];
-        const double from_cov = (double)g.counts[i];
         for (int64_t e = g.row_ptr[i]; e < g.row_ptr[i + 1]; e++) {
             const int32_t j = g.col[e];
-            const double to_cov = (double)g.counts[j];
-            const double mean_cov = (from_cov + to_cov) / 2.0;
-            const double w = -std::log(mean_cov);
+            const double w = wtab[(size_t)g.counts[i] + (size_t)g.counts[j]];   // -ln((from_cov + to_cov) / 2.0), djfind.rs:103-106
             const int32_t to_pid = pg.pid_of_node[(size_t)j];
             const int32_t id = (int32_t)pg.e_from.size();
             pg.e_from.push_back(pid);
@@ -175,8 +190,12 @@ inline void petgraph_dijkstra(const PetGraph &pg, int32_t start, std::vector<dou
     const double none = std::numeric_limits<double>::quiet_NaN();
     score.assign((size_t)pg.n, none);
     has.assign((size_t)pg.n, 0);
-    std::vector<uint8_t> visited((size_t)pg.n, 0);
-    MinScoredHeap heap;
+    static thread_local std::vector<uint8_t> tl_visited;   // (one TLS lookup per call: the loop below works on references)
+    static thread_local MinScoredHeap tl_heap;
+    std::vector<uint8_t> &visited = tl_visited;
+    MinScoredHeap &heap = tl_heap;
+    visited.assign((size_t)pg.n, 0);
+    heap.d.clear();
     score[(size_t)start] = 0.0;
     has[(size_t)start] = 1;
     heap.push(0.0, start);
@@ -203,58 +222,69 @@ inline void petgraph_dijkstra(const PetGraph &pg, int32_t start, std::vector<dou
     }
 }
 
+// the custom back-trace of djfind.rs:176-228 from `end` to `start` over the scores of one dijkstra run; false when it breaks off
+inline bool trace_back(const PetGraph &pg, int32_t start, int32_t end, const std::vector<double> &dist, const std::vector<uint8_t> &has,
+                       std::vector<int32_t> &path)
+{
+    const size_t MAX_ITERATIONS = 1000;
+    const double FLOAT_EPSILON = 1e-9;
+    path.assign(1, end);
+    int32_t current = end;
+    bool path_valid = false;
+    size_t iterations = 0;
+    while (current != start) {
+        iterations++;
+        if (iterations > MAX_ITERATIONS) break;
+        int32_t best_prev = -1;
+        double best_dist = std::numeric_limits<double>::infinity();
+        const double current_dist = dist[(size_t)current];
+        for (int32_t e = pg.in_head[(size_t)current]; e >= 0; e = pg.in_next[(size_t)e]) {   // neighbors_directed(Incoming)
+            const int32_t neighbor = pg.e_from[(size_t)e];
+            if (!has[(size_t)neighbor]) continue;
+            // graph.find_edge(neighbor, current): the first match in neighbor's outgoing list (k-mer graphs have no
+            // parallel edges, so it is this edge's weight)
+            double edge_weight = pg.e_w[(size_t)e];
+            for (int32_t f = pg.out_head[(size_t)neighbor]; f >= 0; f = pg.out_next[(size_t)f])
+                if (pg.e_to[(size_t)f] == current) {
+                    edge_weight = pg.e_w[(size_t)f];
+                    break;
+                }
+            const double neighbor_dist = dist[(size_t)neighbor];
+            const double expected_dist = neighbor_dist + edge_weight;
+            if (std::fabs(expected_dist - current_dist) < FLOAT_EPSILON) {
+                if (neighbor_dist < best_dist) {
+                    best_dist = neighbor_dist;
+                    best_prev = neighbor;
+                }
+            }
+        }
+        if (best_prev < 0) break;
+        path.push_back(best_prev);
+        current = best_prev;
+        if (current == start) path_valid = true;
+    }
+    return path_valid;
+}
+
 // djfind.rs:157-247.  start_nodes / end_nodes are pids in node-index order.  Returns false when no valid path exists.
 inline bool find_shortest_path(const PetGraph &pg, const std::vector<int32_t> &start_nodes, const std::vector<int32_t> &end_nodes,
                                std::vector<int32_t> &best_path, double &best_weight)
 {
     bool found = false;
     double min_total_weight = std::numeric_limits<double>::infinity();
-    const size_t MAX_ITERATIONS = 1000;
-    const double FLOAT_EPSILON = 1e-9;
-    std::vector<double> dist;
-    std::vector<uint8_t> has;
+    static thread_local std::vector<double> tl_dist;
+    static thread_local std::vector<uint8_t> tl_has;
+    static thread_local std::vector<int32_t> tl_path;
+    std::vector<double> &dist = tl_dist;
+    std::vector<uint8_t> &has = tl_has;
+    std::vector<int32_t> &path = tl_path;
     for (const int32_t start : start_nodes) {
         petgraph_dijkstra(pg, start, dist, has);
         for (const int32_t end : end_nodes) {
             if (!has[(size_t)end]) continue;
             const double total_weight = dist[(size_t)end];
             if (!(total_weight < min_total_weight)) continue;
-            std::vector<int32_t> path{end};
-            int32_t current = end;
-            bool path_valid = false;
-            size_t iterations = 0;
-            while (current != start) {
-                iterations++;
-                if (iterations > MAX_ITERATIONS) break;
-                int32_t best_prev = -1;
-                double best_dist = std::numeric_limits<double>::infinity();
-                const double current_dist = dist[(size_t)current];
-                for (int32_t e = pg.in_head[(size_t)current]; e >= 0; e = pg.in_next[(size_t)e]) {   // neighbors_directed(Incoming)
-                    const int32_t neighbor = pg.e_from[(size_t)e];
-                    if (!has[(size_t)neighbor]) continue;
-                    // graph.find_edge(neighbor, current): the first match in neighbor's outgoing list (k-mer graphs have no
-                    // parallel edges, so it is this edge's weight)
-                    double edge_weight = pg.e_w[(size_t)e];
-                    for (int32_t f = pg.out_head[(size_t)neighbor]; f >= 0; f = pg.out_next[(size_t)f])
-                        if (pg.e_to[(size_t)f] == current) {
-                            edge_weight = pg.e_w[(size_t)f];
-                            break;
-                        }
-                    const double neighbor_dist = dist[(size_t)neighbor];
-                    const double expected_dist = neighbor_dist + edge_weight;
-                    if (std::fabs(expected_dist - current_dist) < FLOAT_EPSILON) {
-                        if (neighbor_dist < best_dist) {
-                            best_dist = neighbor_dist;
-                            best_prev = neighbor;
-                        }
-                    }
-                }
-                if (best_prev < 0) break;
-                path.push_back(best_prev);
-                current = best_prev;
-                if (current == start) path_valid = true;
-            }
-            if (path_valid) {
+            if (trace_back(pg, start, end, dist, has, path)) {
                 best_path.assign(path.rbegin(), path.rend());
                 best_weight = total_weight;
                 min_total_weight = total_weight;
@@ -306,7 +336,8 @@ inline PathResult path_between(const GroupGraph &g, const PetGraph &pg, const st
 inline std::string shortest_path_contig(const GroupGraph &g, const std::string &start_anchor, const std::string &end_anchor)
 {
     if (g.n == 0) return std::string();   // (the reference fails earlier: no k-mers, empty result either way)
-    PetGraph pg;
+    static thread_local PetGraph tl_pg;   // (vectors keep their capacity from group to group)
+    PetGraph &pg = tl_pg;
     build_petgraph(g, pg);
     const PathResult r = path_between(g, pg, start_anchor, end_anchor);
     return r.ok ? r.sequence : std::string();
@@ -316,7 +347,8 @@ inline std::string shortest_path_contig(const GroupGraph &g, const std::string &
 inline std::string shortest_path_auto_contig(const GroupGraph &g)
 {
     if (g.n == 0) return std::string();
-    PetGraph pg;
+    static thread_local PetGraph tl_pg;
+    PetGraph &pg = tl_pg;
     build_petgraph(g, pg);
     // find_endpoint_candidates
     double sum = 0.0;
@@ -347,14 +379,24 @@ inline std::string shortest_path_auto_contig(const GroupGraph &g)
     bool have = false;
     double best_score = 0.0;
     std::string best_seq;
+    std::vector<double> dist;
+    std::vector<uint8_t> has;
+    std::vector<int32_t> rpath, path;
     for (const int32_t s : start_c) {
+        bool have_dist = false;   // (the reference runs dijkstra(s) again for every t; the scores are the same)
         for (const int32_t t : end_c) {
             if (evaluated >= MAX_PAIRS) break;
             evaluated++;
             // (the reference matches the two full K-mer strings with contains(): only the candidates themselves qualify)
-            std::vector<int32_t> path;
-            double w = 0.0;
-            if (!find_shortest_path(pg, std::vector<int32_t>{s}, std::vector<int32_t>{t}, path, w)) continue;
+            if (!have_dist) {
+                petgraph_dijkstra(pg, s, dist, has);
+                have_dist = true;
+            }
+            if (!has[(size_t)t]) continue;
+            const double w = dist[(size_t)t];
+            if (!(w < std::numeric_limits<double>::infinity())) continue;   // find_shortest_path: total_weight < min_total_weight (inf)
+            if (!trace_back(pg, s, t, dist, has, rpath)) continue;
+            path.assign(rpath.rbegin(), rpath.rend());
             // score_path
             const double path_length = (double)(path.size() * (size_t)g.K);
             const double mean_coverage = 1.0 / (w / (double)path.size());
