@@ -27,6 +27,8 @@ import sys
 import threading
 import time
 
+import ctypes
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -437,17 +439,31 @@ def main():
         except Exception as exc:
             next_rows = dict(next_rows or {})
             next_rows["sweep"] = {"error": str(exc)[:200]}
-        try:   # the reference's default method on the same 20 000 groups: nodes + CSR on the device, path search on the host's cores
-            eng.assemble_sequences(sd, so, sg, k=31, min_coverage=2, method="shortest_path_auto")   # warm-up: page-locked result blocks get cached
-            t0 = time.perf_counter()
-            sp = eng.assemble_sequences(sd, so, sg, k=31, min_coverage=2, method="shortest_path_auto")
-            dt_sp = time.perf_counter() - t0
-            lens = np.diff(sp.offsets)
-            next_rows["shortest_path_auto"] = {"umis": n_s, "wall_ms": dt_sp * 1e3, "ms_device": sp.ms_device, "ms_host_search": sp.ms_host,
-                                               "host_threads": os.cpu_count(), "groups_with_contig": int((lens > 0).sum()),
+        try:   # the reference's default family of methods: count + CSR + path search per group, all on the device; reads resident in HBM in,
+            #    contigs on the host out (first 200 000 groups of the batch)
+            from rogtk_b200 import _ffi as _f2
+            n_p = min(n_umis, 200000)
+            dptr_p = (ctypes.c_void_p * 1)(d_data)
+            dlen_p = (ctypes.c_int64 * 1)(n_p * R * L)
+            col_p = _f2.StrCol(layout=_f2.UTF8_I64, n_buffers=1, n_rows=n_p * R, validity=None, validity_bit_offset=0, offsets_or_views=d_off,
+                               data=dptr_p, data_len=dlen_p)
+            ap_p = _f2.AssemblyParamsC(k=cfg["k"], min_coverage=cfg["min_cov"], method=_f2.METHODS["shortest_path_auto"], min_length=0, only_largest=1)
+            for _ in range(2):   # (the first call sizes the cached blocks)
+                so_p = _f2.StringBatchC()
+                t0 = time.perf_counter()
+                eng._check(eng._lib.rogtk_gpu_assemble_batch(eng._ctx, ctypes.byref(col_p), ctypes.c_void_p(d_goff), n_p, ctypes.byref(ap_p),
+                                                             _f2.INPUT_ON_DEVICE, ctypes.byref(so_p)))
+                dt_sp = time.perf_counter() - t0
+                offs_p = np.ctypeslib.as_array(ctypes.cast(so_p.offsets, ctypes.POINTER(ctypes.c_int64)), shape=(n_p + 1,)).copy()
+                ms_dev_p, ms_host_p = float(so_p.ms_device), float(so_p.ms_host)
+                eng._lib.rogtk_gpu_free_strings(eng._ctx, ctypes.byref(so_p))
+            lens = np.diff(offs_p)
+            next_rows = dict(next_rows or {})
+            next_rows["shortest_path_auto"] = {"umis": n_p, "wall_ms": dt_sp * 1e3, "ms_device": ms_dev_p, "ms_host": ms_host_p,
+                                               "groups_per_s": n_p / dt_sp, "groups_with_contig": int((lens > 0).sum()),
                                                "mean_contig_bp": float(lens[lens > 0].mean()) if (lens > 0).any() else 0.0,
-                                               "api": "rogtk_gpu_assemble_batch(method=shortest_path_auto): count + CSR on the GPU, "
-                                                      "petgraph-exact search per group on the host (csrc/pathfind_host.h)"}
+                                               "api": "rogtk_gpu_assemble_batch(method=shortest_path_auto, ROGTK_INPUT_ON_DEVICE): count + CSR + "
+                                                      "petgraph-exact search (one thread per group, csrc/pathfind_device.cuh) on the GPU"}
         except Exception as exc:
             next_rows = dict(next_rows or {})
             next_rows["shortest_path_auto"] = {"error": str(exc)[:200]}

@@ -221,7 +221,31 @@ void evaluate_cell(rogtk_gpu_ctx *ctx, CountedK &ck, uint32_t cov, int method, c
         }
         return;
     }
-    // path finding: node arrays + CSR of this threshold on the host
+    if (!node_rank && !ctx->host_pathfind) {
+        // path finding on the device: one thread per group runs the procedure of pathfind_core.h on the batch's nodes + CSR
+        rogtk_graph_batch t;
+        const int rc = rogtk_gpu_rethreshold(ctx, &ck.db, eff, ROGTK_EMIT_CSR | ROGTK_OUTPUT_ON_DEVICE, &t);
+        if (rc != ROGTK_OK) throw ArgFail{rc, ctx->last_error};
+        if (ms_device) *ms_device += t.ms_total;
+        HostStrings local;
+        HostStrings &dst = hs ? *hs : local;
+        try {
+            DevAnchors da;
+            da.s = an.s; da.e = an.e; da.so = an.so; da.eo = an.eo; da.sd = an.sd; da.ed = an.ed;
+            pathfind_rows_device(ctx, &t, method, da, min_length, dst.off, dst.data, ms_device);
+            dst.flags.assign((size_t)ng, 0);
+        } catch (...) {
+            rogtk_gpu_free_batch(ctx, &t);
+            throw;
+        }
+        rogtk_gpu_free_batch(ctx, &t);
+        if (lengths_only) {
+            lengths_only->assign((size_t)ng, 0);
+            for (int64_t g = 0; g < ng; g++) (*lengths_only)[(size_t)g] = dst.len(g);
+        }
+        return;
+    }
+    // path finding on the host (a boomphf node rank was given, or ROGTK_HOST_PATHFIND): node arrays + CSR of this threshold come back
     rogtk_graph_batch hb;
     const int rc = rogtk_gpu_rethreshold(ctx, &ck.db, eff, ROGTK_EMIT_CSR, &hb);
     if (rc != ROGTK_OK) throw ArgFail{rc, ctx->last_error};
@@ -433,8 +457,32 @@ extern "C" int rogtk_gpu_assemble_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
             counted.emplace_back();
             CountedK &ck = counted.back();
             out->n_count_passes++;
+            if (p->method != ROGTK_METHOD_COMPRESSION && !p->node_rank && !ctx->host_pathfind) {
+                // path finding on the device: nodes + successor CSR stay in HBM, one thread per group searches (pathfind_device.cuh)
+                rogtk_graph_batch t;
+                const uint32_t f = (flags & (ROGTK_INPUT_ON_DEVICE | ROGTK_EXACT_K | ROGTK_FORCE_SPILL | ROGTK_NO_MULTIPASS)) | ROGTK_EMIT_CSR |
+                                   ROGTK_OUTPUT_ON_DEVICE;
+                const int rc2 = rogtk_gpu_count_prune_batch(ctx, reads, group_offsets, n_groups, classes[ci], p->min_coverage, f, &t);
+                if (rc2 != ROGTK_OK) throw ArgFail{rc2, ctx->last_error};
+                out->ms_device += t.ms_total;
+                try {
+                    per_class[ci].off.assign((size_t)n_groups + 1, 0);
+                    per_class[ci].flags.assign((size_t)n_groups, 0);
+                    if (t.k_eff >= 0) {
+                        DevAnchors da;
+                        da.s = an.s; da.e = an.e; da.so = an.so; da.eo = an.eo; da.sd = an.sd; da.ed = an.ed;
+                        pathfind_rows_device(ctx, &t, p->method, da, min_length, per_class[ci].off, per_class[ci].data, &out->ms_device);
+                    }
+                } catch (...) {
+                    rogtk_gpu_free_batch(ctx, &t);
+                    throw;
+                }
+                rogtk_gpu_free_batch(ctx, &t);
+                continue;
+            }
             if (p->method != ROGTK_METHOD_COMPRESSION) {
-                // path finding runs on the host: node arrays + successor CSR straight to host memory (chunked, copies overlapped)
+                // path finding on the host (a boomphf node rank was given, or ROGTK_HOST_PATHFIND): node arrays + successor CSR straight
+                // to host memory (chunked, copies overlapped)
                 rogtk_graph_batch hb;
                 const uint32_t f = (flags & (ROGTK_INPUT_ON_DEVICE | ROGTK_EXACT_K | ROGTK_FORCE_SPILL | ROGTK_NO_MULTIPASS)) | ROGTK_EMIT_CSR;
                 const int rc2 = rogtk_gpu_count_prune_batch(ctx, reads, group_offsets, n_groups, classes[ci], p->min_coverage, f, &hb);

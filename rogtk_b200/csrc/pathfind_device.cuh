@@ -1,0 +1,190 @@
+// pathfind_device.cuh -- the shortest-path assembly methods on the device: ONE THREAD PER GROUP runs the
+// container-free procedure of pathfind_core.h -- the same source the host entries execute, so the result is petgraph's first-pop
+// Dijkstra with Rust's heap order, the 1e-9 back-trace and the automatic method's scoring, bit for bit (edge weights come from a table
+// filled on the host with libm's log).  The procedure is sequential per group by nature (a heap); the parallelism is across groups:
+// a frame has 10^5..10^6 of them.  Working arrays live in HBM (30 B per node + 24 B per edge), groups go in waves bounded by the
+// workspace.  Included by rogtk_gpu.cu after the context definition.
+#pragma once
+#include "pathfind_core.h"
+#include "pathfind_host.h"
+
+namespace {
+
+struct PathArgs {
+    int64_t g0, g1;                 // groups of this wave
+    const int64_t *kmer_offsets;
+    const uint64_t *lo, *hi;
+    const uint16_t *counts;
+    const int64_t *row_ptr;
+    const int32_t *col;
+    int K, method;
+    const char *sa, *ea;            // scalar anchors (device) ...
+    int sl, el;
+    const int64_t *so, *eo;         // ... or one pair per group (LargeUtf8 layout, device)
+    const uint8_t *sd, *ed;
+    const double *wtab;
+    int64_t o0, e0;                 // first node / first edge of the wave
+    int32_t *in_head, *list_a, *list_b, *path, *best_path;
+    double *score;
+    uint8_t *has, *visited;
+    int32_t *in_next, *e_from;
+    rogtk_pf::HeapItem *heap;
+    char *out;                      // slot of group g: kmer_offsets[g] + g * K  (n + K - 1 bytes at most)
+    int32_t *out_len;               // [n_groups]
+    int64_t min_length;
+};
+
+__global__ void __launch_bounds__(128) k_pathfind(PathArgs a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = a.g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < a.g1; g += stride) {
+        const int64_t o = a.kmer_offsets[g];
+        const int64_t n = a.kmer_offsets[g + 1] - o;
+        if (n <= 0) {
+            a.out_len[g] = 0;
+            continue;
+        }
+        const int64_t ln = o - a.o0, le = a.row_ptr[o] - a.e0, gi = g - a.g0;
+        const rogtk_pf::View v{a.K, (int32_t)n, a.lo + o, a.hi ? a.hi + o : nullptr, a.counts + o, a.row_ptr + o, a.col, a.wtab};
+        const rogtk_pf::Scratch s{a.in_head + ln, a.in_next + le, a.e_from + le, a.score + ln, a.has + ln, a.visited + ln, a.heap + le + gi,
+                                  a.path + ln + gi, a.best_path + ln + gi, a.list_a + ln, a.list_b + ln};
+        char *out = a.out + o + g * a.K;
+        int32_t len;
+        if (a.method == ROGTK_METHOD_SHORTEST_PATH) {
+            const char *sa = a.so ? reinterpret_cast<const char *>(a.sd) + a.so[g] : a.sa;
+            const char *ea = a.eo ? reinterpret_cast<const char *>(a.ed) + a.eo[g] : a.ea;
+            const int sl = a.so ? (int)(a.so[g + 1] - a.so[g]) : a.sl;
+            const int el = a.eo ? (int)(a.eo[g + 1] - a.eo[g]) : a.el;
+            len = rogtk_pf::anchored_contig(v, s, sa, sl, ea, el, out);
+        } else {
+            len = rogtk_pf::auto_contig(v, s, out);
+        }
+        a.out_len[g] = (int64_t)len >= a.min_length ? len : 0;   // src/fracture.rs:258-262
+    }
+}
+
+// edges before every group: dst[g] = row_ptr[kmer_offsets[g]], g in [0, n_groups]
+__global__ void k_group_edge_base(const int64_t *kmer_offsets, const int64_t *row_ptr, int64_t n_groups, int64_t *dst)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g <= n_groups) dst[g] = row_ptr[kmer_offsets[g]];
+}
+
+struct DevAnchors {   // what pathfind_rows_device needs from the caller's anchors (host pointers)
+    const char *s = nullptr, *e = nullptr;
+    const int64_t *so = nullptr, *eo = nullptr;
+    const uint8_t *sd = nullptr, *ed = nullptr;
+};
+
+// db: device-resident batch WITH its successor CSR.  One string per group into off / data (host vectors), "" where there is no contig.
+void pathfind_rows_device(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *db, int method, const DevAnchors &an, int64_t min_length,
+                          std::vector<int64_t> &off, std::vector<uint8_t> &data, float *ms_device)
+{
+    const int64_t ng = db->n_groups, N = db->n_kmers;
+    const int K = db->k_eff;
+    off.assign((size_t)ng + 1, 0);
+    data.clear();
+    if (ng == 0 || N == 0 || K < 1) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CacheScope cache_scope(ctx->cache);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (!ctx->d_wtab) {   // -ln(sum / 2) for every sum of two u16 counts, from the host's libm (pathfind_host.h)
+        CK(cudaMalloc(&ctx->d_wtab, (2 * 65535 + 1) * sizeof(double)));
+        CK(cudaMemcpy(ctx->d_wtab, rogtk_host::edge_weight_table(), (2 * 65535 + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // group sizes on the host: nodes from kmer_offsets, edges from row_ptr at the group starts
+    std::vector<int64_t> h_off((size_t)ng + 1), h_eb((size_t)ng + 1);
+    {
+        DevBuf eb((size_t)(ng + 1) * 8, st);
+        k_group_edge_base<<<blocks_for(ng + 1, 256), 256, 0, st>>>(db->kmer_offsets, db->csr_row_ptr, ng, eb.as<int64_t>());
+        ctx->launches++;
+        CK(cudaMemcpyAsync(h_off.data(), db->kmer_offsets, (size_t)(ng + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_eb.data(), eb.p, (size_t)(ng + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    // anchors
+    DevBuf d_sa, d_ea, d_so, d_eo, d_sd, d_ed;
+    PathArgs a{};
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+        b.alloc(std::max<size_t>(bytes, 16), st);
+        if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+    };
+    if (method == ROGTK_METHOD_SHORTEST_PATH) {
+        if (an.so) {
+            up(d_so, an.so, (size_t)(ng + 1) * 8);
+            up(d_eo, an.eo, (size_t)(ng + 1) * 8);
+            up(d_sd, an.sd, (size_t)an.so[ng]);
+            up(d_ed, an.ed, (size_t)an.eo[ng]);
+            a.so = d_so.as<int64_t>(); a.eo = d_eo.as<int64_t>(); a.sd = d_sd.as<uint8_t>(); a.ed = d_ed.as<uint8_t>();
+        } else {
+            a.sl = an.s ? (int)strlen(an.s) : 0;
+            a.el = an.e ? (int)strlen(an.e) : 0;
+            up(d_sa, an.s, (size_t)a.sl);
+            up(d_ea, an.e, (size_t)a.el);
+            a.sa = d_sa.as<char>(); a.ea = d_ea.as<char>();
+        }
+    }
+    a.kmer_offsets = db->kmer_offsets; a.lo = db->kmers_lo; a.hi = K > 32 ? db->kmers_hi : nullptr; a.counts = db->counts;
+    a.row_ptr = db->csr_row_ptr; a.col = db->csr_col; a.K = K; a.method = method; a.wtab = ctx->d_wtab; a.min_length = min_length;
+    const size_t out_bytes = (size_t)N + (size_t)ng * (size_t)K + 16;
+    DevBuf d_out(out_bytes, st), d_len((size_t)ng * 4, st);
+    a.out = d_out.as<char>(); a.out_len = d_len.as<int32_t>();
+    CK(cudaEventRecord(ctx->ev[12], st));
+    // waves: 30 B per node + 24 B per edge + per-group slack within half the workspace
+    const int64_t budget = std::max<int64_t>(64 << 20, (int64_t)(ctx->workspace_bytes / 2));
+    int64_t g0 = 0;
+    while (g0 < ng) {
+        int64_t g1 = g0, bytes = 0;
+        while (g1 < ng) {
+            const int64_t n = h_off[(size_t)g1 + 1] - h_off[(size_t)g1], m = h_eb[(size_t)g1 + 1] - h_eb[(size_t)g1];
+            const int64_t need = 30 * n + 24 * m + 64;
+            if (g1 > g0 && bytes + need > budget) break;
+            bytes += need;
+            g1++;
+        }
+        const int64_t nw = h_off[(size_t)g1] - h_off[(size_t)g0], mw = h_eb[(size_t)g1] - h_eb[(size_t)g0], gw = g1 - g0;
+        const size_t nn = (size_t)std::max<int64_t>(nw, 1), mm = (size_t)std::max<int64_t>(mw, 1), gg = (size_t)gw + 2;
+        DevBuf in_head(nn * 4, st), list_a(nn * 4, st), list_b(nn * 4, st), path((nn + gg) * 4, st), best_path((nn + gg) * 4, st), score(nn * 8, st),
+            has(nn, st), visited(nn, st), in_next(mm * 4, st), e_from(mm * 4, st), heap((mm + gg) * sizeof(rogtk_pf::HeapItem), st);
+        a.g0 = g0; a.g1 = g1; a.o0 = h_off[(size_t)g0]; a.e0 = h_eb[(size_t)g0];
+        a.in_head = in_head.as<int32_t>(); a.list_a = list_a.as<int32_t>(); a.list_b = list_b.as<int32_t>(); a.path = path.as<int32_t>();
+        a.best_path = best_path.as<int32_t>(); a.score = score.as<double>(); a.has = has.as<uint8_t>(); a.visited = visited.as<uint8_t>();
+        a.in_next = in_next.as<int32_t>(); a.e_from = e_from.as<int32_t>(); a.heap = heap.as<rogtk_pf::HeapItem>();
+        const unsigned grid = (unsigned)std::min<int64_t>((gw + 127) / 128, (int64_t)ctx->sm_count * 16);
+        k_pathfind<<<grid, 128, 0, st>>>(a);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(st));   // (the wave's buffers are reused by the next one)
+        g0 = g1;
+    }
+    CK(cudaEventRecord(ctx->ev[13], st));
+    // strings to the host: lengths, then the slots that hold something
+    std::vector<int32_t> h_len((size_t)ng);
+    CK(cudaMemcpyAsync(h_len.data(), d_len.p, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int64_t g = 0; g < ng; g++) off[(size_t)g + 1] = off[(size_t)g] + h_len[(size_t)g];
+    data.resize((size_t)off[(size_t)ng]);
+    if (!data.empty()) {
+        uint8_t *h_out = (uint8_t *)pinned_get(ctx, out_bytes);
+        try {
+            CK(cudaMemcpyAsync(h_out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            host_parallel(ng, ctx->stage_threads, 4096, [&](int64_t x0, int64_t x1) {
+                for (int64_t g = x0; g < x1; g++)
+                    if (h_len[(size_t)g]) memcpy(data.data() + off[(size_t)g], h_out + h_off[(size_t)g] + g * K, (size_t)h_len[(size_t)g]);
+            });
+        } catch (...) {
+            pinned_put(ctx, h_out);
+            throw;
+        }
+        pinned_put(ctx, h_out);
+    }
+    if (ms_device) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        *ms_device += ms;
+    }
+    CK(cudaGetLastError());
+}
+
+}  // namespace

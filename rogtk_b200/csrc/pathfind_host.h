@@ -19,6 +19,7 @@
 // Everything order-dependent (edge insertion, anchor lists, tie-breaks) is derived from the ids, so a Rust host that passes the
 // boomphf order gets the reference's tie behaviour.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -26,6 +27,8 @@
 #include <mutex>
 #include <string>
 #include <vector>
+
+#include "pathfind_core.h"
 
 namespace rogtk_host {
 
@@ -332,10 +335,42 @@ inline PathResult path_between(const GroupGraph &g, const PetGraph &pg, const st
     return r;
 }
 
+// Without a boomphf rank the node ids are the ascending order and the container-free procedure of pathfind_core.h applies -- the
+// code the GPU runs per group (k_pathfind); with a rank the petgraph restatement above is used.
+struct CoreScratch {
+    std::vector<int32_t> in_head, in_next, e_from, path, best_path, list_a, list_b;
+    std::vector<double> score;
+    std::vector<uint8_t> has, visited;
+    std::vector<rogtk_pf::HeapItem> heap;
+    std::vector<char> out;
+    rogtk_pf::Scratch bind(int32_t n, int32_t m, int K)
+    {
+        const size_t pn = (size_t)std::min<int32_t>(n, rogtk_pf::PF_MAX_ITERATIONS + 1) + 1;
+        in_head.resize((size_t)n); in_next.resize((size_t)m + 1); e_from.resize((size_t)m + 1);
+        score.resize((size_t)n); has.resize((size_t)n); visited.resize((size_t)n); heap.resize((size_t)m + 2);
+        path.resize(pn); best_path.resize(pn); list_a.resize((size_t)n); list_b.resize((size_t)n);
+        out.resize((size_t)n + (size_t)K + 8);
+        return rogtk_pf::Scratch{in_head.data(), in_next.data(), e_from.data(), score.data(), has.data(), visited.data(), heap.data(),
+                                 path.data(), best_path.data(), list_a.data(), list_b.data()};
+    }
+};
+inline std::string core_contig(const GroupGraph &g, const std::string *start_anchor, const std::string *end_anchor)
+{
+    static thread_local CoreScratch tl;
+    CoreScratch &cs = tl;
+    rogtk_pf::View v{g.K, g.n, g.lo, g.hi, g.counts, g.row_ptr, g.col, edge_weight_table()};
+    const rogtk_pf::Scratch s = cs.bind(g.n, rogtk_pf::edge_count(v), g.K);
+    const int32_t len = start_anchor ? rogtk_pf::anchored_contig(v, s, start_anchor->data(), (int)start_anchor->size(), end_anchor->data(),
+                                                                 (int)end_anchor->size(), cs.out.data())
+                                     : rogtk_pf::auto_contig(v, s, cs.out.data());
+    return std::string(cs.out.data(), (size_t)len);
+}
+
 // AssemblyMethod::ShortestPath (reference src/fracture.rs:385-416): the contig, or "" when anchors / path are missing
 inline std::string shortest_path_contig(const GroupGraph &g, const std::string &start_anchor, const std::string &end_anchor)
 {
     if (g.n == 0) return std::string();   // (the reference fails earlier: no k-mers, empty result either way)
+    if (!g.rank) return core_contig(g, &start_anchor, &end_anchor);
     static thread_local PetGraph tl_pg;   // (vectors keep their capacity from group to group)
     PetGraph &pg = tl_pg;
     build_petgraph(g, pg);
@@ -347,6 +382,7 @@ inline std::string shortest_path_contig(const GroupGraph &g, const std::string &
 inline std::string shortest_path_auto_contig(const GroupGraph &g)
 {
     if (g.n == 0) return std::string();
+    if (!g.rank) return core_contig(g, nullptr, nullptr);
     static thread_local PetGraph tl_pg;
     PetGraph &pg = tl_pg;
     build_petgraph(g, pg);

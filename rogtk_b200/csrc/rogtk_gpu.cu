@@ -53,6 +53,8 @@ struct rogtk_gpu_ctx {
     std::string last_error;
     int64_t launches = 0;
     uint8_t *peek_slot = nullptr;   // mapped pinned words the counter reads land in (host_util.cuh: Peek)
+    double *d_wtab = nullptr;       // edge-weight table of the device path search (pathfind_device.cuh)
+    bool host_pathfind = false;     // ROGTK_HOST_PATHFIND: run the shortest-path methods on the host cores instead
     int sm_count = 148;
     size_t smem_optin = 0;
     void *flush_buf = nullptr;
@@ -393,6 +395,7 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
             const unsigned hw = std::thread::hardware_concurrency();
             ctx->stage_threads = (int)std::min(16u, std::max(1u, hw / 2));
             if (const char *e = getenv("ROGTK_STAGE_THREADS")) ctx->stage_threads = std::max(1, atoi(e));
+            if (const char *e = getenv("ROGTK_HOST_PATHFIND")) ctx->host_pathfind = atoi(e) != 0;
         }
         if (const char *e = getenv("ROGTK_DEBUG_POOL_CAP")) ctx->tune.debug_pool_cap = atoll(e);   // tests: exhaust the survivor pool
         if (const char *e = getenv("ROGTK_WALK_RL")) {   // experiments: 0 = round-1 counting kernel, 3..6 = log2(windows per lane range)
@@ -430,6 +433,7 @@ extern "C" void rogtk_gpu_destroy(rogtk_gpu_ctx *ctx)
     for (auto &kv : ctx->pinned_size) cudaFreeHost(kv.first);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->peek_slot) cudaFreeHost(ctx->peek_slot);
+    if (ctx->d_wtab) cudaFree(ctx->d_wtab);
     if (ctx->cache) {   // the context's device memory goes away with it (nobody else's cached memory is touched)
         cudaDeviceSynchronize();
         delete ctx->cache;
@@ -2221,6 +2225,7 @@ extern "C" int rogtk_gpu_flush_l2(rogtk_gpu_ctx *ctx)
     return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? ROGTK_OK : ROGTK_ERR_CUDA;
 }
 
+#include "pathfind_device.cuh"
 #include "assemble_host.cuh"
 #include "multi_host.cuh"
 #include "spectrum_nccl.cuh"

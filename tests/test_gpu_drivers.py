@@ -309,3 +309,37 @@ def test_fracture_entries_mirror_the_pyo3_functions(engine, oracle, tmp_path):
         rogtk_b200.fracture_fasta(str(fa), 20, 1, min_length=5000, engine=engine)
     with pytest.raises(ValueError, match="No contigs found"):
         rogtk_b200.fracture_fasta(str(fa), 70, 1, min_length=1, engine=engine)   # k > 64: no contigs (src/fracture.rs:286-289)
+
+
+def test_path_search_on_the_device_equals_the_host_route(oracle, monkeypatch):
+    """The shortest-path methods run per group on the device (one thread per group, pathfind_device.cuh executing pathfind_core.h);
+    ROGTK_HOST_PATHFIND=1 keeps them on the host cores (the route a boomphf node_rank takes).  Same strings, for scalar and per-group
+    anchors, the automatic method, K = 16 / 32 / 64, min_length, and with a workspace small enough for several waves; both equal the
+    oracle's petgraph restatement."""
+    import rogtk_b200
+    rng = np.random.default_rng(77)
+    groups, templates = _template_groups(rng, 300, 14, 90, 220, err=0.02)
+    groups[17] = []
+    groups[40] = [groups[40][0]]
+    data, offs, val, goff = groups_to_arrow(groups)
+    sl = [t[:7] for t in templates]
+    el = [t[-7:] for t in templates]
+    monkeypatch.setenv("ROGTK_HOST_PATHFIND", "1")
+    with rogtk_b200.Engine(device=0) as host_eng:
+        monkeypatch.delenv("ROGTK_HOST_PATHFIND")
+        with rogtk_b200.Engine(device=0) as dev_eng, rogtk_b200.Engine(device=0, workspace_bytes=1 << 20) as small_eng:
+            for k, mc in ((13, 1), (21, 2), (40, 1)):
+                for kw in (dict(method="shortest_path_auto"), dict(method="shortest_path", anchors_per_group=(sl, el)),
+                           dict(method="shortest_path", start_anchor=templates[3][:6], end_anchor=templates[3][-6:]),
+                           dict(method="shortest_path_auto", min_length=150)):
+                    want = host_eng.assemble_sequences(data, offs, goff, k=k, min_coverage=mc, validity=val, **kw).strings()
+                    got = dev_eng.assemble_sequences(data, offs, goff, k=k, min_coverage=mc, validity=val, **kw).strings()
+                    assert got == want, (k, mc, kw.get("method"))
+                    assert small_eng.assemble_sequences(data, offs, goff, k=k, min_coverage=mc, validity=val, **kw).strings() == want
+                    if k == 13 and "start_anchor" not in kw:   # (at min_coverage 2 / K = 64 the template ends are rarely covered)
+                        assert sum(1 for s in got if s) > 200
+            # and against the oracle (per-group anchors, K = 32)
+            got = dev_eng.assemble_sequences(data, offs, goff, k=21, min_coverage=2, validity=val, method="shortest_path", anchors_per_group=(sl, el)).strings()
+            for g, reads in enumerate(groups):
+                want, _ = oracle.assemble_sequences_py([r for r in reads if r is not None], 21, 2, "shortest_path", sl[g], el[g], only_largest=True)
+                assert got[g] == (want[0] if want else ""), g

@@ -84,6 +84,10 @@ def test_host_path_matches_python_restatement(lib, oracle, k, alphabet, n_reads,
                 assert got == want, (k, mc, g, sa, ea)
                 n_found += want is not None
             assert _host_path(lib, b, g, None, None) == oracle.auto_path_finding_contig(nodes, K), (k, mc, g, "auto")
+            # no rank: the container-free procedure the GPU runs per group (pathfind_core.h); identity rank: the petgraph restatement
+            ident = np.arange(len(nodes))
+            for (sa, ea) in ((t[:5], t[-5:]), ("", ""), (None, None)):
+                assert _host_path(lib, b, g, sa, ea) == _host_path(lib, b, g, sa, ea, rank=ident), (k, mc, g, sa, ea, "core vs petgraph")
             # a permuted node order changes edge insertion order, anchor order and tie-breaks consistently on both sides
             perm = rng.permutation(len(nodes))          # rank[i] = id of ascending node i
             order = [None] * len(nodes)
