@@ -515,7 +515,6 @@ def main():
     e2e = None
     cpu = None
     if not args.no_e2e:
-        import ctypes
         # host memory is shared by all ranks of the node: the e2e leg takes the first e_umis UMIs of the rank's shard, as many
         # as fit in 40 % of the available host memory divided by the ranks (pinned input + pinned result, ~27 KB per UMI)
         try:
