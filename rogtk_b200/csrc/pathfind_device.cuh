@@ -32,7 +32,9 @@ struct PathArgs {
     char *out;                      // slot of group g: kmer_offsets[g] + g * K  (n + K - 1 bytes at most)
     int32_t *out_len;               // [n_groups]
     int64_t min_length;
+    int64_t max_nodes;              // larger groups are left to the host (one thread would take seconds for 10^4..10^5 nodes)
 };
+constexpr int64_t PF_DEVICE_MAX_NODES = 4096;
 
 __global__ void __launch_bounds__(128) k_pathfind(PathArgs a)
 {
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(128) k_pathfind(PathArgs a)
     for (int64_t g = a.g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < a.g1; g += stride) {
         const int64_t o = a.kmer_offsets[g];
         const int64_t n = a.kmer_offsets[g + 1] - o;
-        if (n <= 0) {
+        if (n <= 0 || n > a.max_nodes) {
             a.out_len[g] = 0;
             continue;
         }
@@ -127,6 +129,7 @@ void pathfind_rows_device(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *db, int m
     }
     a.kmer_offsets = db->kmer_offsets; a.lo = db->kmers_lo; a.hi = K > 32 ? db->kmers_hi : nullptr; a.counts = db->counts;
     a.row_ptr = db->csr_row_ptr; a.col = db->csr_col; a.K = K; a.method = method; a.wtab = ctx->d_wtab; a.min_length = min_length;
+    a.max_nodes = PF_DEVICE_MAX_NODES;
     const size_t out_bytes = (size_t)N + (size_t)ng * (size_t)K + 16;
     DevBuf d_out(out_bytes, st), d_len((size_t)ng * 4, st);
     a.out = d_out.as<char>(); a.out_len = d_len.as<int32_t>();
@@ -138,7 +141,7 @@ void pathfind_rows_device(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *db, int m
         int64_t g1 = g0, bytes = 0;
         while (g1 < ng) {
             const int64_t n = h_off[(size_t)g1 + 1] - h_off[(size_t)g1], m = h_eb[(size_t)g1 + 1] - h_eb[(size_t)g1];
-            const int64_t need = 30 * n + 24 * m + 64;
+            const int64_t need = 30 * n + 24 * m + 64;   // (groups the kernel skips keep their place: the arrays are indexed by node / edge offset)
             if (g1 > g0 && bytes + need > budget) break;
             bytes += need;
             g1++;
@@ -162,6 +165,54 @@ void pathfind_rows_device(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *db, int m
     std::vector<int32_t> h_len((size_t)ng);
     CK(cudaMemcpyAsync(h_len.data(), d_len.p, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    // groups beyond PF_DEVICE_MAX_NODES: their arrays come to the host and the same procedure runs there, one group per core
+    std::vector<int64_t> big;
+    for (int64_t g = 0; g < ng; g++)
+        if (h_off[(size_t)g + 1] - h_off[(size_t)g] > PF_DEVICE_MAX_NODES) big.push_back(g);
+    std::vector<std::string> big_rows(big.size());
+    if (!big.empty()) {
+        struct HostGroup {
+            std::vector<uint64_t> lo, hi;
+            std::vector<uint16_t> counts;
+            std::vector<int64_t> row_ptr;
+            std::vector<int32_t> col;
+        };
+        std::vector<HostGroup> hg(big.size());
+        for (size_t b = 0; b < big.size(); b++) {
+            const int64_t g = big[b], o = h_off[(size_t)g], n = h_off[(size_t)g + 1] - o, e0 = h_eb[(size_t)g], m = h_eb[(size_t)g + 1] - e0;
+            HostGroup &x = hg[b];
+            x.lo.resize((size_t)n); x.counts.resize((size_t)n); x.row_ptr.resize((size_t)n + 1); x.col.resize((size_t)std::max<int64_t>(m, 1));
+            CK(cudaMemcpyAsync(x.lo.data(), db->kmers_lo + o, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            if (K > 32) {
+                x.hi.resize((size_t)n);
+                CK(cudaMemcpyAsync(x.hi.data(), db->kmers_hi + o, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            }
+            CK(cudaMemcpyAsync(x.counts.data(), db->counts + o, (size_t)n * 2, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(x.row_ptr.data(), db->csr_row_ptr + o, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+            if (m) CK(cudaMemcpyAsync(x.col.data(), db->csr_col + e0, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        host_parallel((int64_t)big.size(), ctx->stage_threads, 1, [&](int64_t x0, int64_t x1) {
+            for (int64_t b = x0; b < x1; b++) {
+                HostGroup &x = hg[(size_t)b];
+                const int64_t g = big[(size_t)b], base = x.row_ptr[0];
+                for (auto &v : x.row_ptr) v -= base;   // col holds this group's rows only
+                rogtk_host::GroupGraph gg;
+                gg.K = K; gg.n = (int32_t)x.lo.size(); gg.lo = x.lo.data(); gg.hi = K > 32 ? x.hi.data() : nullptr; gg.counts = x.counts.data();
+                gg.row_ptr = x.row_ptr.data(); gg.col = x.col.data();
+                std::string c;
+                if (method == ROGTK_METHOD_SHORTEST_PATH) {
+                    const std::string sa = an.so ? std::string((const char *)an.sd + an.so[g], (size_t)(an.so[g + 1] - an.so[g])) : std::string(an.s ? an.s : "");
+                    const std::string ea = an.eo ? std::string((const char *)an.ed + an.eo[g], (size_t)(an.eo[g + 1] - an.eo[g])) : std::string(an.e ? an.e : "");
+                    c = rogtk_host::shortest_path_contig(gg, sa, ea);
+                } else {
+                    c = rogtk_host::shortest_path_auto_contig(gg);
+                }
+                if ((int64_t)c.size() >= min_length) big_rows[(size_t)b] = std::move(c);
+            }
+        });
+        for (size_t b = 0; b < big.size(); b++) h_len[(size_t)big[b]] = (int32_t)big_rows[b].size();
+    }
     for (int64_t g = 0; g < ng; g++) off[(size_t)g + 1] = off[(size_t)g] + h_len[(size_t)g];
     data.resize((size_t)off[(size_t)ng]);
     if (!data.empty()) {
@@ -171,13 +222,16 @@ void pathfind_rows_device(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *db, int m
             CK(cudaStreamSynchronize(st));
             host_parallel(ng, ctx->stage_threads, 4096, [&](int64_t x0, int64_t x1) {
                 for (int64_t g = x0; g < x1; g++)
-                    if (h_len[(size_t)g]) memcpy(data.data() + off[(size_t)g], h_out + h_off[(size_t)g] + g * K, (size_t)h_len[(size_t)g]);
+                    if (h_len[(size_t)g] && h_off[(size_t)g + 1] - h_off[(size_t)g] <= PF_DEVICE_MAX_NODES)
+                        memcpy(data.data() + off[(size_t)g], h_out + h_off[(size_t)g] + g * K, (size_t)h_len[(size_t)g]);
             });
         } catch (...) {
             pinned_put(ctx, h_out);
             throw;
         }
         pinned_put(ctx, h_out);
+        for (size_t b = 0; b < big.size(); b++)
+            if (!big_rows[b].empty()) memcpy(data.data() + off[(size_t)big[b]], big_rows[b].data(), big_rows[b].size());
     }
     if (ms_device) {
         float ms = 0;

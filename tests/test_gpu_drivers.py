@@ -338,6 +338,17 @@ def test_path_search_on_the_device_equals_the_host_route(oracle, monkeypatch):
                     assert small_eng.assemble_sequences(data, offs, goff, k=k, min_coverage=mc, validity=val, **kw).strings() == want
                     if k == 13 and "start_anchor" not in kw:   # (at min_coverage 2 / K = 64 the template ends are rarely covered)
                         assert sum(1 for s in got if s) > 200
+            # a group beyond the device kernel's node limit (4096) is searched on the host inside the same call
+            big_t = "".join(rng.choice(list("ACGT"), 7000))
+            big = [big_t[i:i + 150] for i in range(0, 7000 - 150, 40)] + [big_t[:150], big_t[-150:]]
+            d2, o2, v2, g2 = groups_to_arrow([groups[0], big, groups[1]])
+            # (a path of more than 1001 nodes does not exist for the reference: its back-trace gives up after 1000 steps, src/djfind.rs:185)
+            for kw in (dict(method="shortest_path_auto"), dict(method="shortest_path", start_anchor=big_t[:8], end_anchor=big_t[-8:]),
+                       dict(method="shortest_path", start_anchor=big_t[:8], end_anchor=big_t[892:900])):
+                want = host_eng.assemble_sequences(d2, o2, g2, k=21, min_coverage=1, validity=v2, **kw).strings()
+                got = dev_eng.assemble_sequences(d2, o2, g2, k=21, min_coverage=1, validity=v2, **kw).strings()
+                assert got == want
+            assert got[1] == big_t[:900]
             # and against the oracle (per-group anchors, K = 32)
             got = dev_eng.assemble_sequences(data, offs, goff, k=21, min_coverage=2, validity=val, method="shortest_path", anchors_per_group=(sl, el)).strings()
             for g, reads in enumerate(groups):
