@@ -40,13 +40,21 @@ struct View {   // one group's pruned nodes (ascending) + successor CSR rows
     const double *wtab;          // [131071] -ln(sum / 2)
 };
 
+// what the search keeps per node / per edge, packed so that one 32-byte sector answers a relaxation (the device kernel is bound by
+// scattered sector traffic: score, flags, count and list head of a node used to live in four arrays)
+struct NodeRec {
+    double score;
+    int32_t in_head;
+    uint16_t count;
+    uint8_t has, visited;
+};
+struct EdgeRec {
+    int32_t in_next, e_from;
+};
+
 struct Scratch {   // all sized by the group: n nodes, m = row_ptr[n] - row_ptr[0] edges
-    int32_t *in_head;    // [n]
-    int32_t *in_next;    // [m]
-    int32_t *e_from;     // [m]
-    double *score;       // [n]
-    uint8_t *has;        // [n]
-    uint8_t *visited;    // [n]
+    NodeRec *node;       // [n]
+    EdgeRec *edge;       // [m]
     HeapItem *heap;      // [m + 1]
     int32_t *path;       // [min(n, 1001) + 1]  back-trace, end first
     int32_t *best_path;  // [min(n, 1001) + 1]  best so far, start first
@@ -80,26 +88,30 @@ PF_HD bool kmer_ends_with(const View &g, int32_t i, const char *a, int len)
 }
 
 PF_HD int32_t edge_count(const View &g) { return (int32_t)(g.row_ptr[g.n] - g.row_ptr[0]); }
-PF_HD double edge_weight(const View &g, int32_t from, int32_t e)   // e: group-local edge id
+PF_HD double edge_weight(const View &g, const Scratch &s, int32_t from, int32_t to)
 {
-    const int32_t to = g.col[g.row_ptr[0] + e];
-    return g.wtab[(uint32_t)g.counts[from] + (uint32_t)g.counts[to]];
+    return g.wtab[(uint32_t)s.node[from].count + (uint32_t)s.node[to].count];
 }
 PF_HD int32_t edge_to(const View &g, int32_t e) { return g.col[g.row_ptr[0] + e]; }
 // node's outgoing edges newest first: e = out_first(i), then e - 1 while e >= out_last(i)
 PF_HD int32_t out_first(const View &g, int32_t i) { return (int32_t)(g.row_ptr[i + 1] - g.row_ptr[0]) - 1; }
 PF_HD int32_t out_last(const View &g, int32_t i) { return (int32_t)(g.row_ptr[i] - g.row_ptr[0]); }
 
-// incoming lists (newest edge first) + the source of every edge
+// incoming lists (newest edge first), the source of every edge, the node records
 PF_HD void build_in_lists(const View &g, const Scratch &s)
 {
-    for (int32_t i = 0; i < g.n; i++) s.in_head[i] = -1;
+    for (int32_t i = 0; i < g.n; i++) {
+        s.node[i].in_head = -1;
+        s.node[i].count = g.counts[i];
+        s.node[i].has = 0;
+        s.node[i].visited = 0;
+    }
     for (int32_t i = 0; i < g.n; i++)
         for (int32_t e = out_last(g, i); e <= out_first(g, i); e++) {
             const int32_t to = edge_to(g, e);
-            s.e_from[e] = i;
-            s.in_next[e] = s.in_head[to];
-            s.in_head[to] = e;
+            s.edge[e].e_from = i;
+            s.edge[e].in_next = s.node[to].in_head;
+            s.node[to].in_head = e;
         }
 }
 
@@ -157,33 +169,35 @@ PF_HD bool heap_pop(HeapItem *d, int32_t &size, HeapItem &out)
 PF_HD void dijkstra(const View &g, const Scratch &s, int32_t start)
 {
     for (int32_t i = 0; i < g.n; i++) {
-        s.has[i] = 0;
-        s.visited[i] = 0;
+        s.node[i].has = 0;
+        s.node[i].visited = 0;
     }
     int32_t size = 0;
-    s.score[start] = 0.0;
-    s.has[start] = 1;
+    s.node[start].score = 0.0;
+    s.node[start].has = 1;
     heap_push(s.heap, size, 0.0, start);
     HeapItem it;
     while (heap_pop(s.heap, size, it)) {
         const int32_t node = it.node;
-        if (s.visited[node]) continue;
+        if (s.node[node].visited) continue;
+        const uint32_t node_count = s.node[node].count;
         for (int32_t e = out_first(g, node); e >= out_last(g, node); e--) {   // graph.edges(node): newest edge first
             const int32_t next = edge_to(g, e);
-            if (s.visited[next]) continue;
-            const double next_score = it.score + edge_weight(g, node, e);
-            if (s.has[next]) {
-                if (next_score < s.score[next]) {
-                    s.score[next] = next_score;
+            NodeRec &nx = s.node[next];
+            if (nx.visited) continue;
+            const double next_score = it.score + g.wtab[node_count + (uint32_t)nx.count];
+            if (nx.has) {
+                if (next_score < nx.score) {
+                    nx.score = next_score;
                     heap_push(s.heap, size, next_score, next);
                 }
             } else {
-                s.score[next] = next_score;
-                s.has[next] = 1;
+                nx.score = next_score;
+                nx.has = 1;
                 heap_push(s.heap, size, next_score, next);
             }
         }
-        s.visited[node] = 1;
+        s.node[node].visited = 1;
     }
 }
 
@@ -202,18 +216,14 @@ PF_HD int32_t trace_back(const View &g, const Scratch &s, int32_t start, int32_t
         if (iterations > PF_MAX_ITERATIONS) break;
         int32_t best_prev = -1;
         double best_dist = INFINITY;
-        const double current_dist = s.score[current];
-        for (int32_t e = s.in_head[current]; e >= 0; e = s.in_next[e]) {   // neighbors_directed(Incoming)
-            const int32_t neighbor = s.e_from[e];
-            if (!s.has[neighbor]) continue;
-            // graph.find_edge(neighbor, current): the first match in neighbor's outgoing list (no parallel edges in a k-mer graph)
-            double w = edge_weight(g, neighbor, e);
-            for (int32_t f = out_first(g, neighbor); f >= out_last(g, neighbor); f--)
-                if (edge_to(g, f) == current) {
-                    w = edge_weight(g, neighbor, f);
-                    break;
-                }
-            const double neighbor_dist = s.score[neighbor];
+        const double current_dist = s.node[current].score;
+        for (int32_t e = s.node[current].in_head; e >= 0; e = s.edge[e].in_next) {   // neighbors_directed(Incoming)
+            const int32_t neighbor = s.edge[e].e_from;
+            if (!s.node[neighbor].has) continue;
+            // graph.find_edge(neighbor, current): the first match in neighbor's outgoing list; a k-mer graph has no parallel edges, so
+            // it is this edge, and its weight depends on the two end nodes only
+            const double w = edge_weight(g, s, neighbor, current);
+            const double neighbor_dist = s.node[neighbor].score;
             const double expected_dist = neighbor_dist + w;
             if (fabs(expected_dist - current_dist) < FLOAT_EPSILON) {
                 if (neighbor_dist < best_dist) {
@@ -241,8 +251,8 @@ PF_HD int32_t find_shortest_path(const View &g, const Scratch &s, const int32_t 
         dijkstra(g, s, start);
         for (int32_t b = 0; b < n_ends; b++) {
             const int32_t end = ends[b];
-            if (!s.has[end]) continue;
-            const double total_weight = s.score[end];
+            if (!s.node[end].has) continue;
+            const double total_weight = s.node[end].score;
             if (!(total_weight < min_total_weight)) continue;
             const int32_t len = trace_back(g, s, start, end);
             if (len > 0) {
@@ -297,7 +307,7 @@ PF_HD int32_t auto_contig(const View &g, const Scratch &s, char *out)
     int32_t ns = 0, ne = 0;
     for (int32_t i = 0; i < g.n; i++) {
         if (g.counts[i] < thr) continue;
-        const bool has_in = s.in_head[i] >= 0;
+        const bool has_in = s.node[i].in_head >= 0;
         const int32_t out_degree = (int32_t)(g.row_ptr[i + 1] - g.row_ptr[i]);
         if (!has_in && out_degree > 0) s.list_a[ns++] = i;
         if (out_degree == 0 && has_in) s.list_b[ne++] = i;
@@ -325,8 +335,8 @@ PF_HD int32_t auto_contig(const View &g, const Scratch &s, char *out)
                 dijkstra(g, s, st);
                 have_dist = true;
             }
-            if (!s.has[en]) continue;
-            const double w = s.score[en];
+            if (!s.node[en].has) continue;
+            const double w = s.node[en].score;
             if (!(w < INFINITY)) continue;
             const int32_t len = trace_back(g, s, st, en);
             if (len == 0) continue;

@@ -2,7 +2,7 @@
 // container-free procedure of pathfind_core.h -- the same source the host entries execute, so the result is petgraph's first-pop
 // Dijkstra with Rust's heap order, the 1e-9 back-trace and the automatic method's scoring, bit for bit (edge weights come from a table
 // filled on the host with libm's log).  The procedure is sequential per group by nature (a heap); the parallelism is across groups:
-// a frame has 10^5..10^6 of them.  Working arrays live in HBM (30 B per node + 24 B per edge), groups go in waves bounded by the
+// a frame has 10^5..10^6 of them.  Working arrays live in HBM (32 B per node + 24 B per edge), groups go in waves bounded by the
 // workspace.  Included by rogtk_gpu.cu after the context definition.
 #pragma once
 #include "pathfind_core.h"
@@ -24,10 +24,9 @@ struct PathArgs {
     const uint8_t *sd, *ed;
     const double *wtab;
     int64_t o0, e0;                 // first node / first edge of the wave
-    int32_t *in_head, *list_a, *list_b, *path, *best_path;
-    double *score;
-    uint8_t *has, *visited;
-    int32_t *in_next, *e_from;
+    int32_t *list_a, *list_b, *path, *best_path;
+    rogtk_pf::NodeRec *node;
+    rogtk_pf::EdgeRec *edge;
     rogtk_pf::HeapItem *heap;
     char *out;                      // slot of group g: kmer_offsets[g] + g * K  (n + K - 1 bytes at most)
     int32_t *out_len;               // [n_groups]
@@ -48,8 +47,7 @@ __global__ void __launch_bounds__(128) k_pathfind(PathArgs a)
         }
         const int64_t ln = o - a.o0, le = a.row_ptr[o] - a.e0, gi = g - a.g0;
         const rogtk_pf::View v{a.K, (int32_t)n, a.lo + o, a.hi ? a.hi + o : nullptr, a.counts + o, a.row_ptr + o, a.col, a.wtab};
-        const rogtk_pf::Scratch s{a.in_head + ln, a.in_next + le, a.e_from + le, a.score + ln, a.has + ln, a.visited + ln, a.heap + le + gi,
-                                  a.path + ln + gi, a.best_path + ln + gi, a.list_a + ln, a.list_b + ln};
+        const rogtk_pf::Scratch s{a.node + ln, a.edge + le, a.heap + le + gi, a.path + ln + gi, a.best_path + ln + gi, a.list_a + ln, a.list_b + ln};
         char *out = a.out + o + g * a.K;
         int32_t len;
         if (a.method == ROGTK_METHOD_SHORTEST_PATH) {
@@ -134,26 +132,25 @@ void pathfind_rows_device(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *db, int m
     DevBuf d_out(out_bytes, st), d_len((size_t)ng * 4, st);
     a.out = d_out.as<char>(); a.out_len = d_len.as<int32_t>();
     CK(cudaEventRecord(ctx->ev[12], st));
-    // waves: 30 B per node + 24 B per edge + per-group slack within half the workspace
+    // waves: 32 B per node + 24 B per edge + per-group slack within half the workspace
     const int64_t budget = std::max<int64_t>(64 << 20, (int64_t)(ctx->workspace_bytes / 2));
     int64_t g0 = 0;
     while (g0 < ng) {
         int64_t g1 = g0, bytes = 0;
         while (g1 < ng) {
             const int64_t n = h_off[(size_t)g1 + 1] - h_off[(size_t)g1], m = h_eb[(size_t)g1 + 1] - h_eb[(size_t)g1];
-            const int64_t need = 30 * n + 24 * m + 64;   // (groups the kernel skips keep their place: the arrays are indexed by node / edge offset)
+            const int64_t need = 32 * n + 24 * m + 64;   // (groups the kernel skips keep their place: the arrays are indexed by node / edge offset)
             if (g1 > g0 && bytes + need > budget) break;
             bytes += need;
             g1++;
         }
         const int64_t nw = h_off[(size_t)g1] - h_off[(size_t)g0], mw = h_eb[(size_t)g1] - h_eb[(size_t)g0], gw = g1 - g0;
         const size_t nn = (size_t)std::max<int64_t>(nw, 1), mm = (size_t)std::max<int64_t>(mw, 1), gg = (size_t)gw + 2;
-        DevBuf in_head(nn * 4, st), list_a(nn * 4, st), list_b(nn * 4, st), path((nn + gg) * 4, st), best_path((nn + gg) * 4, st), score(nn * 8, st),
-            has(nn, st), visited(nn, st), in_next(mm * 4, st), e_from(mm * 4, st), heap((mm + gg) * sizeof(rogtk_pf::HeapItem), st);
+        DevBuf node(nn * sizeof(rogtk_pf::NodeRec), st), edge(mm * sizeof(rogtk_pf::EdgeRec), st), list_a(nn * 4, st), list_b(nn * 4, st),
+            path((nn + gg) * 4, st), best_path((nn + gg) * 4, st), heap((mm + gg) * sizeof(rogtk_pf::HeapItem), st);
         a.g0 = g0; a.g1 = g1; a.o0 = h_off[(size_t)g0]; a.e0 = h_eb[(size_t)g0];
-        a.in_head = in_head.as<int32_t>(); a.list_a = list_a.as<int32_t>(); a.list_b = list_b.as<int32_t>(); a.path = path.as<int32_t>();
-        a.best_path = best_path.as<int32_t>(); a.score = score.as<double>(); a.has = has.as<uint8_t>(); a.visited = visited.as<uint8_t>();
-        a.in_next = in_next.as<int32_t>(); a.e_from = e_from.as<int32_t>(); a.heap = heap.as<rogtk_pf::HeapItem>();
+        a.node = node.as<rogtk_pf::NodeRec>(); a.edge = edge.as<rogtk_pf::EdgeRec>(); a.list_a = list_a.as<int32_t>(); a.list_b = list_b.as<int32_t>();
+        a.path = path.as<int32_t>(); a.best_path = best_path.as<int32_t>(); a.heap = heap.as<rogtk_pf::HeapItem>();
         const unsigned grid = (unsigned)std::min<int64_t>((gw + 127) / 128, (int64_t)ctx->sm_count * 16);
         k_pathfind<<<grid, 128, 0, st>>>(a);
         ctx->launches++;

@@ -338,20 +338,18 @@ inline PathResult path_between(const GroupGraph &g, const PetGraph &pg, const st
 // Without a boomphf rank the node ids are the ascending order and the container-free procedure of pathfind_core.h applies -- the
 // code the GPU runs per group (k_pathfind); with a rank the petgraph restatement above is used.
 struct CoreScratch {
-    std::vector<int32_t> in_head, in_next, e_from, path, best_path, list_a, list_b;
-    std::vector<double> score;
-    std::vector<uint8_t> has, visited;
+    std::vector<int32_t> path, best_path, list_a, list_b;
+    std::vector<rogtk_pf::NodeRec> node;
+    std::vector<rogtk_pf::EdgeRec> edge;
     std::vector<rogtk_pf::HeapItem> heap;
     std::vector<char> out;
     rogtk_pf::Scratch bind(int32_t n, int32_t m, int K)
     {
         const size_t pn = (size_t)std::min<int32_t>(n, rogtk_pf::PF_MAX_ITERATIONS + 1) + 1;
-        in_head.resize((size_t)n); in_next.resize((size_t)m + 1); e_from.resize((size_t)m + 1);
-        score.resize((size_t)n); has.resize((size_t)n); visited.resize((size_t)n); heap.resize((size_t)m + 2);
+        node.resize((size_t)n); edge.resize((size_t)m + 1); heap.resize((size_t)m + 2);
         path.resize(pn); best_path.resize(pn); list_a.resize((size_t)n); list_b.resize((size_t)n);
         out.resize((size_t)n + (size_t)K + 8);
-        return rogtk_pf::Scratch{in_head.data(), in_next.data(), e_from.data(), score.data(), has.data(), visited.data(), heap.data(),
-                                 path.data(), best_path.data(), list_a.data(), list_b.data()};
+        return rogtk_pf::Scratch{node.data(), edge.data(), heap.data(), path.data(), best_path.data(), list_a.data(), list_b.data()};
     }
 };
 inline std::string core_contig(const GroupGraph &g, const std::string *start_anchor, const std::string *end_anchor)
