@@ -221,7 +221,7 @@ void evaluate_cell(rogtk_gpu_ctx *ctx, CountedK &ck, uint32_t cov, int method, c
         }
         return;
     }
-    if (!node_rank && !ctx->host_pathfind) {
+    if (!node_rank && !ctx->host_pathfind && ng >= ctx->pathfind_min_groups) {
         // path finding on the device: one thread per group runs the procedure of pathfind_core.h on the batch's nodes + CSR
         rogtk_graph_batch t;
         const int rc = rogtk_gpu_rethreshold(ctx, &ck.db, eff, ROGTK_EMIT_CSR | ROGTK_OUTPUT_ON_DEVICE, &t);
@@ -457,7 +457,7 @@ extern "C" int rogtk_gpu_assemble_batch(rogtk_gpu_ctx *ctx, const rogtk_strcol *
             counted.emplace_back();
             CountedK &ck = counted.back();
             out->n_count_passes++;
-            if (p->method != ROGTK_METHOD_COMPRESSION && !p->node_rank && !ctx->host_pathfind) {
+            if (p->method != ROGTK_METHOD_COMPRESSION && !p->node_rank && !ctx->host_pathfind && n_groups >= ctx->pathfind_min_groups) {
                 // path finding on the device: nodes + successor CSR stay in HBM, one thread per group searches (pathfind_device.cuh)
                 rogtk_graph_batch t;
                 const uint32_t f = (flags & (ROGTK_INPUT_ON_DEVICE | ROGTK_EXACT_K | ROGTK_FORCE_SPILL | ROGTK_NO_MULTIPASS)) | ROGTK_EMIT_CSR |

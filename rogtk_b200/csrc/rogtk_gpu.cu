@@ -55,6 +55,8 @@ struct rogtk_gpu_ctx {
     uint8_t *peek_slot = nullptr;   // mapped pinned words the counter reads land in (host_util.cuh: Peek)
     double *d_wtab = nullptr;       // edge-weight table of the device path search (pathfind_device.cuh)
     bool host_pathfind = false;     // ROGTK_HOST_PATHFIND: run the shortest-path methods on the host cores instead
+    int64_t pathfind_min_groups = 16384;   // frames with fewer groups search on the host (ROGTK_PATHFIND_MIN_GROUPS): one device thread per
+                                           // group takes ~70 us per node whatever the frame size, a host core ~50 us per GROUP
     int sm_count = 148;
     size_t smem_optin = 0;
     void *flush_buf = nullptr;
@@ -396,6 +398,7 @@ extern "C" rogtk_gpu_ctx *rogtk_gpu_create(int device, size_t workspace_bytes, i
             ctx->stage_threads = (int)std::min(16u, std::max(1u, hw / 2));
             if (const char *e = getenv("ROGTK_STAGE_THREADS")) ctx->stage_threads = std::max(1, atoi(e));
             if (const char *e = getenv("ROGTK_HOST_PATHFIND")) ctx->host_pathfind = atoi(e) != 0;
+            if (const char *e = getenv("ROGTK_PATHFIND_MIN_GROUPS")) ctx->pathfind_min_groups = atoll(e);
         }
         if (const char *e = getenv("ROGTK_DEBUG_POOL_CAP")) ctx->tune.debug_pool_cap = atoll(e);   // tests: exhaust the survivor pool
         if (const char *e = getenv("ROGTK_WALK_RL")) {   // experiments: 0 = round-1 counting kernel, 3..6 = log2(windows per lane range)

@@ -327,6 +327,7 @@ def test_path_search_on_the_device_equals_the_host_route(oracle, monkeypatch):
     monkeypatch.setenv("ROGTK_HOST_PATHFIND", "1")
     with rogtk_b200.Engine(device=0) as host_eng:
         monkeypatch.delenv("ROGTK_HOST_PATHFIND")
+        monkeypatch.setenv("ROGTK_PATHFIND_MIN_GROUPS", "0")   # (frames of fewer than 16 384 groups search on the host by default)
         with rogtk_b200.Engine(device=0) as dev_eng, rogtk_b200.Engine(device=0, workspace_bytes=1 << 20) as small_eng:
             for k, mc in ((13, 1), (21, 2), (40, 1)):
                 for kw in (dict(method="shortest_path_auto"), dict(method="shortest_path", anchors_per_group=(sl, el)),
