@@ -21,7 +21,8 @@ namespace {
 
 struct HostStrings {   // one string per group, LargeUtf8 layout, plain host memory
     std::vector<int64_t> off;
-    std::vector<uint8_t> data, flags;
+    ByteVec data;                 // (pathfind_device.cuh: resize() without a zero-fill)
+    std::vector<uint8_t> flags;
     std::string get(int64_t g) const { return std::string(data.begin() + off[(size_t)g], data.begin() + off[(size_t)g + 1]); }
     int64_t len(int64_t g) const { return off[(size_t)g + 1] - off[(size_t)g]; }
 };
@@ -340,7 +341,8 @@ void hand_over_strings(rogtk_gpu_ctx *ctx, const HostStrings &hs, rogtk_string_b
     uint8_t *f = (uint8_t *)pinned_get(ctx, (size_t)std::max<int64_t>(ng, 1));
     own->ptrs.push_back(f);
     memcpy(o, hs.off.data(), (size_t)(ng + 1) * 8);
-    if (out->n_bytes) memcpy(d, hs.data.data(), (size_t)out->n_bytes);
+    if (out->n_bytes)   // (hundreds of MB for a large frame: all staging threads copy)
+        host_parallel(out->n_bytes, ctx->stage_threads, 8 << 20, [&](int64_t x0, int64_t x1) { memcpy(d + x0, hs.data.data() + x0, (size_t)(x1 - x0)); });
     if (ng) memcpy(f, hs.flags.data(), (size_t)ng);
     out->offsets = o;
     out->data = d;

@@ -10,6 +10,26 @@
 
 namespace {
 
+// byte buffer whose resize() does not zero-fill (the bytes are written right after: a 300 MB memset is a tenth of the call)
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+    template <typename U>
+    struct rebind {
+        using other = NoInitAlloc<U>;
+    };
+    template <typename U>
+    void construct(U *p) noexcept
+    {
+        ::new (static_cast<void *>(p)) U;
+    }
+    template <typename U, typename... A>
+    void construct(U *p, A &&...a)
+    {
+        ::new (static_cast<void *>(p)) U(std::forward<A>(a)...);
+    }
+};
+using ByteVec = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
+
 struct PathArgs {
     int64_t g0, g1;                 // groups of this wave
     const int64_t *kmer_offsets;
@@ -78,7 +98,7 @@ struct DevAnchors {   // what pathfind_rows_device needs from the caller's ancho
 
 // db: device-resident batch WITH its successor CSR.  One string per group into off / data (host vectors), "" where there is no contig.
 void pathfind_rows_device(rogtk_gpu_ctx *ctx, const rogtk_graph_batch *db, int method, const DevAnchors &an, int64_t min_length,
-                          std::vector<int64_t> &off, std::vector<uint8_t> &data, float *ms_device)
+                          std::vector<int64_t> &off, ByteVec &data, float *ms_device)
 {
     const int64_t ng = db->n_groups, N = db->n_kmers;
     const int K = db->k_eff;
