@@ -64,3 +64,15 @@ def test_assemble_frame_matches_per_group_reference_calls(engine, oracle, tmp_pa
                 assert fl & 1
                 continue
             assert got == (want[0] if want else ""), (u, method)
+
+
+def test_read_fasta_sequences(tmp_path):
+    """The FASTA side of fracture_fasta (reference src/fracture.rs:161-186 reads records with bio::io::fasta): header lines dropped,
+    wrapped lines joined, blank lines and a missing final newline tolerated, text before the first header ignored; case and
+    non-ACGT records are left to the device (upper-casing and the whole-read drop happen there)."""
+    from rogtk_b200.fracture import read_fasta_sequences
+    fa = tmp_path / "x.fa"
+    fa.write_bytes(b"junk before any header\n>r1 desc\nACGT\nacgt\n\n>r2\r\nTTTT\r\n>empty\n>r3\nACGTN\nGG")
+    assert read_fasta_sequences(fa) == [b"ACGTacgt", b"TTTT", b"", b"ACGTNGG"]
+    (tmp_path / "none.fa").write_bytes(b"")
+    assert read_fasta_sequences(tmp_path / "none.fa") == []
